@@ -1,0 +1,204 @@
+/*
+ * protstruc_b200 — C-ABI of the B200 (sm_100a) geometric-feature hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one method (or
+ * free function) of the reference's Python surface, cited as file:line into the
+ * reference tree (dohlee/protstruc).  The reference has no FFI of its own (it is
+ * pure Python), so these are the functions a maintainer would bind with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every pointer is a DEVICE pointer into memory owned by the caller
+ *     (the Python side allocates outputs with torch and passes data_ptr());
+ *     kernels never allocate or free device memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     launches are asynchronous on that stream, no hidden synchronisation;
+ *   - every function returns PS_OK (0) or a negative ps_status code and records a
+ *     human-readable message retrievable with ps_last_error_string() (thread local);
+ *   - coordinates are fp32, row-major contiguous (B, L, A, 3);
+ *   - masks: `mask_dtype` is PS_MASK_BOOL (1 byte per element, 0/1) or
+ *     PS_MASK_F32 (fp32, arbitrary values, multiplied like the reference does).
+ */
+#ifndef PROTSTRUC_B200_H_
+#define PROTSTRUC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ps_status {
+    PS_OK = 0,
+    PS_ERR_BAD_SHAPE = -1,     /* a dimension is <= 0 or exceeds a kernel limit      */
+    PS_ERR_NULL_POINTER = -2,  /* a required pointer is NULL                         */
+    PS_ERR_BAD_DTYPE = -3,     /* unknown mask_dtype / kind code                     */
+    PS_ERR_BAD_SLOT = -4,      /* atom slot index outside [0, A)                     */
+    PS_ERR_MISALIGNED = -5,    /* pointer alignment requirement violated             */
+    PS_ERR_CUDA = -6           /* CUDA runtime error (message has cudaGetErrorString) */
+} ps_status;
+
+enum { PS_MASK_BOOL = 0, PS_MASK_F32 = 1 };
+enum { PS_ANGLE_DIHEDRAL = 0, PS_ANGLE_PLANAR = 1 };
+
+/* Library / build identification. */
+int ps_abi_version(void);                 /* bumps on any signature change            */
+const char* ps_build_info(void);          /* "sm_100a nvcc <ver> ..."                  */
+const char* ps_last_error_string(void);   /* message of the last failing call (thread) */
+int ps_device_sm_count(int device);       /* >0, or negative ps_status                 */
+
+/*
+ * K1 — all-atom pairwise distance matrix with the pair mask fused in.
+ * Replaces StructureBatch.pairwise_distance_matrix  (protstruc/protstruc.py:455-484):
+ *   dist[b,i,j,a,c]      = || xyz[b,i,a,:] - xyz[b,j,c,:] ||_2           (NOT masked; NaN flows)
+ *   dist_mask[b,i,j,a,c] = atom_mask[b,i,a] * atom_mask[b,j,c]            (dtype of atom_mask)
+ * xyz (B,L,A,3) f32; atom_mask (B,L,A) of mask_dtype; dist (B,L,L,A,A) f32;
+ * dist_mask (B,L,L,A,A) of mask_dtype.  atom_mask/dist_mask may both be NULL
+ * (distances only).  dist may be NULL (mask only).  Output pointers must be
+ * 16-byte aligned for the staged fast path (A == 15); otherwise a generic
+ * kernel is used.
+ */
+int ps_pair_dist_mask(const float* xyz, const void* atom_mask, int mask_dtype,
+                      float* dist, void* dist_mask,
+                      int B, int L, int A, void* stream);
+
+/*
+ * K2 — pairwise dihedral / planar angle between residues for arbitrary atom-slot lists.
+ * Replaces StructureBatch.pairwise_dihedrals / pairwise_planar_angles
+ * (protstruc/protstruc.py:620-660) including the gather of _pairwise_xyz (:589-618)
+ * and geometry.dihedral / geometry.angle (protstruc/geometry.py:39-124).
+ *   kind = PS_ANGLE_DIHEDRAL: n_i + n_j == 4;  kind = PS_ANGLE_PLANAR: n_i + n_j == 3
+ *   the point list is slots_i of residue i followed by slots_j of residue j
+ * out (B,L,L) f32.
+ */
+int ps_pair_angles(const float* xyz, int B, int L, int A,
+                   const int* slots_i, int n_i, const int* slots_j, int n_j,
+                   int kind, float* out, void* stream);
+
+/*
+ * K2f — the trRosetta-style triple in one pass over the pairs.
+ * Replaces the three angle calls of StructureBatch.inter_residue_geometry
+ * (protstruc/protstruc.py:810-815), exactly as the reference defines them:
+ *   omega[b,i,j] = dihedral(CA_i, CB_i, CA_j, CB_j)
+ *   theta[b,i,j] = dihedral(N_i,  CA_i, CB_i, CB_j)
+ *   phi  [b,i,j] = angle   (CA_i, CB_i, CB_j)
+ * virtual_cb != 0: CB is recomputed in-register from N, CA, C with the
+ * ideal-geometry coefficients of protstruc/geometry.py:217-221 instead of read from slot 4.
+ * Any of omega/theta/phi may be NULL.
+ */
+int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
+                        float* omega, float* theta, float* phi, void* stream);
+
+/*
+ * K1+K2f — the full pairwise feature set in ONE kernel: distance matrix, pair mask
+ * and omega/theta/phi.  Replaces StructureBatch.inter_residue_geometry
+ * (protstruc/protstruc.py:790-817); d_ca/d_cb/d_no are views of `dist` taken by the caller.
+ * Requires A >= 5.  mask_dtype must be PS_MASK_BOOL for the single-kernel path
+ * (PS_MASK_F32 runs the distance/mask/angle kernels back to back on `stream`).
+ */
+int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_dtype,
+                              float* dist, void* dist_mask,
+                              float* omega, float* theta, float* phi,
+                              int B, int L, int A, void* stream);
+
+/*
+ * K3 — per-residue backbone features.
+ * Replaces StructureBatch.backbone_dihedrals (protstruc/protstruc.py:486-541) with the
+ * terminal masks of :435-453, and StructureBatch.backbone_orientations (:543-571) →
+ * geometry.gram_schmidt (protstruc/geometry.py:413-439).
+ *   residue_mask (B,L) uint8 0/1;  chain_idx (B,L) f32, NaN = padding
+ *   dihedrals (B,L,3) f32 [phi,psi,omega]; dihedral_mask (B,L,3) uint8
+ *   frames (B,L,3,3) f32, columns e1,e2,e3 from slots (a1,a2,a3)
+ * Either the (dihedrals, dihedral_mask) pair or frames may be NULL.
+ * residue_mask / chain_idx are only required when dihedrals are requested.
+ */
+int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chain_idx,
+                int B, int L, int A, int a1, int a2, int a3,
+                float* dihedrals, uint8_t* dihedral_mask, float* frames, void* stream);
+
+/*
+ * K4 — masked per-structure, per-axis mean / population std, optionally applied.
+ * Replaces StructureBatch.standardize (protstruc/protstruc.py:696-734), with the
+ * per-structure broadcast the reference intends.
+ *   mu, sd (B,3) f32 out;  xyz_out (B,L,A,3) f32 = (xyz - mu) / sd, may alias xyz, may be NULL.
+ */
+int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype,
+                    int B, int L, int A, float* mu, float* sd, float* xyz_out, void* stream);
+
+/*
+ * Affine per-structure map used by unstandardize (protstruc/protstruc.py:736-744):
+ *   out = xyz * scale[b,:] + shift[b,:]   (two separately rounded fp32 ops)
+ */
+int ps_scale_shift(const float* xyz, const float* scale, const float* shift,
+                   int B, int L, int A, float* xyz_out, void* stream);
+
+/*
+ * NaN-skipping mean of one atom slot over residues.
+ * Replaces StructureBatch.center_of_mass (protstruc/protstruc.py:746-757).  out (B,3) f32.
+ */
+int ps_center_of_mass(const float* xyz, int B, int L, int A, int slot, float* out, void* stream);
+
+/*
+ * Per-structure translation, used by center_at / translate (protstruc/protstruc.py:662-679, 759-788):
+ *   out[b,l,a,:] = xyz[b,l,a,:] + t[b,:]   (t has B rows, or 1 row when t_rows == 1)
+ */
+int ps_translate(const float* xyz, const float* t, int t_rows,
+                 int B, int L, int A, float* xyz_out, void* stream);
+
+/*
+ * K5 — one forward-diffusion step.  Replaces StructureBatch.diffuse_xyz
+ * (protstruc/protstruc.py:864-878):
+ *   out = fl( fl(sqrt(1-beta_b) * x) + fl(z * sqrt(beta_b)) )     (no FMA contraction)
+ * noise != NULL: z is read from `noise` (bit-matches the reference given the same z).
+ * noise == NULL: z ~ N(0,1) from Philox4x32-10 keyed by `seed`; the counter of element e is
+ *   (e / 4 + elem_offset / 4, step) so the stream does not depend on the launch shape or
+ *   on how the batch is sharded across GPUs (elem_offset = first global element of this shard,
+ *   must be a multiple of 4).
+ * x, out: `B * per_b` f32 elements (per_b = L*A*3); beta (B,) f32.  out may alias x.
+ */
+int ps_diffuse(const float* x, const float* beta, const float* noise,
+               uint64_t seed, uint64_t step, uint64_t elem_offset,
+               float* out, int B, int64_t per_b, void* stream);
+
+/*
+ * K5m — T consecutive diffusion steps fused in registers (one read, one write of x):
+ *   for t in [0,T): x = fl(fl(sqrt(1-betas[t,b]) * x) + fl(z_t * sqrt(betas[t,b])))
+ * z_t is the Philox stream of ps_diffuse with step = step0 + t, so the result is bit-identical
+ * to T calls of ps_diffuse(noise = NULL).  betas (T,B) f32.
+ */
+int ps_diffuse_steps(const float* x, const float* betas, int T,
+                     uint64_t seed, uint64_t step0, uint64_t elem_offset,
+                     float* out, int B, int64_t per_b, void* stream);
+
+/* Fills `out` with the N(0,1) stream ps_diffuse would use (for distribution tests). */
+int ps_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t step,
+                     uint64_t elem_offset, void* stream);
+
+/*
+ * Free-function geometry on flat point lists, replacing protstruc/geometry.py:
+ *   ps_geom_angle     — geometry.angle      (:39-71)   a,b,c  (n,3) → out (n)
+ *   ps_geom_dihedral  — geometry.dihedral   (:74-124)  a,b,c,d (n,3) → out (n)
+ *   ps_geom_gram_schmidt — geometry.gram_schmidt (:413-439) a,b,c (n,3) → out (n,3,3)
+ * to_degree != 0 converts like torch.rad2deg / np.degrees (multiply by 180/pi in fp32).
+ */
+int ps_geom_angle(const float* a, const float* b, const float* c, int64_t n,
+                  int to_degree, float* out, void* stream);
+int ps_geom_dihedral(const float* a, const float* b, const float* c, const float* d,
+                     int64_t n, int to_degree, float* out, void* stream);
+int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t n,
+                         float* out, void* stream);
+
+/*
+ * Tuning hook for K1 (benchmarks / profiling only; not part of the drop-in surface).
+ * variant bit-field: bits 0-1 sqrt mode (0 = sqrt.approx.f32, 1 = sqrt.approx.ftz.f32,
+ * 2 = sqrt.rn.f32); bits 4-7 warps per CTA override (0 = default); bit 8 = force generic kernel.
+ */
+int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
+                         float* dist, void* dist_mask,
+                         int B, int L, int A, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTSTRUC_B200_H_ */

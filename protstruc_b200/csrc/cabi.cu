@@ -1,0 +1,195 @@
+// extern "C" boundary of libprotstruc_b200.so — declarations in include/protstruc_b200.h.
+// Thin argument adapters over the *_impl launchers; no device work happens here.
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace ps {
+
+// launchers defined in the kernel translation units
+int pair_dist_mask_impl(const float*, const void*, int, float*, void*, float*, float*, float*, int,
+                        int, int, int, cudaStream_t);
+int pair_angles_impl(const float*, int, int, int, const int*, int, const int*, int, int, float*,
+                     cudaStream_t);
+int trrosetta_angles_impl(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
+int backbone_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, int, float*,
+                  uint8_t*, float*, cudaStream_t);
+int geom_angle_impl(const float*, const float*, const float*, long long, int, float*, cudaStream_t);
+int geom_dihedral_impl(const float*, const float*, const float*, const float*, long long, int,
+                       float*, cudaStream_t);
+int geom_gram_schmidt_impl(const float*, const float*, const float*, long long, float*,
+                           cudaStream_t);
+int masked_stats_impl(const float*, const void*, int, int, int, int, float*, float*, float*,
+                      cudaStream_t);
+int scale_shift_impl(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
+int translate_impl(const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int center_of_mass_impl(const float*, int, int, int, int, float*, cudaStream_t);
+int diffuse_impl(const float*, const float*, int, const float*, uint64_t, uint64_t, uint64_t, float*,
+                 int, long long, cudaStream_t);
+int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStream_t);
+
+namespace {
+thread_local char g_last_error[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+    set_error("%s: %s (%s)", what, cudaGetErrorString(err), cudaGetErrorName(err));
+    return PS_ERR_CUDA;
+}
+
+int check_launch(const char* kernel_name) {
+    const cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, kernel_name);
+    return PS_OK;
+}
+
+int sm_count_for_current_device() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached_sms = 0;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
+    if (dev != cached_dev) {
+        int sms = 0;
+        err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceGetAttribute(SM count)");
+        cached_dev = dev;
+        cached_sms = sms;
+    }
+    return cached_sms;
+}
+
+}  // namespace ps
+
+#define PS_STREAM(s) (static_cast<cudaStream_t>(s))
+#define PS_STRINGIFY_(x) #x
+#define PS_STRINGIFY(x) PS_STRINGIFY_(x)
+
+extern "C" {
+
+int ps_abi_version(void) { return 1; }
+
+const char* ps_build_info(void) {
+    return "protstruc_b200 sm_100a; nvcc " PS_STRINGIFY(__CUDACC_VER_MAJOR__) "." PS_STRINGIFY(
+        __CUDACC_VER_MINOR__) "." PS_STRINGIFY(__CUDACC_VER_BUILD__);
+}
+
+const char* ps_last_error_string(void) { return ps::g_last_error; }
+
+int ps_device_sm_count(int device) {
+    int sms = 0;
+    const cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (err != cudaSuccess) return ps::cuda_fail(err, "cudaDeviceGetAttribute(SM count)");
+    return sms;
+}
+
+int ps_pair_dist_mask(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                      void* dist_mask, int B, int L, int A, void* stream) {
+    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr,
+                                   nullptr, B, L, A, 0, PS_STREAM(stream));
+}
+
+int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                         void* dist_mask, int B, int L, int A, int variant, void* stream) {
+    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr,
+                                   nullptr, B, L, A, variant, PS_STREAM(stream));
+}
+
+int ps_pair_angles(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
+                   const int* slots_j, int n_j, int kind, float* out, void* stream) {
+    return ps::pair_angles_impl(xyz, B, L, A, slots_i, n_i, slots_j, n_j, kind, out,
+                                PS_STREAM(stream));
+}
+
+int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb, float* omega,
+                        float* theta, float* phi, void* stream) {
+    return ps::trrosetta_angles_impl(xyz, B, L, A, virtual_cb, omega, theta, phi, PS_STREAM(stream));
+}
+
+int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                              void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
+                              int A, void* stream) {
+    if (!(omega && theta && phi && dist && dist_mask && atom_mask)) {
+        ps::set_error("inter_residue_geometry: all inputs and outputs are required");
+        return PS_ERR_NULL_POINTER;
+    }
+    if (A == 15) {
+        return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta,
+                                       phi, B, L, A, 0, PS_STREAM(stream));
+    }
+    // other atom counts: generic distance kernel + the fused angle kernel, back to back
+    int rc = ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr,
+                                     nullptr, B, L, A, 0, PS_STREAM(stream));
+    if (rc != PS_OK) return rc;
+    return ps::trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, PS_STREAM(stream));
+}
+
+int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chain_idx, int B, int L,
+                int A, int a1, int a2, int a3, float* dihedrals, uint8_t* dihedral_mask,
+                float* frames, void* stream) {
+    return ps::backbone_impl(xyz, residue_mask, chain_idx, B, L, A, a1, a2, a3, dihedrals,
+                             dihedral_mask, frames, PS_STREAM(stream));
+}
+
+int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
+                    float* mu, float* sd, float* xyz_out, void* stream) {
+    return ps::masked_stats_impl(xyz, atom_mask, mask_dtype, B, L, A, mu, sd, xyz_out,
+                                 PS_STREAM(stream));
+}
+
+int ps_scale_shift(const float* xyz, const float* scale, const float* shift, int B, int L, int A,
+                   float* xyz_out, void* stream) {
+    return ps::scale_shift_impl(xyz, scale, shift, B, L, A, xyz_out, PS_STREAM(stream));
+}
+
+int ps_center_of_mass(const float* xyz, int B, int L, int A, int slot, float* out, void* stream) {
+    return ps::center_of_mass_impl(xyz, B, L, A, slot, out, PS_STREAM(stream));
+}
+
+int ps_translate(const float* xyz, const float* t, int t_rows, int B, int L, int A, float* xyz_out,
+                 void* stream) {
+    return ps::translate_impl(xyz, t, t_rows, B, L, A, xyz_out, PS_STREAM(stream));
+}
+
+int ps_diffuse(const float* x, const float* beta, const float* noise, uint64_t seed, uint64_t step,
+               uint64_t elem_offset, float* out, int B, int64_t per_b, void* stream) {
+    return ps::diffuse_impl(x, beta, 1, noise, seed, step, elem_offset, out, B, per_b,
+                            PS_STREAM(stream));
+}
+
+int ps_diffuse_steps(const float* x, const float* betas, int T, uint64_t seed, uint64_t step0,
+                     uint64_t elem_offset, float* out, int B, int64_t per_b, void* stream) {
+    return ps::diffuse_impl(x, betas, T, nullptr, seed, step0, elem_offset, out, B, per_b,
+                            PS_STREAM(stream));
+}
+
+int ps_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t step, uint64_t elem_offset,
+                     void* stream) {
+    return ps::philox_normal_impl(out, n, seed, step, elem_offset, PS_STREAM(stream));
+}
+
+int ps_geom_angle(const float* a, const float* b, const float* c, int64_t n, int to_degree,
+                  float* out, void* stream) {
+    return ps::geom_angle_impl(a, b, c, n, to_degree, out, PS_STREAM(stream));
+}
+
+int ps_geom_dihedral(const float* a, const float* b, const float* c, const float* d, int64_t n,
+                     int to_degree, float* out, void* stream) {
+    return ps::geom_dihedral_impl(a, b, c, d, n, to_degree, out, PS_STREAM(stream));
+}
+
+int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t n, float* out,
+                         void* stream) {
+    return ps::geom_gram_schmidt_impl(a, b, c, n, out, PS_STREAM(stream));
+}
+
+}  // extern "C"

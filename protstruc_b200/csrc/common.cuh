@@ -1,0 +1,136 @@
+// Shared device helpers for the protstruc_b200 kernels (sm_100a only).
+//
+// Arithmetic contract: the angle / frame helpers reproduce the reference's op order
+// (protstruc/geometry.py:24-124, 413-439) with explicitly rounded fp32 operations
+// (__fmul_rn / __fsub_rn / __fadd_rn are never contracted into FMAs by nvcc), because
+// the reference computes cross and dot products as separate numpy / ATen array ops and
+// its degenerate cases (diagonal pairs, collinear atoms) depend on exact cancellation.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/protstruc_b200.h"
+
+namespace ps {
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t err, const char* what);
+int check_launch(const char* kernel_name);
+int sm_count_for_current_device();
+
+#define PS_REQUIRE(cond, code, ...)     \
+    do {                                \
+        if (!(cond)) {                  \
+            ::ps::set_error(__VA_ARGS__); \
+            return (code);              \
+        }                               \
+    } while (0)
+
+// ---------------------------------------------------------------- small vector type
+struct V3 {
+    float x, y, z;
+};
+
+__device__ __forceinline__ V3 ld3(const float* __restrict__ p) {
+    V3 v;
+    v.x = __ldg(p);
+    v.y = __ldg(p + 1);
+    v.z = __ldg(p + 2);
+    return v;
+}
+
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) {
+    return V3{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)};
+}
+
+// np.cross / torch.cross on the last axis: two rounded products, one rounded subtraction.
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    V3 r;
+    r.x = __fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y));
+    r.y = __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z));
+    r.z = __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x));
+    return r;
+}
+
+// (x * y).sum(-1): products are materialised (rounded) first, then summed left to right.
+__device__ __forceinline__ float dot3(V3 a, V3 b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+
+// x.norm(dim=-1): IEEE sqrt of the sum of squares.
+__device__ __forceinline__ float norm3(V3 a) {
+    return __fsqrt_rn(dot3(a, a));
+}
+
+__device__ __forceinline__ V3 scale3(V3 a, float s) {
+    return V3{__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)};
+}
+
+__device__ __forceinline__ V3 div3(V3 a, float s) {
+    return V3{__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)};
+}
+
+// geometry.dihedral (protstruc/geometry.py:110-124).
+__device__ __forceinline__ float dihedral4(V3 a, V3 b, V3 c, V3 d) {
+    const V3 b0 = sub3(a, b);
+    const V3 b1 = sub3(c, b);
+    const V3 b2 = sub3(d, c);
+    const V3 n1 = cross3(b0, b1);
+    const V3 n2 = cross3(b2, b1);
+    const V3 m = cross3(n1, n2);
+    const float x = dot3(n1, n2);
+    const float y = __fdiv_rn(dot3(m, b1), norm3(b1));
+    return atan2f(y, x);
+}
+
+// geometry.angle (protstruc/geometry.py:64-71); no clamp, exactly like the reference.
+__device__ __forceinline__ float angle3(V3 a, V3 b, V3 c) {
+    const V3 ba = sub3(a, b);
+    const V3 bc = sub3(c, b);
+    const float cosine = __fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc)));
+    return acosf(cosine);
+}
+
+// Virtual CB from N, CA, C (protstruc/geometry.py:217-221):
+//   b = CA - N, c = C - CA, a = b x c;  CB = -0.58273431 a + 0.56802827 b - 0.54067466 c + CA
+// evaluated left to right with separately rounded ops as the torch expression does.
+__device__ __forceinline__ V3 virtual_cb(V3 n, V3 ca, V3 c) {
+    const V3 vb = sub3(ca, n);
+    const V3 vc = sub3(c, ca);
+    const V3 va = cross3(vb, vc);
+    V3 r;
+    r.x = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.x), __fmul_rn(0.56802827f, vb.x)),
+                              __fmul_rn(0.54067466f, vc.x)), ca.x);
+    r.y = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.y), __fmul_rn(0.56802827f, vb.y)),
+                              __fmul_rn(0.54067466f, vc.y)), ca.y);
+    r.z = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.z), __fmul_rn(0.56802827f, vb.z)),
+                              __fmul_rn(0.54067466f, vc.z)), ca.z);
+    return r;
+}
+
+// ---------------------------------------------------------------- bulk async copy (TMA engine)
+// smem -> global bulk copy, tracked by the per-thread bulk async-group.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// Wait until the smem source of all committed groups has been read (buffer reusable).
+__device__ __forceinline__ void bulk_wait_read_all() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// Wait until all committed groups are complete (writes performed).
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// Make generic-proxy smem writes visible to the async proxy before a bulk copy reads them.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace ps

@@ -1,0 +1,201 @@
+// K5 — forward diffusion of the coordinates.
+//
+// Replaces StructureBatch.diffuse_xyz (protstruc/protstruc.py:864-878):
+//     noise = randn_like(xyz) * sqrt(beta_b);  xyz = sqrt(1 - beta_b) * xyz + noise
+// which the reference evaluates as three separately rounded fp32 ops (no FMA); __fmul_rn /
+// __fadd_rn below pin that rounding so that, given the same noise tensor, results are bit-equal.
+//
+// Random numbers: counter-based Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.  The counter
+// of a group of four consecutive elements is (global_group_index, step), the key is the seed, so
+// the stream is a pure function of (seed, step, global element index): independent of the launch
+// shape, of the number of GPUs the batch is sharded over, and identical between the single-step
+// kernel and the fused multi-step kernel.
+//
+// Roofline: single step = HBM/L2 read + write of 4 B per element (the noise is never
+// materialised); the 300-step schedule of BASELINE config 4 (23.6 MB of state) is launch/L2-bound
+// when run as 300 launches, so ps_diffuse_steps keeps the state in registers for all T steps and
+// touches HBM once (ALU-bound on Philox + log/sincos).
+
+#include "common.cuh"
+
+namespace ps {
+
+namespace {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+struct U4 {
+    uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
+        c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return c;
+}
+
+// Two uniforms -> two N(0,1).  u1 in (0,1], angle in (0, 2pi].
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u2 = fmaf(static_cast<float>(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    return make_float2(r * s, r * c);
+}
+
+__device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t seed, float (&z)[4]) {
+    const U4 ctr{static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32),
+                 static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32)};
+    const U4 r = philox4x32_10(ctr, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const float2 a = box_muller(r.x, r.y);
+    const float2 b = box_muller(r.z, r.w);
+    z[0] = a.x;
+    z[1] = a.y;
+    z[2] = b.x;
+    z[3] = b.y;
+}
+
+__device__ __forceinline__ float diffuse_one(float x, float z, float sa, float sb) {
+    return __fadd_rn(__fmul_rn(sa, x), __fmul_rn(z, sb));
+}
+
+// Injected-noise variant: purely elementwise.
+__global__ void __launch_bounds__(256) diffuse_noise_kernel(const float* __restrict__ x,
+                                                            const float* __restrict__ beta,
+                                                            const float* __restrict__ noise,
+                                                            long long per_b, long long total,
+                                                            float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += stride) {
+        const float bt = __ldg(beta + e / per_b);
+        const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
+        const float sb = __fsqrt_rn(bt);
+        out[e] = diffuse_one(x[e], __ldg(noise + e), sa, sb);
+    }
+}
+
+// Philox variant: one thread per group of 4 consecutive elements, T steps in registers.
+// betas is (T, B).
+__global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ betas, int T,
+                                                             int B, uint64_t seed, uint64_t step0,
+                                                             uint64_t group_offset, long long per_b,
+                                                             long long total,
+                                                             float* __restrict__ out) {
+    const long long groups = (total + 3) / 4;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
+         g += stride) {
+        const long long e0 = g * 4;
+        float v[4];
+        int bidx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long e = e0 + k;
+            const bool ok = e < total;
+            v[k] = ok ? x[e] : 0.f;
+            bidx[k] = ok ? static_cast<int>(e / per_b) : 0;
+        }
+        const bool same_b = bidx[0] == bidx[3];
+        for (int t = 0; t < T; ++t) {
+            float z[4];
+            normal4(static_cast<uint64_t>(g) + group_offset, step0 + static_cast<uint64_t>(t), seed, z);
+            const float* __restrict__ bt_row = betas + static_cast<long long>(t) * B;
+            if (same_b) {
+                const float bt = __ldg(bt_row + bidx[0]);
+                const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
+                const float sb = __fsqrt_rn(bt);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = diffuse_one(v[k], z[k], sa, sb);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float bt = __ldg(bt_row + bidx[k]);
+                    v[k] = diffuse_one(v[k], z[k], __fsqrt_rn(__fsub_rn(1.0f, bt)), __fsqrt_rn(bt));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e0 + k < total) out[e0 + k] = v[k];
+    }
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, long long n,
+                                                            uint64_t seed, uint64_t step,
+                                                            uint64_t group_offset) {
+    const long long groups = (n + 3) / 4;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
+         g += stride) {
+        float z[4];
+        normal4(static_cast<uint64_t>(g) + group_offset, step, seed, z);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (g * 4 + k < n) out[g * 4 + k] = z[k];
+    }
+}
+
+int grid_for(long long work_items, int* grid) {
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long g = (work_items + 255) / 256;
+    const long long cap = static_cast<long long>(sms) * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    *grid = static_cast<int>(g);
+    return PS_OK;
+}
+
+}  // namespace
+
+int diffuse_impl(const float* x, const float* betas, int T, const float* noise, uint64_t seed,
+                 uint64_t step0, uint64_t elem_offset, float* out, int B, long long per_b,
+                 cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && per_b > 0 && T > 0, PS_ERR_BAD_SHAPE,
+               "diffuse: B=%d per_b=%lld T=%d must be > 0", B, per_b, T);
+    PS_REQUIRE(x && betas && out, PS_ERR_NULL_POINTER, "diffuse: NULL pointer");
+    PS_REQUIRE((elem_offset & 3u) == 0, PS_ERR_MISALIGNED,
+               "diffuse: elem_offset must be a multiple of 4");
+    const long long total = per_b * B;
+    int grid = 0;
+    if (noise) {
+        PS_REQUIRE(T == 1, PS_ERR_BAD_SHAPE, "diffuse: injected noise supports a single step");
+        int rc = grid_for(total, &grid);
+        if (rc != PS_OK) return rc;
+        diffuse_noise_kernel<<<grid, 256, 0, stream>>>(x, betas, noise, per_b, total, out);
+        return check_launch("diffuse_noise_kernel");
+    }
+    int rc = grid_for((total + 3) / 4, &grid);
+    if (rc != PS_OK) return rc;
+    diffuse_philox_kernel<<<grid, 256, 0, stream>>>(x, betas, T, B, seed, step0, elem_offset / 4,
+                                                    per_b, total, out);
+    return check_launch("diffuse_philox_kernel");
+}
+
+int philox_normal_impl(float* out, long long n, uint64_t seed, uint64_t step, uint64_t elem_offset,
+                       cudaStream_t stream) {
+    PS_REQUIRE(n >= 0, PS_ERR_BAD_SHAPE, "philox_normal: n=%lld", n);
+    if (n == 0) return PS_OK;
+    PS_REQUIRE(out, PS_ERR_NULL_POINTER, "philox_normal: out is NULL");
+    PS_REQUIRE((elem_offset & 3u) == 0, PS_ERR_MISALIGNED,
+               "philox_normal: elem_offset must be a multiple of 4");
+    int grid = 0;
+    int rc = grid_for((n + 3) / 4, &grid);
+    if (rc != PS_OK) return rc;
+    philox_normal_kernel<<<grid, 256, 0, stream>>>(out, n, seed, step, elem_offset / 4);
+    return check_launch("philox_normal_kernel");
+}
+
+}  // namespace ps

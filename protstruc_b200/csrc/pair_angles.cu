@@ -1,0 +1,157 @@
+// K2 — pairwise dihedral / planar angles between residues, and the fused trRosetta triple.
+//
+// Replaces StructureBatch.pairwise_dihedrals / pairwise_planar_angles
+// (protstruc/protstruc.py:620-660) — including the (B, L^2, n, 3) gather the reference
+// materialises in _pairwise_xyz (:589-618) — and the three angle calls of
+// inter_residue_geometry (:810-815).
+//
+// Roofline: NOT HBM-bound.  A pair costs ~60 geometric + ~100 transcendental lane-instructions
+// (atan2f / acosf, IEEE division and sqrt) against 4 B (12 B fused) written, so the binding roof
+// is FP32/SFU issue; HBM fraction is reported but is not the target.  The kernel therefore
+// minimises instructions: per-(b,i) invariants are hoisted out of the j loop, the five atoms of
+// residue j a thread needs are loaded once, and lanes walk consecutive j so loads/stores coalesce.
+//
+// Grid: blockIdx.x = (b*L + i) row, threads stride over j.  Rows of L floats are written fully
+// coalesced.
+
+#include "common.cuh"
+
+namespace ps {
+
+namespace {
+
+struct SlotList {
+    int s[4];   // atom slot of point k
+    int from_j[4];  // 0: residue i, 1: residue j
+    int n;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256) pair_angles_kernel(const float* __restrict__ xyz,
+                                                          float* __restrict__ out, int L, int A,
+                                                          SlotList sl, long long rows) {
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long b = row / L;
+        const float* __restrict__ xi = xyz + row * A * 3;
+        const float* __restrict__ xb = xyz + b * L * A * 3;
+        V3 pt[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < sl.n && !sl.from_j[k]) pt[k] = ld3(xi + sl.s[k] * 3);
+        for (int j = threadIdx.x; j < L; j += blockDim.x) {
+            const float* __restrict__ xj = xb + static_cast<long long>(j) * A * 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < sl.n && sl.from_j[k]) pt[k] = ld3(xj + sl.s[k] * 3);
+            float v;
+            if (KIND == PS_ANGLE_DIHEDRAL)
+                v = dihedral4(pt[0], pt[1], pt[2], pt[3]);
+            else
+                v = angle3(pt[0], pt[1], pt[2]);
+            out[row * L + j] = v;
+        }
+    }
+}
+
+// omega = dihedral(CA_i, CB_i, CA_j, CB_j); theta = dihedral(N_i, CA_i, CB_i, CB_j);
+// phi = angle(CA_i, CB_i, CB_j).  Shares loads and the i-only sub-expressions.
+template <bool VIRTUAL_CB>
+__global__ void __launch_bounds__(256) trrosetta_kernel(const float* __restrict__ xyz,
+                                                        float* __restrict__ omega,
+                                                        float* __restrict__ theta,
+                                                        float* __restrict__ phi, int L, int A,
+                                                        long long rows) {
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long b = row / L;
+        const float* __restrict__ xi = xyz + row * A * 3;
+        const float* __restrict__ xb = xyz + b * L * A * 3;
+        const V3 n_i = ld3(xi + 0), ca_i = ld3(xi + 3);
+        const V3 cb_i = VIRTUAL_CB ? virtual_cb(n_i, ca_i, ld3(xi + 6)) : ld3(xi + 12);
+        for (int j = threadIdx.x; j < L; j += blockDim.x) {
+            const float* __restrict__ xj = xb + static_cast<long long>(j) * A * 3;
+            const V3 ca_j = ld3(xj + 3);
+            const V3 cb_j = VIRTUAL_CB ? virtual_cb(ld3(xj + 0), ca_j, ld3(xj + 6)) : ld3(xj + 12);
+            const long long o = row * L + j;
+            if (omega) omega[o] = dihedral4(ca_i, cb_i, ca_j, cb_j);
+            if (theta) theta[o] = dihedral4(n_i, ca_i, cb_i, cb_j);
+            if (phi) phi[o] = angle3(ca_i, cb_i, cb_j);
+        }
+    }
+}
+
+int grid_for_rows(long long rows, int* grid) {
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long g = rows;
+    const long long cap = static_cast<long long>(sms) * 64;
+    if (g > cap) g = cap;
+    *grid = static_cast<int>(g);
+    return PS_OK;
+}
+
+int threads_for_L(int L) {
+    int t = 32;
+    while (t < L && t < 256) t <<= 1;
+    return t;
+}
+
+}  // namespace
+
+int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
+                     const int* slots_j, int n_j, int kind, float* out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "pair_angles: B=%d L=%d A=%d must be > 0",
+               B, L, A);
+    PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "pair_angles: NULL pointer");
+    PS_REQUIRE(kind == PS_ANGLE_DIHEDRAL || kind == PS_ANGLE_PLANAR, PS_ERR_BAD_DTYPE,
+               "pair_angles: unknown kind %d", kind);
+    const int need = kind == PS_ANGLE_DIHEDRAL ? 4 : 3;
+    PS_REQUIRE(n_i >= 0 && n_j >= 0 && n_i + n_j == need, PS_ERR_BAD_SHAPE,
+               "pair_angles: kind %d needs %d atoms in total, got %d + %d", kind, need, n_i, n_j);
+    PS_REQUIRE((n_i == 0 || slots_i) && (n_j == 0 || slots_j), PS_ERR_NULL_POINTER,
+               "pair_angles: NULL slot list");
+    SlotList sl;
+    sl.n = need;
+    for (int k = 0; k < 4; ++k) {
+        sl.s[k] = 0;
+        sl.from_j[k] = 0;
+    }
+    for (int k = 0; k < need; ++k) {
+        const bool from_j = k >= n_i;
+        const int s = from_j ? slots_j[k - n_i] : slots_i[k];
+        PS_REQUIRE(s >= 0 && s < A, PS_ERR_BAD_SLOT, "pair_angles: slot %d outside [0,%d)", s, A);
+        sl.s[k] = s;
+        sl.from_j[k] = from_j ? 1 : 0;
+    }
+    const long long rows = static_cast<long long>(B) * L;
+    int grid = 0;
+    int rc = grid_for_rows(rows, &grid);
+    if (rc != PS_OK) return rc;
+    const int threads = threads_for_L(L);
+    if (kind == PS_ANGLE_DIHEDRAL)
+        pair_angles_kernel<PS_ANGLE_DIHEDRAL><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows);
+    else
+        pair_angles_kernel<PS_ANGLE_PLANAR><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows);
+    return check_launch("pair_angles_kernel");
+}
+
+int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
+                          float* theta, float* phi, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE,
+               "trrosetta_angles: B=%d L=%d A=%d must be > 0", B, L, A);
+    PS_REQUIRE(xyz, PS_ERR_NULL_POINTER, "trrosetta_angles: xyz is NULL");
+    PS_REQUIRE(omega || theta || phi, PS_ERR_NULL_POINTER, "trrosetta_angles: no output requested");
+    PS_REQUIRE(A >= (use_virtual_cb ? 3 : 5), PS_ERR_BAD_SHAPE,
+               "trrosetta_angles: A=%d has no %s slot", A, use_virtual_cb ? "C" : "CB");
+    const long long rows = static_cast<long long>(B) * L;
+    int grid = 0;
+    int rc = grid_for_rows(rows, &grid);
+    if (rc != PS_OK) return rc;
+    const int threads = threads_for_L(L);
+    if (use_virtual_cb)
+        trrosetta_kernel<true><<<grid, threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
+    else
+        trrosetta_kernel<false><<<grid, threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
+    return check_launch("trrosetta_kernel");
+}
+
+}  // namespace ps

@@ -1,0 +1,436 @@
+// K1 — all-atom pairwise distance matrix + fused pair mask (+ optionally the trRosetta angles).
+//
+// Replaces StructureBatch.pairwise_distance_matrix (protstruc/protstruc.py:455-484) and, in its
+// fused form, StructureBatch.inter_residue_geometry (protstruc/protstruc.py:790-817).
+//
+// Roofline: store-bound.  Per residue pair (b,i,j) the kernel writes A*A fp32 distances plus A*A
+// mask bytes (1125 B at A = 15) and reads ~2 residues of coordinates from L1/L2; there is no
+// reuse to exploit and no GEMM shape (K = 3), so the design goal is: as few issued instructions
+// per output element as possible and perfectly coalesced, asynchronous stores.
+//
+// Data layout in HBM (row-major, contiguous):
+//   xyz        (B, L, A, 3)      fp32
+//   atom_mask  (B, L, A)         bool (1 B) or fp32
+//   dist       (B, L, L, A, A)   fp32      -> a flat array of P = B*L*L pair blocks of A*A floats
+//   dist_mask  (B, L, L, A, A)   same dtype as atom_mask
+//
+// Staged kernel (A = 15, the reference's MAX_N_ATOMS_PER_RESIDUE):
+//   * the pair blocks are a flat list; a TILE is 32 consecutive pair blocks = 7200 elements
+//     = 28,800 B of distances + 7,200 B of mask, both multiples of 16 B, so every tile starts
+//     16-byte aligned whatever L is (no head/tail peeling for odd L);
+//   * one WARP owns one tile at a time: lane = pair.  The lane keeps the 15 atoms of residue j in
+//     registers (packed as f32x2 so the FADD2/FMUL2/FFMA2 pipe does two atoms per instruction),
+//     streams the 15 atoms of residue i through (uniform, L1-broadcast loads) and writes its
+//     225 distances into the warp's shared-memory tile at lane*225 + a*15 + c — a stride of 225
+//     words between lanes, which is 1 mod 32, hence bank-conflict free;
+//   * the finished tile leaves through the TMA engine: one elected lane issues
+//     cp.async.bulk.global.shared::cta (SASS: UBLKCP) for the distance tile and one for the mask
+//     tile.  Address generation and coalescing cost no issue slots, stores are 100 % full-line;
+//   * warps are independent (no __syncthreads): while one warp waits for its tile to drain the
+//     other warps of the persistent CTA compute.  Grid = #SMs, one CTA per SM.
+// Generic kernel (any A, misaligned outputs): one thread per output element, coalesced scalar
+// stores, integer decode per element.  Slower (issue-bound) but shape-agnostic.
+
+#include "common.cuh"
+
+namespace ps {
+
+namespace {
+
+constexpr int kTilePairs = 32;  // pairs per warp tile (= lanes)
+
+enum SqrtMode { kSqrtApprox = 0, kSqrtApproxFtz = 1, kSqrtRn = 2 };
+
+template <int MODE>
+__device__ __forceinline__ float sqrt_mode(float v) {
+    float r;
+    if (MODE == kSqrtApprox) {
+        // MUFU.SQRT with subnormal pre-scaling; max relative error 2^-23 (PTX ISA), sqrt(0)=0,
+        // NaN -> NaN, +inf -> +inf.
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    } else if (MODE == kSqrtApproxFtz) {
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    } else {
+        r = __fsqrt_rn(v);
+    }
+    return r;
+}
+
+// What one launch of the staged kernel produces.
+enum OutKind {
+    kDistBoolMask = 0,  // distances + 1-byte mask        (the reference's from_pdb path)
+    kDistOnly = 1,      // distances only
+    kF32MaskOnly = 2,   // fp32 mask product only          (the reference's from_pdb_id path)
+    kBoolMaskOnly = 3   // 1-byte mask only
+};
+
+template <int A>
+struct TileGeom {
+    static constexpr int kElemsPerPair = A * A;
+    static constexpr int kTileElems = kTilePairs * A * A;
+    static constexpr int kDistBytes = kTileElems * 4;
+    static constexpr int kMaskBytes = kTileElems;
+    static_assert(kDistBytes % 16 == 0 && kMaskBytes % 16 == 0, "tile must be 16-B granular");
+};
+
+template <int KIND>
+__host__ __device__ constexpr bool kind_has_f32() {
+    return KIND == kDistBoolMask || KIND == kDistOnly || KIND == kF32MaskOnly;
+}
+template <int KIND>
+__host__ __device__ constexpr bool kind_has_u8() {
+    return KIND == kDistBoolMask || KIND == kBoolMaskOnly;
+}
+template <int A, int KIND>
+__host__ __device__ constexpr int warp_smem_bytes() {
+    return (kind_has_f32<KIND>() ? TileGeom<A>::kDistBytes : 0) +
+           (kind_has_u8<KIND>() ? TileGeom<A>::kMaskBytes : 0);
+}
+
+struct PairDistParams {
+    const float* __restrict__ xyz;
+    const void* __restrict__ atom_mask;
+    float* __restrict__ dist;    // f32 output (distances, or the fp32 mask for kF32MaskOnly)
+    uint8_t* __restrict__ mask;  // 1-byte mask output
+    float* __restrict__ omega;   // fused angles (may be null)
+    float* __restrict__ theta;
+    float* __restrict__ phi;
+    int L;
+    long long LL;         // L*L
+    long long num_pairs;  // B*L*L
+    long long num_tiles;  // ceil(num_pairs / 32)
+};
+
+// Gather the A mask bytes of one residue into a bit field (bit a = mask[a] != 0).
+template <int A>
+__device__ __forceinline__ uint32_t load_mask_bits(const uint8_t* __restrict__ m) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int a = 0; a < A; ++a) bits |= (__ldg(m + a) != 0 ? 1u : 0u) << a;
+    return bits;
+}
+
+template <int A, int KIND, int SQRT, bool ANGLES>
+__global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams p) {
+    using G = TileGeom<A>;
+    constexpr int NP = (A + 1) / 2;  // f32x2 packs per coordinate
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+
+    unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * warp_smem_bytes<A, KIND>();
+    float* tile_f32 = reinterpret_cast<float*>(wbase);
+    uint8_t* tile_u8 = wbase + (kind_has_f32<KIND>() ? G::kDistBytes : 0);
+
+    const long long tile_stride = static_cast<long long>(gridDim.x) * warps_per_cta;
+    for (long long tile = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;
+         tile < p.num_tiles; tile += tile_stride) {
+        const long long pair0 = tile * kTilePairs;
+        long long pair = pair0 + lane;
+        if (pair >= p.num_pairs) pair = p.num_pairs - 1;  // tail lanes recompute the last pair
+        const long long b = pair / p.LL;
+        const int rem = static_cast<int>(pair - b * p.LL);
+        const int i = rem / p.L;
+        const int j = rem - i * p.L;
+        const long long res_i = b * p.L + i;
+        const long long res_j = b * p.L + j;
+        const float* __restrict__ xi_ptr = p.xyz + res_i * (A * 3);
+        const float* __restrict__ xj_ptr = p.xyz + res_j * (A * 3);
+
+        // Residue j: A atoms in registers, SoA, packed two atoms per 64-bit register pair.
+        float2 xj[NP], yj[NP], zj[NP];
+        float mjf[A];  // fp32 mask row (kF32MaskOnly)
+        uint32_t mi_bits = 0, mj_bits = 0;
+        if (KIND != kF32MaskOnly && KIND != kBoolMaskOnly) {
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
+                xj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 0), __ldg(xj_ptr + 3 * c1 + 0));
+                yj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 1), __ldg(xj_ptr + 3 * c1 + 1));
+                zj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
+            }
+        }
+        if (kind_has_u8<KIND>()) {
+            const uint8_t* am = static_cast<const uint8_t*>(p.atom_mask);
+            mi_bits = load_mask_bits<A>(am + res_i * A);
+            mj_bits = load_mask_bits<A>(am + res_j * A);
+        }
+        if (KIND == kF32MaskOnly) {
+            const float* am = static_cast<const float*>(p.atom_mask);
+#pragma unroll
+            for (int c = 0; c < A; ++c) mjf[c] = __ldg(am + res_j * A + c);
+        }
+
+        // The previous tile of this warp must have left shared memory before we overwrite it.
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+
+        float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
+        uint8_t* my_u8 = tile_u8 + lane * G::kElemsPerPair;
+
+        if (KIND == kDistBoolMask || KIND == kDistOnly) {
+#pragma unroll 3
+            for (int a = 0; a < A; ++a) {
+                const float xi = __ldg(xi_ptr + 3 * a + 0);
+                const float yi = __ldg(xi_ptr + 3 * a + 1);
+                const float zi = __ldg(xi_ptr + 3 * a + 2);
+                const float2 nx = make_float2(-xi, -xi);
+                const float2 ny = make_float2(-yi, -yi);
+                const float2 nz = make_float2(-zi, -zi);
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const float2 dx = __fadd2_rn(xj[k], nx);
+                    const float2 dy = __fadd2_rn(yj[k], ny);
+                    const float2 dz = __fadd2_rn(zj[k], nz);
+                    float2 s = __fmul2_rn(dx, dx);
+                    s = __ffma2_rn(dy, dy, s);
+                    s = __ffma2_rn(dz, dz, s);
+                    my_f32[a * A + 2 * k] = sqrt_mode<SQRT>(s.x);
+                    if (2 * k + 1 < A) my_f32[a * A + 2 * k + 1] = sqrt_mode<SQRT>(s.y);
+                }
+                if (KIND == kDistBoolMask) {
+                    // row a of the pair mask: mask_i[a] ? mask_j[:] : 0, one byte per atom c
+                    const uint32_t row = ((mi_bits >> a) & 1u) ? mj_bits : 0u;
+#pragma unroll
+                    for (int c = 0; c < A; ++c)
+                        my_u8[a * A + c] = static_cast<uint8_t>((row >> c) & 1u);
+                }
+            }
+        } else if (KIND == kF32MaskOnly) {
+            const float* am = static_cast<const float*>(p.atom_mask);
+#pragma unroll 3
+            for (int a = 0; a < A; ++a) {
+                const float mi = __ldg(am + res_i * A + a);
+#pragma unroll
+                for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
+            }
+        } else {  // kBoolMaskOnly
+#pragma unroll 3
+            for (int a = 0; a < A; ++a) {
+                const uint32_t row = ((mi_bits >> a) & 1u) ? mj_bits : 0u;
+#pragma unroll
+                for (int c = 0; c < A; ++c)
+                    my_u8[a * A + c] = static_cast<uint8_t>((row >> c) & 1u);
+            }
+        }
+
+        if (ANGLES) {
+            // trRosetta triple of this lane's pair, reference definitions
+            // (protstruc/protstruc.py:810-815): real CB in slot 4.
+            const V3 n_i = ld3(xi_ptr + 0), ca_i = ld3(xi_ptr + 3), cb_i = ld3(xi_ptr + 12);
+            const V3 ca_j = ld3(xj_ptr + 3), cb_j = ld3(xj_ptr + 12);
+            if (pair0 + lane < p.num_pairs) {
+                if (p.omega) p.omega[pair] = dihedral4(ca_i, cb_i, ca_j, cb_j);
+                if (p.theta) p.theta[pair] = dihedral4(n_i, ca_i, cb_i, cb_j);
+                if (p.phi) p.phi[pair] = angle3(ca_i, cb_i, cb_j);
+            }
+        }
+
+        __syncwarp();
+        const long long elem0 = pair0 * G::kElemsPerPair;
+        if (pair0 + kTilePairs <= p.num_pairs) {
+            // Full tile: hand it to the TMA engine.
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (kind_has_f32<KIND>()) bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
+                if (kind_has_u8<KIND>()) bulk_store_s2g(p.mask + elem0, tile_u8, G::kMaskBytes);
+                bulk_commit();
+            }
+        } else {
+            // Tail tile (num_pairs % 32 != 0): byte count is not 16-B granular, copy by hand.
+            const int n = static_cast<int>(p.num_pairs - pair0) * G::kElemsPerPair;
+            if (kind_has_f32<KIND>())
+                for (int e = lane; e < n; e += 32) p.dist[elem0 + e] = tile_f32[e];
+            if (kind_has_u8<KIND>())
+                for (int e = lane; e < n; e += 32) p.mask[elem0 + e] = tile_u8[e];
+            __syncwarp();
+        }
+    }
+    // Shared memory must stay allocated until the engine has read the last tile.
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ generic fallback
+// One thread per output element; handles any A and any pointer alignment.
+template <int SQRT>
+__global__ void __launch_bounds__(256) pair_generic_kernel(
+    const float* __restrict__ xyz, const void* __restrict__ atom_mask, int mask_dtype,
+    float* __restrict__ dist, void* __restrict__ dist_mask, int L, int A, long long total) {
+    const long long AA = static_cast<long long>(A) * A;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += stride) {
+        const long long pair = e / AA;
+        const int r = static_cast<int>(e - pair * AA);
+        const int a = r / A;
+        const int c = r - a * A;
+        const long long bi = pair / L;  // b*L + i
+        const int j = static_cast<int>(pair - bi * L);
+        const long long b = bi / L;
+        const long long res_i = bi;
+        const long long res_j = b * L + j;
+        if (dist) {
+            const float* pi = xyz + (res_i * A + a) * 3;
+            const float* pj = xyz + (res_j * A + c) * 3;
+            const float dx = __ldg(pi) - __ldg(pj);
+            const float dy = __ldg(pi + 1) - __ldg(pj + 1);
+            const float dz = __ldg(pi + 2) - __ldg(pj + 2);
+            dist[e] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        }
+        if (dist_mask) {
+            if (mask_dtype == PS_MASK_BOOL) {
+                const uint8_t* am = static_cast<const uint8_t*>(atom_mask);
+                const bool v = (__ldg(am + res_i * A + a) != 0) && (__ldg(am + res_j * A + c) != 0);
+                static_cast<uint8_t*>(dist_mask)[e] = v ? 1 : 0;
+            } else {
+                const float* am = static_cast<const float*>(atom_mask);
+                static_cast<float*>(dist_mask)[e] =
+                    __fmul_rn(__ldg(am + res_i * A + a), __ldg(am + res_j * A + c));
+            }
+        }
+    }
+}
+
+template <int A, int KIND, int SQRT, bool ANGLES>
+int launch_tiles(const PairDistParams& p, int warps_override, cudaStream_t stream) {
+    constexpr int per_warp = warp_smem_bytes<A, KIND>();
+    constexpr int kMaxSmem = 227 * 1024;
+    int warps = kMaxSmem / per_warp;
+    if (warps > 8) warps = 8;
+    if (warps_override > 0 && warps_override < warps) warps = warps_override;
+    if (warps < 1) {
+        set_error("pair_tiles_kernel: a warp tile of %d B does not fit in shared memory", per_warp);
+        return PS_ERR_BAD_SHAPE;
+    }
+    const int smem = warps * per_warp;
+    auto kernel = pair_tiles_kernel<A, KIND, SQRT, ANGLES>;
+    cudaError_t err =
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_tiles_kernel)");
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long ctas = (p.num_tiles + warps - 1) / warps;
+    if (ctas > sms) ctas = sms;
+    kernel<<<static_cast<unsigned>(ctas), warps * 32, smem, stream>>>(p);
+    return check_launch("pair_tiles_kernel");
+}
+
+template <int A, int KIND, bool ANGLES>
+int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int warps_override,
+                      cudaStream_t stream) {
+    switch (sqrt_mode_id) {
+        case kSqrtApprox:
+            return launch_tiles<A, KIND, kSqrtApprox, ANGLES>(p, warps_override, stream);
+        case kSqrtApproxFtz:
+            return launch_tiles<A, KIND, kSqrtApproxFtz, ANGLES>(p, warps_override, stream);
+        case kSqrtRn:
+            return launch_tiles<A, KIND, kSqrtRn, ANGLES>(p, warps_override, stream);
+        default:
+            set_error("unknown sqrt mode %d", sqrt_mode_id);
+            return PS_ERR_BAD_DTYPE;
+    }
+}
+
+int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                   void* dist_mask, int B, int L, int A, int sqrt_mode_id, cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * L * L * A * A;
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(sms) * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (sqrt_mode_id == kSqrtRn)
+        pair_generic_kernel<kSqrtRn><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+    else if (sqrt_mode_id == kSqrtApproxFtz)
+        pair_generic_kernel<kSqrtApproxFtz><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+    else
+        pair_generic_kernel<kSqrtApprox><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+    return check_launch("pair_generic_kernel");
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// Host entry used by the C-ABI wrappers (cabi.cu).
+int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                        void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
+                        int A, int variant, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "pair_dist_mask: B=%d L=%d A=%d must be > 0",
+               B, L, A);
+    PS_REQUIRE(xyz != nullptr, PS_ERR_NULL_POINTER, "pair_dist_mask: xyz is NULL");
+    PS_REQUIRE((atom_mask == nullptr) == (dist_mask == nullptr), PS_ERR_NULL_POINTER,
+               "pair_dist_mask: atom_mask and dist_mask must both be given or both be NULL");
+    PS_REQUIRE(dist != nullptr || dist_mask != nullptr, PS_ERR_NULL_POINTER,
+               "pair_dist_mask: nothing to compute (dist and dist_mask are NULL)");
+    PS_REQUIRE(mask_dtype == PS_MASK_BOOL || mask_dtype == PS_MASK_F32, PS_ERR_BAD_DTYPE,
+               "pair_dist_mask: unknown mask_dtype %d", mask_dtype);
+    PS_REQUIRE(static_cast<long long>(L) * L < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "pair_dist_mask: L=%d too large", L);
+    const bool want_angles = omega || theta || phi;
+    PS_REQUIRE(!want_angles || A >= 5, PS_ERR_BAD_SHAPE,
+               "inter_residue_geometry needs the CB slot (A >= 5), got A=%d", A);
+
+    const int sqrt_id = variant & 3;
+    const int warps_override = (variant >> 4) & 15;
+    const bool force_generic = (variant >> 8) & 1;
+
+    const bool fast = (A == 15) && !force_generic && aligned16(dist) && aligned16(dist_mask);
+    if (!fast) {
+        PS_REQUIRE(!want_angles, PS_ERR_BAD_SHAPE,
+                   "fused angles are only available on the staged A=15 path");
+        return launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
+    }
+
+    PairDistParams p;
+    p.xyz = xyz;
+    p.atom_mask = atom_mask;
+    p.dist = dist;
+    p.mask = static_cast<uint8_t*>(dist_mask);
+    p.omega = omega;
+    p.theta = theta;
+    p.phi = phi;
+    p.L = L;
+    p.LL = static_cast<long long>(L) * L;
+    p.num_pairs = p.LL * B;
+    p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
+
+    if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
+        if (dist && dist_mask) {
+            return want_angles
+                       ? launch_tiles_sqrt<15, kDistBoolMask, true>(p, sqrt_id, warps_override, stream)
+                       : launch_tiles_sqrt<15, kDistBoolMask, false>(p, sqrt_id, warps_override, stream);
+        }
+        if (dist) {
+            return want_angles
+                       ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, stream)
+                       : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, stream);
+        }
+        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
+        return launch_tiles<15, kBoolMaskOnly, kSqrtApprox, false>(p, warps_override, stream);
+    }
+    // fp32 mask: distances (+angles) first, then the mask product through the same tile path.
+    if (dist) {
+        int rc = want_angles
+                     ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, stream)
+                     : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, stream);
+        if (rc != PS_OK) return rc;
+    } else {
+        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
+    }
+    PairDistParams pm = p;
+    pm.dist = static_cast<float*>(dist_mask);
+    pm.mask = nullptr;
+    pm.omega = pm.theta = pm.phi = nullptr;
+    return launch_tiles<15, kF32MaskOnly, kSqrtApprox, false>(pm, warps_override, stream);
+}
+
+}  // namespace ps

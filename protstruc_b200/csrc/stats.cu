@@ -1,0 +1,258 @@
+// K4 — masked per-structure statistics and the per-structure affine maps around them.
+//
+// Replaces StructureBatch.standardize / unstandardize (protstruc/protstruc.py:696-744),
+// center_of_mass (:746-757) and the in-place translation of center_at / translate
+// (:662-679, 759-788).
+//
+// Roofline: HBM read + write of the (B,L,A,3) coordinates (25 B per atom with a bool mask).
+// One CTA per structure: pass 1 (masked sum, count) and pass 2 (masked squared deviation) read the
+// structure's coordinates, which stay in L1/L2 (92 KB at L=512), pass 3 writes the normalised
+// coordinates, so HBM sees one read and one write.  Warp-shuffle + shared-memory block reductions;
+// partial sums are accumulated in fp64 (the reference sums in fp32 with ATen's cascade summation —
+// both are well inside the 1e-5 relative parity tolerance, fp64 is simply the more exact of the two).
+
+#include "common.cuh"
+
+namespace ps {
+
+namespace {
+
+constexpr int kStatsThreads = 512;
+
+// torch.nan_to_num(x, nan=0.0): NaN -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX.
+__device__ __forceinline__ float nan_to_num0(float v) {
+    if (v != v) return 0.f;
+    if (v == __int_as_float(0x7f800000)) return 3.4028234663852886e38f;
+    if (v == __int_as_float(0xff800000)) return -3.4028234663852886e38f;
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sums 4 doubles per thread across the block; result valid in every thread.
+__device__ __forceinline__ void block_sum4(double (&v)[4], double (*scratch)[4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();  // scratch reuse across calls
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) scratch[warp][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double t = lane < nwarps ? scratch[lane][k] : 0.0;
+        v[k] = warp_sum(t);
+    }
+}
+
+template <int MASK_DTYPE>
+__device__ __forceinline__ float mask_value(const void* __restrict__ m, long long idx) {
+    if (MASK_DTYPE == PS_MASK_BOOL)
+        return __ldg(static_cast<const uint8_t*>(m) + idx) != 0 ? 1.f : 0.f;
+    return __ldg(static_cast<const float*>(m) + idx);
+}
+
+template <int MASK_DTYPE>
+__global__ void __launch_bounds__(kStatsThreads) masked_stats_kernel(
+    const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
+    float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
+    __shared__ double scratch[kStatsThreads / 32][4];
+    const long long b = blockIdx.x;
+    const float* __restrict__ x = xyz + b * atoms_per_struct * 3;
+    const long long m0 = b * atoms_per_struct;
+
+    // pass 1: sum(nan_to_num(x * m)) per axis, sum(m)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
+        const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
+        acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 0), m)));
+        acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 1), m)));
+        acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 2), m)));
+        acc[3] += static_cast<double>(m);
+    }
+    block_sum4(acc, scratch);
+    const float count = static_cast<float>(acc[3]);
+    float mu[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = __fdiv_rn(static_cast<float>(acc[k]), count);
+
+    // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
+    double dev[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
+        const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d = __fsub_rn(nan_to_num0(__ldg(x + 3 * t + k)), mu[k]);
+            dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m));
+        }
+    }
+    block_sum4(dev, scratch);
+    float sd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sd[k] = __fsqrt_rn(__fdiv_rn(static_cast<float>(dev[k]), count));
+
+    if (threadIdx.x < 3) {
+        mu_out[b * 3 + threadIdx.x] = mu[threadIdx.x];
+        sd_out[b * 3 + threadIdx.x] = sd[threadIdx.x];
+    }
+
+    // pass 3: (x - mu) / sd on every atom (masked or not, NaN stays NaN)
+    if (xyz_out) {
+        float* __restrict__ o = xyz_out + b * atoms_per_struct * 3;
+        const int n = atoms_per_struct * 3;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int k = e % 3;
+            const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
+            const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
+            o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+        }
+    }
+}
+
+// out = x * scale[b, axis] + shift[b, axis]  (unstandardize) — two rounded ops.
+__global__ void __launch_bounds__(256) scale_shift_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift,
+                                                          long long per_b, long long total,
+                                                          float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += stride) {
+        const long long b = e / per_b;
+        const int k = static_cast<int>((e - b * per_b) % 3);
+        out[e] = __fadd_rn(__fmul_rn(x[e], __ldg(scale + b * 3 + k)), __ldg(shift + b * 3 + k));
+    }
+}
+
+// out = x + t[b or 0, axis]
+__global__ void __launch_bounds__(256) translate_kernel(const float* __restrict__ x,
+                                                        const float* __restrict__ t, int t_rows,
+                                                        long long per_b, long long total,
+                                                        float* __restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += stride) {
+        const long long b = e / per_b;
+        const int k = static_cast<int>((e - b * per_b) % 3);
+        const long long row = t_rows == 1 ? 0 : b;
+        out[e] = __fadd_rn(x[e], __ldg(t + row * 3 + k));
+    }
+}
+
+// nanmean over residues of one atom slot: one warp per structure.
+__global__ void __launch_bounds__(128) center_of_mass_kernel(const float* __restrict__ xyz, int B,
+                                                             int L, int A, int slot,
+                                                             float* __restrict__ out) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= B) return;
+    const float* __restrict__ x = xyz + static_cast<long long>(warp_global) * L * A * 3 + slot * 3;
+    double s[3] = {0.0, 0.0, 0.0};
+    double n[3] = {0.0, 0.0, 0.0};
+    for (int l = lane; l < L; l += 32) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = __ldg(x + static_cast<long long>(l) * A * 3 + k);
+            if (v == v) {
+                s[k] += static_cast<double>(v);
+                n[k] += 1.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s[k] = warp_sum(s[k]);
+        n[k] = warp_sum(n[k]);
+    }
+    if (lane < 3) {
+        const double sk = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
+        const double nk = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);
+        // torch.nanmean = nansum / count, both in fp32
+        out[warp_global * 3 + lane] = __fdiv_rn(static_cast<float>(sk), static_cast<float>(nk));
+    }
+}
+
+int elementwise_grid(long long total, int* grid) {
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long g = (total + 255) / 256;
+    const long long cap = static_cast<long long>(sms) * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    *grid = static_cast<int>(g);
+    return PS_OK;
+}
+
+}  // namespace
+
+int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
+                      float* mu, float* sd, float* xyz_out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "masked_stats: B=%d L=%d A=%d must be > 0",
+               B, L, A);
+    PS_REQUIRE(xyz && atom_mask && mu && sd, PS_ERR_NULL_POINTER, "masked_stats: NULL pointer");
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "masked_stats: structure too large (L*A*3 >= 2^31)");
+    const int atoms = L * A;
+    if (mask_dtype == PS_MASK_BOOL)
+        masked_stats_kernel<PS_MASK_BOOL><<<B, kStatsThreads, 0, stream>>>(xyz, atom_mask, atoms, mu,
+                                                                           sd, xyz_out);
+    else if (mask_dtype == PS_MASK_F32)
+        masked_stats_kernel<PS_MASK_F32><<<B, kStatsThreads, 0, stream>>>(xyz, atom_mask, atoms, mu,
+                                                                          sd, xyz_out);
+    else {
+        set_error("masked_stats: unknown mask_dtype %d", mask_dtype);
+        return PS_ERR_BAD_DTYPE;
+    }
+    return check_launch("masked_stats_kernel");
+}
+
+int scale_shift_impl(const float* xyz, const float* scale, const float* shift, int B, int L, int A,
+                     float* xyz_out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "scale_shift: B=%d L=%d A=%d must be > 0",
+               B, L, A);
+    PS_REQUIRE(xyz && scale && shift && xyz_out, PS_ERR_NULL_POINTER, "scale_shift: NULL pointer");
+    const long long per_b = static_cast<long long>(L) * A * 3;
+    const long long total = per_b * B;
+    int grid = 0;
+    int rc = elementwise_grid(total, &grid);
+    if (rc != PS_OK) return rc;
+    scale_shift_kernel<<<grid, 256, 0, stream>>>(xyz, scale, shift, per_b, total, xyz_out);
+    return check_launch("scale_shift_kernel");
+}
+
+int translate_impl(const float* xyz, const float* t, int t_rows, int B, int L, int A,
+                   float* xyz_out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "translate: B=%d L=%d A=%d must be > 0", B,
+               L, A);
+    PS_REQUIRE(xyz && t && xyz_out, PS_ERR_NULL_POINTER, "translate: NULL pointer");
+    PS_REQUIRE(t_rows == 1 || t_rows == B, PS_ERR_BAD_SHAPE, "translate: t_rows=%d must be 1 or B=%d",
+               t_rows, B);
+    const long long per_b = static_cast<long long>(L) * A * 3;
+    const long long total = per_b * B;
+    int grid = 0;
+    int rc = elementwise_grid(total, &grid);
+    if (rc != PS_OK) return rc;
+    translate_kernel<<<grid, 256, 0, stream>>>(xyz, t, t_rows, per_b, total, xyz_out);
+    return check_launch("translate_kernel");
+}
+
+int center_of_mass_impl(const float* xyz, int B, int L, int A, int slot, float* out,
+                        cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE,
+               "center_of_mass: B=%d L=%d A=%d must be > 0", B, L, A);
+    PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "center_of_mass: NULL pointer");
+    PS_REQUIRE(slot >= 0 && slot < A, PS_ERR_BAD_SLOT, "center_of_mass: slot %d outside [0,%d)",
+               slot, A);
+    const int warps_per_block = 4;
+    const int blocks = (B + warps_per_block - 1) / warps_per_block;
+    center_of_mass_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(xyz, B, L, A, slot, out);
+    return check_launch("center_of_mass_kernel");
+}
+
+}  // namespace ps

@@ -1,0 +1,495 @@
+"""`StructureBatch` — the reference's batch API for the geometric-feature hot path, on B200 kernels.
+
+Drop-in for the hot-path surface of the reference class (reference protstruc/protstruc.py:32-956):
+same method names, argument meaning, return shapes / dtypes and exceptions.  Every feature method
+launches a hand-written sm_100a kernel through the C-ABI in `include/protstruc_b200.h`; PyTorch
+only owns the device buffers and the stream.  There is no CPU path: tensors are moved to the CUDA
+device at construction, and a compute call without a CUDA tensor or without the built library
+raises.
+
+Parity decisions that differ from a literal reading of the reference are listed in DESIGN.md
+("quirk ledger", following SURVEY.md Appendix A): fp32 contract (Q3), per-structure broadcast in
+`standardize` (Q1), last-axis cross product in frames (Q2), derived state created on the data's
+device (Q10), usable mask arguments in `standardize` (Q8).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .general import ATOM
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+# ------------------------------------------------------------------------------------------------
+# RNG stream of diffuse_xyz: (seed, step) of the Philox generator inside the kernels.
+class _PhiloxStream:
+    """Process-wide counter-based stream: seed follows torch's global seed, `step` advances by one
+    per diffusion step, so consecutive calls never reuse random numbers."""
+
+    def __init__(self) -> None:
+        self.seed: Optional[int] = None
+        self.step = 0
+
+    def reserve(self, n_steps: int, generator: Optional[torch.Generator]) -> Tuple[int, int]:
+        seed = int(generator.initial_seed() if generator is not None else torch.initial_seed())
+        seed &= (1 << 64) - 1
+        if seed != self.seed:
+            self.seed, self.step = seed, 0
+        first = self.step
+        self.step += n_steps
+        return seed, first
+
+
+_philox = _PhiloxStream()
+
+
+def manual_seed(seed: int) -> None:
+    """Seeds torch's global generator and restarts the diffusion noise stream."""
+    torch.manual_seed(seed)
+    _philox.seed, _philox.step = int(seed) & ((1 << 64) - 1), 0
+
+
+def _always_tensor(x):
+    return torch.from_numpy(x) if isinstance(x, np.ndarray) else x
+
+
+def _target_device(xyz: torch.Tensor, device) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if xyz.is_cuda:
+        return xyz.device
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return xyz.device  # no GPU: construction and validation still work, compute raises
+
+
+class StructureBatch:
+    """A padded batch of protein structures: `xyz` (B, L, A, 3) fp32 plus masks."""
+
+    def __init__(
+        self,
+        xyz: torch.Tensor,
+        atom_mask: Optional[torch.Tensor] = None,
+        chain_idx: Optional[torch.Tensor] = None,
+        chain_ids: Optional[List[List[str]]] = None,
+        seq: Optional[List[Dict[str, str]]] = None,
+        residue_idx: Optional[torch.Tensor] = None,
+        device=None,
+    ):
+        if (chain_idx is not None and chain_ids is None) or (chain_idx is None and chain_ids is not None):
+            raise ValueError("Both `chain_idx` and `chain_ids` should be provided or None.")
+        if xyz.ndim != 4 or xyz.shape[-1] != 3:
+            raise ValueError(f"`xyz` must have shape (batch, residues, atoms, 3), got {tuple(xyz.shape)}")
+
+        dev = _target_device(xyz, device)
+        # fp32 is the contract of the kernels (fp64 input is converted here)
+        self.xyz = xyz.to(device=dev, dtype=torch.float32).contiguous()
+        self.atom_mask = atom_mask.to(dev) if atom_mask is not None else None
+        self.batch_size, self.n_residues, self.max_n_atoms_per_residue = self.xyz.shape[:3]
+
+        if atom_mask is not None:
+            if tuple(atom_mask.shape) != tuple(self.xyz.shape[:3]):
+                raise ValueError(
+                    f"`atom_mask` shape {tuple(atom_mask.shape)} does not match xyz {tuple(self.xyz.shape[:3])}"
+                )
+            self.residue_mask = self.atom_mask.any(dim=-1)
+        else:
+            self.residue_mask = torch.ones(self.batch_size, self.n_residues, dtype=torch.bool, device=dev)
+
+        if chain_idx is not None:
+            for i, chidx in enumerate(chain_idx):
+                msk = ~torch.isnan(chidx)
+                assert chidx[msk].min() == 0, f"Protein {i}: Chain index should start from zero"
+            self.chain_idx = chain_idx.to(dev)
+        else:
+            self.chain_idx = torch.zeros(self.batch_size, self.n_residues, device=dev)
+
+        self.chain_ids = chain_ids
+        self.seq = seq
+        self.residue_idx = residue_idx
+        self._standardized = False
+        # first global element of this shard in the diffusion noise stream (see sharding.py)
+        self._noise_elem_offset = 0
+
+    # -------------------------------------------------------------------------------- constructors
+    @classmethod
+    def from_xyz(
+        cls,
+        xyz: ArrayLike,
+        atom_mask: Optional[ArrayLike] = None,
+        chain_idx: Optional[ArrayLike] = None,
+        chain_ids: Optional[List[List[str]]] = None,
+        seq: Optional[List[Dict[str, str]]] = None,
+        **kwargs,
+    ) -> "StructureBatch":
+        """Builds a batch from coordinates (B, L, A, 3); numpy inputs are accepted
+        (reference protstruc.py:93-128)."""
+        return cls(_always_tensor(xyz), _always_tensor(atom_mask), _always_tensor(chain_idx), chain_ids, seq,
+                   **kwargs)
+
+    # ------------------------------------------------------------------------------------- getters
+    def get_batch_size(self) -> int:
+        return self.batch_size
+
+    def get_xyz(self) -> torch.Tensor:
+        return self.xyz
+
+    def get_atom_mask(self) -> torch.Tensor:
+        return self.atom_mask
+
+    def get_residue_mask(self) -> torch.Tensor:
+        """CA-slot mask as bool (reference protstruc.py:372-378; not the same as `self.residue_mask`)."""
+        return self.atom_mask[:, :, ATOM.CA].bool()
+
+    def get_chain_idx(self) -> torch.Tensor:
+        return self.chain_idx.long()
+
+    def get_chain_ids(self):
+        return self.chain_ids
+
+    def get_seq(self):
+        return self.seq
+
+    def get_total_lengths(self) -> torch.Tensor:
+        return self.residue_mask.cumsum(dim=1).argmax(dim=1) + 1
+
+    def get_max_n_residues(self) -> int:
+        return self.n_residues
+
+    def get_max_n_atoms_per_residue(self) -> int:
+        return self.max_n_atoms_per_residue
+
+    def get_n_terminal_mask(self) -> torch.Tensor:
+        """True where the previous residue belongs to another chain (NaN-padded compare), times the
+        residue mask (reference protstruc.py:435-443).  O(B*L) index bookkeeping, evaluated with
+        torch on the device; the fused kernel recomputes it internally for backbone_dihedrals."""
+        nan = torch.full_like(self.chain_idx[:, :1], float("nan"))
+        padded = torch.cat([nan, self.chain_idx], dim=1)
+        return (padded[:, :-1] != padded[:, 1:]).bool() * self.residue_mask
+
+    def get_c_terminal_mask(self) -> torch.Tensor:
+        """True where the next residue belongs to another chain (reference protstruc.py:445-453)."""
+        nan = torch.full_like(self.chain_idx[:, :1], float("nan"))
+        padded = torch.cat([self.chain_idx, nan], dim=1)
+        return (padded[:, :-1] != padded[:, 1:]).bool() * self.residue_mask
+
+    # ------------------------------------------------------------------------------ native plumbing
+    def _lib(self):
+        if not self.xyz.is_cuda:
+            raise _cabi.NativeLibraryError(
+                "StructureBatch holds CPU tensors (no CUDA device was available at construction); "
+                "protstruc_b200 computes on B200 only and has no CPU fallback"
+            )
+        return _cabi.load()
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.xyz.device).cuda_stream
+
+    def _dims(self) -> Tuple[int, int, int]:
+        return self.batch_size, self.n_residues, self.max_n_atoms_per_residue
+
+    def _mask_for_kernel(self, mask: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        """Returns (contiguous mask tensor the kernel can read, PS_MASK_* code)."""
+        if mask.dtype == torch.bool:
+            return mask.contiguous(), _cabi.PS_MASK_BOOL
+        return mask.to(torch.float32).contiguous(), _cabi.PS_MASK_F32
+
+    # ------------------------------------------------------------------------------------ features
+    def pairwise_distance_matrix(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """All-atom pairwise distances and the pair mask (reference protstruc.py:455-484).
+
+        Returns `dist` (B, L, L, A, A) fp32 — NOT masked, NaN coordinates give NaN distances — and
+        `dist_mask` of the same shape and of `atom_mask`'s dtype (bool stays bool)."""
+        lib = self._lib()
+        if self.atom_mask is None:
+            raise TypeError("'NoneType' object is not subscriptable (pairwise_distance_matrix needs atom_mask)")
+        B, L, A = self._dims()
+        dev = self.xyz.device
+        mask, code = self._mask_for_kernel(self.atom_mask)
+        dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
+        dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ps_pair_dist_mask(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
+                                       dist_mask.data_ptr(), B, L, A, self._stream())
+        _cabi.check(rc, "ps_pair_dist_mask")
+        if dist_mask.dtype != self.atom_mask.dtype:
+            dist_mask = dist_mask.to(self.atom_mask.dtype)
+        return dist, dist_mask
+
+    def _slots(self, atoms_i: List[str], atoms_j: List[str]) -> Tuple[List[int], List[int]]:
+        for atom in atoms_i + atoms_j:
+            if not ATOM.is_valid(atom):
+                raise ValueError(f"Atom {atom} is not valid.")
+        return [int(ATOM[a]) for a in atoms_i], [int(ATOM[a]) for a in atoms_j]
+
+    def _pair_angles(self, atoms_i: List[str], atoms_j: List[str], kind: int, need: int) -> torch.Tensor:
+        si, sj = self._slots(atoms_i, atoms_j)
+        if len(si) + len(sj) != need:
+            raise ValueError(f"expected {need} atoms in total, got {len(si)} + {len(sj)}")
+        lib = self._lib()
+        B, L, A = self._dims()
+        for s in si + sj:
+            if s >= A:
+                raise IndexError(f"index {s} is out of bounds for dimension 2 with size {A}")
+        out = torch.empty(B, L, L, dtype=torch.float32, device=self.xyz.device)
+        with torch.cuda.device(self.xyz.device):
+            rc = lib.ps_pair_angles(self.xyz.data_ptr(), B, L, A, _cabi.int_array(si), len(si),
+                                    _cabi.int_array(sj), len(sj), kind, out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_pair_angles")
+        return out
+
+    def pairwise_dihedrals(self, atoms_i: List[str], atoms_j: List[str]) -> torch.Tensor:
+        """Dihedral of (atoms_i of residue i, atoms_j of residue j), 4 atoms in total → (B, L, L)
+        (reference protstruc.py:620-640)."""
+        return self._pair_angles(atoms_i, atoms_j, _cabi.PS_ANGLE_DIHEDRAL, 4)
+
+    def pairwise_planar_angles(self, atoms_i: List[str], atoms_j: List[str]) -> torch.Tensor:
+        """Planar angle of 3 atoms split between residue i and residue j → (B, L, L)
+        (reference protstruc.py:642-660)."""
+        return self._pair_angles(atoms_i, atoms_j, _cabi.PS_ANGLE_PLANAR, 3)
+
+    def trrosetta_angles(self, virtual_cb: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """omega, theta, phi exactly as inter_residue_geometry defines them, in one pass
+        (reference protstruc.py:810-815).  `virtual_cb=True` recomputes CB from N, CA, C with the
+        ideal-geometry coefficients (reference geometry.py:217-221) instead of reading slot 4."""
+        lib = self._lib()
+        B, L, A = self._dims()
+        dev = self.xyz.device
+        omega = torch.empty(B, L, L, dtype=torch.float32, device=dev)
+        theta = torch.empty_like(omega)
+        phi = torch.empty_like(omega)
+        with torch.cuda.device(dev):
+            rc = lib.ps_trrosetta_angles(self.xyz.data_ptr(), B, L, A, int(bool(virtual_cb)),
+                                         omega.data_ptr(), theta.data_ptr(), phi.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_trrosetta_angles")
+        return omega, theta, phi
+
+    def inter_residue_geometry(self) -> Dict[str, torch.Tensor]:
+        """trRosetta-style inter-residue geometry (reference protstruc.py:790-817): d_ca, d_cb, d_no
+        (strided views of the full distance tensor, with masks) and omega / theta / phi, produced by
+        ONE fused kernel launch."""
+        lib = self._lib()
+        if self.atom_mask is None:
+            raise TypeError("'NoneType' object is not subscriptable (inter_residue_geometry needs atom_mask)")
+        B, L, A = self._dims()
+        if A <= int(ATOM.CB):
+            raise IndexError(f"index {int(ATOM.CB)} is out of bounds for dimension 2 with size {A}")
+        dev = self.xyz.device
+        mask, code = self._mask_for_kernel(self.atom_mask)
+        dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
+        dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
+        omega = torch.empty(B, L, L, dtype=torch.float32, device=dev)
+        theta = torch.empty_like(omega)
+        phi = torch.empty_like(omega)
+        with torch.cuda.device(dev):
+            rc = lib.ps_inter_residue_geometry(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
+                                               dist_mask.data_ptr(), omega.data_ptr(), theta.data_ptr(),
+                                               phi.data_ptr(), B, L, A, self._stream())
+        _cabi.check(rc, "ps_inter_residue_geometry")
+        if dist_mask.dtype != self.atom_mask.dtype:
+            dist_mask = dist_mask.to(self.atom_mask.dtype)
+        ret = {}
+        ret["d_ca"] = dist[:, :, :, ATOM.CA, ATOM.CA]
+        ret["d_ca_mask"] = dist_mask[:, :, :, ATOM.CA, ATOM.CA]
+        ret["d_cb"] = dist[:, :, :, ATOM.CB, ATOM.CB]
+        ret["d_cb_mask"] = dist_mask[:, :, :, ATOM.CB, ATOM.CB]
+        ret["d_no"] = dist[:, :, :, ATOM.N, ATOM.O]
+        ret["d_no_mask"] = dist_mask[:, :, :, ATOM.N, ATOM.O]
+        ret["omega"] = omega
+        ret["theta"] = theta
+        ret["phi"] = phi
+        return ret
+
+    def _backbone(self, want_dihedrals: bool, frame_slots: Optional[Tuple[int, int, int]]):
+        lib = self._lib()
+        B, L, A = self._dims()
+        dev = self.xyz.device
+        dihedrals = dihedral_mask = frames = None
+        rm_ptr = ch_ptr = dh_ptr = dm_ptr = fr_ptr = None
+        keep = []
+        if want_dihedrals:
+            if A < 3:
+                raise IndexError(f"index 2 is out of bounds for dimension 2 with size {A}")
+            rm = self.residue_mask.to(torch.uint8).contiguous()
+            ch = self.chain_idx.to(torch.float32).contiguous()
+            keep += [rm, ch]
+            dihedrals = torch.empty(B, L, 3, dtype=torch.float32, device=dev)
+            dihedral_mask = torch.empty(B, L, 3, dtype=torch.bool, device=dev)
+            rm_ptr, ch_ptr, dh_ptr, dm_ptr = rm.data_ptr(), ch.data_ptr(), dihedrals.data_ptr(), dihedral_mask.data_ptr()
+        a1 = a2 = a3 = 0
+        if frame_slots is not None:
+            a1, a2, a3 = frame_slots
+            frames = torch.empty(B, L, 3, 3, dtype=torch.float32, device=dev)
+            fr_ptr = frames.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.ps_backbone(self.xyz.data_ptr(), rm_ptr, ch_ptr, B, L, A, a1, a2, a3, dh_ptr, dm_ptr,
+                                 fr_ptr, self._stream())
+        _cabi.check(rc, "ps_backbone")
+        return dihedrals, dihedral_mask, frames
+
+    def backbone_dihedrals(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """phi, psi, omega per residue (B, L, 3) in radians and the bool validity mask (B, L, 3);
+        zero at chain termini (reference protstruc.py:486-541)."""
+        dihedrals, dihedral_mask, _ = self._backbone(True, None)
+        return dihedrals, dihedral_mask
+
+    def backbone_orientations(self, a1: str = "N", a2: str = "CA", a3: str = "C") -> torch.Tensor:
+        """Gram-Schmidt frames (B, L, 3, 3), columns e1, e2, e3 (reference protstruc.py:543-571)."""
+        slots = (int(ATOM[a1]), int(ATOM[a2]), int(ATOM[a3]))  # KeyError on unknown names, like the reference
+        A = self.max_n_atoms_per_residue
+        for s in slots:
+            if s >= A:
+                raise IndexError(f"index {s} is out of bounds for dimension 2 with size {A}")
+        return self._backbone(False, slots)[2]
+
+    def backbone_features(self, a1: str = "N", a2: str = "CA", a3: str = "C"):
+        """dihedrals, dihedral_mask and frames from a single kernel launch (extension)."""
+        slots = (int(ATOM[a1]), int(ATOM[a2]), int(ATOM[a3]))
+        return self._backbone(True, slots)
+
+    def backbone_translations(self, atom: str = "CA") -> torch.Tensor:
+        """View `xyz[:, :, ATOM[atom]]` (B, L, 3); aliases xyz (reference protstruc.py:573-587)."""
+        return self.xyz[:, :, ATOM[atom]]
+
+    # ------------------------------------------------------------------------------------ mutators
+    def translate(self, translation: torch.Tensor, atomwise: bool = False) -> None:
+        """In-place translation by (B, L, 3) / (B, 1, 3) or atomwise (B, L, A, 3) tensors
+        (reference protstruc.py:662-679).  Elementwise add on the device."""
+        translation = translation.to(self.xyz.device)
+        if not atomwise:
+            translation = translation.unsqueeze(-2)
+        self.xyz += translation
+
+    def standardize(self, atom_mask: Optional[torch.Tensor] = None,
+                    residue_mask: Optional[torch.Tensor] = None) -> None:
+        """Per-structure, per-axis masked standardisation; sets `mu`, `std` (B, 3)
+        (reference protstruc.py:696-734)."""
+        if atom_mask is not None and residue_mask is not None:
+            raise ValueError("Only one of atom_mask and residue_mask can be specified.")
+        if self._standardized:
+            raise ValueError("Coordinates are already standardized.")
+        if self.atom_mask is None:
+            raise TypeError("standardize needs an atom_mask")
+        lib = self._lib()
+        dev = self.xyz.device
+        if atom_mask is not None:
+            use = atom_mask.to(dev) * self.atom_mask
+        elif residue_mask is not None:
+            use = residue_mask.to(dev).unsqueeze(-1) * self.atom_mask
+        else:
+            use = self.atom_mask
+        mask, code = self._mask_for_kernel(use)
+        B, L, A = self._dims()
+        mu = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        sd = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        out = torch.empty_like(self.xyz)
+        with torch.cuda.device(dev):
+            rc = lib.ps_masked_stats(self.xyz.data_ptr(), mask.data_ptr(), code, B, L, A, mu.data_ptr(),
+                                     sd.data_ptr(), out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_masked_stats")
+        self.mu, self.std = mu, sd
+        self.xyz = out
+        self._standardized = True
+
+    def unstandardize(self) -> None:
+        """Inverse of `standardize` (reference protstruc.py:736-744)."""
+        if not self._standardized:
+            raise ValueError("Cannot unstandardize structures that are not standardized.")
+        lib = self._lib()
+        B, L, A = self._dims()
+        out = torch.empty_like(self.xyz)
+        with torch.cuda.device(self.xyz.device):
+            rc = lib.ps_scale_shift(self.xyz.data_ptr(), self.std.data_ptr(), self.mu.data_ptr(), B, L, A,
+                                    out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_scale_shift")
+        self.xyz = out
+        self._standardized = False
+
+    def center_of_mass(self) -> torch.Tensor:
+        """NaN-skipping mean of the CA coordinates over ALL residues, (B, 3); not mask-aware, like
+        the reference (protstruc.py:746-757)."""
+        lib = self._lib()
+        B, L, A = self._dims()
+        if A <= int(ATOM.CA):
+            raise IndexError(f"index {int(ATOM.CA)} is out of bounds for dimension 2 with size {A}")
+        out = torch.empty(B, 3, dtype=torch.float32, device=self.xyz.device)
+        with torch.cuda.device(self.xyz.device):
+            rc = lib.ps_center_of_mass(self.xyz.data_ptr(), B, L, A, int(ATOM.CA), out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_center_of_mass")
+        return out
+
+    def center_at(self, center: Optional[torch.Tensor] = None) -> None:
+        """Translates every structure so that its CA centre sits at `center` ((B, 3), (3,) or None
+        for the origin); in place (reference protstruc.py:759-788)."""
+        if center is None:
+            center = torch.zeros(1, 3)
+        if center.ndim > 2 or center.shape[-1] != 3:
+            raise ValueError(f"`center` must have a shape of (batch_size, 3) or (3,), got {center.shape}.")
+        if center.ndim == 2 and center.shape[0] != self.batch_size:
+            raise ValueError(f"`center` must have a shape of (batch_size, 3) or (3,), got {center.shape}.")
+        if center.ndim == 1:
+            center = center.unsqueeze(0)
+        lib = self._lib()
+        dev = self.xyz.device
+        B, L, A = self._dims()
+        translation = (center.to(device=dev, dtype=torch.float32) - self.center_of_mass()).contiguous()
+        with torch.cuda.device(dev):
+            rc = lib.ps_translate(self.xyz.data_ptr(), translation.data_ptr(), translation.shape[0], B, L, A,
+                                  self.xyz.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_translate")
+
+    def diffuse_xyz(self, beta: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                    generator: Optional[torch.Generator] = None) -> None:
+        """One forward-diffusion step xyz <- sqrt(1-beta) xyz + sqrt(beta) z, beta (B,)
+        (reference protstruc.py:864-878).  Rebinds `self.xyz` to a new tensor.
+
+        `noise` (extension): inject z explicitly — the result is then bit-identical to the
+        reference evaluated with the same z.  Otherwise z comes from the kernel's own Philox
+        stream, seeded by `generator` (or torch's global seed)."""
+        lib = self._lib()
+        dev = self.xyz.device
+        B, L, A = self._dims()
+        beta = beta.to(device=dev, dtype=torch.float32).contiguous()
+        if beta.shape != (B,):
+            raise ValueError(f"`beta` must have shape ({B},), got {tuple(beta.shape)}")
+        out = torch.empty_like(self.xyz)
+        per_b = L * A * 3
+        if noise is not None:
+            if noise.shape != self.xyz.shape:
+                raise ValueError(f"`noise` must have shape {tuple(self.xyz.shape)}, got {tuple(noise.shape)}")
+            z = noise.to(device=dev, dtype=torch.float32).contiguous()
+            with torch.cuda.device(dev):
+                rc = lib.ps_diffuse(self.xyz.data_ptr(), beta.data_ptr(), z.data_ptr(), 0, 0, 0, out.data_ptr(),
+                                    B, per_b, self._stream())
+        else:
+            seed, step = _philox.reserve(1, generator)
+            with torch.cuda.device(dev):
+                rc = lib.ps_diffuse(self.xyz.data_ptr(), beta.data_ptr(), None, seed, step,
+                                    self._noise_elem_offset, out.data_ptr(), B, per_b, self._stream())
+        _cabi.check(rc, "ps_diffuse")
+        self.xyz = out
+
+    def diffuse_xyz_steps(self, betas: torch.Tensor, generator: Optional[torch.Generator] = None) -> None:
+        """T diffusion steps fused in one kernel (extension); `betas` is (T, B).  Bit-identical to
+        calling `diffuse_xyz(betas[t])` for t = 0..T-1 on the same noise stream."""
+        lib = self._lib()
+        dev = self.xyz.device
+        B, L, A = self._dims()
+        betas = betas.to(device=dev, dtype=torch.float32).contiguous()
+        if betas.ndim != 2 or betas.shape[1] != B:
+            raise ValueError(f"`betas` must have shape (T, {B}), got {tuple(betas.shape)}")
+        T = betas.shape[0]
+        if T == 0:
+            return
+        out = torch.empty_like(self.xyz)
+        seed, step0 = _philox.reserve(T, generator)
+        with torch.cuda.device(dev):
+            rc = lib.ps_diffuse_steps(self.xyz.data_ptr(), betas.data_ptr(), T, seed, step0,
+                                      self._noise_elem_offset, out.data_ptr(), B, L * A * 3, self._stream())
+        _cabi.check(rc, "ps_diffuse_steps")
+        self.xyz = out

@@ -1,0 +1,508 @@
+"""GPU suite: the CUDA path (through the façade -> C-ABI -> sm_100a kernels) against
+(a) the golden vectors produced by the real reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances are BASELINE.json's north_star: distances <= 1e-5 relative / 1e-4 A, angles <= 1e-5 rad
+away from collinear degeneracies (circular comparison), masks / NaN placement / indexing bit-exact,
+diffuse_xyz bit-exact given the injected noise.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import protstruc_b200 as ps
+from protstruc_b200 import _cabi
+from oracle import feature_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+SYNTHETIC = ["synthetic_small", "synthetic_floatmask_oddL", "synthetic_A5",
+             "synthetic_A25_like_reference_tests", "synthetic_ragged_33"]
+DEV = "cuda"
+
+
+def make_batch(g):
+    ids = [["A", "B"] for _ in range(g["xyz"].shape[0])]
+    return ps.StructureBatch.from_xyz(g["xyz"], g["atom_mask"], g["chain_idx"], ids)
+
+
+def angle_conditioning(xyz, which):
+    N, CA, CB = 0, 1, 4
+    if which == "omega":
+        p = H.pair_points(xyz, [CA, CB], [CA, CB])
+        return H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+    if which == "theta":
+        p = H.pair_points(xyz, [N, CA, CB], [CB])
+        return H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+    p = H.pair_points(xyz, [CA, CB], [CB])
+    return H.planar_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :])
+
+
+# ------------------------------------------------------------------------------ K1 distances + mask
+@pytest.mark.parametrize("name", SYNTHETIC)
+def test_pairwise_distance_matrix_matches_reference_golden(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    ref_dist, ref_mask = H.t(g["ref_dist"]), H.t(g["ref_dist_mask"])
+    assert dist.is_cuda and dist.dtype == torch.float32 and dist.is_contiguous()
+    assert tuple(dist.shape) == tuple(ref_dist.shape)
+    assert dist_mask.dtype == ref_mask.dtype and tuple(dist_mask.shape) == tuple(ref_mask.shape)
+    H.assert_distances_close(dist, ref_dist)
+    assert torch.equal(dist_mask.cpu(), ref_mask), "pair mask must be bit-exact"
+
+
+def test_pairwise_distance_matrix_real_structure(native_lib):
+    g = H.load_golden("real_1a6v_HL")
+    sb = make_batch(g)
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    assert tuple(dist.shape) == (1, 229, 229, 15, 15)
+    H.assert_distances_close(dist[:, :40, :40], H.t(g["ref_dist_crop"]), "dist crop")
+    assert torch.equal(dist_mask[:, :40, :40].cpu(), H.t(g["ref_dist_mask_crop"]))
+    H.assert_distances_close(dist[:, :, :, 1, 1], H.t(g["ref_d_ca"]), "d_ca")
+    H.assert_distances_close(dist[:, :, :, 4, 4], H.t(g["ref_d_cb"]), "d_cb")
+    H.assert_distances_close(dist[:, :, :, 0, 3], H.t(g["ref_d_no"]), "d_no")
+    assert int(torch.isnan(dist).sum()) == int(g["ref_dist_nan_count"])
+    assert int(dist_mask.sum()) == int(g["ref_dist_mask_sum"])
+    got = float(torch.nansum(dist.double()))
+    assert math.isclose(got, float(g["ref_dist_nansum"]), rel_tol=1e-6)
+    # reference tests/test_StructureBatch.py:122-137: CA-CA >= 0 and ATOM.CA indexes slot 1
+    ca = dist[:, :, :, ps.ATOM.CA, ps.ATOM.CA]
+    assert bool((ca[~torch.isnan(ca)] >= 0).all())
+
+
+@pytest.mark.parametrize("B,L,A,kind", [(3, 37, 15, "bool"), (1, 1, 15, "bool"), (2, 2, 15, "float"),
+                                        (1, 130, 15, "bool"), (2, 19, 10, "bool"), (1, 6, 37, "float"),
+                                        (5, 16, 15, "bool")])
+def test_pairwise_distance_matrix_vs_oracle(native_lib, B, L, A, kind):
+    xyz, mask, chain_idx = H.synthetic_batch(100 + L, B, L, A, kind)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    ref_dist, ref_mask = orc.pair_distances(xyz, mask)
+    H.assert_distances_close(dist, ref_dist)
+    assert dist_mask.dtype == ref_mask.dtype
+    assert torch.equal(dist_mask.cpu(), ref_mask)
+
+
+def test_distance_kernel_variants_agree(native_lib):
+    """Staged (TMA-store) kernel vs generic per-element kernel: same arithmetic, bit-equal; the IEEE
+    sqrt variant stays within 1 ulp of the MUFU variant."""
+    xyz, mask, _ = H.synthetic_batch(7, 2, 45, 15, "bool", nan_masked=False)
+    x = xyz.to(DEV)
+    m = mask.to(DEV)
+    B, L, A = 2, 45, 15
+    outs = {}
+    for variant in (0, 1, 2, 1 << 8, 2 << 4):
+        d = torch.empty(B, L, L, A, A, device=DEV)
+        dm = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        rc = native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
+                                             variant, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "ps_pair_dist_mask_ex")
+        outs[variant] = (d, dm)
+    torch.cuda.synchronize()
+    base, base_mask = outs[0]
+    assert torch.equal(outs[1 << 8][0], base), "generic kernel differs from the staged kernel"
+    assert torch.equal(outs[2 << 4][0], base), "warps-per-CTA override changed the result"
+    for v in outs:
+        assert torch.equal(outs[v][1], base_mask)
+    rel = ((outs[2][0] - base).abs() / outs[2][0].clamp_min(1e-30)).max().item()
+    assert rel <= 2.5e-7, f"MUFU sqrt deviates from IEEE sqrt by {rel}"
+    assert torch.equal(outs[1][0], base), "ftz variant differs on normal-range inputs"
+
+
+def test_distance_properties_at_baseline_config2(native_lib):
+    """BASELINE config 2 (64 x 256 x 15, 3.8 GB of distances): size-independent properties."""
+    B, L, A = 64, 256, 15
+    g = torch.Generator(device=DEV).manual_seed(2)
+    xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
+    mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    # symmetry: dist[b,i,j,a,c] == dist[b,j,i,c,a], bit for bit
+    for b in (0, 31, 63):
+        d = dist[b]
+        assert torch.equal(d, d.permute(1, 0, 3, 2)), "distance tensor is not symmetric"
+        assert bool((torch.diagonal(torch.diagonal(d, dim1=0, dim2=1), dim1=0, dim2=1) == 0).all())
+    # mask identity: sum_{i,j,a,c} m_i[a] m_j[c] = (sum m)^2 per structure
+    per_struct = dist_mask.view(B, -1).sum(dim=1, dtype=torch.int64)
+    assert torch.equal(per_struct, mask.view(B, -1).sum(dim=1, dtype=torch.int64) ** 2)
+    # spot check against the oracle on random structures / residue blocks
+    for b, i0, j0 in ((0, 0, 0), (17, 100, 200), (63, 250, 3)):
+        sub_i = xyz[b, i0:i0 + 6].cpu()
+        sub_j = xyz[b, j0:j0 + 6].cpu()
+        ref = torch.norm(sub_i[:, None, :, None] - sub_j[None, :, None, :], dim=-1)
+        H.assert_distances_close(dist[b, i0:i0 + 6, j0:j0 + 6], ref, "spot block")
+
+
+# ------------------------------------------------------------------------------ K2 pairwise angles
+@pytest.mark.parametrize("name", ["synthetic_small", "synthetic_floatmask_oddL", "synthetic_A5", "synthetic_ragged_33",
+                                  "real_1a6v_HL"])
+def test_inter_residue_geometry_matches_reference_golden(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    out = sb.inter_residue_geometry()
+    xyz = H.t(g["xyz"])
+    assert set(out) == {"d_ca", "d_ca_mask", "d_cb", "d_cb_mask", "d_no", "d_no_mask", "omega", "theta", "phi"}
+    for which in ("omega", "theta"):
+        H.assert_angles_close(out[which], H.t(g[f"ref_{which}"]), angle_conditioning(xyz, which), which)
+    H.assert_angles_close(out["phi"], H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi", circular=False)
+    # diagonal conventions: omega = theta = 0, phi = NaN where the residue is complete
+    L = xyz.shape[1]
+    eye = torch.eye(L, dtype=torch.bool)
+    ref_omega = H.t(g["ref_omega"])
+    same_zero = (out["omega"].cpu()[:, eye] == 0) == (ref_omega[:, eye] == 0)
+    assert bool(same_zero.all())
+    if name == "real_1a6v_HL":
+        H.assert_distances_close(out["d_ca"], H.t(g["ref_d_ca"]), "d_ca")
+        H.assert_distances_close(out["d_no"], H.t(g["ref_d_no"]), "d_no")
+        assert torch.equal(out["d_ca_mask"].cpu(), H.t(g["ref_d_ca_mask"]))
+    else:
+        ref_dist, ref_mask = H.t(g["ref_dist"]), H.t(g["ref_dist_mask"])
+        H.assert_distances_close(out["d_cb"], ref_dist[:, :, :, 4, 4], "d_cb")
+        assert torch.equal(out["d_no_mask"].cpu(), ref_mask[:, :, :, 0, 3])
+
+
+@pytest.mark.parametrize("name", ["synthetic_small", "synthetic_A5", "real_1a6v_HL"])
+def test_pairwise_angle_methods_match_reference_golden(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    xyz = H.t(g["xyz"])
+    omega = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
+    theta = sb.pairwise_dihedrals(["N", "CA", "CB"], ["CB"])
+    phi = sb.pairwise_planar_angles(["CA", "CB"], ["CB"])
+    assert tuple(omega.shape) == tuple(g["ref_omega"].shape) and omega.dtype == torch.float32
+    H.assert_angles_close(omega, H.t(g["ref_omega"]), angle_conditioning(xyz, "omega"), "omega")
+    H.assert_angles_close(theta, H.t(g["ref_theta"]), angle_conditioning(xyz, "theta"), "theta")
+    H.assert_angles_close(phi, H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi", circular=False)
+    # the fused kernels use the same device functions -> bit-identical to the generic kernel
+    fo, ft, fp = sb.trrosetta_angles()
+    for a, b in ((fo, omega), (ft, theta), (fp, phi)):
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+    if name != "real_1a6v_HL":
+        gen = sb.pairwise_dihedrals(["n", "ca", "c"], ["N"])  # case-insensitive names
+        p = H.pair_points(xyz, [0, 1, 2], [0])
+        cond = H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+        H.assert_angles_close(gen, H.t(g["ref_psi_like_dihedral_N_CA_C_N"]), cond, "generic dihedral")
+        pl = sb.pairwise_planar_angles(["CA"], ["CA", "C"])
+        p = H.pair_points(xyz, [1], [1, 2])
+        H.assert_angles_close(pl, H.t(g["ref_planar_CA_CA_C"]), H.planar_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :]),
+                              "generic planar", circular=False)
+
+
+def test_pairwise_angles_at_backbone_scale_vs_oracle(native_lib):
+    """A slice of BASELINE config 3 (backbone N,CA,C,O,CB; L = 512) small enough for the CPU oracle."""
+    xyz, mask, _ = H.synthetic_batch(3, 2, 512, 5, "bool", nan_masked=False, full_length=True)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    omega, theta, phi = sb.trrosetta_angles()
+    ro, rt, rp = orc.trrosetta_angles(xyz)
+    H.assert_angles_close(omega, ro, angle_conditioning(xyz, "omega"), "omega")
+    H.assert_angles_close(theta, rt, angle_conditioning(xyz, "theta"), "theta")
+    H.assert_angles_close(phi, rp, angle_conditioning(xyz, "phi"), "phi", circular=False)
+    assert bool((omega.abs() <= math.pi + 1e-6).all()) and bool((phi[~torch.isnan(phi)] >= 0).all())
+
+
+def test_virtual_cb_option_vs_oracle(native_lib):
+    xyz, mask, _ = H.synthetic_batch(21, 2, 40, 15, "bool", nan_masked=False, full_length=True)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    omega, theta, phi = sb.trrosetta_angles(virtual_cb=True)
+    ro, rt, rp = orc.trrosetta_angles_virtual_cb(xyz)
+    x5 = xyz[:, :, :5].clone()
+    x5[:, :, 4] = orc.virtual_cb(xyz[:, :, 0], xyz[:, :, 1], xyz[:, :, 2])
+    H.assert_angles_close(omega, ro, angle_conditioning(x5, "omega"), "omega(virtual CB)")
+    H.assert_angles_close(theta, rt, angle_conditioning(x5, "theta"), "theta(virtual CB)")
+    H.assert_angles_close(phi, rp, angle_conditioning(x5, "phi"), "phi(virtual CB)", circular=False)
+
+
+# ------------------------------------------------------------------------------ K3 backbone
+@pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
+def test_backbone_features_match_reference_golden(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    xyz = H.t(g["xyz"])
+    dihedrals, dihedral_mask = sb.backbone_dihedrals()
+    ref = H.t(g["ref_bb_dihedrals"])
+    assert dihedral_mask.dtype == torch.bool and tuple(dihedrals.shape) == tuple(ref.shape)
+    assert torch.equal(dihedral_mask.cpu(), H.t(g["ref_bb_dihedral_mask"])), "dihedral mask must be bit-exact"
+    assert torch.equal(sb.get_n_terminal_mask().cpu(), H.t(g["ref_nterm"]))
+    assert torch.equal(sb.get_c_terminal_mask().cpu(), H.t(g["ref_cterm"]))
+    n, ca, c = xyz[:, :, 0].double(), xyz[:, :, 1].double(), xyz[:, :, 2].double()
+    big = torch.full(xyz.shape[:2], 1.0, dtype=torch.float64)
+    cond = torch.stack([big.clone(), big.clone(), big.clone()], dim=-1)
+    cond[:, 1:, 0] = H.dihedral_conditioning(c[:, :-1], n[:, 1:], ca[:, 1:], c[:, 1:])
+    cond[:, :-1, 1] = H.dihedral_conditioning(n[:, :-1], ca[:, :-1], c[:, :-1], n[:, 1:])
+    cond[:, :-1, 2] = H.dihedral_conditioning(ca[:, :-1], c[:, :-1], n[:, 1:], ca[:, 1:])
+    cond = torch.nan_to_num(cond, nan=0.0)
+    H.assert_angles_close(dihedrals, ref, cond, "backbone dihedrals")
+    # exact zero fill at termini (reference tests/test_StructureBatch.py:91-95)
+    assert torch.equal(dihedrals.cpu() == 0, ref == 0)
+    frames = sb.backbone_orientations()
+    ref_frames = H.t(g["ref_frames"])
+    H.assert_same_nan(frames, ref_frames, "frames")
+    ok = ~torch.isnan(ref_frames)
+    err = (frames.cpu()[ok] - ref_frames[ok]).abs().max().item() if ok.any() else 0.0
+    assert err <= 2e-6, f"frames deviate by {err}"
+    d2, m2, f2 = sb.backbone_features()
+    assert torch.equal(torch.nan_to_num(d2), torch.nan_to_num(dihedrals)) and torch.equal(m2, dihedral_mask)
+    assert torch.equal(torch.nan_to_num(f2), torch.nan_to_num(frames))
+
+
+def test_reference_backbone_dihedral_test_case(native_lib):
+    """Port of reference tests/test_StructureBatch.py:68-95 (float64 uniform xyz, 3 chains, A = 25)."""
+    rng = np.random.default_rng(0)
+    n_proteins, L, A = 16, 100, 25
+    xyz = rng.random((n_proteins, L, A, 3))
+    chain_idx = np.zeros((n_proteins, L))
+    chain_idx[:, 20:60] = 1.0
+    chain_idx[:, 60:] = 2.0
+    sb = ps.StructureBatch.from_xyz(xyz, chain_idx=chain_idx, chain_ids=[["A", "B", "C"]] * n_proteins)
+    assert sb.get_max_n_atoms_per_residue() == 25
+    dihedrals, dihedral_mask = sb.backbone_dihedrals()
+    assert dihedrals.shape == (n_proteins, L, 3) and dihedral_mask.shape == (n_proteins, L, 3)
+    assert bool(((dihedrals >= -np.pi) & (dihedrals <= np.pi)).all())
+    assert bool(((dihedrals >= -np.pi) & (dihedrals < 0)).any()) and bool(((dihedrals >= 0) & (dihedrals <= np.pi)).any())
+    nterm, cterm = sb.get_n_terminal_mask(), sb.get_c_terminal_mask()
+    assert bool((nterm.sum(dim=1) == 3).all()) and bool((cterm.sum(dim=1) == 3).all())
+    assert bool((dihedrals[nterm][:, 0] == 0.0).all())
+    assert bool((dihedrals[cterm][:, [1, 2]] == 0.0).all())
+    ref, ref_mask = orc.backbone_dihedrals(torch.from_numpy(xyz).float(), torch.from_numpy(chain_idx).float(),
+                                           torch.ones(n_proteins, L, dtype=torch.bool))
+    assert torch.equal(dihedral_mask.cpu(), ref_mask)
+    assert H.circular_diff(dihedrals.cpu(), ref).max().item() < 1e-4  # unit-cube coordinates: ill conditioned
+
+
+def test_ideal_backbone_gives_identity_frames(native_lib):
+    """reference tests/test_geometry.py:246-262: `frame == eye(3)` exactly."""
+    import json
+    ka = json.loads((H.GOLDEN / "MANIFEST.json").read_text())["known_answers"]
+    ideal = torch.tensor(ka["ideal_backbone_n_ca_c_cb"])  # (4, 3): N, CA, C, CB
+    xyz = torch.zeros(16, 30, 15, 3)
+    xyz[:, :, :3] = ideal[:3]
+    xyz[:, :, 4] = ideal[3]
+    sb = ps.StructureBatch.from_xyz(xyz)
+    frames = sb.backbone_orientations()
+    assert frames.shape == (16, 30, 3, 3)
+    assert bool((frames.cpu() == torch.eye(3).expand(16, 30, -1, -1)).all())
+    fr = ps.geometry.gram_schmidt(xyz[:, :, 0], xyz[:, :, 1], xyz[:, :, 2])
+    assert bool((fr.cpu() == torch.eye(3).expand(16, 30, -1, -1)).all())
+    tr = sb.backbone_translations()
+    assert tr.shape == (16, 30, 3) and tr.data_ptr() == sb.xyz[:, :, 1].data_ptr()  # a view, like the reference
+
+
+# ------------------------------------------------------------------------------ K4 statistics
+@pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
+def test_standardize_and_center_of_mass_match_reference_golden(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    com = sb.center_of_mass()
+    ref_com = H.t(g["ref_com"])
+    H.assert_same_nan(com, ref_com, "com")
+    assert torch.allclose(com.cpu(), ref_com, rtol=1e-5, atol=1e-4, equal_nan=True)
+    original = sb.get_xyz().clone()
+    sb.standardize()
+    assert tuple(sb.mu.shape) == (sb.batch_size, 3) and tuple(sb.std.shape) == (sb.batch_size, 3)
+    assert torch.allclose(sb.mu.cpu(), H.t(g["ref_mu"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(sb.std.cpu(), H.t(g["ref_sd"]), rtol=1e-5, atol=1e-6)
+    ref_xyz = H.t(g["ref_std_xyz"])
+    H.assert_same_nan(sb.get_xyz(), ref_xyz, "standardized xyz")
+    assert torch.allclose(sb.get_xyz().cpu(), ref_xyz, rtol=1e-4, atol=1e-5, equal_nan=True)
+    with pytest.raises(ValueError):
+        sb.standardize()
+    sb.unstandardize()
+    # reference tests/test_StructureBatch.py:246-255
+    assert torch.allclose(sb.get_xyz(), original, rtol=1e-4, atol=1e-5, equal_nan=True)
+    with pytest.raises(ValueError):
+        sb.unstandardize()
+
+
+def test_center_at_moves_the_ca_centre(native_lib):
+    """reference tests/test_StructureBatch.py:258-275."""
+    xyz, mask, chain_idx = H.synthetic_batch(5, 4, 50, 15, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    sb.center_at()
+    assert torch.allclose(sb.center_of_mass(), torch.zeros(4, 3, device=DEV), atol=1e-4)
+    target = torch.tensor([[1.0, 2.0, 3.0]]).repeat(4, 1)
+    sb.center_at(target)
+    assert torch.allclose(sb.center_of_mass().cpu(), target, atol=1e-4)
+    sb.center_at(torch.tensor([5.0, 5.0, 5.0]))
+    assert torch.allclose(sb.center_of_mass().cpu(), torch.full((4, 3), 5.0), atol=1e-4)
+    with pytest.raises(ValueError):
+        sb.center_at(torch.zeros(3, 3))
+    with pytest.raises(ValueError):
+        sb.center_at(torch.zeros(4, 2))
+
+
+def test_standardize_statistics_vs_oracle_config4_slice(native_lib):
+    """BASELINE config 4 shape (L = 128, A = 15), 64 of its 1024 structures."""
+    xyz, mask, _ = H.synthetic_batch(4, 64, 128, 15, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    sb.standardize()
+    ref_xyz, mu, sd = orc.standardize_per_structure(xyz, mask)
+    assert torch.allclose(sb.mu.cpu(), mu, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(sb.std.cpu(), sd, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sb.get_xyz().cpu(), ref_xyz, rtol=1e-4, atol=1e-5, equal_nan=True)
+    valid = sb.get_xyz()[mask.to(DEV)]
+    assert not bool(torch.isnan(valid).any())  # reference tests/test_StructureBatch.py:218-226
+
+
+# ------------------------------------------------------------------------------ K5 diffusion
+@pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
+def test_diffuse_xyz_is_bit_exact_given_the_noise(native_lib, name):
+    g = H.load_golden(name)
+    sb = make_batch(g)
+    before = sb.get_xyz()
+    sb.diffuse_xyz(H.t(g["ref_beta"]), noise=H.t(g["ref_noise"]))
+    after = sb.get_xyz()
+    assert after.data_ptr() != before.data_ptr()  # rebinds, does not alias
+    ref = H.t(g["ref_diffused"])
+    H.assert_same_nan(after, ref, "diffused")
+    assert torch.equal(torch.nan_to_num(after.cpu()), torch.nan_to_num(ref)), "diffuse_xyz must be bit-exact"
+
+
+def test_philox_stream_matches_the_oracle_definition_and_is_normal(native_lib):
+    n = 1 << 20
+    out = torch.empty(n, device=DEV)
+    rc = native_lib.ps_philox_normal(out.data_ptr(), n, 1234, 5, 0, torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "ps_philox_normal")
+    z = out.cpu().double().numpy()
+    ref = orc.philox_normal(n, seed=1234, step=5)
+    assert np.max(np.abs(z - ref)) < 2e-5  # same counters / same Box-Muller, fp32 vs fp64 evaluation
+    assert abs(z.mean()) < 4e-3 and abs(z.std() - 1.0) < 4e-3
+    assert abs(((z - z.mean()) ** 3).mean()) < 1e-2 and abs(((z - z.mean()) ** 4).mean() - 3.0) < 3e-2
+    # Kolmogorov-Smirnov distance to N(0,1)
+    zs = np.sort(z)
+    cdf = 0.5 * (1.0 + np.vectorize(math.erf)(zs[::64] / math.sqrt(2.0)))
+    emp = (np.arange(0, n, 64) + 0.5) / n
+    assert np.max(np.abs(cdf - emp)) < 3e-3
+    # tail sanity: finite, |z| can exceed 4
+    assert np.isfinite(z).all() and np.abs(z).max() > 4.0
+    shard = torch.empty(4096, device=DEV)
+    rc = native_lib.ps_philox_normal(shard.data_ptr(), 4096, 1234, 5, 40000, torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "ps_philox_normal")
+    assert torch.equal(shard, out[40000:44096]), "stream must be addressed by the global element index"
+
+
+def test_diffusion_distribution_fused_steps_and_shard_invariance(native_lib):
+    B, L, A, T = 8, 128, 15, 300
+    betas_all = orc.cosine_variance_schedule(T)[:T]  # t = 0 .. T-1, like the tutorial loop
+    betas = betas_all[:, None].repeat(1, B)
+    xyz, mask, _ = H.synthetic_batch(44, B, L, A, "bool", nan_masked=False, full_length=True)
+    ps.manual_seed(99)
+    seq = ps.StructureBatch.from_xyz(xyz, mask)
+    seq.standardize()
+    start = seq.get_xyz().clone()
+    for t in range(T):
+        seq.diffuse_xyz(betas[t])
+    ps.manual_seed(99)
+    fused = ps.StructureBatch.from_xyz(xyz, mask)
+    fused.standardize()
+    fused.diffuse_xyz_steps(betas)
+    assert torch.equal(seq.get_xyz(), fused.get_xyz()), "fused T-step kernel must equal T single steps bit for bit"
+    final = fused.get_xyz()
+    assert abs(final.mean().item()) < 0.02 and abs(final.std().item() - 1.0) < 0.02  # final std 1.001
+    assert not torch.equal(final, start)
+    # sharding the batch over 2 "ranks" reproduces the unsharded result exactly
+    from protstruc_b200.sharding import shard_structure_batch
+    parts = []
+    for rank in range(2):
+        ps.manual_seed(99)
+        sb = shard_structure_batch(start.cpu(), mask, rank=rank, world_size=2)
+        sb.diffuse_xyz_steps(betas[:, rank * 4:(rank + 1) * 4])
+        parts.append(sb.get_xyz())
+    assert torch.equal(torch.cat(parts), final)
+    # one step: the implied noise (x' - sqrt(1-b) x) / sqrt(b) is N(0,1)
+    ps.manual_seed(5)
+    one = ps.StructureBatch.from_xyz(xyz, mask)
+    beta = torch.full((B,), 0.25)
+    x0 = one.get_xyz().clone()
+    one.diffuse_xyz(beta)
+    z = (one.get_xyz() - math.sqrt(0.75) * x0) / 0.5
+    assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
+
+
+# ------------------------------------------------------------------------------ geometry free functions
+def test_geometry_known_answers(native_lib):
+    """reference tests/test_geometry.py:10-190 and tests/test_decorator.py type propagation."""
+    assert ps.geometry.dot(torch.tensor([1, 2, 3]), torch.tensor([4, 5, 6])) == 32
+    assert ps.geometry.dot(np.array([1, 2, 3]), np.array([4, 5, 6])) == 32
+    a32 = np.array([[1, 2, 3], [4, 5, 6]]).astype(np.float32)
+    nrm = ps.geometry.norm(a32)
+    assert isinstance(nrm, np.ndarray) and nrm.shape == (2, 1) and np.allclose(nrm, [[14**0.5], [77**0.5]])
+    nt = ps.geometry.norm(torch.from_numpy(a32))
+    assert isinstance(nt, torch.Tensor) and nt.shape == (2, 1)
+    a = np.array([[1, 0, 0], [1, 0, 0]], dtype=np.float32)
+    b = np.zeros((2, 3), dtype=np.float32)
+    c = np.array([[0, 1, 0], [0.5, np.sqrt(3) / 2, 0]], dtype=np.float32)
+    ang = ps.geometry.angle(a, b, c, to_degree=True)
+    assert isinstance(ang, np.ndarray) and ang.shape == (2,) and np.allclose(ang, [90.0, 60.0])
+    ang_t = ps.geometry.angle(torch.from_numpy(a), torch.from_numpy(b), torch.from_numpy(c), to_degree=True)
+    assert isinstance(ang_t, torch.Tensor) and torch.allclose(ang_t.cpu(), torch.tensor([90.0, 60.0]))
+    pts = [np.array([[1, 0, 0]], dtype=np.float32), np.zeros((1, 3), dtype=np.float32),
+           np.array([[0, 1, 0]], dtype=np.float32), np.array([[0, 1, 1]], dtype=np.float32)]
+    dih = ps.geometry.dihedral(*pts, to_degree=True)
+    assert isinstance(dih, np.ndarray) and dih.shape == (1,) and np.allclose(dih, [-90.0])
+    dih_t = ps.geometry.dihedral(*[torch.from_numpy(p) for p in pts], to_degree=True)
+    assert isinstance(dih_t, torch.Tensor) and dih_t.shape == (1,) and torch.allclose(dih_t.cpu(), torch.tensor([-90.0]))
+    dih_113 = ps.geometry.dihedral(*[torch.from_numpy(p).reshape(1, 1, 3) for p in pts], to_degree=True)
+    assert dih_113.shape == (1, 1)
+    mixed = ps.geometry.dihedral(pts[0], torch.from_numpy(pts[1]), pts[2], pts[3])
+    assert isinstance(mixed, torch.Tensor) and abs(mixed.item() + math.pi / 2) < 1e-6
+    fr = ps.geometry.gram_schmidt(torch.randn(16, 30, 3), torch.randn(16, 30, 3), torch.randn(16, 30, 3))
+    assert fr.shape == (16, 30, 3, 3)
+    ident = torch.einsum("bnij,bnik->bnjk", fr, fr)
+    assert torch.allclose(ident.cpu(), torch.eye(3).expand(16, 30, 3, 3), atol=1e-5)
+
+
+def test_geometry_functions_vs_oracle_random(native_lib):
+    g = torch.Generator().manual_seed(8)
+    pts = [3.0 * torch.randn(5000, 3, generator=g) for _ in range(4)]
+    dih = ps.geometry.dihedral(*pts)
+    ref = orc.dihedral(*pts)
+    cond = H.dihedral_conditioning(*[p.double() for p in pts])
+    H.assert_angles_close(dih, ref, cond, "geometry.dihedral")
+    ang = ps.geometry.angle(*pts[:3])
+    H.assert_angles_close(ang, orc.planar_angle(*pts[:3]), H.planar_conditioning(*[p.double() for p in pts[:3]]),
+                          "geometry.angle", circular=False)
+    fr = ps.geometry.gram_schmidt(*pts[:3])
+    assert torch.allclose(fr.cpu(), orc.frames_from_points(*pts[:3]), atol=2e-6)
+
+
+# ------------------------------------------------------------------------------ API behaviour on the device
+def test_error_behaviour_matches_the_reference(native_lib):
+    xyz, mask, _ = H.synthetic_batch(9, 2, 8, 15, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    with pytest.raises(ValueError, match="Atom XX is not valid."):
+        sb.pairwise_dihedrals(["CA", "XX"], ["CA", "CB"])
+    with pytest.raises(KeyError):
+        sb.backbone_orientations(a1="XX")
+    with pytest.raises(KeyError):
+        sb.backbone_translations("nope")
+    with pytest.raises(ValueError):
+        sb.standardize(atom_mask=mask, residue_mask=mask.any(-1))
+    no_mask = ps.StructureBatch.from_xyz(xyz)
+    with pytest.raises(TypeError):
+        no_mask.pairwise_distance_matrix()
+    d, m = no_mask.backbone_dihedrals()  # works without atom_mask, like the reference
+    assert d.shape == (2, 8, 3)
+    # C-ABI level: bad arguments give a status code and a message, never a crash
+    rc = native_lib.ps_pair_dist_mask(None, None, 0, None, None, 1, 1, 15, None)
+    assert rc == -2 and b"xyz" in native_lib.ps_last_error_string()
+    rc = native_lib.ps_pair_dist_mask(sb.xyz.data_ptr(), None, 0, sb.xyz.data_ptr(), None, 0, 8, 15, None)
+    assert rc == -1
+
+
+def test_dtype_and_input_handling(native_lib):
+    """float64 numpy input (what the reference's tests feed) is accepted and computed in fp32; mask dtypes
+    other than bool / float32 come back in the caller's dtype."""
+    rng = np.random.default_rng(3)
+    xyz64 = rng.standard_normal((2, 10, 15, 3)) * 5
+    mask_i64 = (rng.random((2, 10, 15)) < 0.6).astype(np.int64)
+    sb = ps.StructureBatch.from_xyz(xyz64, mask_i64)
+    assert sb.get_xyz().dtype == torch.float32
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    ref_dist, ref_mask = orc.pair_distances(torch.from_numpy(xyz64).float(), torch.from_numpy(mask_i64))
+    H.assert_distances_close(dist, ref_dist)
+    assert dist_mask.dtype == torch.int64 and torch.equal(dist_mask.cpu(), ref_mask)
+    assert sb.get_total_lengths().shape == (2,)

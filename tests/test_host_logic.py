@@ -1,0 +1,166 @@
+"""CPU suite, part 3: host-side logic of the façade — argument validation with the reference's
+exception types, index bookkeeping, batch sharding (incl. a world_size-2 gloo run) — and the
+guarantee that nothing computes on the CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import protstruc_b200 as ps
+from protstruc_b200 import _cabi, sharding
+from oracle import feature_oracle as orc
+from tests import helpers as H
+
+
+def cpu_batch(B=2, L=10, A=15, **kw):
+    xyz, mask, chain_idx = H.synthetic_batch(1, B, L, A)
+    ids = [["A", "B"]] * B
+    return ps.StructureBatch.from_xyz(xyz, mask, chain_idx, ids, device="cpu", **kw), xyz, mask, chain_idx
+
+
+def test_constructor_contract():
+    """reference protstruc/protstruc.py:55-91."""
+    xyz = np.random.rand(4, 20, 25, 3)
+    sb = ps.StructureBatch.from_xyz(xyz, device="cpu")
+    assert sb.get_batch_size() == 4 and sb.get_max_n_residues() == 20 and sb.get_max_n_atoms_per_residue() == 25
+    assert sb.get_xyz().dtype == torch.float32
+    assert sb.residue_mask.dtype == torch.bool and bool(sb.residue_mask.all())
+    assert tuple(sb.chain_idx.shape) == (4, 20) and bool((sb.chain_idx == 0).all())
+    with pytest.raises(ValueError, match="Both `chain_idx` and `chain_ids`"):
+        ps.StructureBatch.from_xyz(xyz, chain_idx=np.zeros((4, 20)), device="cpu")
+    with pytest.raises(ValueError, match="Both `chain_idx` and `chain_ids`"):
+        ps.StructureBatch.from_xyz(xyz, chain_ids=[["A"]] * 4, device="cpu")
+    with pytest.raises(AssertionError, match="Chain index should start from zero"):
+        ps.StructureBatch.from_xyz(xyz, chain_idx=np.ones((4, 20)), chain_ids=[["A"]] * 4, device="cpu")
+    with pytest.raises(ValueError):
+        ps.StructureBatch.from_xyz(np.zeros((4, 20, 3)), device="cpu")
+
+
+def test_terminal_masks_and_getters_match_the_oracle():
+    sb, xyz, mask, chain_idx = cpu_batch(B=4, L=33)
+    nterm, cterm = orc.terminal_masks(chain_idx, mask.any(-1))
+    assert torch.equal(sb.get_n_terminal_mask(), nterm) and torch.equal(sb.get_c_terminal_mask(), cterm)
+    assert torch.equal(sb.get_residue_mask(), mask[:, :, 1].bool())
+    assert sb.get_chain_idx().dtype == torch.int64
+    assert torch.equal(sb.get_total_lengths(), mask.any(-1).cumsum(1).argmax(1) + 1)
+    # three chains -> three termini each (reference tests/test_StructureBatch.py:24-40)
+    ci = np.zeros((16, 100))
+    ci[:, 20:60] = 1.0
+    ci[:, 60:] = 2.0
+    sb3 = ps.StructureBatch.from_xyz(np.random.rand(16, 100, 25, 3), chain_idx=ci, chain_ids=[["A", "B", "C"]] * 16,
+                                     device="cpu")
+    assert bool((sb3.get_n_terminal_mask().sum(axis=1) == 3).all())
+    assert bool((sb3.get_c_terminal_mask().sum(axis=1) == 3).all())
+
+
+def test_validation_errors_are_raised_before_any_launch():
+    sb, xyz, mask, _ = cpu_batch()
+    with pytest.raises(ValueError, match="Atom QQ is not valid."):
+        sb.pairwise_dihedrals(["QQ", "CB"], ["CA", "CB"])
+    with pytest.raises(ValueError, match="Atom zz is not valid."):
+        sb.pairwise_planar_angles(["CA", "CB"], ["zz"])
+    with pytest.raises(KeyError):
+        sb.backbone_orientations(a2="CX")
+    with pytest.raises(KeyError):
+        sb.backbone_translations("CX")
+    with pytest.raises(ValueError, match="Only one of atom_mask and residue_mask"):
+        sb.standardize(atom_mask=mask, residue_mask=mask.any(-1))
+    with pytest.raises(ValueError, match="Cannot unstandardize"):
+        sb.unstandardize()
+    sb._standardized = True
+    with pytest.raises(ValueError, match="already standardized"):
+        sb.standardize()
+    sb._standardized = False
+    with pytest.raises(ValueError, match="`center` must have a shape"):
+        sb.center_at(torch.zeros(2, 2))
+    with pytest.raises(ValueError, match="`center` must have a shape"):
+        sb.center_at(torch.zeros(5, 3))
+    assert sb.backbone_translations().shape == (2, 10, 3)
+
+
+def test_there_is_no_cpu_compute_path():
+    sb, *_ = cpu_batch()
+    for call in (sb.pairwise_distance_matrix, sb.inter_residue_geometry, sb.backbone_dihedrals,
+                 sb.backbone_orientations, sb.center_of_mass, sb.standardize,
+                 lambda: sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"]),
+                 lambda: sb.diffuse_xyz(torch.zeros(2))):
+        with pytest.raises(_cabi.NativeLibraryError, match="no CPU fallback"):
+            call()
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.NativeLibraryError):
+            ps.geometry.angle(np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    from pathlib import Path
+    pkg = Path(ps.__file__).resolve().parent
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        text = f.read_text()
+        assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_atom_vocabulary():
+    """reference protstruc/general.py:4-23 and tests/test_constants.py."""
+    assert [int(ps.ATOM[n]) for n in ("N", "CA", "C", "O", "CB")] == [0, 1, 2, 3, 4]
+    assert ps.ATOM["ca"] == ps.ATOM.CA and ps.ATOM["Cb"] == 4 and ps.ATOM.is_valid("cb") and not ps.ATOM.is_valid("CG")
+    assert ps.MAX_N_ATOMS_PER_RESIDUE == 15
+
+
+def test_shard_bounds_partition_the_batch():
+    for B in (0, 1, 7, 8, 64, 4096):
+        for world in (1, 2, 3, 4, 8):
+            spans = [sharding.shard_bounds(B, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sharding.shard_sizes(B, world)
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(8, 2, 2)
+    xyz, mask, chain_idx = H.synthetic_batch(3, 8, 16, 15)
+    part = sharding.shard_structure_batch(xyz, mask, chain_idx, [["A", "B"]] * 8, rank=1, world_size=4, device="cpu")
+    assert part.get_batch_size() == 2 and torch.equal(torch.nan_to_num(part.get_xyz()), torch.nan_to_num(xyz[2:4]))
+    assert part._noise_elem_offset == 2 * 16 * 15 * 3
+    assert sharding.shard_structure_batch(xyz[:1], mask[:1], rank=1, world_size=2, device="cpu") is None
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, B, L, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        xyz, mask, chain_idx = H.synthetic_batch(77, B, L, 15)
+        start, stop = sharding.shard_bounds(B, world, rank)
+        # the CPU oracle stands in for the kernels here: this test covers the sharding / gather plumbing
+        omega, theta, phi = orc.trrosetta_angles(xyz[start:stop])
+        d, _ = orc.pair_distances(xyz[start:stop], mask[start:stop])
+        local = {"omega": omega, "theta": theta, "phi": phi, "d_ca": d[:, :, :, 1, 1].contiguous()}
+        full = sharding.gather_compact_features(local, B)
+        if rank == 0:
+            torch.save(full, os.path.join(result_dir, "gathered.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_two_gloo_shards_reassemble_to_the_unsharded_result(tmp_path):
+    B, L, world = 5, 12, 2
+    mp.spawn(_gloo_worker, args=(world, _free_port(), B, L, str(tmp_path)), nprocs=world, join=True)
+    gathered = torch.load(tmp_path / "gathered.pt")
+    torch.set_num_threads(1)
+    xyz, mask, _ = H.synthetic_batch(77, B, L, 15)
+    omega, theta, phi = orc.trrosetta_angles(xyz)
+    d, _ = orc.pair_distances(xyz, mask)
+    for name, ref in (("omega", omega), ("theta", theta), ("phi", phi), ("d_ca", d[:, :, :, 1, 1])):
+        got = gathered[name]
+        assert got.shape == ref.shape
+        assert torch.equal(torch.nan_to_num(got, nan=-9.0), torch.nan_to_num(ref, nan=-9.0)), name
