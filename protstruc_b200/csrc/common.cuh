@@ -54,9 +54,12 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
     return r;
 }
 
-// (x * y).sum(-1): products are materialised (rounded) first, then summed left to right.
+// (x * y).sum(-1): products are materialised (rounded) first, then accumulated left to right
+// starting from +0 like ATen's sum does.  The leading +0 matters: three -0 products (zero-padded
+// residues) must sum to +0, otherwise atan2(+0, -0) = pi where the reference returns 0.
 __device__ __forceinline__ float dot3(V3 a, V3 b) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+    const float acc = __fadd_rn(0.0f, __fmul_rn(a.x, b.x));
+    return __fadd_rn(__fadd_rn(acc, __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
 }
 
 // x.norm(dim=-1): IEEE sqrt of the sum of squares.

@@ -39,7 +39,11 @@ namespace {
 
 constexpr int kTilePairs = 32;  // pairs per warp tile (= lanes)
 
-enum SqrtMode { kSqrtApprox = 0, kSqrtApproxFtz = 1, kSqrtRn = 2 };
+// Default is the single-instruction MUFU.SQRT (sqrt.approx.ftz.f32): relative error <= 2^-23, sqrt(0) = 0,
+// NaN -> NaN, +inf -> +inf.  "ftz" only matters for a sum of squares below 1.18e-38, i.e. distances
+// below 1.1e-19 A, which are returned as 0 (well inside the 1e-4 A tolerance); the non-ftz flavour
+// costs three more issue slots per element, the IEEE one eight.
+enum SqrtMode { kSqrtApproxFtz = 0, kSqrtApprox = 1, kSqrtRn = 2 };
 
 template <int MODE>
 __device__ __forceinline__ float sqrt_mode(float v) {
@@ -96,7 +100,6 @@ struct PairDistParams {
     float* __restrict__ theta;
     float* __restrict__ phi;
     int L;
-    long long LL;         // L*L
     long long num_pairs;  // B*L*L
     long long num_tiles;  // ceil(num_pairs / 32)
 };
@@ -108,6 +111,70 @@ __device__ __forceinline__ uint32_t load_mask_bits(const uint8_t* __restrict__ m
 #pragma unroll
     for (int a = 0; a < A; ++a) bits |= (__ldg(m + a) != 0 ? 1u : 0u) << a;
     return bits;
+}
+
+// Writes one lane's A*A mask bytes (byte a*A + c = mask_i[a] & mask_j[c]) into the warp's mask tile
+// with 32-bit shared-memory stores only.
+//
+// The lane's block starts at byte 225*lane of the tile, i.e. at byte s = lane & 3 of an aligned word.
+//  1. R = the 15 bytes of row "mask_j" as four words (a 4-bit -> 4-byte spread is one IMAD + one LOP3);
+//  2. the masked rows (R & -mask_i[a]) are concatenated into the unshifted block words B[0..56]; 4
+//     consecutive block bytes always come from two consecutive words of the masked-row array, so
+//     every B word is a single PRMT with a compile-time selector;
+//  3. the block is moved to its byte alignment with one funnel shift per word (runtime s);
+//  4. the word that straddles two lanes' blocks is completed with the neighbour's first word
+//     (one shuffle) and written by the lower lane only.
+// Lane stride is 56.25 words: start words floor(56.25*l) hit 32 distinct banks -> conflict free.
+// ~1.2 issue slots per mask byte instead of 3 for byte-wise stores (which also bank-conflict).
+template <int A>
+__device__ __forceinline__ void write_mask_block(uint32_t* __restrict__ tile_words, int lane,
+                                                 uint32_t mi_bits, uint32_t mj_bits) {
+    static_assert(A == 15, "the word-wise mask writer is laid out for 15 atoms per residue");
+    constexpr int kWordsPerRow = 4;              // 15 bytes + 1 pad byte
+    constexpr int kBlockWords = (A * A + 3) / 4;  // 57
+    uint32_t r[kWordsPerRow];
+#pragma unroll
+    for (int w = 0; w < kWordsPerRow; ++w)
+        r[w] = (((mj_bits >> (4 * w)) & 0xFu) * 0x00204081u) & 0x01010101u;
+    uint32_t rm[A * kWordsPerRow + 1];
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const uint32_t keep = 0u - ((mi_bits >> a) & 1u);
+#pragma unroll
+        for (int w = 0; w < kWordsPerRow; ++w) rm[a * kWordsPerRow + w] = r[w] & keep;
+    }
+    rm[A * kWordsPerRow] = 0u;
+    uint32_t blk[kBlockWords];
+#pragma unroll
+    for (int k = 0; k < kBlockWords; ++k) {
+        // source position of block byte t: row t / 15, column t % 15 -> word 4*row + col/4, byte col%4
+        const int t0 = 4 * k;
+        const int s0 = (t0 / A) * kWordsPerRow + ((t0 % A) >> 2);
+        uint32_t sel = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int t = t0 + q;
+            if (t < A * A) {
+                const int sw = (t / A) * kWordsPerRow + ((t % A) >> 2);
+                sel |= static_cast<uint32_t>((sw - s0) * 4 + ((t % A) & 3)) << (4 * q);
+            } else {
+                sel |= 7u << (4 * q);  // byte 3 of the zero word rm[60]
+            }
+        }
+        blk[k] = __byte_perm(rm[s0], rm[s0 + 1], sel);
+    }
+    const int shift_bits = (lane & 3) * 8;
+    uint32_t out[kBlockWords];
+    out[0] = blk[0] << shift_bits;
+#pragma unroll
+    for (int k = 1; k < kBlockWords; ++k) out[k] = __funnelshift_l(blk[k - 1], blk[k], shift_bits);
+    // the last word of this lane is the first word of lane + 1 unless that lane starts word-aligned
+    const uint32_t neighbour_first = __shfl_down_sync(0xffffffffu, out[0], 1);
+    if (((lane + 1) & 3) != 0 && lane < 31) out[kBlockWords - 1] |= neighbour_first;
+    uint32_t* dst = tile_words + ((A * A * lane) >> 2);
+    if ((lane & 3) == 0) dst[0] = out[0];
+#pragma unroll
+    for (int k = 1; k < kBlockWords; ++k) dst[k] = out[k];
 }
 
 template <int A, int KIND, int SQRT, bool ANGLES>
@@ -130,12 +197,19 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
         const long long pair0 = tile * kTilePairs;
         long long pair = pair0 + lane;
         if (pair >= p.num_pairs) pair = p.num_pairs - 1;  // tail lanes recompute the last pair
-        const long long b = pair / p.LL;
-        const int rem = static_cast<int>(pair - b * p.LL);
-        const int i = rem / p.L;
-        const int j = rem - i * p.L;
-        const long long res_i = b * p.L + i;
-        const long long res_j = b * p.L + j;
+        // pair -> (row = b*L + i, j); 32-bit division whenever the pair count allows it
+        unsigned row, j;
+        if (p.num_pairs <= 0xFFFFFFFFll) {
+            const unsigned pr = static_cast<unsigned>(pair);
+            row = pr / static_cast<unsigned>(p.L);
+            j = pr - row * static_cast<unsigned>(p.L);
+        } else {
+            row = static_cast<unsigned>(pair / p.L);
+            j = static_cast<unsigned>(pair - static_cast<long long>(row) * p.L);
+        }
+        const unsigned i = row % static_cast<unsigned>(p.L);
+        const long long res_i = row;
+        const long long res_j = static_cast<long long>(row - i) + j;
         const float* __restrict__ xi_ptr = p.xyz + res_i * (A * 3);
         const float* __restrict__ xj_ptr = p.xyz + res_j * (A * 3);
 
@@ -168,35 +242,51 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
         __syncwarp();
 
         float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
-        uint8_t* my_u8 = tile_u8 + lane * G::kElemsPerPair;
 
         if (KIND == kDistBoolMask || KIND == kDistOnly) {
-#pragma unroll 3
-            for (int a = 0; a < A; ++a) {
-                const float xi = __ldg(xi_ptr + 3 * a + 0);
-                const float yi = __ldg(xi_ptr + 3 * a + 1);
-                const float zi = __ldg(xi_ptr + 3 * a + 2);
-                const float2 nx = make_float2(-xi, -xi);
-                const float2 ny = make_float2(-yi, -yi);
-                const float2 nz = make_float2(-zi, -zi);
+            // Rows (atoms a of residue i) are processed in groups of kRowsPerGroup; the coordinates of
+            // the next group are requested before the current group is computed so that the L1
+            // round trip of the (warp-uniform) x_i loads is off the critical path.
+            constexpr int kRowsPerGroup = 3;
+            constexpr int kGroups = (A + kRowsPerGroup - 1) / kRowsPerGroup;
+            float cur[kRowsPerGroup][3], nxt[kRowsPerGroup][3];
 #pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                    const float2 dx = __fadd2_rn(xj[k], nx);
-                    const float2 dy = __fadd2_rn(yj[k], ny);
-                    const float2 dz = __fadd2_rn(zj[k], nz);
-                    float2 s = __fmul2_rn(dx, dx);
-                    s = __ffma2_rn(dy, dy, s);
-                    s = __ffma2_rn(dz, dz, s);
-                    my_f32[a * A + 2 * k] = sqrt_mode<SQRT>(s.x);
-                    if (2 * k + 1 < A) my_f32[a * A + 2 * k + 1] = sqrt_mode<SQRT>(s.y);
-                }
-                if (KIND == kDistBoolMask) {
-                    // row a of the pair mask: mask_i[a] ? mask_j[:] : 0, one byte per atom c
-                    const uint32_t row = ((mi_bits >> a) & 1u) ? mj_bits : 0u;
+            for (int r = 0; r < kRowsPerGroup; ++r)
 #pragma unroll
-                    for (int c = 0; c < A; ++c)
-                        my_u8[a * A + c] = static_cast<uint8_t>((row >> c) & 1u);
+                for (int k = 0; k < 3; ++k) cur[r][k] = (r < A) ? __ldg(xi_ptr + 3 * r + k) : 0.f;
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                const int a0 = g * kRowsPerGroup;
+#pragma unroll
+                for (int r = 0; r < kRowsPerGroup; ++r) {
+                    const int an = a0 + kRowsPerGroup + r;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) nxt[r][k] = (an < A) ? __ldg(xi_ptr + 3 * an + k) : 0.f;
                 }
+#pragma unroll
+                for (int r = 0; r < kRowsPerGroup; ++r) {
+                    const int a = a0 + r;
+                    if (A % kRowsPerGroup != 0 && a >= A) break;
+                    const float2 nx = make_float2(-cur[r][0], -cur[r][0]);
+                    const float2 ny = make_float2(-cur[r][1], -cur[r][1]);
+                    const float2 nz = make_float2(-cur[r][2], -cur[r][2]);
+                    float* row = my_f32 + a * A;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float2 dx = __fadd2_rn(xj[k], nx);
+                        const float2 dy = __fadd2_rn(yj[k], ny);
+                        const float2 dz = __fadd2_rn(zj[k], nz);
+                        float2 s = __fmul2_rn(dx, dx);
+                        s = __ffma2_rn(dy, dy, s);
+                        s = __ffma2_rn(dz, dz, s);
+                        row[2 * k] = sqrt_mode<SQRT>(s.x);
+                        if (2 * k + 1 < A) row[2 * k + 1] = sqrt_mode<SQRT>(s.y);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRowsPerGroup; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cur[r][k] = nxt[r][k];
             }
         } else if (KIND == kF32MaskOnly) {
             const float* am = static_cast<const float*>(p.atom_mask);
@@ -206,15 +296,8 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
 #pragma unroll
                 for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
             }
-        } else {  // kBoolMaskOnly
-#pragma unroll 3
-            for (int a = 0; a < A; ++a) {
-                const uint32_t row = ((mi_bits >> a) & 1u) ? mj_bits : 0u;
-#pragma unroll
-                for (int c = 0; c < A; ++c)
-                    my_u8[a * A + c] = static_cast<uint8_t>((row >> c) & 1u);
-            }
         }
+        if (kind_has_u8<KIND>()) write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
 
         if (ANGLES) {
             // trRosetta triple of this lane's pair, reference definitions
@@ -347,11 +430,11 @@ int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, floa
     if (sqrt_mode_id == kSqrtRn)
         pair_generic_kernel<kSqrtRn><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
             xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
-    else if (sqrt_mode_id == kSqrtApproxFtz)
-        pair_generic_kernel<kSqrtApproxFtz><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+    else if (sqrt_mode_id == kSqrtApprox)
+        pair_generic_kernel<kSqrtApprox><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
             xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
     else
-        pair_generic_kernel<kSqrtApprox><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        pair_generic_kernel<kSqrtApproxFtz><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
             xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
     return check_launch("pair_generic_kernel");
 }
@@ -373,8 +456,8 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
                "pair_dist_mask: nothing to compute (dist and dist_mask are NULL)");
     PS_REQUIRE(mask_dtype == PS_MASK_BOOL || mask_dtype == PS_MASK_F32, PS_ERR_BAD_DTYPE,
                "pair_dist_mask: unknown mask_dtype %d", mask_dtype);
-    PS_REQUIRE(static_cast<long long>(L) * L < (1ll << 31), PS_ERR_BAD_SHAPE,
-               "pair_dist_mask: L=%d too large", L);
+    PS_REQUIRE(static_cast<long long>(B) * L < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "pair_dist_mask: B*L=%lld residues exceed 2^31", static_cast<long long>(B) * L);
     const bool want_angles = omega || theta || phi;
     PS_REQUIRE(!want_angles || A >= 5, PS_ERR_BAD_SHAPE,
                "inter_residue_geometry needs the CB slot (A >= 5), got A=%d", A);
@@ -399,8 +482,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.theta = theta;
     p.phi = phi;
     p.L = L;
-    p.LL = static_cast<long long>(L) * L;
-    p.num_pairs = p.LL * B;
+    p.num_pairs = static_cast<long long>(L) * L * B;
     p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
 
     if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
@@ -415,7 +497,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
                        : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, stream);
         }
         PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
-        return launch_tiles<15, kBoolMaskOnly, kSqrtApprox, false>(p, warps_override, stream);
+        return launch_tiles<15, kBoolMaskOnly, kSqrtApproxFtz, false>(p, warps_override, stream);
     }
     // fp32 mask: distances (+angles) first, then the mask product through the same tile path.
     if (dist) {
@@ -430,7 +512,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     pm.dist = static_cast<float*>(dist_mask);
     pm.mask = nullptr;
     pm.omega = pm.theta = pm.phi = nullptr;
-    return launch_tiles<15, kF32MaskOnly, kSqrtApprox, false>(pm, warps_override, stream);
+    return launch_tiles<15, kF32MaskOnly, kSqrtApproxFtz, false>(pm, warps_override, stream);
 }
 
 }  // namespace ps

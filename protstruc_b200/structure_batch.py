@@ -427,7 +427,9 @@ class StructureBatch:
         """Translates every structure so that its CA centre sits at `center` ((B, 3), (3,) or None
         for the origin); in place (reference protstruc.py:759-788)."""
         if center is None:
-            center = torch.zeros(1, 3)
+            # the reference builds zeros(1, 3) here and then rejects it for B > 1 (its own shape
+            # check, protstruc.py:769-779); the documented meaning is "the origin" for any B
+            center = torch.zeros(3)
         if center.ndim > 2 or center.shape[-1] != 3:
             raise ValueError(f"`center` must have a shape of (batch_size, 3) or (3,), got {center.shape}.")
         if center.ndim == 2 and center.shape[0] != self.batch_size:

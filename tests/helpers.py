@@ -68,7 +68,7 @@ def planar_conditioning(a, b, c) -> torch.Tensor:
 
 
 def assert_angles_close(actual: torch.Tensor, expected: torch.Tensor, cond: torch.Tensor, what: str,
-                        circular: bool = True, well_tol: float = ANGLE_TOL):
+                        circular: bool = True, well_tol: float = ANGLE_TOL, all_finite_tol: float = None):
     """<= 1e-5 rad where the geometry is well conditioned (min sin >= 0.1), <= 1e-6 / sin below that
     (SURVEY 8c), NaN placement bit-exact; degenerate entries (sin == 0 or NaN) must agree in NaN-ness
     and are otherwise exempt from the value check unless both are finite and `sin` is NaN-free."""
@@ -80,6 +80,11 @@ def assert_angles_close(actual: torch.Tensor, expected: torch.Tensor, cond: torc
     if good.any():
         worst = diff[good].max().item()
         assert worst <= well_tol, f"{what}: max deviation {worst:.3g} rad in the well-conditioned region"
+    if all_finite_tol is not None and finite.any():
+        # dihedrals: the kernels issue the reference's exact fp32 op sequence up to the final sqrt / div /
+        # atan2, so even degenerate and padded entries must agree to a few ulp of pi
+        worst_all = diff[finite].max().item()
+        assert worst_all <= all_finite_tol, f"{what}: max deviation {worst_all:.3g} rad over all finite entries"
     soft = finite & (cond > 0) & (cond < SIN_GATE)
     if soft.any():
         ratio = (diff[soft] / (1e-6 / cond[soft])).max().item()
