@@ -192,7 +192,8 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
 /*
  * Tuning hook for K1 (benchmarks / profiling only; not part of the drop-in surface).
  * variant bit-field: bits 0-1 sqrt mode (0 = sqrt.approx.ftz.f32 [default], 1 = sqrt.approx.f32,
- * 2 = sqrt.rn.f32); bits 4-7 warps per CTA override (0 = default); bit 8 = force generic kernel.
+ * 2 = sqrt.rn.f32); bits 4-7 tile buffers per CTA override (0 = default); bit 8 = force generic kernel;
+ * bit 9 = use the non-default number of warps per tile.
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,

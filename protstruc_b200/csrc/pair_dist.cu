@@ -37,7 +37,8 @@ namespace ps {
 
 namespace {
 
-constexpr int kTilePairs = 32;  // pairs per warp tile (= lanes)
+constexpr int kTilePairs = 32;  // pairs per tile (= lanes)
+constexpr int kDefaultWarpsPerTile = 2;  // see pair_tiles_kernel; variant bit 9 selects the other value
 
 // Default is the single-instruction MUFU.SQRT (sqrt.approx.ftz.f32): relative error <= 2^-23, sqrt(0) = 0,
 // NaN -> NaN, +inf -> +inf.  "ftz" only matters for a sum of squares below 1.18e-38, i.e. distances
@@ -102,6 +103,10 @@ struct PairDistParams {
     int L;
     long long num_pairs;  // B*L*L
     long long num_tiles;  // ceil(num_pairs / 32)
+    // Column-strip schedule: tiles t and t + strip_stride cover the same 32 residues j (one residue i
+    // row further down), so a warp that walks t, t + S, t + 2S, ... keeps residue j in registers.
+    long long strip_stride;   // S = L / gcd(L, 32) tiles
+    long long strip_members;  // M = ceil(num_tiles / S)
 };
 
 // Gather the A mask bytes of one residue into a bit field (bit a = mask[a] != 0).
@@ -177,23 +182,66 @@ __device__ __forceinline__ void write_mask_block(uint32_t* __restrict__ tile_wor
     for (int k = 1; k < kBlockWords; ++k) dst[k] = out[k];
 }
 
-template <int A, int KIND, int SQRT, bool ANGLES>
-__global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams p) {
+// Synchronises the WPT warps that share one tile (named barrier `slot + 1`; plain __syncwarp for WPT = 1).
+template <int WPT>
+__device__ __forceinline__ void tile_sync(int slot) {
+    if (WPT == 1) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "n"(WPT * 32) : "memory");
+    }
+}
+
+// WPT = warps per tile.  WPT = 1: one warp computes the whole tile.  WPT = 2: two warps share the tile
+// buffer — warp 0 takes rows [0, 8) and the angle triple, warp 1 rows [8, 15) and the mask block — which
+// doubles the resident warps (12 per SM) for the same shared-memory footprint; the extra thread-level
+// parallelism hides the fixed-latency dependency stalls that dominate with 6 warps per SM.
+template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
+__global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_tiles_kernel(const PairDistParams p) {
     using G = TileGeom<A>;
     constexpr int NP = (A + 1) / 2;  // f32x2 packs per coordinate
+    constexpr int kSplitRow = (WPT == 1) ? A : (A + 1) / 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
+    const int slot = warp / WPT;   // tile buffer of this warp
+    const int wsub = warp % WPT;   // role inside the tile
+    const int slots_per_cta = (blockDim.x >> 5) / WPT;
+    const bool does_rows_lo = (wsub == 0);
+    const bool does_mask = (wsub == WPT - 1);
+    const bool does_angles = (wsub == 0);
+    const bool is_issuer = (wsub == 0) && (lane == 0);
+    const int row_begin = does_rows_lo ? 0 : kSplitRow;
+    const int row_end = (WPT == 1 || !does_rows_lo) ? A : kSplitRow;
 
-    unsigned char* wbase = smem_raw + static_cast<size_t>(warp) * warp_smem_bytes<A, KIND>();
+    unsigned char* wbase = smem_raw + static_cast<size_t>(slot) * warp_smem_bytes<A, KIND>();
     float* tile_f32 = reinterpret_cast<float*>(wbase);
     uint8_t* tile_u8 = wbase + (kind_has_f32<KIND>() ? G::kDistBytes : 0);
 
-    const long long tile_stride = static_cast<long long>(gridDim.x) * warps_per_cta;
-    for (long long tile = static_cast<long long>(blockIdx.x) * warps_per_cta + warp;
-         tile < p.num_tiles; tile += tile_stride) {
+    // Work partition: the (strip, member) grid of S x M tile positions is walked strip-major and cut
+    // into equal contiguous ranges, one per tile buffer of the persistent grid (balanced to +-1 tile).
+    const long long workers = static_cast<long long>(gridDim.x) * slots_per_cta;
+    const long long worker = static_cast<long long>(blockIdx.x) * slots_per_cta + slot;
+    const long long positions = p.strip_stride * p.strip_members;
+    const long long u_begin = positions / workers * worker + (positions % workers) * worker / workers;
+    const long long u_end = positions / workers * (worker + 1) + (positions % workers) * (worker + 1) / workers;
+    long long strip = u_begin / p.strip_members;
+    long long member = u_begin - strip * p.strip_members;
+
+    // Residue j of this lane: A atoms in registers, SoA, packed two atoms per 64-bit register pair.
+    float2 xj[NP], yj[NP], zj[NP];
+    float mjf[A];  // fp32 mask row (kF32MaskOnly)
+    uint32_t mj_bits = 0;
+    long long loaded_res_j = -1;
+
+    for (long long u = u_begin; u < u_end; ++u, ++member) {
+        if (member == p.strip_members) {
+            member = 0;
+            ++strip;
+        }
+        const long long tile = strip + p.strip_stride * member;
+        if (tile >= p.num_tiles) continue;  // the last member of the higher strips may not exist
         const long long pair0 = tile * kTilePairs;
         long long pair = pair0 + lane;
         if (pair >= p.num_pairs) pair = p.num_pairs - 1;  // tail lanes recompute the last pair
@@ -213,33 +261,33 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
         const float* __restrict__ xi_ptr = p.xyz + res_i * (A * 3);
         const float* __restrict__ xj_ptr = p.xyz + res_j * (A * 3);
 
-        // Residue j: A atoms in registers, SoA, packed two atoms per 64-bit register pair.
-        float2 xj[NP], yj[NP], zj[NP];
-        float mjf[A];  // fp32 mask row (kF32MaskOnly)
-        uint32_t mi_bits = 0, mj_bits = 0;
-        if (KIND != kF32MaskOnly && KIND != kBoolMaskOnly) {
+        // Reload residue j only when the strip (or the structure) changed; warp-uniform decision.
+        if (!__all_sync(0xffffffffu, res_j == loaded_res_j)) {
+            loaded_res_j = res_j;
+            if (KIND != kF32MaskOnly && KIND != kBoolMaskOnly) {
 #pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
-                xj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 0), __ldg(xj_ptr + 3 * c1 + 0));
-                yj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 1), __ldg(xj_ptr + 3 * c1 + 1));
-                zj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
+                for (int k = 0; k < NP; ++k) {
+                    const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
+                    xj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 0), __ldg(xj_ptr + 3 * c1 + 0));
+                    yj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 1), __ldg(xj_ptr + 3 * c1 + 1));
+                    zj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
+                }
+            }
+            if (kind_has_u8<KIND>() && does_mask)
+                mj_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_j * A);
+            if (KIND == kF32MaskOnly) {
+                const float* am = static_cast<const float*>(p.atom_mask);
+#pragma unroll
+                for (int c = 0; c < A; ++c) mjf[c] = __ldg(am + res_j * A + c);
             }
         }
-        if (kind_has_u8<KIND>()) {
-            const uint8_t* am = static_cast<const uint8_t*>(p.atom_mask);
-            mi_bits = load_mask_bits<A>(am + res_i * A);
-            mj_bits = load_mask_bits<A>(am + res_j * A);
-        }
-        if (KIND == kF32MaskOnly) {
-            const float* am = static_cast<const float*>(p.atom_mask);
-#pragma unroll
-            for (int c = 0; c < A; ++c) mjf[c] = __ldg(am + res_j * A + c);
-        }
+        uint32_t mi_bits = 0;
+        if (kind_has_u8<KIND>() && does_mask)
+            mi_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_i * A);
 
-        // The previous tile of this warp must have left shared memory before we overwrite it.
-        if (lane == 0) bulk_wait_read_all();
-        __syncwarp();
+        // The previous tile of this buffer must have left shared memory before it is overwritten.
+        if (is_issuer) bulk_wait_read_all();
+        tile_sync<WPT>(slot);
 
         float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
 
@@ -248,39 +296,39 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
             // the next group are requested before the current group is computed so that the L1
             // round trip of the (warp-uniform) x_i loads is off the critical path.
             constexpr int kRowsPerGroup = 3;
-            constexpr int kGroups = (A + kRowsPerGroup - 1) / kRowsPerGroup;
             float cur[kRowsPerGroup][3], nxt[kRowsPerGroup][3];
 #pragma unroll
             for (int r = 0; r < kRowsPerGroup; ++r)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) cur[r][k] = (r < A) ? __ldg(xi_ptr + 3 * r + k) : 0.f;
+                for (int k = 0; k < 3; ++k)
+                    cur[r][k] = (row_begin + r < row_end) ? __ldg(xi_ptr + 3 * (row_begin + r) + k) : 0.f;
 #pragma unroll 1
-            for (int g = 0; g < kGroups; ++g) {
-                const int a0 = g * kRowsPerGroup;
+            for (int a0 = row_begin; a0 < row_end; a0 += kRowsPerGroup) {
 #pragma unroll
                 for (int r = 0; r < kRowsPerGroup; ++r) {
                     const int an = a0 + kRowsPerGroup + r;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) nxt[r][k] = (an < A) ? __ldg(xi_ptr + 3 * an + k) : 0.f;
+                    for (int k = 0; k < 3; ++k) nxt[r][k] = (an < row_end) ? __ldg(xi_ptr + 3 * an + k) : 0.f;
                 }
 #pragma unroll
                 for (int r = 0; r < kRowsPerGroup; ++r) {
                     const int a = a0 + r;
-                    if (A % kRowsPerGroup != 0 && a >= A) break;
-                    const float2 nx = make_float2(-cur[r][0], -cur[r][0]);
-                    const float2 ny = make_float2(-cur[r][1], -cur[r][1]);
-                    const float2 nz = make_float2(-cur[r][2], -cur[r][2]);
-                    float* row = my_f32 + a * A;
+                    if (a < row_end) {
+                        const float2 nx = make_float2(-cur[r][0], -cur[r][0]);
+                        const float2 ny = make_float2(-cur[r][1], -cur[r][1]);
+                        const float2 nz = make_float2(-cur[r][2], -cur[r][2]);
+                        float* out_row = my_f32 + a * A;
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) {
-                        const float2 dx = __fadd2_rn(xj[k], nx);
-                        const float2 dy = __fadd2_rn(yj[k], ny);
-                        const float2 dz = __fadd2_rn(zj[k], nz);
-                        float2 s = __fmul2_rn(dx, dx);
-                        s = __ffma2_rn(dy, dy, s);
-                        s = __ffma2_rn(dz, dz, s);
-                        row[2 * k] = sqrt_mode<SQRT>(s.x);
-                        if (2 * k + 1 < A) row[2 * k + 1] = sqrt_mode<SQRT>(s.y);
+                        for (int k = 0; k < NP; ++k) {
+                            const float2 dx = __fadd2_rn(xj[k], nx);
+                            const float2 dy = __fadd2_rn(yj[k], ny);
+                            const float2 dz = __fadd2_rn(zj[k], nz);
+                            float2 s = __fmul2_rn(dx, dx);
+                            s = __ffma2_rn(dy, dy, s);
+                            s = __ffma2_rn(dz, dz, s);
+                            out_row[2 * k] = sqrt_mode<SQRT>(s.x);
+                            if (2 * k + 1 < A) out_row[2 * k + 1] = sqrt_mode<SQRT>(s.y);
+                        }
                     }
                 }
 #pragma unroll
@@ -290,20 +338,22 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
             }
         } else if (KIND == kF32MaskOnly) {
             const float* am = static_cast<const float*>(p.atom_mask);
-#pragma unroll 3
-            for (int a = 0; a < A; ++a) {
+#pragma unroll 1
+            for (int a = row_begin; a < row_end; ++a) {
                 const float mi = __ldg(am + res_i * A + a);
 #pragma unroll
                 for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
             }
         }
-        if (kind_has_u8<KIND>()) write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
+        if (kind_has_u8<KIND>() && does_mask)
+            write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
 
-        if (ANGLES) {
+        if (ANGLES && does_angles) {
             // trRosetta triple of this lane's pair, reference definitions
             // (protstruc/protstruc.py:810-815): real CB in slot 4.
             const V3 n_i = ld3(xi_ptr + 0), ca_i = ld3(xi_ptr + 3), cb_i = ld3(xi_ptr + 12);
-            const V3 ca_j = ld3(xj_ptr + 3), cb_j = ld3(xj_ptr + 12);
+            const V3 ca_j{xj[0].y, yj[0].y, zj[0].y};  // atom 1 = second half of pack 0
+            const V3 cb_j{xj[2].x, yj[2].x, zj[2].x};  // atom 4 = first half of pack 2
             if (pair0 + lane < p.num_pairs) {
                 if (p.omega) p.omega[pair] = dihedral4(ca_i, cb_i, ca_j, cb_j);
                 if (p.theta) p.theta[pair] = dihedral4(n_i, ca_i, cb_i, cb_j);
@@ -311,29 +361,30 @@ __global__ void __launch_bounds__(256, 1) pair_tiles_kernel(const PairDistParams
             }
         }
 
-        __syncwarp();
         const long long elem0 = pair0 * G::kElemsPerPair;
         if (pair0 + kTilePairs <= p.num_pairs) {
             // Full tile: hand it to the TMA engine.
             fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
+            tile_sync<WPT>(slot);
+            if (is_issuer) {
                 if (kind_has_f32<KIND>()) bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
                 if (kind_has_u8<KIND>()) bulk_store_s2g(p.mask + elem0, tile_u8, G::kMaskBytes);
                 bulk_commit();
             }
         } else {
             // Tail tile (num_pairs % 32 != 0): byte count is not 16-B granular, copy by hand.
+            tile_sync<WPT>(slot);
             const int n = static_cast<int>(p.num_pairs - pair0) * G::kElemsPerPair;
+            const int t = wsub * 32 + lane;
             if (kind_has_f32<KIND>())
-                for (int e = lane; e < n; e += 32) p.dist[elem0 + e] = tile_f32[e];
+                for (int e = t; e < n; e += 32 * WPT) p.dist[elem0 + e] = tile_f32[e];
             if (kind_has_u8<KIND>())
-                for (int e = lane; e < n; e += 32) p.mask[elem0 + e] = tile_u8[e];
-            __syncwarp();
+                for (int e = t; e < n; e += 32 * WPT) p.mask[elem0 + e] = tile_u8[e];
+            tile_sync<WPT>(slot);
         }
     }
     // Shared memory must stay allocated until the engine has read the last tile.
-    if (lane == 0) bulk_wait_all();
+    if (is_issuer) bulk_wait_all();
     __syncwarp();
 }
 
@@ -378,40 +429,48 @@ __global__ void __launch_bounds__(256) pair_generic_kernel(
     }
 }
 
-template <int A, int KIND, int SQRT, bool ANGLES>
-int launch_tiles(const PairDistParams& p, int warps_override, cudaStream_t stream) {
-    constexpr int per_warp = warp_smem_bytes<A, KIND>();
+template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
+int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t stream) {
+    constexpr int per_slot = warp_smem_bytes<A, KIND>();
     constexpr int kMaxSmem = 227 * 1024;
-    int warps = kMaxSmem / per_warp;
-    if (warps > 8) warps = 8;
-    if (warps_override > 0 && warps_override < warps) warps = warps_override;
-    if (warps < 1) {
-        set_error("pair_tiles_kernel: a warp tile of %d B does not fit in shared memory", per_warp);
+    constexpr int kMaxWarps = (WPT == 1) ? 8 : 12;
+    int slots = kMaxSmem / per_slot;
+    if (slots * WPT > kMaxWarps) slots = kMaxWarps / WPT;
+    if (slots_override > 0 && slots_override < slots) slots = slots_override;
+    if (slots < 1) {
+        set_error("pair_tiles_kernel: a tile of %d B does not fit in shared memory", per_slot);
         return PS_ERR_BAD_SHAPE;
     }
-    const int smem = warps * per_warp;
-    auto kernel = pair_tiles_kernel<A, KIND, SQRT, ANGLES>;
+    const int smem = slots * per_slot;
+    auto kernel = pair_tiles_kernel<A, KIND, SQRT, ANGLES, WPT>;
     cudaError_t err =
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_tiles_kernel)");
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
-    long long ctas = (p.num_tiles + warps - 1) / warps;
+    long long ctas = (p.num_tiles + slots - 1) / slots;
     if (ctas > sms) ctas = sms;
-    kernel<<<static_cast<unsigned>(ctas), warps * 32, smem, stream>>>(p);
+    kernel<<<static_cast<unsigned>(ctas), slots * WPT * 32, smem, stream>>>(p);
     return check_launch("pair_tiles_kernel");
 }
 
+template <int A, int KIND, int SQRT, bool ANGLES>
+int launch_tiles(const PairDistParams& p, int slots_override, int wpt, cudaStream_t stream) {
+    if (wpt == 2 && (KIND == kDistBoolMask || KIND == kDistOnly))
+        return launch_tiles_wpt<A, KIND, SQRT, ANGLES, 2>(p, slots_override, stream);
+    return launch_tiles_wpt<A, KIND, SQRT, ANGLES, 1>(p, slots_override, stream);
+}
+
 template <int A, int KIND, bool ANGLES>
-int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int warps_override,
+int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int slots_override, int wpt,
                       cudaStream_t stream) {
     switch (sqrt_mode_id) {
-        case kSqrtApprox:
-            return launch_tiles<A, KIND, kSqrtApprox, ANGLES>(p, warps_override, stream);
         case kSqrtApproxFtz:
-            return launch_tiles<A, KIND, kSqrtApproxFtz, ANGLES>(p, warps_override, stream);
+            return launch_tiles<A, KIND, kSqrtApproxFtz, ANGLES>(p, slots_override, wpt, stream);
+        case kSqrtApprox:
+            return launch_tiles<A, KIND, kSqrtApprox, ANGLES>(p, slots_override, wpt, stream);
         case kSqrtRn:
-            return launch_tiles<A, KIND, kSqrtRn, ANGLES>(p, warps_override, stream);
+            return launch_tiles<A, KIND, kSqrtRn, ANGLES>(p, slots_override, wpt, stream);
         default:
             set_error("unknown sqrt mode %d", sqrt_mode_id);
             return PS_ERR_BAD_DTYPE;
@@ -463,8 +522,9 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
                "inter_residue_geometry needs the CB slot (A >= 5), got A=%d", A);
 
     const int sqrt_id = variant & 3;
-    const int warps_override = (variant >> 4) & 15;
+    const int warps_override = (variant >> 4) & 15;  // tile buffers (slots) per CTA
     const bool force_generic = (variant >> 8) & 1;
+    const int wpt = ((variant >> 9) & 1) ? (3 - kDefaultWarpsPerTile) : kDefaultWarpsPerTile;
 
     const bool fast = (A == 15) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
@@ -484,26 +544,34 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.L = L;
     p.num_pairs = static_cast<long long>(L) * L * B;
     p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
+    int g = L, h = kTilePairs;  // gcd(L, 32)
+    while (h != 0) {
+        const int r = g % h;
+        g = h;
+        h = r;
+    }
+    p.strip_stride = L / g;
+    p.strip_members = (p.num_tiles + p.strip_stride - 1) / p.strip_stride;
 
     if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
         if (dist && dist_mask) {
             return want_angles
-                       ? launch_tiles_sqrt<15, kDistBoolMask, true>(p, sqrt_id, warps_override, stream)
-                       : launch_tiles_sqrt<15, kDistBoolMask, false>(p, sqrt_id, warps_override, stream);
+                       ? launch_tiles_sqrt<15, kDistBoolMask, true>(p, sqrt_id, warps_override, wpt, stream)
+                       : launch_tiles_sqrt<15, kDistBoolMask, false>(p, sqrt_id, warps_override, wpt, stream);
         }
         if (dist) {
             return want_angles
-                       ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, stream)
-                       : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, stream);
+                       ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, wpt, stream)
+                       : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, wpt, stream);
         }
         PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
-        return launch_tiles<15, kBoolMaskOnly, kSqrtApproxFtz, false>(p, warps_override, stream);
+        return launch_tiles<15, kBoolMaskOnly, kSqrtApproxFtz, false>(p, warps_override, 1, stream);
     }
     // fp32 mask: distances (+angles) first, then the mask product through the same tile path.
     if (dist) {
         int rc = want_angles
-                     ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, stream)
-                     : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, stream);
+                     ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, wpt, stream)
+                     : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, wpt, stream);
         if (rc != PS_OK) return rc;
     } else {
         PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
@@ -512,7 +580,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     pm.dist = static_cast<float*>(dist_mask);
     pm.mask = nullptr;
     pm.omega = pm.theta = pm.phi = nullptr;
-    return launch_tiles<15, kF32MaskOnly, kSqrtApproxFtz, false>(pm, warps_override, stream);
+    return launch_tiles<15, kF32MaskOnly, kSqrtApproxFtz, false>(pm, warps_override, 1, stream);
 }
 
 }  // namespace ps

@@ -94,7 +94,7 @@ def test_distance_kernel_variants_agree(native_lib):
     m = mask.to(DEV)
     B, L, A = 2, 45, 15
     outs = {}
-    for variant in (0, 1, 2, 1 << 8, 2 << 4):
+    for variant in (0, 1, 2, 1 << 8, 2 << 4, 1 << 9):
         d = torch.empty(B, L, L, A, A, device=DEV)
         dm = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
         rc = native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
@@ -104,7 +104,8 @@ def test_distance_kernel_variants_agree(native_lib):
     torch.cuda.synchronize()
     base, base_mask = outs[0]
     assert torch.equal(outs[1 << 8][0], base), "generic kernel differs from the staged kernel"
-    assert torch.equal(outs[2 << 4][0], base), "warps-per-CTA override changed the result"
+    assert torch.equal(outs[2 << 4][0], base), "tile-buffers-per-CTA override changed the result"
+    assert torch.equal(outs[1 << 9][0], base), "warps-per-tile variant changed the result"
     for v in outs:
         assert torch.equal(outs[v][1], base_mask)
     rel = ((outs[2][0] - base).abs() / outs[2][0].clamp_min(1e-30)).max().item()

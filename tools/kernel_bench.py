@@ -75,9 +75,10 @@ def main():
     th, ph = torch.empty_like(om), torch.empty_like(om)
     nbytes = B * (L * L * A * A * 5 + L * A * 13)
     variants = {"sqrt.approx.ftz (default)": 0, "sqrt.approx": 1, "sqrt.rn": 2, "generic kernel": 1 << 8}
+    variants["1 warp per tile (6 warps/SM)"] = 1 << 9
     if not args.quick:
-        for w in (2, 3, 4, 5):
-            variants[f"default, {w} warps/CTA"] = w << 4
+        for w in (3, 4, 5):
+            variants[f"default, {w} tile buffers/CTA"] = w << 4
     for label, v in variants.items():
         def run(v=v):
             _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(),
@@ -100,7 +101,7 @@ def main():
     out["results"].append(entry(f"K1 dist + fp32 mask (2 launches) B{B} L{L} A{A}", best, med, B * L * L * A * A * 8, peak))
     del dmaskf, maskf
 
-    def run_fused():
+    def run_fused():  # noqa: E306
         _cabi.check(lib.ps_inter_residue_geometry(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(),
                                                   om.data_ptr(), th.data_ptr(), ph.data_ptr(), B, L, A, s), "fused")
     best, med = time_call(run_fused)

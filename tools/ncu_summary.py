@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Condenses an .ncu-rep (read here, without a GPU) into the small text summary kept under profiles/.
+
+    python tools/ncu_summary.py gpurun_out/k1.ncu-rep > profiles/r1_k1_ncu_summary.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum",
+    "sm__cycles_elapsed.avg.per_second",
+    "dram__bytes_read.sum",
+    "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed.avg.per_cycle_elapsed",
+    "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread",
+    "launch__block_size",
+    "launch__grid_size",
+    "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_shared_mem",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu summary of {rep} ({len(data)} profiled launch(es)); ncu --set full --clock-control none")
+    for d in data:
+        print(f"\nkernel: {d[col['Kernel Name']]}")
+        for k in KEYS:
+            if k in col:
+                print(f"  {k:72s} {d[col[k]]:>18s} {units[col[k]]}")
+        print("  warp stall reasons (average warps stalled per issue-active cycle):")
+        stalls = []
+        for h, i in col.items():
+            if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
+                try:
+                    stalls.append((float(d[i]), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+                except ValueError:
+                    pass
+        for v, name in sorted(stalls, reverse=True)[:10]:
+            print(f"    {name:28s} {v:8.3f}")
+        t_ms = float(d[col["gpu__time_duration.sum"]]) * (1e-3 if units[col["gpu__time_duration.sum"]] == "us" else 1.0)
+        wr = float(d[col["dram__bytes_write.sum"]])
+        wu = units[col["dram__bytes_write.sum"]]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(wu, 1.0)
+        print(f"  derived: DRAM write rate under ncu = {wr * scale / (t_ms / 1e3) / 1e9:.1f} GB/s "
+              f"(ncu timings are cold-cache / serialised; bench.py carries the number of record)")
+
+
+if __name__ == "__main__":
+    main()
