@@ -198,6 +198,11 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,
                          int B, int L, int A, int variant, void* stream);
+/* Same hook for the fused kernel (ps_inter_residue_geometry with a variant bit-field). */
+int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype,
+                                 float* dist, void* dist_mask,
+                                 float* omega, float* theta, float* phi,
+                                 int B, int L, int A, int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     "ps_trrosetta_angles": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_void_p]),
     "ps_inter_residue_geometry": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
                                           c_void_p]),
+    "ps_inter_residue_geometry_ex": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
+                                             c_int, c_void_p]),
     "ps_backbone": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, _fp, _fp, _fp,
                             c_void_p]),
     "ps_masked_stats": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_void_p]),

@@ -122,15 +122,21 @@ int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_
         ps::set_error("inter_residue_geometry: all inputs and outputs are required");
         return PS_ERR_NULL_POINTER;
     }
-    if (A == 15) {
-        return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta,
-                                       phi, B, L, A, 0, PS_STREAM(stream));
+    // A == 15 and L >= 32: one fused launch; otherwise the generic distance kernel followed by the
+    // fused angle kernel (decided inside pair_dist_mask_impl)
+    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, B,
+                                   L, A, 0, PS_STREAM(stream));
+}
+
+int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                                 void* dist_mask, float* omega, float* theta, float* phi, int B,
+                                 int L, int A, int variant, void* stream) {
+    if (!(omega && theta && phi && dist && dist_mask && atom_mask)) {
+        ps::set_error("inter_residue_geometry_ex: all inputs and outputs are required");
+        return PS_ERR_NULL_POINTER;
     }
-    // other atom counts: generic distance kernel + the fused angle kernel, back to back
-    int rc = ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr,
-                                     nullptr, B, L, A, 0, PS_STREAM(stream));
-    if (rc != PS_OK) return rc;
-    return ps::trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, PS_STREAM(stream));
+    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, B,
+                                   L, A, variant, PS_STREAM(stream));
 }
 
 int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chain_idx, int B, int L,

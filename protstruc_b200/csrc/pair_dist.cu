@@ -101,12 +101,19 @@ struct PairDistParams {
     float* __restrict__ theta;
     float* __restrict__ phi;
     int L;
+    long long num_rows;   // B*L residues
     long long num_pairs;  // B*L*L
     long long num_tiles;  // ceil(num_pairs / 32)
     // Column-strip schedule: tiles t and t + strip_stride cover the same 32 residues j (one residue i
     // row further down), so a warp that walks t, t + S, t + 2S, ... keeps residue j in registers.
     long long strip_stride;   // S = L / gcd(L, 32) tiles
     long long strip_members;  // M = ceil(num_tiles / S)
+    // Strips are cut into chunks of `chunk_members` consecutive members; a (chunk, strip) cell is the
+    // unit a worker walks.  Cells are ordered strip-fastest, so workers that run side by side write
+    // ADJACENT tiles (same member, neighbouring strips): the concurrent stores of the whole GPU form a
+    // few contiguous fronts in HBM instead of ~900 scattered streams.
+    long long chunk_members;  // C
+    long long num_cells;      // S * ceil(M / C)
 };
 
 // Gather the A mask bytes of one residue into a bit field (bit a = mask[a] != 0).
@@ -192,15 +199,29 @@ __device__ __forceinline__ void tile_sync(int slot) {
     }
 }
 
+constexpr int kStageFloats = 96;  // two residues of A*3 = 45 floats, padded
+constexpr int kStageBytesPerWarp = 2 * kStageFloats * 4;  // double buffered
+
 // WPT = warps per tile.  WPT = 1: one warp computes the whole tile.  WPT = 2: two warps share the tile
-// buffer — warp 0 takes rows [0, 8) and the angle triple, warp 1 rows [8, 15) and the mask block — which
+// buffer — warp 0 takes the first rows and the angle triple, warp 1 the remaining rows and the mask block — which
 // doubles the resident warps (12 per SM) for the same shared-memory footprint; the extra thread-level
 // parallelism hides the fixed-latency dependency stalls that dominate with 6 warps per SM.
+//
+// Residue i (the row side of the pair) changes with every tile, so its 45 coordinates + 15 mask
+// bytes are a compulsory L2 round trip per tile.  They are therefore fetched ONE TILE AHEAD: while tile
+// k is computed, three coalesced loads per lane bring the two residues tile k+1 can touch (a tile of 32
+// pairs spans at most two residue-i rows when L >= 32) into registers; they are parked in a small
+// double-buffered per-warp staging area and the row loop reads them with broadcast LDS.  The mask bits
+// of both residues come from one byte load per lane and a ballot.
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_tiles_kernel(const PairDistParams p) {
     using G = TileGeom<A>;
+    static_assert(2 * A * 3 <= kStageFloats, "staging area too small");
     constexpr int NP = (A + 1) / 2;  // f32x2 packs per coordinate
-    constexpr int kSplitRow = (WPT == 1) ? A : (A + 1) / 2;
+    // Row split between the two warps of a tile, balanced against their extra duties: the angle triple
+    // (warp 0, ~300 issue slots per tile) and the mask block (warp 1, ~255) versus ~80 per row.
+    constexpr int kSplitRow = (WPT == 1) ? A : (ANGLES ? (A - 1) / 2 : (A * 3) / 5);
+    constexpr bool kNeedsXyz = (KIND == kDistBoolMask || KIND == kDistOnly);
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int lane = threadIdx.x & 31;
@@ -209,8 +230,8 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     const int wsub = warp % WPT;   // role inside the tile
     const int slots_per_cta = (blockDim.x >> 5) / WPT;
     const bool does_rows_lo = (wsub == 0);
-    const bool does_mask = (wsub == WPT - 1);
-    const bool does_angles = (wsub == 0);
+    const bool does_mask = kind_has_u8<KIND>() && (wsub == WPT - 1);
+    const bool does_angles = ANGLES && (wsub == 0);
     const bool is_issuer = (wsub == 0) && (lane == 0);
     const int row_begin = does_rows_lo ? 0 : kSplitRow;
     const int row_end = (WPT == 1 || !does_rows_lo) ? A : kSplitRow;
@@ -218,16 +239,71 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     unsigned char* wbase = smem_raw + static_cast<size_t>(slot) * warp_smem_bytes<A, KIND>();
     float* tile_f32 = reinterpret_cast<float*>(wbase);
     uint8_t* tile_u8 = wbase + (kind_has_f32<KIND>() ? G::kDistBytes : 0);
+    float* stage = reinterpret_cast<float*>(smem_raw + static_cast<size_t>(slots_per_cta) * warp_smem_bytes<A, KIND>() +
+                                            static_cast<size_t>(warp) * kStageBytesPerWarp);
 
-    // Work partition: the (strip, member) grid of S x M tile positions is walked strip-major and cut
-    // into equal contiguous ranges, one per tile buffer of the persistent grid (balanced to +-1 tile).
+    // Work partition: the linear order u = (cell * C + step) over (chunk, strip) cells is cut into equal
+    // contiguous ranges, one per tile buffer of the persistent grid (balanced to +-1 position).
     const long long workers = static_cast<long long>(gridDim.x) * slots_per_cta;
     const long long worker = static_cast<long long>(blockIdx.x) * slots_per_cta + slot;
-    const long long positions = p.strip_stride * p.strip_members;
-    const long long u_begin = positions / workers * worker + (positions % workers) * worker / workers;
+    const long long positions = p.num_cells * p.chunk_members;
+    long long u = positions / workers * worker + (positions % workers) * worker / workers;
     const long long u_end = positions / workers * (worker + 1) + (positions % workers) * (worker + 1) / workers;
-    long long strip = u_begin / p.strip_members;
-    long long member = u_begin - strip * p.strip_members;
+    long long cell = u / p.chunk_members;
+    long long step = u - cell * p.chunk_members;
+    long long strip = cell % p.strip_stride;
+    long long member0 = (cell / p.strip_stride) * p.chunk_members;
+    auto next_tile = [&]() -> long long {
+        while (u < u_end) {
+            if (step == p.chunk_members) {
+                step = 0;
+                ++cell;
+                strip = cell % p.strip_stride;
+                member0 = (cell / p.strip_stride) * p.chunk_members;
+            }
+            const long long member = member0 + step;
+            const long long t = strip + p.strip_stride * member;
+            ++u;
+            ++step;
+            if (member < p.strip_members && t < p.num_tiles) return t;  // ragged edges of the cell grid
+        }
+        return -1;
+    };
+    // first residue-i row a tile touches
+    auto first_row_of = [&](long long t) -> long long {
+        const long long first_pair = t * kTilePairs;
+        if (p.num_pairs <= 0xFFFFFFFFll) return static_cast<unsigned>(first_pair) / static_cast<unsigned>(p.L);
+        return first_pair / p.L;
+    };
+
+    // Residue-i prefetch registers: floats lane, lane+32, lane+64 of the 2-residue block, one mask byte.
+    float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f;
+    uint32_t pf_mask_ballot = 0;
+    auto prefetch_issue = [&](long long t) {
+        const long long r0 = first_row_of(t);
+        const long long last_float = p.num_rows * (A * 3) - 1;
+        if (kNeedsXyz) {
+            const long long base = r0 * (A * 3);
+            const long long i0 = base + lane, i1 = base + lane + 32, i2 = base + lane + 64;
+            pf0 = __ldg(p.xyz + (i0 < last_float ? i0 : last_float));
+            pf1 = __ldg(p.xyz + (i1 < last_float ? i1 : last_float));
+            pf2 = __ldg(p.xyz + (i2 < last_float ? i2 : last_float));
+        }
+        if (kind_has_u8<KIND>()) {
+            const uint8_t* am = static_cast<const uint8_t*>(p.atom_mask);
+            const long long idx = r0 * A + lane;
+            const long long last = p.num_rows * A - 1;
+            const bool bit = (lane < 2 * A) && (__ldg(am + (idx < last ? idx : last)) != 0);
+            pf_mask_ballot = __ballot_sync(0xffffffffu, bit);
+        }
+    };
+    auto prefetch_commit = [&](float* buf) {
+        if (kNeedsXyz) {
+            buf[lane] = pf0;
+            buf[lane + 32] = pf1;
+            if (lane + 64 < kStageFloats) buf[lane + 64] = pf2;
+        }
+    };
 
     // Residue j of this lane: A atoms in registers, SoA, packed two atoms per 64-bit register pair.
     float2 xj[NP], yj[NP], zj[NP];
@@ -235,13 +311,20 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     uint32_t mj_bits = 0;
     long long loaded_res_j = -1;
 
-    for (long long u = u_begin; u < u_end; ++u, ++member) {
-        if (member == p.strip_members) {
-            member = 0;
-            ++strip;
-        }
-        const long long tile = strip + p.strip_stride * member;
-        if (tile >= p.num_tiles) continue;  // the last member of the higher strips may not exist
+    long long tile = next_tile();
+    int parity = 0;
+    uint32_t mask_ballot = 0;
+    if (tile >= 0) {
+        prefetch_issue(tile);
+        prefetch_commit(stage);
+        mask_ballot = pf_mask_ballot;
+        __syncwarp();
+    }
+    while (tile >= 0) {
+        const long long upcoming = next_tile();
+        if (upcoming >= 0) prefetch_issue(upcoming);  // consumed after this tile's rows
+
+        const float* __restrict__ xi_stage = stage + parity * kStageFloats;
         const long long pair0 = tile * kTilePairs;
         long long pair = pair0 + lane;
         if (pair >= p.num_pairs) pair = p.num_pairs - 1;  // tail lanes recompute the last pair
@@ -258,13 +341,15 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
         const unsigned i = row % static_cast<unsigned>(p.L);
         const long long res_i = row;
         const long long res_j = static_cast<long long>(row - i) + j;
-        const float* __restrict__ xi_ptr = p.xyz + res_i * (A * 3);
+        // 0 or 1: which of the two staged residues this lane's pair uses (lane 0 holds the first row)
+        const int which = static_cast<int>(row - __shfl_sync(0xffffffffu, row, 0));
+        const float* __restrict__ xi = xi_stage + which * (A * 3);
         const float* __restrict__ xj_ptr = p.xyz + res_j * (A * 3);
 
         // Reload residue j only when the strip (or the structure) changed; warp-uniform decision.
         if (!__all_sync(0xffffffffu, res_j == loaded_res_j)) {
             loaded_res_j = res_j;
-            if (KIND != kF32MaskOnly && KIND != kBoolMaskOnly) {
+            if (kNeedsXyz) {
 #pragma unroll
                 for (int k = 0; k < NP; ++k) {
                     const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
@@ -273,17 +358,14 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                     zj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
                 }
             }
-            if (kind_has_u8<KIND>() && does_mask)
-                mj_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_j * A);
+            if (does_mask) mj_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_j * A);
             if (KIND == kF32MaskOnly) {
                 const float* am = static_cast<const float*>(p.atom_mask);
 #pragma unroll
                 for (int c = 0; c < A; ++c) mjf[c] = __ldg(am + res_j * A + c);
             }
         }
-        uint32_t mi_bits = 0;
-        if (kind_has_u8<KIND>() && does_mask)
-            mi_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_i * A);
+        const uint32_t mi_bits = (mask_ballot >> (which * A)) & ((1u << A) - 1u);
 
         // The previous tile of this buffer must have left shared memory before it is overwritten.
         if (is_issuer) bulk_wait_read_all();
@@ -291,24 +373,23 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 
         float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
 
-        if (KIND == kDistBoolMask || KIND == kDistOnly) {
-            // Rows (atoms a of residue i) are processed in groups of kRowsPerGroup; the coordinates of
-            // the next group are requested before the current group is computed so that the L1
-            // round trip of the (warp-uniform) x_i loads is off the critical path.
+        if (kNeedsXyz) {
+            // Rows (atoms a of residue i) are processed in groups of kRowsPerGroup; the staged coordinates
+            // of the next group are read (broadcast LDS) before the current group is computed.
             constexpr int kRowsPerGroup = 3;
             float cur[kRowsPerGroup][3], nxt[kRowsPerGroup][3];
 #pragma unroll
             for (int r = 0; r < kRowsPerGroup; ++r)
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
-                    cur[r][k] = (row_begin + r < row_end) ? __ldg(xi_ptr + 3 * (row_begin + r) + k) : 0.f;
+                    cur[r][k] = (row_begin + r < row_end) ? xi[3 * (row_begin + r) + k] : 0.f;
 #pragma unroll 1
             for (int a0 = row_begin; a0 < row_end; a0 += kRowsPerGroup) {
 #pragma unroll
                 for (int r = 0; r < kRowsPerGroup; ++r) {
                     const int an = a0 + kRowsPerGroup + r;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) nxt[r][k] = (an < row_end) ? __ldg(xi_ptr + 3 * an + k) : 0.f;
+                    for (int k = 0; k < 3; ++k) nxt[r][k] = (an < row_end) ? xi[3 * an + k] : 0.f;
                 }
 #pragma unroll
                 for (int r = 0; r < kRowsPerGroup; ++r) {
@@ -345,13 +426,12 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                 for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
             }
         }
-        if (kind_has_u8<KIND>() && does_mask)
-            write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
+        if (does_mask) write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
 
-        if (ANGLES && does_angles) {
+        if (does_angles) {
             // trRosetta triple of this lane's pair, reference definitions
             // (protstruc/protstruc.py:810-815): real CB in slot 4.
-            const V3 n_i = ld3(xi_ptr + 0), ca_i = ld3(xi_ptr + 3), cb_i = ld3(xi_ptr + 12);
+            const V3 n_i{xi[0], xi[1], xi[2]}, ca_i{xi[3], xi[4], xi[5]}, cb_i{xi[12], xi[13], xi[14]};
             const V3 ca_j{xj[0].y, yj[0].y, zj[0].y};  // atom 1 = second half of pack 0
             const V3 cb_j{xj[2].x, yj[2].x, zj[2].x};  // atom 4 = first half of pack 2
             if (pair0 + lane < p.num_pairs) {
@@ -360,6 +440,9 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                 if (p.phi) p.phi[pair] = angle3(ca_i, cb_i, cb_j);
             }
         }
+
+        // Park the prefetched residue-i data of the upcoming tile in the other staging buffer.
+        if (upcoming >= 0) prefetch_commit(stage + (parity ^ 1) * kStageFloats);
 
         const long long elem0 = pair0 * G::kElemsPerPair;
         if (pair0 + kTilePairs <= p.num_pairs) {
@@ -382,6 +465,10 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                 for (int e = t; e < n; e += 32 * WPT) p.mask[elem0 + e] = tile_u8[e];
             tile_sync<WPT>(slot);
         }
+        __syncwarp();  // staging buffer of the upcoming tile is complete
+        mask_ballot = pf_mask_ballot;
+        tile = upcoming;
+        parity ^= 1;
     }
     // Shared memory must stay allocated until the engine has read the last tile.
     if (is_issuer) bulk_wait_all();
@@ -431,12 +518,16 @@ __global__ void __launch_bounds__(256) pair_generic_kernel(
 
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t stream) {
-    constexpr int per_slot = warp_smem_bytes<A, KIND>();
+    constexpr int per_slot = warp_smem_bytes<A, KIND>() + WPT * kStageBytesPerWarp;
     constexpr int kMaxSmem = 227 * 1024;
     constexpr int kMaxWarps = (WPT == 1) ? 8 : 12;
     int slots = kMaxSmem / per_slot;
     if (slots * WPT > kMaxWarps) slots = kMaxWarps / WPT;
-    if (slots_override > 0 && slots_override < slots) slots = slots_override;
+    // Measured on B200 (profiles/r1g_k1_sweep_v6_cells.json): with two warps per tile, four tile buffers
+    // (8 warps, 147 KB) sustain 6.1-6.3 TB/s on the distance + mask kernels, five or six buffers 3-8 % less.
+    if (WPT == 2 && kind_has_f32<KIND>() && kind_has_u8<KIND>() && slots > 4) slots = 4;
+    if (slots_override > 0 && slots_override <= kMaxSmem / per_slot && slots_override * WPT <= kMaxWarps)
+        slots = slots_override;
     if (slots < 1) {
         set_error("pair_tiles_kernel: a tile of %d B does not fit in shared memory", per_slot);
         return PS_ERR_BAD_SHAPE;
@@ -450,7 +541,14 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     if (sms < 0) return sms;
     long long ctas = (p.num_tiles + slots - 1) / slots;
     if (ctas > sms) ctas = sms;
-    kernel<<<static_cast<unsigned>(ctas), slots * WPT * 32, smem, stream>>>(p);
+    PairDistParams q = p;
+    const long long workers = ctas * slots;
+    long long chunks_per_strip = (workers + q.strip_stride / 2) / q.strip_stride;  // ~ one cell per worker
+    if (chunks_per_strip < 1) chunks_per_strip = 1;
+    if (chunks_per_strip > q.strip_members) chunks_per_strip = q.strip_members;
+    q.chunk_members = (q.strip_members + chunks_per_strip - 1) / chunks_per_strip;
+    q.num_cells = q.strip_stride * ((q.strip_members + q.chunk_members - 1) / q.chunk_members);
+    kernel<<<static_cast<unsigned>(ctas), slots * WPT * 32, smem, stream>>>(q);
     return check_launch("pair_tiles_kernel");
 }
 
@@ -502,6 +600,9 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 }  // namespace
 
+int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
+                          float* theta, float* phi, cudaStream_t stream);  // pair_angles.cu
+
 // Host entry used by the C-ABI wrappers (cabi.cu).
 int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                         void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
@@ -526,11 +627,12 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     const bool force_generic = (variant >> 8) & 1;
     const int wpt = ((variant >> 9) & 1) ? (3 - kDefaultWarpsPerTile) : kDefaultWarpsPerTile;
 
-    const bool fast = (A == 15) && !force_generic && aligned16(dist) && aligned16(dist_mask);
+    // the staged kernel needs L >= 32 (a tile of 32 pairs then touches at most two residue-i rows)
+    const bool fast = (A == 15) && (L >= kTilePairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
-        PS_REQUIRE(!want_angles, PS_ERR_BAD_SHAPE,
-                   "fused angles are only available on the staged A=15 path");
-        return launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
+        int rc = launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
+        if (rc != PS_OK || !want_angles) return rc;
+        return trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, stream);
     }
 
     PairDistParams p;
@@ -542,6 +644,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.theta = theta;
     p.phi = phi;
     p.L = L;
+    p.num_rows = static_cast<long long>(L) * B;
     p.num_pairs = static_cast<long long>(L) * L * B;
     p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
     int g = L, h = kTilePairs;  // gcd(L, 32)
@@ -552,6 +655,8 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     }
     p.strip_stride = L / g;
     p.strip_members = (p.num_tiles + p.strip_stride - 1) / p.strip_stride;
+    p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
+    p.num_cells = p.strip_stride;
 
     if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
         if (dist && dist_mask) {

@@ -77,7 +77,7 @@ def main():
     variants = {"sqrt.approx.ftz (default)": 0, "sqrt.approx": 1, "sqrt.rn": 2, "generic kernel": 1 << 8}
     variants["1 warp per tile (6 warps/SM)"] = 1 << 9
     if not args.quick:
-        for w in (3, 4, 5):
+        for w in (3, 5, 6):
             variants[f"default, {w} tile buffers/CTA"] = w << 4
     for label, v in variants.items():
         def run(v=v):
