@@ -75,8 +75,23 @@ __device__ __forceinline__ V3 div3(V3 a, float s) {
     return V3{__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)};
 }
 
+__device__ __forceinline__ bool has_nan3(V3 a) { return (a.x != a.x) | (a.y != a.y) | (a.z != a.z); }
+
+// Missing atoms are NaN coordinates in the reference's tensors (protstruc/pdb.py:133-135) and every
+// NaN input coordinate makes the angle NaN (each cross / dot product mixes all three components).
+// Returning NaN up front is therefore exact, and it keeps NaN-carrying lanes out of the slow paths of
+// the IEEE division / square root / atan2f / acosf sequences (a 25 % hit on the fused kernel with half
+// of the atoms missing).  The cheap probe is a plain sum; only when it is NaN (a NaN, or +inf and -inf
+// together) are the coordinates inspected one by one, so infinities still take the full computation.
+__device__ __forceinline__ bool any_nan_coordinate(V3 a, V3 b, V3 c) {
+    const float probe = ((a.x + a.y) + (a.z + b.x)) + ((b.y + b.z) + (c.x + c.y)) + c.z;
+    if (probe == probe) return false;
+    return has_nan3(a) || has_nan3(b) || has_nan3(c);
+}
+
 // geometry.dihedral (protstruc/geometry.py:110-124).
 __device__ __forceinline__ float dihedral4(V3 a, V3 b, V3 c, V3 d) {
+    if (any_nan_coordinate(a, b, c) || has_nan3(d)) return __int_as_float(0x7fc00000);
     const V3 b0 = sub3(a, b);
     const V3 b1 = sub3(c, b);
     const V3 b2 = sub3(d, c);
@@ -90,6 +105,7 @@ __device__ __forceinline__ float dihedral4(V3 a, V3 b, V3 c, V3 d) {
 
 // geometry.angle (protstruc/geometry.py:64-71); no clamp, exactly like the reference.
 __device__ __forceinline__ float angle3(V3 a, V3 b, V3 c) {
+    if (any_nan_coordinate(a, b, c)) return __int_as_float(0x7fc00000);
     const V3 ba = sub3(a, b);
     const V3 bc = sub3(c, b);
     const float cosine = __fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc)));

@@ -41,6 +41,7 @@ def main():
         A = 15
         xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
         mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
+        xyz = torch.where(mask[..., None], xyz, torch.full_like(xyz, float("nan"))).contiguous()
         dist = torch.empty(B, L, L, A, A, device=DEV)
         dmask = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
         om = torch.empty(B, L, L, device=DEV)

@@ -61,10 +61,13 @@ def main():
     out = {"device": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak, "results": []}
     g = torch.Generator(device=DEV).manual_seed(0)
 
-    def inputs(B, L, A):
+    def inputs(B, L, A, nan_masked=True):
+        """xyz ~ 10 N(0,1), Bernoulli(0.5) mask, masked slots NaN (as the PDB ingest yields)."""
         xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
         mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
-        return xyz, mask
+        if nan_masked:
+            xyz = torch.where(mask[..., None], xyz, torch.full_like(xyz, float("nan")))
+        return xyz.contiguous(), mask
 
     # ---- K1 at the metric shape (L=512, A=15), variants
     B, L, A = 16, 512, 15
@@ -132,7 +135,7 @@ def main():
 
     # ---- config 3: 256 x 512 backbone (A=5), omega/theta/phi
     B, L, A = 256, 512, 5
-    xyz, _ = inputs(B, L, A)
+    xyz, _ = inputs(B, L, A, nan_masked=False)  # config 3: backbone slots, all valid
     om = torch.empty(B, L, L, device=DEV)
     th, ph = torch.empty_like(om), torch.empty_like(om)
 
