@@ -147,6 +147,46 @@ int ps_translate(const float* xyz, const float* t, int t_rows,
                  int B, int L, int A, float* xyz_out, void* stream);
 
 /*
+ * Rigid-frame family.
+ *  ps_local_xyz — StructureBatch.get_local_xyz (protstruc/protstruc.py:347-362):
+ *      out[b,l,a,:] = R_{b,l}^T xyz[b,l,a,:] - xyz[b,l,ca_slot,:], R from Gram-Schmidt on slots (a1,a2,a3)
+ *  ps_rotate — StructureBatch.rotate (protstruc/protstruc.py:681-694): xyz_out = R_b xyz, rotation is
+ *      (rot_rows,3,3) with rot_rows = B or 1; xyz_out must not alias xyz
+ *  ps_frames_to_backbone — StructureBatch.from_backbone_orientations_translations
+ *      (protstruc/protstruc.py:263-319): xyz[b,l,a,:] = R_{b,l} ideal[a,:] + t_{b,l} for a < n_ideal,
+ *      0 otherwise; atom_mask (B,L,A) f32 = 1 for the placed atoms.  `ideal` is (n_ideal,3) f32 on the device.
+ *  ps_translate_bcast — StructureBatch.translate (protstruc/protstruc.py:662-679): xyz_out = xyz + t where
+ *      t is addressed as t[b*stride_b + l*stride_l + a*stride_a + k] (strides in elements, 0 = broadcast).
+ */
+int ps_local_xyz(const float* xyz, int B, int L, int A, int a1, int a2, int a3, int ca_slot,
+                 float* out, void* stream);
+int ps_rotate(const float* xyz, const float* rotation, int rot_rows, int B, int L, int A,
+              float* xyz_out, void* stream);
+int ps_frames_to_backbone(const float* orientations, const float* translations, const float* ideal,
+                          int n_ideal, int B, int L, int A, float* xyz, float* atom_mask, void* stream);
+int ps_translate_bcast(const float* xyz, const float* t, int64_t stride_b, int64_t stride_l,
+                       int64_t stride_a, int B, int L, int A, float* xyz_out, void* stream);
+
+/*
+ * Batched Kabsch — the solve inside StructureBatch.align (protstruc/protstruc.py:880-918,
+ * geometry.kabsch protstruc/geometry.py:442-480): for every structure the rotation / translation that best maps
+ * the selected atoms of `source` onto `target`:  rotation (B,3,3), translation (B,3) with
+ * target ~= rotation @ source + translation.  source (B,n_atoms,3), target (target_rows,n_atoms,3) with
+ * target_rows = B or 1, mask (B,n_atoms) uint8.
+ */
+int ps_kabsch(const float* source, const float* target, const uint8_t* mask, int target_rows, int B,
+              int n_atoms, float* rotation, float* translation, void* stream);
+
+/*
+ * Top-k nearest residues — StructureBatch.get_topk_nearest_residue_mask
+ * (protstruc/protstruc.py:819-862), one structure: CA distance to the closest of n_query points, residues
+ * with valid == 0 pushed to 1e9, the k smallest marked.  scratch: L floats of device workspace.  out (L) uint8.
+ */
+int ps_topk_nearest_residue_mask(const float* xyz, const uint8_t* valid, const float* query, int n_query,
+                                 int L, int A, int ca_slot, int k, float* scratch, uint8_t* out,
+                                 void* stream);
+
+/*
  * K5 — one forward-diffusion step.  Replaces StructureBatch.diffuse_xyz
  * (protstruc/protstruc.py:864-878):
  *   out = fl( fl(sqrt(1-beta_b) * x) + fl(z * sqrt(beta_b)) )     (no FMA contraction)

@@ -187,6 +187,91 @@ def frames(xyz: torch.Tensor, a1: int = 0, a2: int = 1, a3: int = 2) -> torch.Te
     return frames_from_points(xyz[:, :, a1], xyz[:, :, a2], xyz[:, :, a3])
 
 
+# ------------------------------------------------------------------ rigid-frame family (row f1)
+def local_xyz(xyz: torch.Tensor) -> torch.Tensor:
+    """reference protstruc/protstruc.py:353-362 — R^T x minus the residue's global CA."""
+    n_atoms = xyz.shape[2]
+    orientation = frames(xyz)[:, :, None].expand(-1, -1, n_atoms, -1, -1)
+    local = torch.einsum("bnaji,bnaj->bnai", orientation, xyz)
+    return local - xyz[:, :, SLOT["CA"]].unsqueeze(-2)
+
+
+def rotate(xyz: torch.Tensor, rotation: torch.Tensor) -> torch.Tensor:
+    """reference protstruc/protstruc.py:688-694"""
+    rotation = rotation[None, None, None] if rotation.ndim == 2 else rotation[:, None, None]
+    return torch.einsum("bnaij,bnaj->bnai", rotation, xyz)
+
+
+def ideal_backbone(include_cb: bool = False) -> torch.Tensor:
+    """reference protstruc/geometry.py:206-224 with the constants of protstruc/constants/ideal.py."""
+    NA, AC, NAC = 1.458, 1.523, 1.937
+    ca = torch.zeros(3)
+    c = torch.tensor([AC, 0.0, 0.0])
+    n = torch.tensor([NA * math.cos(NAC), NA * math.sin(NAC), 0.0])
+    if include_cb:
+        _b, _c = (ca - n), (c - ca)
+        _a = torch.linalg.cross(_b, _c)
+        cb = -0.58273431 * _a + 0.56802827 * _b - 0.54067466 * _c + ca
+        return torch.stack([n, ca, c, cb])
+    return torch.stack([n, ca, c])
+
+
+def frames_to_backbone(orientations: torch.Tensor, translations: torch.Tensor, include_cb: bool = False,
+                       n_slots: int = 15) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference protstruc/protstruc.py:289-314 — rotate + translate the ideal residue, zero-pad to 15 slots."""
+    B, L = orientations.shape[:2]
+    ideal = ideal_backbone(include_cb).expand(B, L, -1, -1)
+    n_atoms = ideal.shape[2]
+    rot = orientations[:, :, None].expand(-1, -1, n_atoms, -1, -1)
+    atoms = torch.einsum("bnaij,bnaj->bnai", rot, ideal) + translations[:, :, None, :]
+    mask = torch.ones_like(atoms[..., 0])
+    atoms = torch.cat([atoms, torch.zeros(B, L, n_slots - n_atoms, 3)], dim=-2)
+    mask = torch.cat([mask, torch.zeros(B, L, n_slots - n_atoms)], dim=-1)
+    return atoms, mask
+
+
+def kabsch(a: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """reference protstruc/geometry.py:454-480 — SVD of the covariance of the centred point sets."""
+    ca, cb = a.mean(dim=-2, keepdim=True), b.mean(dim=-2, keepdim=True)
+    h = torch.einsum("ki,kj->ij", a - ca, b - cb)
+    u, _, vt = torch.linalg.svd(h)
+    v, ut = vt.transpose(-2, -1), u.transpose(-2, -1)
+    d = torch.sign(torch.linalg.det(torch.einsum("ij,jk->ik", v, ut)))
+    diag = torch.eye(3).clone()
+    diag[2, 2] = d
+    rot = torch.einsum("ij,jk,kl->...il", v, diag, ut)
+    return rot, cb.squeeze(-2) - torch.einsum("ij,j->i", rot, ca.squeeze(-2))
+
+
+def align(source_xyz: torch.Tensor, target_xyz: torch.Tensor, atom_mask: torch.Tensor):
+    """reference protstruc/protstruc.py:899-918, with a single target broadcast to every source structure."""
+    B = source_xyz.shape[0]
+    src = source_xyz.reshape(B, -1, 3)
+    tgt = target_xyz.reshape(target_xyz.shape[0], -1, 3).expand(B, -1, -1)
+    msk = atom_mask.reshape(atom_mask.shape[0], -1).bool().expand(B, -1)
+    rots, trans = [], []
+    for s, t, m in zip(src, tgt, msk):
+        r, tr = kabsch(s[m], t[m])
+        rots.append(r)
+        trans.append(tr)
+    rots, trans = torch.stack(rots), torch.stack(trans)
+    moved = rotate(source_xyz, rots) + trans[:, None, None, :]
+    return moved, rots, trans
+
+
+def topk_nearest_residue_mask(xyz: torch.Tensor, residue_mask: torch.Tensor, query_xyz: torch.Tensor, k: int = 128,
+                              mask: torch.Tensor = None) -> torch.Tensor:
+    """reference protstruc/protstruc.py:844-862 (batch of one)."""
+    ca = xyz[0, :, SLOT["CA"]]
+    dist = torch.norm(ca[:, None] - query_xyz, dim=-1)
+    dist, _ = dist.min(dim=-1)
+    valid = residue_mask[0] if mask is None else residue_mask[0] & mask
+    dist[~valid] = 1e9
+    k = min(k, int(valid.sum()))
+    _, idx = dist.topk(k, largest=False)
+    return torch.zeros(xyz.shape[1], dtype=torch.bool).scatter(0, idx, True).unsqueeze(0)
+
+
 # ------------------------------------------------------------------ statistics / diffusion (a13-a15)
 def _standardize_one(xyz: torch.Tensor, atom_mask: torch.Tensor):
     """reference protstruc/protstruc.py:720-733 for a batch of one (the only shape it is valid for)."""

@@ -51,6 +51,12 @@ SIGNATURES = {
     "ps_scale_shift": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, c_void_p]),
     "ps_center_of_mass": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),
     "ps_translate": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),
+    "ps_local_xyz": (c_int, [_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _fp, c_void_p]),
+    "ps_rotate": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),
+    "ps_frames_to_backbone": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp, c_void_p]),
+    "ps_translate_bcast": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, c_int, c_int, c_int, _fp, c_void_p]),
+    "ps_kabsch": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, _fp, c_void_p]),
+    "ps_topk_nearest_residue_mask": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, _fp, c_void_p]),
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),

@@ -1,0 +1,218 @@
+// Rows f2 and f4 of the scope table: batched Kabsch alignment and the top-k nearest-residue mask.
+//
+// Kabsch — replaces the per-structure Python loop of StructureBatch.align (protstruc/protstruc.py:880-918)
+// around geometry.kabsch (protstruc/geometry.py:442-480): boolean gathers + einsum + 3x3 LAPACK SVD per
+// structure become ONE launch, one CTA per structure: masked centroids, masked 3x3 covariance
+// H = sum (a - ca)(b - cb)^T (warp-shuffle + shared-memory reductions, fp64 partial sums), then a
+// closed 3x3 solve by one thread.  With H = U S V^T the reference forms R = V diag(1,1,sign det(V U^T)) U^T;
+// that equals  v0 u0^T + v1 u1^T + (v0 x v1)(u0 x u1)^T  for the two leading singular pairs, which needs no
+// sign bookkeeping: v0, v1 come from a Jacobi eigen-decomposition of H^T H, u_k = H v_k / |H v_k|.
+// Roofline: HBM read of the two coordinate sets (24 B + 1 B per atom), tiny; latency-bound.
+//
+// top-k — replaces StructureBatch.get_topk_nearest_residue_mask (protstruc/protstruc.py:819-862):
+// CA-to-query distances, min over the queries, invalid residues pushed to 1e9, the k smallest selected.
+// Selection is by rank counting (O(L^2) compares, L is a few thousand at most) with index tie-break.
+
+#include "common.cuh"
+
+namespace ps {
+
+namespace {
+
+constexpr int kKabschThreads = 256;
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int N>
+__device__ __forceinline__ void block_sum(double (&v)[N], double (*scratch)[N]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum_d(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) scratch[warp][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double t = lane < nwarps ? scratch[lane][k] : 0.0;
+        v[k] = warp_sum_d(t);
+    }
+}
+
+// Cyclic Jacobi for a symmetric 3x3 matrix; eigenvectors in the columns of V, eigenvalues in w.
+__device__ void jacobi_eigen3(double (&a)[3][3], double (&V)[3][3], double (&w)[3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-32 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; ++p) {
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < 3; ++k) {  // A <- A J
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {  // A <- J^T A
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {  // V <- V J
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq;
+                    V[k][q] = s * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = a[i][i];
+}
+
+__global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
+    const float* __restrict__ src, const float* __restrict__ dst, const uint8_t* __restrict__ mask,
+    int dst_rows, int n_atoms, float* __restrict__ rot, float* __restrict__ trans) {
+    __shared__ double scratch[kKabschThreads / 32][9];
+    const long long b = blockIdx.x;
+    const float* __restrict__ a = src + b * n_atoms * 3;
+    const float* __restrict__ t = dst + (dst_rows == 1 ? 0 : b) * static_cast<long long>(n_atoms) * 3;
+    const uint8_t* __restrict__ m = mask + b * n_atoms;
+
+    // pass 1: centroids of the selected atoms (reference: a.mean(dim=-2), b.mean(dim=-2))
+    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = threadIdx.x; k < n_atoms; k += blockDim.x) {
+        if (__ldg(m + k)) {
+            s[0] += __ldg(a + 3 * k + 0); s[1] += __ldg(a + 3 * k + 1); s[2] += __ldg(a + 3 * k + 2);
+            s[3] += __ldg(t + 3 * k + 0); s[4] += __ldg(t + 3 * k + 1); s[5] += __ldg(t + 3 * k + 2);
+            s[6] += 1.0;
+        }
+    }
+    block_sum<9>(s, scratch);
+    const double cnt = s[6];
+    const double ca[3] = {s[0] / cnt, s[1] / cnt, s[2] / cnt};
+    const double cb[3] = {s[3] / cnt, s[4] / cnt, s[5] / cnt};
+
+    // pass 2: H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = threadIdx.x; k < n_atoms; k += blockDim.x) {
+        if (__ldg(m + k)) {
+            const double ax = __ldg(a + 3 * k + 0) - ca[0], ay = __ldg(a + 3 * k + 1) - ca[1], az = __ldg(a + 3 * k + 2) - ca[2];
+            const double bx = __ldg(t + 3 * k + 0) - cb[0], by = __ldg(t + 3 * k + 1) - cb[1], bz = __ldg(t + 3 * k + 2) - cb[2];
+            h[0] += ax * bx; h[1] += ax * by; h[2] += ax * bz;
+            h[3] += ay * bx; h[4] += ay * by; h[5] += ay * bz;
+            h[6] += az * bx; h[7] += az * by; h[8] += az * bz;
+        }
+    }
+    block_sum<9>(h, scratch);
+
+    if (threadIdx.x == 0) {
+        double H[3][3] = {{h[0], h[1], h[2]}, {h[3], h[4], h[5]}, {h[6], h[7], h[8]}};
+        double K[3][3];  // H^T H
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) K[i][j] = H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j];
+        double V[3][3], w[3];
+        jacobi_eigen3(K, V, w);
+        int i0 = 0;  // indices of the two largest eigenvalues
+        if (w[1] > w[i0]) i0 = 1;
+        if (w[2] > w[i0]) i0 = 2;
+        int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+        if (w[i2] > w[i1]) i1 = i2;
+        double v0[3] = {V[0][i0], V[1][i0], V[2][i0]}, v1[3] = {V[0][i1], V[1][i1], V[2][i1]};
+        double u0[3], u1[3];
+        for (int i = 0; i < 3; ++i) {
+            u0[i] = H[i][0] * v0[0] + H[i][1] * v0[1] + H[i][2] * v0[2];
+            u1[i] = H[i][0] * v1[0] + H[i][1] * v1[1] + H[i][2] * v1[2];
+        }
+        const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+        for (int i = 0; i < 3; ++i) u0[i] /= n0;
+        const double p = u1[0] * u0[0] + u1[1] * u0[1] + u1[2] * u0[2];
+        for (int i = 0; i < 3; ++i) u1[i] -= p * u0[i];
+        const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        for (int i = 0; i < 3; ++i) u1[i] /= n1;
+        const double v2[3] = {v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0]};
+        const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+        double R[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i][j] = v0[i] * u0[j] + v1[i] * u1[j] + v2[i] * u2[j];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) rot[b * 9 + i * 3 + j] = static_cast<float>(R[i][j]);
+            trans[b * 3 + i] = static_cast<float>(cb[i] - (R[i][0] * ca[0] + R[i][1] * ca[1] + R[i][2] * ca[2]));
+        }
+    }
+}
+
+// ---- top-k nearest residues ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) min_query_distance_kernel(const float* __restrict__ xyz,
+                                                                 const uint8_t* __restrict__ valid,
+                                                                 const float* __restrict__ query, int n_query,
+                                                                 int L, int A, int ca_slot,
+                                                                 float* __restrict__ dmin) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= L) return;
+    const V3 ca = ld3(xyz + (static_cast<long long>(r) * A + ca_slot) * 3);
+    float best = __int_as_float(0x7f800000);
+    bool any_nan = false;
+    for (int q = 0; q < n_query; ++q) {
+        const V3 d = sub3(ca, ld3(query + q * 3));
+        const float v = norm3(d);
+        any_nan |= (v != v);
+        best = fminf(best, v);
+    }
+    if (any_nan) best = __int_as_float(0x7fc00000);  // torch.min propagates NaN
+    dmin[r] = __ldg(valid + r) ? best : 1e9f;
+}
+
+__global__ void __launch_bounds__(256) rank_select_kernel(const float* __restrict__ dmin, int L, int k,
+                                                          uint8_t* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= L) return;
+    const float mine = dmin[r];
+    int rank = 0;
+    for (int s = 0; s < L; ++s) {
+        const float other = __ldg(dmin + s);
+        // NaN sorts last (torch.topk treats NaN as the largest value)
+        const bool other_nan = other != other, mine_nan = mine != mine;
+        const bool less = (!other_nan && mine_nan) || (!other_nan && !mine_nan && other < mine) ||
+                          ((other == mine || (other_nan && mine_nan)) && s < r);
+        rank += less ? 1 : 0;
+    }
+    out[r] = rank < k ? 1 : 0;
+}
+
+}  // namespace
+
+int kabsch_impl(const float* src, const float* dst, const uint8_t* mask, int dst_rows, int B, int n_atoms,
+                float* rot, float* trans, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && n_atoms > 0, PS_ERR_BAD_SHAPE, "kabsch: B=%d atoms=%d must be > 0", B, n_atoms);
+    PS_REQUIRE(src && dst && mask && rot && trans, PS_ERR_NULL_POINTER, "kabsch: NULL pointer");
+    PS_REQUIRE(dst_rows == 1 || dst_rows == B, PS_ERR_BAD_SHAPE, "kabsch: %d targets for %d structures", dst_rows, B);
+    kabsch_kernel<<<B, kKabschThreads, 0, stream>>>(src, dst, mask, dst_rows, n_atoms, rot, trans);
+    return check_launch("kabsch_kernel");
+}
+
+int topk_nearest_impl(const float* xyz, const uint8_t* valid, const float* query, int n_query, int L, int A,
+                      int ca_slot, int k, float* scratch_dmin, uint8_t* out, cudaStream_t stream) {
+    PS_REQUIRE(L > 0 && A > 0 && n_query > 0, PS_ERR_BAD_SHAPE, "topk_nearest: L=%d A=%d queries=%d", L, A, n_query);
+    PS_REQUIRE(xyz && valid && query && scratch_dmin && out, PS_ERR_NULL_POINTER, "topk_nearest: NULL pointer");
+    PS_REQUIRE(ca_slot >= 0 && ca_slot < A, PS_ERR_BAD_SLOT, "topk_nearest: slot %d outside [0,%d)", ca_slot, A);
+    PS_REQUIRE(k >= 0, PS_ERR_BAD_SHAPE, "topk_nearest: k=%d", k);
+    const unsigned blocks = static_cast<unsigned>((L + 255) / 256);
+    min_query_distance_kernel<<<blocks, 256, 0, stream>>>(xyz, valid, query, n_query, L, A, ca_slot, scratch_dmin);
+    int rc = check_launch("min_query_distance_kernel");
+    if (rc != PS_OK) return rc;
+    rank_select_kernel<<<blocks, 256, 0, stream>>>(scratch_dmin, L, k, out);
+    return check_launch("rank_select_kernel");
+}
+
+}  // namespace ps

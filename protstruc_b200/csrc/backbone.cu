@@ -15,6 +15,29 @@ namespace ps {
 
 namespace {
 
+struct Frame {
+    V3 e1, e2, e3;
+};
+
+// geometry.gram_schmidt (protstruc/geometry.py:430-439), cross product on the last axis.
+__device__ __forceinline__ Frame gram_schmidt_frame(V3 a, V3 b, V3 c) {
+    Frame f;
+    const V3 v1 = sub3(c, b);
+    f.e1 = div3(v1, norm3(v1));
+    const V3 v2 = sub3(a, b);
+    const V3 u2 = sub3(v2, scale3(f.e1, dot3(f.e1, v2)));
+    f.e2 = div3(u2, norm3(u2));
+    f.e3 = cross3(f.e1, f.e2);
+    return f;
+}
+
+__device__ __forceinline__ void store_frame(float* __restrict__ f, const Frame& fr) {
+    // R[row][col], column k = e_k
+    f[0] = fr.e1.x; f[1] = fr.e2.x; f[2] = fr.e3.x;
+    f[3] = fr.e1.y; f[4] = fr.e2.y; f[5] = fr.e3.y;
+    f[6] = fr.e1.z; f[7] = fr.e2.z; f[8] = fr.e3.z;
+}
+
 // torch's float `!=`: NaN compares unequal to everything, itself included.
 __device__ __forceinline__ bool chain_differs(float a, float b) { return a != b; }
 
@@ -60,17 +83,7 @@ __global__ void __launch_bounds__(256) backbone_kernel(
     }
 
     if (frames) {
-        const V3 a = ld3(x + a1 * 3), b = ld3(x + a2 * 3), c = ld3(x + a3 * 3);
-        const V3 v1 = sub3(c, b);
-        const V3 e1 = div3(v1, norm3(v1));
-        const V3 v2 = sub3(a, b);
-        const V3 u2 = sub3(v2, scale3(e1, dot3(e1, v2)));
-        const V3 e2 = div3(u2, norm3(u2));
-        const V3 e3 = cross3(e1, e2);
-        float* __restrict__ f = frames + r * 9;  // R[row][col], column k = e_k
-        f[0] = e1.x; f[1] = e2.x; f[2] = e3.x;
-        f[3] = e1.y; f[4] = e2.y; f[5] = e3.y;
-        f[6] = e1.z; f[7] = e2.z; f[8] = e3.z;
+        store_frame(frames + r * 9, gram_schmidt_frame(ld3(x + a1 * 3), ld3(x + a2 * 3), ld3(x + a3 * 3)));
     }
 }
 
@@ -104,17 +117,86 @@ __global__ void __launch_bounds__(256) geom_gram_schmidt_kernel(const float* __r
                                                                 float* __restrict__ out) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const V3 a = ld3(pa + t * 3), b = ld3(pb + t * 3), c = ld3(pc + t * 3);
-    const V3 v1 = sub3(c, b);
-    const V3 e1 = div3(v1, norm3(v1));
-    const V3 v2 = sub3(a, b);
-    const V3 u2 = sub3(v2, scale3(e1, dot3(e1, v2)));
-    const V3 e2 = div3(u2, norm3(u2));
-    const V3 e3 = cross3(e1, e2);
-    float* __restrict__ f = out + t * 9;
-    f[0] = e1.x; f[1] = e2.x; f[2] = e3.x;
-    f[3] = e1.y; f[4] = e2.y; f[5] = e3.y;
-    f[6] = e1.z; f[7] = e2.z; f[8] = e3.z;
+    store_frame(out + t * 9, gram_schmidt_frame(ld3(pa + t * 3), ld3(pb + t * 3), ld3(pc + t * 3)));
+}
+
+// ---- rigid-frame family ---------------------------------------------------------
+// get_local_xyz (protstruc/protstruc.py:347-362): local = R^T x - CA, with R the residue's Gram-Schmidt
+// frame and CA the residue's GLOBAL alpha-carbon (the reference subtracts it after rotating; kept).
+// One thread per (residue, atom); the frame is recomputed per thread from three L1-resident atoms.
+__global__ void __launch_bounds__(256) local_xyz_kernel(const float* __restrict__ xyz, int A, int a1,
+                                                        int a2, int a3, int ca_slot, long long total,
+                                                        float* __restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long r = t / A;
+    const float* __restrict__ x = xyz + r * A * 3;
+    const Frame f = gram_schmidt_frame(ld3(x + a1 * 3), ld3(x + a2 * 3), ld3(x + a3 * 3));
+    const V3 p = ld3(xyz + t * 3);
+    const V3 ca = ld3(x + ca_slot * 3);
+    // einsum("bnaji,bnaj->bnai"): out_i = sum_j R[j][i] x_j = e_i . x
+    out[t * 3 + 0] = __fsub_rn(dot3(f.e1, p), ca.x);
+    out[t * 3 + 1] = __fsub_rn(dot3(f.e2, p), ca.y);
+    out[t * 3 + 2] = __fsub_rn(dot3(f.e3, p), ca.z);
+}
+
+// rotate (protstruc/protstruc.py:681-694): x' = R_b x with one (3,3) matrix per structure (or one for all).
+__global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ xyz,
+                                                     const float* __restrict__ rot, int rot_rows,
+                                                     long long atoms_per_struct, long long total,
+                                                     float* __restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const float* __restrict__ m = rot + (rot_rows == 1 ? 0 : (t / atoms_per_struct) * 9);
+    const V3 p = ld3(xyz + t * 3);
+    out[t * 3 + 0] = dot3(V3{__ldg(m + 0), __ldg(m + 1), __ldg(m + 2)}, p);
+    out[t * 3 + 1] = dot3(V3{__ldg(m + 3), __ldg(m + 4), __ldg(m + 5)}, p);
+    out[t * 3 + 2] = dot3(V3{__ldg(m + 6), __ldg(m + 7), __ldg(m + 8)}, p);
+}
+
+// from_backbone_orientations_translations (protstruc/protstruc.py:289-314): atom a < n_ideal is
+// R_r ideal[a] + t_r, the remaining slots are zero; the mask is 1 for the placed atoms (fp32).
+__global__ void __launch_bounds__(256) frames_to_backbone_kernel(
+    const float* __restrict__ orientations, const float* __restrict__ translations,
+    const float* __restrict__ ideal, int n_ideal, int A, long long total, float* __restrict__ xyz,
+    float* __restrict__ atom_mask) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long r = t / A;
+    const int a = static_cast<int>(t - r * A);
+    V3 o{0.f, 0.f, 0.f};
+    float m = 0.f;
+    if (a < n_ideal) {
+        const float* __restrict__ R = orientations + r * 9;
+        const V3 q = ld3(ideal + a * 3);
+        const V3 tr = ld3(translations + r * 3);
+        o.x = __fadd_rn(dot3(V3{__ldg(R + 0), __ldg(R + 1), __ldg(R + 2)}, q), tr.x);
+        o.y = __fadd_rn(dot3(V3{__ldg(R + 3), __ldg(R + 4), __ldg(R + 5)}, q), tr.y);
+        o.z = __fadd_rn(dot3(V3{__ldg(R + 6), __ldg(R + 7), __ldg(R + 8)}, q), tr.z);
+        m = 1.f;
+    }
+    xyz[t * 3 + 0] = o.x;
+    xyz[t * 3 + 1] = o.y;
+    xyz[t * 3 + 2] = o.z;
+    atom_mask[t] = m;
+}
+
+// translate (protstruc/protstruc.py:662-679): x += t with a broadcastable translation given by its
+// element strides over (structure, residue, atom); stride 0 = broadcast.
+__global__ void __launch_bounds__(256) translate_bcast_kernel(const float* __restrict__ xyz,
+                                                              const float* __restrict__ tr,
+                                                              long long sb, long long sl, long long sa,
+                                                              int L, int A, long long total,
+                                                              float* __restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long atom = t / 3;
+    const int k = static_cast<int>(t - atom * 3);
+    const long long res = atom / A;
+    const int a = static_cast<int>(atom - res * A);
+    const long long b = res / L;
+    const int l = static_cast<int>(res - b * L);
+    out[t] = __fadd_rn(xyz[t], __ldg(tr + b * sb + l * sl + a * sa + k));
 }
 
 unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
@@ -144,6 +226,53 @@ int backbone_impl(const float* xyz, const uint8_t* residue_mask, const float* ch
                                                            a2, a3, dihedrals, dihedral_mask, frames,
                                                            total);
     return check_launch("backbone_kernel");
+}
+
+int local_xyz_impl(const float* xyz, int B, int L, int A, int a1, int a2, int a3, int ca_slot,
+                   float* out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "local_xyz: B=%d L=%d A=%d must be > 0", B, L, A);
+    PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "local_xyz: NULL pointer");
+    PS_REQUIRE(a1 >= 0 && a1 < A && a2 >= 0 && a2 < A && a3 >= 0 && a3 < A && ca_slot >= 0 && ca_slot < A,
+               PS_ERR_BAD_SLOT, "local_xyz: slot outside [0,%d)", A);
+    const long long total = static_cast<long long>(B) * L * A;
+    local_xyz_kernel<<<blocks_for(total), 256, 0, stream>>>(xyz, A, a1, a2, a3, ca_slot, total, out);
+    return check_launch("local_xyz_kernel");
+}
+
+int rotate_impl(const float* xyz, const float* rot, int rot_rows, int B, int L, int A, float* out,
+                cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "rotate: B=%d L=%d A=%d must be > 0", B, L, A);
+    PS_REQUIRE(xyz && rot && out, PS_ERR_NULL_POINTER, "rotate: NULL pointer");
+    PS_REQUIRE(rot_rows == 1 || rot_rows == B, PS_ERR_BAD_SHAPE, "rotate: %d matrices for %d structures",
+               rot_rows, B);
+    PS_REQUIRE(xyz != out, PS_ERR_MISALIGNED, "rotate: in-place rotation is not supported");
+    const long long per = static_cast<long long>(L) * A;
+    rotate_kernel<<<blocks_for(per * B), 256, 0, stream>>>(xyz, rot, rot_rows, per, per * B, out);
+    return check_launch("rotate_kernel");
+}
+
+int frames_to_backbone_impl(const float* orientations, const float* translations, const float* ideal,
+                            int n_ideal, int B, int L, int A, float* xyz, float* atom_mask,
+                            cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "frames_to_backbone: B=%d L=%d A=%d", B, L, A);
+    PS_REQUIRE(orientations && translations && ideal && xyz && atom_mask, PS_ERR_NULL_POINTER,
+               "frames_to_backbone: NULL pointer");
+    PS_REQUIRE(n_ideal > 0 && n_ideal <= A, PS_ERR_BAD_SHAPE, "frames_to_backbone: %d ideal atoms, A=%d",
+               n_ideal, A);
+    const long long total = static_cast<long long>(B) * L * A;
+    frames_to_backbone_kernel<<<blocks_for(total), 256, 0, stream>>>(orientations, translations, ideal,
+                                                                     n_ideal, A, total, xyz, atom_mask);
+    return check_launch("frames_to_backbone_kernel");
+}
+
+int translate_bcast_impl(const float* xyz, const float* tr, long long sb, long long sl, long long sa,
+                         int B, int L, int A, float* out, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "translate: B=%d L=%d A=%d must be > 0", B, L, A);
+    PS_REQUIRE(xyz && tr && out, PS_ERR_NULL_POINTER, "translate: NULL pointer");
+    PS_REQUIRE(sb >= 0 && sl >= 0 && sa >= 0, PS_ERR_BAD_SHAPE, "translate: negative stride");
+    const long long total = static_cast<long long>(B) * L * A * 3;
+    translate_bcast_kernel<<<blocks_for(total), 256, 0, stream>>>(xyz, tr, sb, sl, sa, L, A, total, out);
+    return check_launch("translate_bcast_kernel");
 }
 
 int geom_angle_impl(const float* a, const float* b, const float* c, long long n, int to_degree,

@@ -29,6 +29,15 @@ int center_of_mass_impl(const float*, int, int, int, int, float*, cudaStream_t);
 int diffuse_impl(const float*, const float*, int, const float*, uint64_t, uint64_t, uint64_t, float*,
                  int, long long, cudaStream_t);
 int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStream_t);
+int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float*, float*, cudaStream_t);
+int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
+                      cudaStream_t);
+int local_xyz_impl(const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
+int rotate_impl(const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int frames_to_backbone_impl(const float*, const float*, const float*, int, int, int, int, float*, float*,
+                            cudaStream_t);
+int translate_bcast_impl(const float*, const float*, long long, long long, long long, int, int, int,
+                         float*, cudaStream_t);
 
 namespace {
 thread_local char g_last_error[512] = "";
@@ -164,6 +173,42 @@ int ps_center_of_mass(const float* xyz, int B, int L, int A, int slot, float* ou
 int ps_translate(const float* xyz, const float* t, int t_rows, int B, int L, int A, float* xyz_out,
                  void* stream) {
     return ps::translate_impl(xyz, t, t_rows, B, L, A, xyz_out, PS_STREAM(stream));
+}
+
+int ps_local_xyz(const float* xyz, int B, int L, int A, int a1, int a2, int a3, int ca_slot,
+                 float* out, void* stream) {
+    return ps::local_xyz_impl(xyz, B, L, A, a1, a2, a3, ca_slot, out, PS_STREAM(stream));
+}
+
+int ps_rotate(const float* xyz, const float* rotation, int rot_rows, int B, int L, int A,
+              float* xyz_out, void* stream) {
+    return ps::rotate_impl(xyz, rotation, rot_rows, B, L, A, xyz_out, PS_STREAM(stream));
+}
+
+int ps_frames_to_backbone(const float* orientations, const float* translations, const float* ideal,
+                          int n_ideal, int B, int L, int A, float* xyz, float* atom_mask,
+                          void* stream) {
+    return ps::frames_to_backbone_impl(orientations, translations, ideal, n_ideal, B, L, A, xyz,
+                                       atom_mask, PS_STREAM(stream));
+}
+
+int ps_translate_bcast(const float* xyz, const float* t, int64_t stride_b, int64_t stride_l,
+                       int64_t stride_a, int B, int L, int A, float* xyz_out, void* stream) {
+    return ps::translate_bcast_impl(xyz, t, stride_b, stride_l, stride_a, B, L, A, xyz_out,
+                                    PS_STREAM(stream));
+}
+
+int ps_kabsch(const float* source, const float* target, const uint8_t* mask, int target_rows, int B,
+              int n_atoms, float* rotation, float* translation, void* stream) {
+    return ps::kabsch_impl(source, target, mask, target_rows, B, n_atoms, rotation, translation,
+                           PS_STREAM(stream));
+}
+
+int ps_topk_nearest_residue_mask(const float* xyz, const uint8_t* valid, const float* query, int n_query,
+                                 int L, int A, int ca_slot, int k, float* scratch, uint8_t* out,
+                                 void* stream) {
+    return ps::topk_nearest_impl(xyz, valid, query, n_query, L, A, ca_slot, k, scratch, out,
+                                 PS_STREAM(stream));
 }
 
 int ps_diffuse(const float* x, const float* beta, const float* noise, uint64_t seed, uint64_t step,

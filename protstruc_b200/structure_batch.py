@@ -19,8 +19,8 @@ from typing import Dict, List, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from . import _cabi
-from .general import ATOM
+from . import _cabi, constants
+from .general import ATOM, MAX_N_ATOMS_PER_RESIDUE
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
@@ -132,6 +132,45 @@ class StructureBatch:
         return cls(_always_tensor(xyz), _always_tensor(atom_mask), _always_tensor(chain_idx), chain_ids, seq,
                    **kwargs)
 
+    @classmethod
+    def from_backbone_orientations_translations(
+        cls,
+        orientations: ArrayLike,
+        translations: ArrayLike,
+        chain_idx: Optional[ArrayLike] = None,
+        chain_ids: Optional[List[List[str]]] = None,
+        seq: Optional[List[Dict[str, str]]] = None,
+        residue_idx: Optional[ArrayLike] = None,
+        include_cb: bool = False,
+        **kwargs,
+    ) -> "StructureBatch":
+        """Places the ideal backbone (N, CA, C and optionally CB) of every residue with its frame:
+        xyz[b,l,a] = R[b,l] @ ideal[a] + t[b,l]; the remaining slots up to 15 are zero and masked out
+        (reference protstruc.py:263-319).  One kernel launch; the mask is fp32 like the reference's."""
+        orientations, translations = _always_tensor(orientations), _always_tensor(translations)
+        if orientations.ndim != 4 or tuple(orientations.shape[2:]) != (3, 3):
+            raise ValueError(f"`orientations` must have shape (batch, residues, 3, 3), got {tuple(orientations.shape)}")
+        B, L = orientations.shape[:2]
+        if tuple(translations.shape) != (B, L, 3):
+            raise ValueError(f"`translations` must have shape ({B}, {L}, 3), got {tuple(translations.shape)}")
+        dev = _target_device(orientations, kwargs.pop("device", None))
+        if dev.type != "cuda":
+            raise _cabi.NativeLibraryError("from_backbone_orientations_translations needs a CUDA device: "
+                                           "there is no CPU fallback")
+        lib = _cabi.load()
+        A = MAX_N_ATOMS_PER_RESIDUE
+        rot = orientations.to(device=dev, dtype=torch.float32).contiguous()
+        tr = translations.to(device=dev, dtype=torch.float32).contiguous()
+        ideal = constants.ideal_backbone(include_cb).to(dev).contiguous()
+        xyz = torch.empty(B, L, A, 3, dtype=torch.float32, device=dev)
+        mask = torch.empty(B, L, A, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ps_frames_to_backbone(rot.data_ptr(), tr.data_ptr(), ideal.data_ptr(), ideal.shape[0], B, L, A,
+                                           xyz.data_ptr(), mask.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(rc, "ps_frames_to_backbone")
+        return cls(xyz, mask, _always_tensor(chain_idx), chain_ids, seq, _always_tensor(residue_idx), device=dev,
+                   **kwargs)
+
     # ------------------------------------------------------------------------------------- getters
     def get_batch_size(self) -> int:
         return self.batch_size
@@ -141,6 +180,20 @@ class StructureBatch:
 
     def get_atom_mask(self) -> torch.Tensor:
         return self.atom_mask
+
+    def get_local_xyz(self) -> torch.Tensor:
+        """Coordinates of every atom in its residue's backbone frame: R^T x minus the residue's (global)
+        CA, exactly the expression of the reference (protstruc.py:347-362).  (B, L, A, 3)."""
+        lib = self._lib()
+        B, L, A = self._dims()
+        if A <= int(ATOM.C):
+            raise IndexError(f"index {int(ATOM.C)} is out of bounds for dimension 2 with size {A}")
+        out = torch.empty_like(self.xyz)
+        with torch.cuda.device(self.xyz.device):
+            rc = lib.ps_local_xyz(self.xyz.data_ptr(), B, L, A, int(ATOM.N), int(ATOM.CA), int(ATOM.C), int(ATOM.CA),
+                                  out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_local_xyz")
+        return out
 
     def get_residue_mask(self) -> torch.Tensor:
         """CA-slot mask as bool (reference protstruc.py:372-378; not the same as `self.residue_mask`)."""
@@ -359,11 +412,41 @@ class StructureBatch:
     # ------------------------------------------------------------------------------------ mutators
     def translate(self, translation: torch.Tensor, atomwise: bool = False) -> None:
         """In-place translation by (B, L, 3) / (B, 1, 3) or atomwise (B, L, A, 3) tensors
-        (reference protstruc.py:662-679).  Elementwise add on the device."""
-        translation = translation.to(self.xyz.device)
+        (reference protstruc.py:662-679).  One broadcast-add kernel; `translation` is read through its
+        broadcast strides, nothing is materialised."""
+        lib = self._lib()
+        dev = self.xyz.device
+        translation = translation.to(device=dev, dtype=torch.float32)
         if not atomwise:
+            if translation.ndim != 3:
+                raise ValueError(f"`translation` must have shape (batch, residues, 3), got {tuple(translation.shape)}")
             translation = translation.unsqueeze(-2)
-        self.xyz += translation
+        if translation.stride(-1) != 1:
+            translation = translation.contiguous()
+        view = translation.expand(self.xyz.shape)  # raises like torch's `+=` if the shapes do not broadcast
+        sb, sl, sa, _ = view.stride()
+        B, L, A = self._dims()
+        with torch.cuda.device(dev):
+            rc = lib.ps_translate_bcast(self.xyz.data_ptr(), view.data_ptr(), sb, sl, sa, B, L, A, self.xyz.data_ptr(),
+                                        self._stream())
+        _cabi.check(rc, "ps_translate_bcast")
+
+    def rotate(self, rotation: torch.Tensor) -> None:
+        """Rotates every structure: (B, 3, 3) per structure or (3, 3) for all; rebinds `self.xyz`
+        (reference protstruc.py:681-694)."""
+        if rotation.ndim not in (2, 3) or tuple(rotation.shape[-2:]) != (3, 3):
+            raise ValueError(f"`rotation` must have shape (batch, 3, 3) or (3, 3), got {tuple(rotation.shape)}")
+        if rotation.ndim == 3 and rotation.shape[0] not in (1, self.batch_size):
+            raise ValueError(f"`rotation` has {rotation.shape[0]} matrices for {self.batch_size} structures")
+        lib = self._lib()
+        dev = self.xyz.device
+        rot = rotation.to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+        B, L, A = self._dims()
+        out = torch.empty_like(self.xyz)
+        with torch.cuda.device(dev):
+            rc = lib.ps_rotate(self.xyz.data_ptr(), rot.data_ptr(), rot.shape[0], B, L, A, out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_rotate")
+        self.xyz = out
 
     def standardize(self, atom_mask: Optional[torch.Tensor] = None,
                     residue_mask: Optional[torch.Tensor] = None) -> None:
@@ -444,6 +527,76 @@ class StructureBatch:
             rc = lib.ps_translate(self.xyz.data_ptr(), translation.data_ptr(), translation.shape[0], B, L, A,
                                   self.xyz.data_ptr(), self._stream())
         _cabi.check(rc, "ps_translate")
+
+    def align(self, target: "StructureBatch", atom_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Superimposes every structure onto `target` (same batch size, or a single structure for all) with
+        the optimal rigid motion over the atoms selected by `atom_mask` (default: atoms valid in both);
+        rotates / translates ALL atoms in place like the reference (protstruc.py:880-918).  The per-structure
+        Kabsch solves run as one kernel launch.  Returns the rotations (B, 3, 3)."""
+        if target.get_batch_size() != 1 and self.batch_size != target.get_batch_size():
+            raise ValueError("Batch size of the two structures must be the same.")
+        if tuple(target.get_xyz().shape[1:]) != tuple(self.xyz.shape[1:]):
+            raise ValueError("Source and target must have the same (residues, atoms) layout.")
+        lib = self._lib()
+        dev = self.xyz.device
+        if atom_mask is None:
+            if self.atom_mask is None or target.get_atom_mask() is None:
+                raise TypeError("align needs atom masks (or an explicit `atom_mask`)")
+            atom_mask = self.atom_mask * target.get_atom_mask().to(dev)
+        B, L, A = self._dims()
+        mask = atom_mask.to(dev).bool().expand(B, L, A).reshape(B, L * A).to(torch.uint8).contiguous()
+        tgt = target.get_xyz().to(device=dev, dtype=torch.float32).contiguous()
+        rot = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+        tr = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ps_kabsch(self.xyz.data_ptr(), tgt.data_ptr(), mask.data_ptr(), tgt.shape[0], B, L * A,
+                               rot.data_ptr(), tr.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_kabsch")
+        self.rotate(rot)
+        self.translate(tr.unsqueeze(1))
+        return rot
+
+    def get_topk_nearest_residue_mask(self, query_xyz: torch.Tensor, k: int = 128,
+                                      mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Boolean (1, L) mask of the k residues whose CA is closest to any of the query points
+        (reference protstruc.py:819-862; single-structure batches only, like the reference)."""
+        if self.batch_size > 1:
+            raise ValueError("get_topk_nearest_residue_mask method is not defined "
+                             "for a StructureBatch with batch size > 1.")
+        lib = self._lib()
+        dev = self.xyz.device
+        B, L, A = self._dims()
+        valid = self.residue_mask[0]
+        if mask is not None:
+            valid = valid & mask.to(dev)
+        k_eff = min(int(k), int(valid.sum().item()))
+        query = query_xyz.to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+        valid_u8 = valid.to(torch.uint8).contiguous()
+        scratch = torch.empty(L, dtype=torch.float32, device=dev)
+        out = torch.empty(L, dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ps_topk_nearest_residue_mask(self.xyz.data_ptr(), valid_u8.data_ptr(), query.data_ptr(),
+                                                  query.shape[0], L, A, int(ATOM.CA), k_eff, scratch.data_ptr(),
+                                                  out.data_ptr(), self._stream())
+        _cabi.check(rc, "ps_topk_nearest_residue_mask")
+        return out.unsqueeze(0)
+
+    def residue_masked_select(self, mask: torch.Tensor) -> "StructureBatch":
+        """New single-structure batch holding only the residues selected by `mask` (1, L)
+        (reference protstruc.py:920-956; `chain_ids` / `seq` are carried over unchanged)."""
+        if self.batch_size > 1:
+            raise ValueError("residue_masked_select method is not defined for a StructureBatch with batch size > 1.")
+        if mask.shape != self.residue_mask.shape:
+            raise ValueError(f"Mask shape {mask.shape} does not match residue mask shape {self.residue_mask.shape}.")
+        if mask.dtype != torch.bool:
+            raise ValueError("Mask must be a boolean tensor.")
+        mask = mask.to(self.xyz.device)
+        xyz = self.xyz[mask].unsqueeze(0)
+        atom_mask = self.atom_mask[mask].unsqueeze(0)
+        chain_idx = self.chain_idx[mask].unsqueeze(0)
+        if self.chain_ids is None:
+            return StructureBatch(xyz, atom_mask, device=self.xyz.device)
+        return StructureBatch(xyz, atom_mask, chain_idx.cpu(), self.chain_ids, self.seq, device=self.xyz.device)
 
     def diffuse_xyz(self, beta: torch.Tensor, noise: Optional[torch.Tensor] = None,
                     generator: Optional[torch.Generator] = None) -> None:

@@ -142,6 +142,98 @@ def run_oracle(xyz, atom_mask, chain_idx, noise, beta):
     return out
 
 
+def random_rotations(n: int, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    q, r = torch.linalg.qr(torch.randn(n, 3, 3, generator=g))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1))[:, None, :]
+    q[:, :, 2] *= torch.linalg.det(q)[:, None]  # proper rotations
+    return q.contiguous()
+
+
+def make_frames_align_topk(StructureBatch):
+    """get_local_xyz, rotate, translate, from_backbone_orientations_translations, align and
+    get_topk_nearest_residue_mask of the reference on a seeded synthetic batch (B = 4, L = 33, no NaN: the
+    reference's align / frames need finite backbone coordinates) and on the real structure for top-k."""
+    xyz, mask, chain_idx = synthetic_inputs(21, 4, 33, 15, "bool", nan_masked=False)
+    B = xyz.shape[0]
+    ids = [["A", "B"] for _ in range(B)]
+    new = lambda: StructureBatch.from_xyz(xyz.clone(), mask.clone(), chain_idx.clone(), ids)  # noqa: E731
+    out = {"xyz": xyz, "atom_mask": mask, "chain_idx": chain_idx}
+    out["ref_local_xyz"] = new().get_local_xyz()
+    rot = random_rotations(B, 5)
+    out["rotation"] = rot
+    sb = new()
+    sb.rotate(rot)
+    out["ref_rotated"] = sb.get_xyz().clone()
+    sb = new()
+    sb.rotate(rot[0])
+    out["ref_rotated_single"] = sb.get_xyz().clone()
+    g = torch.Generator().manual_seed(6)
+    tr_res = torch.randn(B, 33, 3, generator=g)
+    tr_one = torch.randn(B, 1, 3, generator=g)
+    tr_atom = torch.randn(B, 33, 15, 3, generator=g)
+    out.update({"tr_res": tr_res, "tr_one": tr_one, "tr_atom": tr_atom})
+    for name, t, atomwise in (("res", tr_res, False), ("one", tr_one, False), ("atom", tr_atom, True)):
+        sb = new()
+        sb.translate(t.clone(), atomwise=atomwise)
+        out[f"ref_translated_{name}"] = sb.get_xyz().clone()
+    sb = new()
+    frames, trans = sb.backbone_orientations(), sb.backbone_translations().clone()
+    out["frames"], out["frame_translations"] = frames, trans
+    for cb in (False, True):
+        sb2 = StructureBatch.from_backbone_orientations_translations(frames, trans, chain_idx.clone(), ids, None,
+                                                                     include_cb=cb)
+        out[f"ref_from_frames_xyz_cb{int(cb)}"] = sb2.get_xyz()
+        out[f"ref_from_frames_mask_cb{int(cb)}"] = sb2.get_atom_mask()
+    # align: target = rigidly moved + slightly noised copy (per-structure targets and a single target)
+    moved = torch.einsum("bij,bnaj->bnai", random_rotations(B, 9), xyz) + torch.randn(B, 1, 1, 3, generator=g) * 5
+    moved = moved + 0.05 * torch.randn(moved.shape, generator=g)
+    out["align_target"] = moved
+    src, tgt = new(), StructureBatch.from_xyz(moved.clone(), mask.clone(), chain_idx.clone(), ids)
+    src.align(tgt)
+    out["ref_aligned"] = src.get_xyz().clone()
+    # the reference zips over the target batch, so a single target only aligns... run it per structure instead
+    single = []
+    for b in range(B):
+        one = StructureBatch.from_xyz(xyz[b:b + 1].clone(), mask[b:b + 1].clone())
+        one.align(StructureBatch.from_xyz(moved[:1].clone(), mask[:1].clone()),
+                  atom_mask=mask[b:b + 1] * mask[:1])
+        single.append(one.get_xyz())
+    out["ref_aligned_to_first"] = torch.cat(single)
+    # top-k on the real structure (B = 1)
+    arrays = pdb_fixture_reader.read_batch([REFERENCE / "tests" / "1a6v_HL.pdb"])
+    rx, rm = torch.from_numpy(arrays["xyz"]), torch.from_numpy(arrays["atom_mask"])
+    real = StructureBatch.from_xyz(rx, rm)
+    query = rx[0, 100:103, 1].clone() + 0.3
+    out["topk_query"] = query
+    out["ref_topk_k32"] = real.get_topk_nearest_residue_mask(query, k=32)
+    out["ref_topk_k500"] = real.get_topk_nearest_residue_mask(query, k=500)
+    extra = torch.zeros(229, dtype=torch.bool)
+    extra[50:150] = True
+    out["topk_extra_mask"] = extra
+    out["ref_topk_k16_masked"] = real.get_topk_nearest_residue_mask(query, k=16, mask=extra)
+
+    # oracle vs reference
+    dev = {}
+    dev["local_xyz"] = max_deviation(out["ref_local_xyz"], orc.local_xyz(xyz))
+    dev["rotated"] = max_deviation(out["ref_rotated"], orc.rotate(xyz, rot))
+    dev["rotated_single"] = max_deviation(out["ref_rotated_single"], orc.rotate(xyz, rot[0]))
+    for cb in (False, True):
+        ox, om = orc.frames_to_backbone(frames, trans, cb)
+        dev[f"from_frames_xyz_cb{int(cb)}"] = max_deviation(out[f"ref_from_frames_xyz_cb{int(cb)}"], ox)
+        dev[f"from_frames_mask_cb{int(cb)}"] = max_deviation(out[f"ref_from_frames_mask_cb{int(cb)}"], om)
+    dev["aligned"] = max_deviation(out["ref_aligned"], orc.align(xyz, moved, mask * mask)[0])
+    dev["aligned_to_first"] = max_deviation(out["ref_aligned_to_first"], orc.align(xyz, moved[:1], mask * mask[:1])[0])
+    rmask = rm.any(-1)
+    dev["topk_k32"] = max_deviation(out["ref_topk_k32"], orc.topk_nearest_residue_mask(rx, rmask, query, 32))
+    dev["topk_k500"] = max_deviation(out["ref_topk_k500"], orc.topk_nearest_residue_mask(rx, rmask, query, 500))
+    dev["topk_k16_masked"] = max_deviation(out["ref_topk_k16_masked"],
+                                           orc.topk_nearest_residue_mask(rx, rmask, query, 16, extra))
+    np.savez_compressed(HERE / "frames_align_topk.npz", **{k: to_np(v) for k, v in out.items()})
+    print("frames_align_topk", dev)
+    return {"shape": [B, 33, 15], "mask": "bool", "oracle_vs_reference_max_abs": dev}
+
+
 def max_deviation(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = torch.as_tensor(a), torch.as_tensor(b)
     if a.dtype == torch.bool or b.dtype == torch.bool:
@@ -214,6 +306,9 @@ def main():
         payload[f"ref_{k}"] = to_np(ref[k])
     np.savez_compressed(HERE / "real_1a6v_HL.npz", **payload)
     print("real_1a6v_HL", dev)
+
+    # rows f1 / f2 / f4: rigid-frame family, alignment, top-k neighbours
+    manifest["cases"]["frames_align_topk"] = make_frames_align_topk(StructureBatch)
 
     # the reference's own known-answer tests for the primitives (tests/test_geometry.py)
     ka = {}

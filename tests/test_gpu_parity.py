@@ -512,3 +512,84 @@ def test_dtype_and_input_handling(native_lib):
     H.assert_distances_close(dist, ref_dist)
     assert dist_mask.dtype == torch.int64 and torch.equal(dist_mask.cpu(), ref_mask)
     assert sb.get_total_lengths().shape == (2,)
+
+
+# ------------------------------------------------------------------------------ rows f1 / f2 / f4
+def test_rigid_frame_family_matches_reference_golden(native_lib):
+    """get_local_xyz, rotate, translate, from_backbone_orientations_translations (reference
+    protstruc.py:263-362, 662-694; reference tests/test_StructureBatch.py:179-207)."""
+    g = H.load_golden("frames_align_topk")
+    ids = [["A", "B"]] * 4
+    new = lambda: ps.StructureBatch.from_xyz(g["xyz"], g["atom_mask"], g["chain_idx"], ids)  # noqa: E731
+    local = new().get_local_xyz()
+    assert tuple(local.shape) == (4, 33, 15, 3)
+    H.assert_same_nan(local, H.t(g["ref_local_xyz"]), "local xyz")  # zero-padded residues have no frame
+    assert torch.allclose(local.cpu(), H.t(g["ref_local_xyz"]), rtol=1e-5, atol=2e-4, equal_nan=True)
+    sb = new()
+    sb.rotate(H.t(g["rotation"]))
+    assert torch.allclose(sb.get_xyz().cpu(), H.t(g["ref_rotated"]), rtol=1e-5, atol=1e-4)
+    sb = new()
+    sb.rotate(H.t(g["rotation"])[0])
+    assert torch.allclose(sb.get_xyz().cpu(), H.t(g["ref_rotated_single"]), rtol=1e-5, atol=1e-4)
+    for name, atomwise in (("res", False), ("one", False), ("atom", True)):
+        sb = new()
+        before = sb.get_xyz().data_ptr()
+        sb.translate(H.t(g[f"tr_{name}"]), atomwise=atomwise)
+        assert sb.get_xyz().data_ptr() == before  # in place, like the reference's `+=`
+        assert torch.equal(sb.get_xyz().cpu(), H.t(g[f"ref_translated_{name}"])), f"translate {name} must be exact"
+    for cb in (0, 1):
+        sb2 = ps.StructureBatch.from_backbone_orientations_translations(
+            H.t(g["frames"]), H.t(g["frame_translations"]), H.t(g["chain_idx"]), ids, None, include_cb=bool(cb))
+        assert sb2.get_max_n_atoms_per_residue() == 15
+        assert sb2.get_atom_mask().dtype == torch.float32
+        assert torch.equal(sb2.get_atom_mask().cpu(), H.t(g[f"ref_from_frames_mask_cb{cb}"]))
+        H.assert_same_nan(sb2.get_xyz(), H.t(g[f"ref_from_frames_xyz_cb{cb}"]), "frames -> backbone")
+        assert torch.allclose(sb2.get_xyz().cpu(), H.t(g[f"ref_from_frames_xyz_cb{cb}"]), rtol=1e-5, atol=1e-4,
+                              equal_nan=True)
+    # frames -> coordinates -> frames is the identity on the backbone
+    sb = new()
+    rebuilt = ps.StructureBatch.from_backbone_orientations_translations(sb.backbone_orientations(), sb.backbone_translations())
+    assert torch.allclose(rebuilt.backbone_orientations(), sb.backbone_orientations(), atol=1e-5, equal_nan=True)
+    assert torch.allclose(rebuilt.backbone_translations()[~torch.isnan(rebuilt.backbone_translations())],
+                          sb.backbone_translations()[~torch.isnan(rebuilt.backbone_translations())], atol=1e-5)
+
+
+def test_align_matches_reference_golden(native_lib):
+    """Batched Kabsch vs the reference's per-structure SVD loop (protstruc.py:880-918)."""
+    g = H.load_golden("frames_align_topk")
+    src = ps.StructureBatch.from_xyz(g["xyz"], g["atom_mask"])
+    tgt = ps.StructureBatch.from_xyz(g["align_target"], g["atom_mask"])
+    rot = src.align(tgt)
+    assert tuple(rot.shape) == (4, 3, 3)
+    assert torch.allclose(rot @ rot.transpose(1, 2), torch.eye(3, device=DEV).expand(4, 3, 3), atol=1e-5)
+    assert torch.allclose(torch.linalg.det(rot), torch.ones(4, device=DEV), atol=1e-5)
+    assert torch.allclose(src.get_xyz().cpu(), H.t(g["ref_aligned"]), rtol=1e-5, atol=5e-4)
+    # after alignment the masked RMSD to the target is at the noise level (0.05 A per coordinate)
+    m = H.t(g["atom_mask"]).to(DEV)
+    rmsd = ((src.get_xyz() - tgt.get_xyz())[m] ** 2).sum(-1).mean().sqrt().item()
+    assert rmsd < 0.15
+    one = ps.StructureBatch.from_xyz(g["xyz"], g["atom_mask"])
+    one.align(ps.StructureBatch.from_xyz(g["align_target"][:1], g["atom_mask"][:1]))
+    assert torch.allclose(one.get_xyz().cpu(), H.t(g["ref_aligned_to_first"]), rtol=1e-5, atol=5e-4)
+    with pytest.raises(ValueError):
+        src.align(ps.StructureBatch.from_xyz(g["align_target"][:2], g["atom_mask"][:2]))
+
+
+def test_topk_nearest_residue_mask_and_select_match_reference_golden(native_lib):
+    g = H.load_golden("frames_align_topk")
+    real = H.load_golden("real_1a6v_HL")
+    sb = ps.StructureBatch.from_xyz(real["xyz"], real["atom_mask"])
+    q = H.t(g["topk_query"])
+    for k, key in ((32, "ref_topk_k32"), (500, "ref_topk_k500")):
+        got = sb.get_topk_nearest_residue_mask(q, k=k)
+        assert got.dtype == torch.bool and tuple(got.shape) == (1, 229)
+        assert torch.equal(got.cpu(), H.t(g[key]))
+    got = sb.get_topk_nearest_residue_mask(q, k=16, mask=H.t(g["topk_extra_mask"]))
+    assert torch.equal(got.cpu(), H.t(g["ref_topk_k16_masked"]))
+    picked = sb.residue_masked_select(got)
+    assert tuple(picked.get_xyz().shape) == (1, 16, 15, 3)
+    two = ps.StructureBatch.from_xyz(np.zeros((2, 5, 15, 3), dtype=np.float32), np.ones((2, 5, 15), dtype=bool))
+    with pytest.raises(ValueError):
+        two.get_topk_nearest_residue_mask(q)
+    with pytest.raises(ValueError):
+        two.residue_masked_select(torch.ones(2, 5, dtype=torch.bool))
