@@ -129,6 +129,119 @@ __device__ __forceinline__ V3 virtual_cb(V3 n, V3 ca, V3 c) {
     return r;
 }
 
+// ---------------------------------------------------------------- tuned trRosetta triple
+// omega / theta / phi of one residue pair for the two hot kernels (K2f and the fused K1).  Same
+// formulas and the same non-contracted cross / dot products as dihedral4 / angle3 above — so exact
+// cancellations (diagonal pairs, zero-padded residues) and NaN placement are unchanged — but the final
+// scalar steps use single-MUFU primitives refined to ~1 ulp instead of the IEEE division / sqrt /
+// libdevice atan2f sequences (which cost more than the geometry itself):
+//   * y = (m.b1) / |b1|  ->  (m.b1) * rsqrt(b1.b1), one Newton step on the MUFU.RSQ seed;
+//   * atan2 -> min/max quotient by MUFU.RCP + one Newton step, degree-15 odd minimax polynomial on
+//     [0, 1] (max error 7e-9 before rounding), octant fix-ups; zeros, infinities, NaN and out-of-range
+//     magnitudes fall back to atan2f, so atan2(+-0, -0) = +-pi etc. keep their IEEE values.
+// Measured deviation from the reference after this change: see profiles/*parity_report*.json.
+__device__ __forceinline__ float rcp_mufu(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_mufu(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// 1/sqrt(s) to ~1 ulp.  s = 0 gives NaN (inf * 0), which is what the reference's 0/0 gives downstream.
+__device__ __forceinline__ float rsqrt_refined(float s) {
+    const float r = rsqrt_mufu(s);
+    return r * fmaf(-0.5f * s * r, r, 1.5f);
+}
+
+__device__ __forceinline__ float atan2_tuned(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float sum = ax + ay;
+    if (!((mx > 1e-30f) & (mx < 1e30f) & (sum == sum))) return atan2f(y, x);
+    const float r = rcp_mufu(mx);
+    float t = mn * r;
+    t = fmaf(r, fmaf(-t, mx, mn), t);  // quotient refined to ~1 ulp
+    const float s = t * t;
+    float p = 2.622234402e-03f;
+    p = fmaf(p, s, -1.513249334e-02f);
+    p = fmaf(p, s, 4.112178832e-02f);
+    p = fmaf(p, s, -7.366699725e-02f);
+    p = fmaf(p, s, 1.057392880e-01f);
+    p = fmaf(p, s, -1.418597400e-01f);
+    p = fmaf(p, s, 1.999039650e-01f);
+    p = fmaf(p, s, -3.333298564e-01f);
+    float a = fmaf(t * s, p, t);
+    if (ay > ax) a = 1.57079637f - a;
+    if (x < 0.f) a = 3.14159274f - a;
+    return copysignf(a, y);
+}
+
+__device__ __forceinline__ bool atom_has_nan(V3 a) {
+    const float probe = (a.x + a.y) + a.z;
+    return (probe != probe) && has_nan3(a);
+}
+
+// Everything of the triple that depends on residue i only (hoisted out of the j loop by K2f).
+struct TripleRowSide {
+    V3 cb;        // CB_i
+    V3 b0;        // CA_i - CB_i   (omega's b0, phi's ba)
+    V3 tb1;       // CB_i - CA_i   (theta's b1)
+    V3 tn1;       // (N_i - CA_i) x (CB_i - CA_i)   (theta's n1)
+    float inv_tb1_norm;  // 1 / |CB_i - CA_i|
+    float inv_ba_norm;   // 1 / |CA_i - CB_i|
+    bool nan_ca_cb;      // CA_i or CB_i missing
+    bool nan_n;          // N_i missing
+};
+
+__device__ __forceinline__ TripleRowSide triple_row_side(V3 n_i, V3 ca_i, V3 cb_i) {
+    TripleRowSide r;
+    r.cb = cb_i;
+    r.b0 = sub3(ca_i, cb_i);
+    r.tb1 = sub3(cb_i, ca_i);
+    r.tn1 = cross3(sub3(n_i, ca_i), r.tb1);
+    r.inv_tb1_norm = __frcp_rn(norm3(r.tb1));
+    r.inv_ba_norm = __frcp_rn(norm3(r.b0));
+    r.nan_ca_cb = atom_has_nan(ca_i) || atom_has_nan(cb_i);
+    r.nan_n = atom_has_nan(n_i);
+    return r;
+}
+
+// omega = dihedral(CA_i, CB_i, CA_j, CB_j); theta = dihedral(N_i, CA_i, CB_i, CB_j); phi = angle(CA_i, CB_i, CB_j)
+// (reference protstruc/protstruc.py:810-815).
+__device__ __forceinline__ void trrosetta_triple(const TripleRowSide& r, V3 ca_j, V3 cb_j, bool want_omega,
+                                                 bool want_theta, bool want_phi, float& omega, float& theta,
+                                                 float& phi) {
+    const float nan = __int_as_float(0x7fc00000);
+    const bool nan_cb_j = atom_has_nan(cb_j);
+    const bool nan_ca_j = atom_has_nan(ca_j);
+    const V3 bc = sub3(cb_j, r.cb);  // CB_j - CB_i: theta's b2 and phi's bc
+    omega = theta = phi = nan;
+    if (want_omega && !(r.nan_ca_cb || nan_ca_j || nan_cb_j)) {
+        const V3 b1 = sub3(ca_j, r.cb);
+        const V3 b2 = sub3(cb_j, ca_j);
+        const V3 n1 = cross3(r.b0, b1);
+        const V3 n2 = cross3(b2, b1);
+        const V3 m = cross3(n1, n2);
+        const float x = dot3(n1, n2);
+        const float y = __fmul_rn(dot3(m, b1), rsqrt_refined(dot3(b1, b1)));
+        omega = atan2_tuned(y, x);
+    }
+    if (want_theta && !(r.nan_ca_cb || r.nan_n || nan_cb_j)) {
+        const V3 n2 = cross3(bc, r.tb1);
+        const V3 m = cross3(r.tn1, n2);
+        const float x = dot3(r.tn1, n2);
+        const float y = __fmul_rn(dot3(m, r.tb1), r.inv_tb1_norm);
+        theta = atan2_tuned(y, x);
+    }
+    if (want_phi && !(r.nan_ca_cb || nan_cb_j)) {
+        const float cosine = __fmul_rn(__fmul_rn(dot3(r.b0, bc), r.inv_ba_norm), rsqrt_refined(dot3(bc, bc)));
+        phi = acosf(cosine);
+    }
+}
+
 // ---------------------------------------------------------------- bulk async copy (TMA engine)
 // smem -> global bulk copy, tracked by the per-thread bulk async-group.
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {

@@ -43,14 +43,20 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
     return c;
 }
 
-// Two uniforms -> two N(0,1).  u1 in (0,1], angle in (0, 2pi].
+// Two uniforms -> two N(0,1) (Box-Muller).  u1 in (0,1], angle 2*pi*u2 in (0, 2*pi].  The generator is
+// the ALU bottleneck of the fused T-step kernel, so the transcendental steps are the single-MUFU
+// intrinsics: __logf (abs error 2^-21.4 on [0.5, 2]), MUFU.SQRT, and __sincosf on the angle shifted into
+// (-pi, pi] (abs error 2^-21.4 there); sin(t - pi) = -sin t, so the stream definition
+// z = (r sin 2*pi*u2, r cos 2*pi*u2) is unchanged.  Deviation from an fp64 evaluation of the same stream
+// is < 1e-5 for 99.9 % of the samples (tests/test_gpu_parity.py).
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     const float u1 = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float u2 = fmaf(static_cast<float>(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float r = sqrtf(-2.0f * logf(u1));
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    return make_float2(r * s, r * c);
+    __sincosf(fmaf(u2, 6.28318548f, -3.14159274f), &s, &c);
+    return make_float2(-r * s, -r * c);
 }
 
 __device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t seed, float (&z)[4]) {

@@ -67,14 +67,17 @@ __global__ void __launch_bounds__(256) trrosetta_kernel(const float* __restrict_
         const float* __restrict__ xb = xyz + b * L * A * 3;
         const V3 n_i = ld3(xi + 0), ca_i = ld3(xi + 3);
         const V3 cb_i = VIRTUAL_CB ? virtual_cb(n_i, ca_i, ld3(xi + 6)) : ld3(xi + 12);
+        const TripleRowSide side = triple_row_side(n_i, ca_i, cb_i);
         for (int j = threadIdx.x; j < L; j += blockDim.x) {
             const float* __restrict__ xj = xb + static_cast<long long>(j) * A * 3;
             const V3 ca_j = ld3(xj + 3);
             const V3 cb_j = VIRTUAL_CB ? virtual_cb(ld3(xj + 0), ca_j, ld3(xj + 6)) : ld3(xj + 12);
             const long long o = row * L + j;
-            if (omega) omega[o] = dihedral4(ca_i, cb_i, ca_j, cb_j);
-            if (theta) theta[o] = dihedral4(n_i, ca_i, cb_i, cb_j);
-            if (phi) phi[o] = angle3(ca_i, cb_i, cb_j);
+            float w, t, f;
+            trrosetta_triple(side, ca_j, cb_j, omega != nullptr, theta != nullptr, phi != nullptr, w, t, f);
+            if (omega) omega[o] = w;
+            if (theta) theta[o] = t;
+            if (phi) phi[o] = f;
         }
     }
 }
@@ -89,9 +92,12 @@ int grid_for_rows(long long rows, int* grid) {
     return PS_OK;
 }
 
+// Threads per (b, i) row.  Every thread recomputes the row-only part of the angles (~130 issue slots with
+// two IEEE reciprocals / square roots), so a thread should own several j: L / 8 threads, 32..256.
 int threads_for_L(int L) {
-    int t = 32;
-    while (t < L && t < 256) t <<= 1;
+    int t = ((L + 7) / 8 + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
     return t;
 }
 

@@ -435,9 +435,12 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
             const V3 ca_j{xj[0].y, yj[0].y, zj[0].y};  // atom 1 = second half of pack 0
             const V3 cb_j{xj[2].x, yj[2].x, zj[2].x};  // atom 4 = first half of pack 2
             if (pair0 + lane < p.num_pairs) {
-                if (p.omega) p.omega[pair] = dihedral4(ca_i, cb_i, ca_j, cb_j);
-                if (p.theta) p.theta[pair] = dihedral4(n_i, ca_i, cb_i, cb_j);
-                if (p.phi) p.phi[pair] = angle3(ca_i, cb_i, cb_j);
+                float w, t, f;
+                trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, p.omega != nullptr,
+                                 p.theta != nullptr, p.phi != nullptr, w, t, f);
+                if (p.omega) p.omega[pair] = w;
+                if (p.theta) p.theta[pair] = t;
+                if (p.phi) p.phi[pair] = f;
             }
         }
 
