@@ -187,6 +187,18 @@ int ps_topk_nearest_residue_mask(const float* xyz, const uint8_t* valid, const f
                                  void* stream);
 
 /*
+ * PDB text ingest — HOST pointers, no GPU work.  Replaces PDB.read_pdb / tidy_structure /
+ * PDB._initialize_lookup / PDB._compute_atom_xyz (protstruc/pdb.py:24-40, 55-151) without biotite.
+ * Parses one PDB file held in memory into per-residue rows: xyz (capacity,15,3) f32 NaN-filled, atom_mask
+ * (capacity,15) uint8, chain_idx / residue_number (capacity) int32, chain_id / insertion_code / one_letter
+ * (capacity) chars (insertion 0 = none; one_letter 'X' = UNK gap placeholder).  *n_residues receives the row
+ * count; call with capacity = 0 (arrays may be NULL) to size the buffers first.
+ */
+int ps_host_pdb_parse(const char* text, int64_t len, int capacity, float* xyz, uint8_t* atom_mask,
+                      int32_t* chain_idx, char* chain_id, int32_t* residue_number, char* insertion_code,
+                      char* one_letter, int* n_residues);
+
+/*
  * K5 — one forward-diffusion step.  Replaces StructureBatch.diffuse_xyz
  * (protstruc/protstruc.py:864-878):
  *   out = fl( fl(sqrt(1-beta_b) * x) + fl(z * sqrt(beta_b)) )     (no FMA contraction)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "ps_translate_bcast": (c_int, [_fp, _fp, c_int64, c_int64, c_int64, c_int, c_int, c_int, _fp, c_void_p]),
     "ps_kabsch": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, _fp, c_void_p]),
     "ps_topk_nearest_residue_mask": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, _fp, c_void_p]),
+    "ps_host_pdb_parse": (c_int, [c_char_p, c_int64, c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, POINTER(c_int)]),
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),

@@ -32,6 +32,7 @@ int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStre
 int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float*, float*, cudaStream_t);
 int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
                       cudaStream_t);
+int host_pdb_parse_impl(const char*, long long, int, float*, uint8_t*, int32_t*, char*, int32_t*, char*, char*, int*);
 int local_xyz_impl(const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int rotate_impl(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int frames_to_backbone_impl(const float*, const float*, const float*, int, int, int, int, float*, float*,
@@ -209,6 +210,13 @@ int ps_topk_nearest_residue_mask(const float* xyz, const uint8_t* valid, const f
                                  void* stream) {
     return ps::topk_nearest_impl(xyz, valid, query, n_query, L, A, ca_slot, k, scratch, out,
                                  PS_STREAM(stream));
+}
+
+int ps_host_pdb_parse(const char* text, int64_t len, int capacity, float* xyz, uint8_t* atom_mask,
+                      int32_t* chain_idx, char* chain_id, int32_t* residue_number, char* insertion_code,
+                      char* one_letter, int* n_residues) {
+    return ps::host_pdb_parse_impl(text, len, capacity, xyz, atom_mask, chain_idx, chain_id, residue_number,
+                                   insertion_code, one_letter, n_residues);
 }
 
 int ps_diffuse(const float* x, const float* beta, const float* noise, uint64_t seed, uint64_t step,

@@ -133,6 +133,19 @@ class StructureBatch:
                    **kwargs)
 
     @classmethod
+    def from_pdb(cls, pdb_path, **kwargs) -> "StructureBatch":
+        """Builds a batch from one PDB file or a list of them (reference protstruc.py:130-192), parsed by the
+        native ingest (no biotite): xyz (B, L, 15, 3) with NaN for missing atoms and zeros for padding, a bool
+        atom mask, NaN-padded chain indices, chain ids and per-chain sequences."""
+        from . import pdb_ingest
+
+        paths = pdb_path if isinstance(pdb_path, list) else [pdb_path]
+        arrays = pdb_ingest.read_pdb_batch(paths)
+        return cls(torch.from_numpy(arrays["xyz"]), torch.from_numpy(arrays["atom_mask"]),
+                   torch.from_numpy(arrays["chain_idx"]), arrays["chain_ids"], arrays["seq"],
+                   torch.from_numpy(arrays["residue_idx"]), **kwargs)
+
+    @classmethod
     def from_backbone_orientations_translations(
         cls,
         orientations: ArrayLike,
@@ -207,6 +220,16 @@ class StructureBatch:
 
     def get_seq(self):
         return self.seq
+
+    def get_seq_idx(self) -> torch.Tensor:
+        """Integer-encoded sequence (B, L), UNK = 20 beyond each structure (reference protstruc.py:394-409)."""
+        from .pdb_ingest import AA_INDEX
+
+        seq_idx = torch.full((self.batch_size, self.n_residues), AA_INDEX["X"], dtype=torch.long)
+        for i, (seqdict, chain_ids) in enumerate(zip(self.seq, self.chain_ids)):
+            joined = "".join(seqdict[c] for c in chain_ids)
+            seq_idx[i, : len(joined)] = torch.tensor([AA_INDEX[r] for r in joined], dtype=torch.long)
+        return seq_idx.to(self.xyz.device)
 
     def get_total_lengths(self) -> torch.Tensor:
         return self.residue_mask.cumsum(dim=1).argmax(dim=1) + 1

@@ -598,3 +598,20 @@ def test_topk_nearest_residue_mask_and_select_match_reference_golden(native_lib)
         two.get_topk_nearest_residue_mask(q)
     with pytest.raises(ValueError):
         two.residue_masked_select(torch.ones(2, 5, dtype=torch.bool))
+
+
+def test_from_pdb_to_features_on_the_device(native_lib):
+    """Row f3 end to end: PDB text -> native ingest -> device -> kernels, against the oracle on the same arrays."""
+    path = str(H.GOLDEN / "mini_two_chain.pdb")
+    sb = ps.StructureBatch.from_pdb([path, path])
+    assert sb.get_xyz().is_cuda and tuple(sb.get_xyz().shape) == (2, 13, 15, 3)
+    xyz, mask, chain_idx = sb.get_xyz().cpu(), sb.get_atom_mask().cpu(), sb.chain_idx.cpu()
+    dih, dmask = sb.backbone_dihedrals()
+    ref, ref_mask = orc.backbone_dihedrals(xyz, chain_idx, mask.any(-1))
+    assert torch.equal(dmask.cpu(), ref_mask)
+    H.assert_same_nan(dih, ref, "dihedrals from pdb")
+    assert H.circular_diff(torch.nan_to_num(dih.cpu()), torch.nan_to_num(ref)).max().item() < 2e-6
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    rd, rm = orc.pair_distances(xyz, mask)
+    H.assert_distances_close(dist, rd)
+    assert torch.equal(dist_mask.cpu(), rm)

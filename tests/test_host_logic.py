@@ -164,3 +164,68 @@ def test_world_size_two_gloo_shards_reassemble_to_the_unsharded_result(tmp_path)
         got = gathered[name]
         assert got.shape == ref.shape
         assert torch.equal(torch.nan_to_num(got, nan=-9.0), torch.nan_to_num(ref, nan=-9.0)), name
+
+
+# ------------------------------------------------------------------------------ row f3: native PDB ingest (host code)
+def test_native_pdb_ingest_on_the_synthetic_fixture(native_lib):
+    """tests/golden/mini_two_chain.pdb: altlocs, MSE HETATM, hydrogens, water, numbering gap, insertion code,
+    OXT, a second MODEL.  Rules: reference protstruc/pdb.py:24-40, 55-151."""
+    from protstruc_b200 import pdb_ingest
+    from oracle import pdb_fixture_reader as reader
+
+    path = H.GOLDEN / "mini_two_chain.pdb"
+    a = pdb_ingest.read_pdb_arrays(path)
+    assert a["one_letter"] == "AGSMXXKWDAGDS"            # MSE -> M, two UNK placeholders for the 4 -> 7 gap
+    assert a["chain_ids"] == ["H", "L"] and a["seq"] == {"H": "AGSMXXKWDA", "L": "GDS"}
+    assert list(a["residue_number"]) == [1, 2, 3, 4, 5, 6, 7, 8, 8, 9, 1, 2, 3]
+    assert a["insertion_code"][8] == "A" and a["insertion_code"][7] == ""
+    assert list(a["atom_mask"].sum(1)) == [5, 4, 6, 8, 0, 0, 8, 14, 8, 6, 4, 8, 7]   # no H, no SE, no HOH, LYS lacks NZ
+    assert np.isnan(a["xyz"][4]).all() and not a["atom_mask"][1, 4]                    # UNK row / glycine CB
+    assert a["atom_mask"][9, 14] and a["atom_mask"][12, 14]                             # OXT in slot 14
+    x, m, c, ids = reader.read_structure(path)                                          # independent Python restatement
+    assert np.array_equal(a["atom_mask"], m) and np.array_equal(a["chain_idx"], c) and ids == a["chain_ids"]
+    assert np.array_equal(np.nan_to_num(a["xyz"], nan=-9.0), np.nan_to_num(x, nan=-9.0))
+    # first alternate location wins: SER 3 CB is the 'A' conformer
+    text = path.read_text().splitlines()
+    cb_a = next(l for l in text if l[12:16].strip() == "CB" and l[17:20] == "SER" and l[16] == "A")
+    assert np.allclose(a["xyz"][2, 4], [float(cb_a[30:38]), float(cb_a[38:46]), float(cb_a[46:54])])
+
+
+def test_from_pdb_pads_like_the_reference(native_lib):
+    path = str(H.GOLDEN / "mini_two_chain.pdb")
+    sb = ps.StructureBatch.from_pdb([path, path], device="cpu")
+    assert tuple(sb.get_xyz().shape) == (2, 13, 15, 3) and sb.get_atom_mask().dtype == torch.bool
+    assert sb.get_chain_ids() == [["H", "L"], ["H", "L"]]
+    assert bool((sb.get_n_terminal_mask().sum(1) == 2).all()) and bool((sb.get_c_terminal_mask().sum(1) == 2).all())
+    seq_idx = sb.get_seq_idx()
+    assert tuple(seq_idx.shape) == (2, 13) and seq_idx[0, 4] == 20 and seq_idx[0, 0] == 0
+    single = ps.StructureBatch.from_pdb(path, device="cpu")
+    assert single.get_batch_size() == 1 and int(single.get_total_lengths()[0]) == 13
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference tree not present on this box")
+def test_native_pdb_ingest_matches_the_python_restatement_on_the_reference_files(native_lib):
+    """All PDB files shipped with the reference; lengths pinned by its tests (437 / 130 / 184 / 229)."""
+    import glob
+    from protstruc_b200 import pdb_ingest
+    from oracle import pdb_fixture_reader as reader
+
+    files = sorted(glob.glob("/root/reference/tests/*.pdb")) + sorted(glob.glob("/root/reference/docs/tutorials/*.pdb"))
+    assert len(files) >= 10
+    pins = {"6dc4.pdb": 437, "1REX.pdb": 130, "4EOT.pdb": 184, "15c8_HL.pdb": 229, "1a6v_HL.pdb": 229}
+    for f in files:
+        a = pdb_ingest.read_pdb_arrays(f)
+        x, m, c, ids = reader.read_structure(f)
+        assert np.array_equal(a["atom_mask"], m) and np.array_equal(a["chain_idx"], c) and a["chain_ids"] == ids, f
+        assert np.array_equal(np.nan_to_num(a["xyz"], nan=-9.0), np.nan_to_num(x, nan=-9.0)), f
+        name = os.path.basename(f)
+        if name in pins:
+            assert a["xyz"].shape[0] == pins[name], f
+    batch = ps.StructureBatch.from_pdb(["/root/reference/tests/15c8_HL.pdb", "/root/reference/tests/1ad0_DC.pdb",
+                                        "/root/reference/tests/5cjx_HL.pdb"], device="cpu")
+    assert len(batch.get_xyz()) == 3  # reference tests/test_StructureBatch.py:56-65
+    assert bool((batch.get_n_terminal_mask().sum(axis=1) == 2).all())
+    assert bool((batch.get_c_terminal_mask().sum(axis=1) == 2).all())
+    g = H.load_golden("real_1a6v_HL")
+    one = ps.StructureBatch.from_pdb("/root/reference/tests/1a6v_HL.pdb", device="cpu")
+    assert np.array_equal(one.get_atom_mask().numpy(), g["atom_mask"])
