@@ -131,7 +131,7 @@ def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step = 1
+    per_step = 4
     for _ in range(args.warmup):
         cpu_reference_throughput(per_step, threads)
     t0 = time.perf_counter()
@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="structures per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=4, help="structures per GPU per end-to-end step")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=4, help="structures timed for the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="structures timed for the CPU baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -273,10 +273,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     fill_gbs = 3 * dist_t.numel() * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9
+    # DRAM bytes per launch from the committed `ncu --set full` capture of this command
+    # (profiles/r1i_k1_final_ncu_summary.txt: dram__bytes_write 4.711673 GB + dram__bytes_read 4.99 MB at 16 structures)
+    traffic = (4.711673e9 + 4.99456e6) * B / 16 if B == 16 else None
     roofline = {
         "bound": "hbm", "kernel": "pair_tiles_kernel<15, dist+boolmask, angles> (fused inter_residue_geometry)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None, "algorithmic_bytes_per_launch": B * BYTES_PER_STRUCT,
+        "traffic": traffic, "traffic_source": "profiles/r1i_k1_final_ncu_summary.txt (ncu --set full, per launch)",
+        "algorithmic_bytes_per_launch": B * BYTES_PER_STRUCT,
         "avg_launch_ms": avg_launch_ms, "best_launch_ms": min(per_launch_ms),
         "fill_ceiling_gbs": fill_gbs,
     }

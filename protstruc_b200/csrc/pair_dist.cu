@@ -479,41 +479,50 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 }
 
 // ------------------------------------------------------------------ generic fallback
-// One thread per output element; handles any A and any pointer alignment.
+// Any A, any L, any pointer alignment.  A block walks chunks of whole pair blocks; within a chunk thread t
+// owns output element t (so every warp store is one contiguous 128-B line) and derives (pair, a, c) with
+// 32-bit arithmetic only; the (b*L + i, j) decode is a single division per pair.  Coordinates come from L1
+// (six 4-byte loads per element), which makes this kernel load-issue bound at roughly half of the HBM
+// roof — the price of shape generality; A = 15 never takes this path.
 template <int SQRT>
 __global__ void __launch_bounds__(256) pair_generic_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int mask_dtype,
-    float* __restrict__ dist, void* __restrict__ dist_mask, int L, int A, long long total) {
-    const long long AA = static_cast<long long>(A) * A;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += stride) {
-        const long long pair = e / AA;
-        const int r = static_cast<int>(e - pair * AA);
-        const int a = r / A;
-        const int c = r - a * A;
-        const long long bi = pair / L;  // b*L + i
-        const int j = static_cast<int>(pair - bi * L);
-        const long long b = bi / L;
-        const long long res_i = bi;
-        const long long res_j = b * L + j;
-        if (dist) {
-            const float* pi = xyz + (res_i * A + a) * 3;
-            const float* pj = xyz + (res_j * A + c) * 3;
-            const float dx = __ldg(pi) - __ldg(pj);
-            const float dy = __ldg(pi + 1) - __ldg(pj + 1);
-            const float dz = __ldg(pi + 2) - __ldg(pj + 2);
-            dist[e] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-        }
-        if (dist_mask) {
-            if (mask_dtype == PS_MASK_BOOL) {
-                const uint8_t* am = static_cast<const uint8_t*>(atom_mask);
-                const bool v = (__ldg(am + res_i * A + a) != 0) && (__ldg(am + res_j * A + c) != 0);
-                static_cast<uint8_t*>(dist_mask)[e] = v ? 1 : 0;
-            } else {
-                const float* am = static_cast<const float*>(atom_mask);
-                static_cast<float*>(dist_mask)[e] =
-                    __fmul_rn(__ldg(am + res_i * A + a), __ldg(am + res_j * A + c));
+    float* __restrict__ dist, void* __restrict__ dist_mask, int L, int A, long long num_pairs) {
+    const unsigned AA = static_cast<unsigned>(A) * A;
+    const unsigned pairs_per_chunk = AA >= 256 ? 1u : 256u / AA;
+    const unsigned chunk_elems = pairs_per_chunk * AA;
+    const long long num_chunks = (num_pairs + pairs_per_chunk - 1) / pairs_per_chunk;
+    for (long long chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
+        const long long pair0 = chunk * pairs_per_chunk;
+        for (unsigned f = threadIdx.x; f < chunk_elems; f += blockDim.x) {
+            const unsigned pl = f / AA;
+            const unsigned r = f - pl * AA;
+            const long long pair = pair0 + pl;
+            if (pair >= num_pairs) break;
+            const unsigned a = r / A;
+            const unsigned c = r - a * A;
+            const long long res_i = pair / L;  // b*L + i
+            const int j = static_cast<int>(pair - res_i * L);
+            const long long res_j = res_i - (res_i % L) + j;
+            const long long e = pair * AA + r;
+            if (dist) {
+                const float* pi = xyz + (res_i * A + a) * 3;
+                const float* pj = xyz + (res_j * A + c) * 3;
+                const float dx = __ldg(pj) - __ldg(pi);
+                const float dy = __ldg(pj + 1) - __ldg(pi + 1);
+                const float dz = __ldg(pj + 2) - __ldg(pi + 2);
+                dist[e] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+            }
+            if (dist_mask) {
+                if (mask_dtype == PS_MASK_BOOL) {
+                    const uint8_t* am = static_cast<const uint8_t*>(atom_mask);
+                    const bool v = (__ldg(am + res_i * A + a) != 0) && (__ldg(am + res_j * A + c) != 0);
+                    static_cast<uint8_t*>(dist_mask)[e] = v ? 1 : 0;
+                } else {
+                    const float* am = static_cast<const float*>(atom_mask);
+                    static_cast<float*>(dist_mask)[e] =
+                        __fmul_rn(__ldg(am + res_i * A + a), __ldg(am + res_j * A + c));
+                }
             }
         }
     }
@@ -580,22 +589,22 @@ int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int slots_overr
 
 int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                    void* dist_mask, int B, int L, int A, int sqrt_mode_id, cudaStream_t stream) {
-    const long long total = static_cast<long long>(B) * L * L * A * A;
+    const long long num_pairs = static_cast<long long>(B) * L * L;
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
-    long long blocks = (total + 255) / 256;
+    const long long AA = static_cast<long long>(A) * A;
+    const long long pairs_per_chunk = AA >= 256 ? 1 : 256 / AA;
+    long long blocks = (num_pairs + pairs_per_chunk - 1) / pairs_per_chunk;
     const long long cap = static_cast<long long>(sms) * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    const unsigned grid = static_cast<unsigned>(blocks);
     if (sqrt_mode_id == kSqrtRn)
-        pair_generic_kernel<kSqrtRn><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+        pair_generic_kernel<kSqrtRn><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
     else if (sqrt_mode_id == kSqrtApprox)
-        pair_generic_kernel<kSqrtApprox><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+        pair_generic_kernel<kSqrtApprox><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
     else
-        pair_generic_kernel<kSqrtApproxFtz><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-            xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, total);
+        pair_generic_kernel<kSqrtApproxFtz><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
     return check_launch("pair_generic_kernel");
 }
 
