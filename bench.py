@@ -305,7 +305,8 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(Be),
                 "d2h_bytes_per_step": pipe.d2h_bytes(Be), "steps": args.e2e_steps, "batch": Be,
-                "api": "protstruc_b200.host_pipeline.HostFeaturePipeline.run (pinned host in, pinned host out)"},
+                "api": "C-ABI ps_host_inter_residue_geometry via protstruc_b200.host_pipeline.HostFeaturePipeline.run "
+                       "(pinned host in, pinned host out, chunks double-buffered on two streams)"},
         "gpu_launches": args.steps, "clocks": clocks, "impl": "ours",
     }
     print(json.dumps(line), flush=True)

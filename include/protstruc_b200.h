@@ -199,6 +199,20 @@ int ps_host_pdb_parse(const char* text, int64_t len, int capacity, float* xyz, u
                       char* one_letter, int* n_residues);
 
 /*
+ * Host-buffer pipeline: the reference-facing call with HOST arrays in and out (what a caller of
+ * StructureBatch.inter_residue_geometry, protstruc/protstruc.py:790-817, holds).  The pipeline owns its device
+ * workspace (two chunks of `chunk` structures, two streams); ps_host_inter_residue_geometry uploads, launches the
+ * fused kernel and downloads chunk by chunk with copies and compute overlapped, and returns when every result
+ * byte is in host memory.  xyz (B,L,A,3) f32, atom_mask (B,L,A) uint8 0/1, dist (B,L,L,A,A) f32, dist_mask
+ * (B,L,L,A,A) uint8, omega/theta/phi (B,L,L) f32 — all HOST pointers, page-locked for full speed.
+ */
+int ps_host_pipeline_create(int chunk, int L, int A, void** pipeline);
+int ps_host_pipeline_destroy(void* pipeline);
+int ps_host_inter_residue_geometry(void* pipeline, const float* xyz, const uint8_t* atom_mask, int B,
+                                   float* dist, uint8_t* dist_mask, float* omega, float* theta, float* phi);
+int64_t ps_host_pipeline_launches(void* pipeline);  /* fused-kernel launches issued so far */
+
+/*
  * K5 — one forward-diffusion step.  Replaces StructureBatch.diffuse_xyz
  * (protstruc/protstruc.py:864-878):
  *   out = fl( fl(sqrt(1-beta_b) * x) + fl(z * sqrt(beta_b)) )     (no FMA contraction)

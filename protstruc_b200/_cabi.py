@@ -58,6 +58,10 @@ SIGNATURES = {
     "ps_kabsch": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, _fp, c_void_p]),
     "ps_topk_nearest_residue_mask": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, _fp, _fp, c_void_p]),
     "ps_host_pdb_parse": (c_int, [c_char_p, c_int64, c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp, POINTER(c_int)]),
+    "ps_host_pipeline_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "ps_host_pipeline_destroy": (c_int, [c_void_p]),
+    "ps_host_inter_residue_geometry": (c_int, [c_void_p, _fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp]),
+    "ps_host_pipeline_launches": (c_int64, [c_void_p]),
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),

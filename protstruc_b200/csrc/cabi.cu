@@ -32,6 +32,11 @@ int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStre
 int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float*, float*, cudaStream_t);
 int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
                       cudaStream_t);
+struct HostPipeline;
+int host_pipeline_create_impl(int, int, int, HostPipeline**);
+int host_pipeline_destroy_impl(HostPipeline*);
+int host_pipeline_run_impl(HostPipeline*, const float*, const uint8_t*, int, float*, uint8_t*, float*, float*, float*);
+long long host_pipeline_launches_impl(const HostPipeline*);
 int host_pdb_parse_impl(const char*, long long, int, float*, uint8_t*, int32_t*, char*, int32_t*, char*, char*, int*);
 int local_xyz_impl(const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int rotate_impl(const float*, const float*, int, int, int, int, float*, cudaStream_t);
@@ -217,6 +222,24 @@ int ps_host_pdb_parse(const char* text, int64_t len, int capacity, float* xyz, u
                       char* one_letter, int* n_residues) {
     return ps::host_pdb_parse_impl(text, len, capacity, xyz, atom_mask, chain_idx, chain_id, residue_number,
                                    insertion_code, one_letter, n_residues);
+}
+
+int ps_host_pipeline_create(int chunk, int L, int A, void** pipeline) {
+    return ps::host_pipeline_create_impl(chunk, L, A, reinterpret_cast<ps::HostPipeline**>(pipeline));
+}
+
+int ps_host_pipeline_destroy(void* pipeline) {
+    return ps::host_pipeline_destroy_impl(static_cast<ps::HostPipeline*>(pipeline));
+}
+
+int ps_host_inter_residue_geometry(void* pipeline, const float* xyz, const uint8_t* atom_mask, int B,
+                                   float* dist, uint8_t* dist_mask, float* omega, float* theta, float* phi) {
+    return ps::host_pipeline_run_impl(static_cast<ps::HostPipeline*>(pipeline), xyz, atom_mask, B, dist, dist_mask,
+                                      omega, theta, phi);
+}
+
+int64_t ps_host_pipeline_launches(void* pipeline) {
+    return ps::host_pipeline_launches_impl(static_cast<const ps::HostPipeline*>(pipeline));
 }
 
 int ps_diffuse(const float* x, const float* beta, const float* noise, uint64_t seed, uint64_t step,

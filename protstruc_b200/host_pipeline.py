@@ -1,14 +1,15 @@
 """Host-buffer entry to the full pairwise feature set (the call a user of the reference makes).
 
-`HostFeaturePipeline.run(xyz_host, atom_mask_host, out)` takes HOST arrays (pinned for full
-speed), computes `inter_residue_geometry` on the GPU and leaves every result — the full
-(B, L, L, A, A) distance tensor, its mask, omega / theta / phi — in HOST buffers, like the reference
-does.  Structures are streamed through the GPU in chunks on two CUDA streams so that the
-host->device copy, the kernel and the device->host copy of consecutive chunks overlap; the
+`HostFeaturePipeline.run(xyz_host, atom_mask_host, out)` takes HOST tensors (pinned for full speed),
+computes `inter_residue_geometry` on the GPU and leaves every result — the full (B, L, L, A, A) distance
+tensor, its mask, omega / theta / phi — in HOST buffers, like the reference does.  It is a thin wrapper
+over the native pipeline behind `ps_host_inter_residue_geometry` (protstruc_b200/csrc/host_pipeline.cu):
+chunks double-buffered on two CUDA streams so uploads, the fused kernel and downloads overlap; the
 device->host copy (~298 MB per 512-residue structure over PCIe) is what bounds this path.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Dict, Optional
 
 import torch
@@ -17,26 +18,31 @@ from . import _cabi
 
 
 class HostFeaturePipeline:
-    def __init__(self, chunk: int, L: int, A: int = 15, device: Optional[torch.device] = None, n_slots: int = 2):
+    def __init__(self, chunk: int, L: int, A: int = 15, device: Optional[torch.device] = None):
         if not torch.cuda.is_available():
             raise _cabi.NativeLibraryError("HostFeaturePipeline needs a CUDA device: there is no CPU fallback")
         self.lib = _cabi.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.chunk, self.L, self.A = chunk, L, A
-        dev = self.device
-        self.slots = []
-        for _ in range(n_slots):
-            self.slots.append({
-                "stream": torch.cuda.Stream(device=dev),
-                "xyz": torch.empty(chunk, L, A, 3, dtype=torch.float32, device=dev),
-                "mask": torch.empty(chunk, L, A, dtype=torch.bool, device=dev),
-                "dist": torch.empty(chunk, L, L, A, A, dtype=torch.float32, device=dev),
-                "dist_mask": torch.empty(chunk, L, L, A, A, dtype=torch.bool, device=dev),
-                "omega": torch.empty(chunk, L, L, dtype=torch.float32, device=dev),
-                "theta": torch.empty(chunk, L, L, dtype=torch.float32, device=dev),
-                "phi": torch.empty(chunk, L, L, dtype=torch.float32, device=dev),
-            })
-        self.launches = 0
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.ps_host_pipeline_create(chunk, L, A, ctypes.byref(handle)), "ps_host_pipeline_create")
+        self._handle = handle
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self.lib.ps_host_pipeline_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.ps_host_pipeline_launches(self._handle))
 
     @staticmethod
     def allocate_host_outputs(B: int, L: int, A: int = 15, pinned: bool = True) -> Dict[str, torch.Tensor]:
@@ -54,27 +60,21 @@ class HostFeaturePipeline:
         return B * self.L * self.L * (self.A * self.A * 5 + 12)
 
     def run(self, xyz_host: torch.Tensor, mask_host: torch.Tensor, out: Dict[str, torch.Tensor]) -> None:
-        """xyz_host (B, L, A, 3) fp32, mask_host (B, L, A) bool, out: dict from allocate_host_outputs.
-        Returns after every result byte is in host memory."""
+        """xyz_host (B, L, A, 3) fp32, mask_host (B, L, A) bool, out: dict from allocate_host_outputs — all on the
+        host.  Returns after every result byte is in host memory."""
         B = xyz_host.shape[0]
         L, A = self.L, self.A
-        if tuple(xyz_host.shape[1:]) != (L, A, 3) or mask_host.dtype != torch.bool:
-            raise ValueError("host inputs must be (B, L, A, 3) fp32 and (B, L, A) bool for this pipeline")
+        if xyz_host.is_cuda or mask_host.is_cuda or tuple(xyz_host.shape[1:]) != (L, A, 3) or \
+                xyz_host.dtype != torch.float32 or mask_host.dtype != torch.bool or tuple(mask_host.shape) != (B, L, A):
+            raise ValueError("host inputs must be CPU tensors of shape (B, L, A, 3) fp32 and (B, L, A) bool")
+        xyz_host, mask_host = xyz_host.contiguous(), mask_host.contiguous()
+        for name, dt in (("dist", torch.float32), ("dist_mask", torch.bool), ("omega", torch.float32),
+                         ("theta", torch.float32), ("phi", torch.float32)):
+            t = out[name]
+            if t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.shape[0] < B:
+                raise ValueError(f"out[{name!r}] must be a contiguous CPU {dt} tensor with at least {B} rows")
         with torch.cuda.device(self.device):
-            for k, start in enumerate(range(0, B, self.chunk)):
-                n = min(self.chunk, B - start)
-                slot = self.slots[k % len(self.slots)]
-                s = slot["stream"]
-                with torch.cuda.stream(s):
-                    slot["xyz"][:n].copy_(xyz_host[start:start + n], non_blocking=True)
-                    slot["mask"][:n].copy_(mask_host[start:start + n], non_blocking=True)
-                    rc = self.lib.ps_inter_residue_geometry(
-                        slot["xyz"].data_ptr(), slot["mask"].data_ptr(), _cabi.PS_MASK_BOOL,
-                        slot["dist"].data_ptr(), slot["dist_mask"].data_ptr(), slot["omega"].data_ptr(),
-                        slot["theta"].data_ptr(), slot["phi"].data_ptr(), n, L, A, s.cuda_stream)
-                    _cabi.check(rc, "ps_inter_residue_geometry")
-                    self.launches += 1
-                    for name in ("dist", "dist_mask", "omega", "theta", "phi"):
-                        out[name][start:start + n].copy_(slot[name][:n], non_blocking=True)
-            for slot in self.slots:
-                slot["stream"].synchronize()
+            rc = self.lib.ps_host_inter_residue_geometry(
+                self._handle, xyz_host.data_ptr(), mask_host.data_ptr(), B, out["dist"].data_ptr(),
+                out["dist_mask"].data_ptr(), out["omega"].data_ptr(), out["theta"].data_ptr(), out["phi"].data_ptr())
+        _cabi.check(rc, "ps_host_inter_residue_geometry")

@@ -615,3 +615,29 @@ def test_from_pdb_to_features_on_the_device(native_lib):
     rd, rm = orc.pair_distances(xyz, mask)
     H.assert_distances_close(dist, rd)
     assert torch.equal(dist_mask.cpu(), rm)
+
+
+def test_host_buffer_pipeline_matches_the_device_api(native_lib):
+    """C-ABI ps_host_inter_residue_geometry: host arrays in, host arrays out, chunked (ragged last chunk)."""
+    from protstruc_b200.host_pipeline import HostFeaturePipeline
+
+    B, L, A = 5, 40, 15
+    xyz, mask, _ = H.synthetic_batch(31, B, L, A, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    ref = sb.inter_residue_geometry()
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    pipe = HostFeaturePipeline(chunk=2, L=L, A=A)
+    for pinned in (True, False):
+        out = HostFeaturePipeline.allocate_host_outputs(B, L, A, pinned=pinned)
+        x_h = xyz.pin_memory() if pinned else xyz.clone()
+        m_h = mask.pin_memory() if pinned else mask.clone()
+        pipe.run(x_h, m_h, out)
+        assert not out["dist"].is_cuda
+        assert torch.equal(torch.nan_to_num(out["dist"], nan=-1.0), torch.nan_to_num(dist.cpu(), nan=-1.0))
+        assert torch.equal(out["dist_mask"], dist_mask.cpu())
+        for k in ("omega", "theta", "phi"):
+            assert torch.equal(torch.nan_to_num(out[k], nan=-9.0), torch.nan_to_num(ref[k].cpu(), nan=-9.0)), k
+    assert pipe.launches == 2 * 3  # ceil(5 / 2) chunks per run
+    with pytest.raises(ValueError):
+        pipe.run(xyz.cuda(), mask, out)
+    pipe.close()
