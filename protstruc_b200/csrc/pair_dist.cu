@@ -501,9 +501,19 @@ __global__ void __launch_bounds__(256) pair_generic_kernel(
             if (pair >= num_pairs) break;
             const unsigned a = r / A;
             const unsigned c = r - a * A;
-            const long long res_i = pair / L;  // b*L + i
-            const int j = static_cast<int>(pair - res_i * L);
-            const long long res_j = res_i - (res_i % L) + j;
+            long long res_i;  // b*L + i
+            unsigned j, i;
+            if (num_pairs <= 0xFFFFFFFFll) {  // 32-bit decode whenever the pair count allows it
+                const unsigned row = static_cast<unsigned>(pair) / static_cast<unsigned>(L);
+                j = static_cast<unsigned>(pair) - row * static_cast<unsigned>(L);
+                i = row % static_cast<unsigned>(L);
+                res_i = row;
+            } else {
+                res_i = pair / L;
+                j = static_cast<unsigned>(pair - res_i * L);
+                i = static_cast<unsigned>(res_i % L);
+            }
+            const long long res_j = res_i - i + j;
             const long long e = pair * AA + r;
             if (dist) {
                 const float* pi = xyz + (res_i * A + a) * 3;
