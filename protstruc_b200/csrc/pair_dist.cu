@@ -481,9 +481,9 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 // ------------------------------------------------------------------ generic fallback
 // Any A, any L, any pointer alignment.  A block walks chunks of whole pair blocks; within a chunk thread t
 // owns output element t (so every warp store is one contiguous 128-B line) and derives (pair, a, c) with
-// 32-bit arithmetic only; the (b*L + i, j) decode is a single division per pair.  Coordinates come from L1
-// (six 4-byte loads per element), which makes this kernel load-issue bound at roughly half of the HBM
-// roof — the price of shape generality; A = 15 never takes this path.
+// 32-bit arithmetic whenever the pair count allows it.  Coordinates and mask bytes come from L1 (eight small
+// loads per element), which keeps this kernel far from the HBM roof (measured 0.74 TB/s on the bench shape) —
+// the price of shape generality; A = 15 with L >= 32 never takes this path.
 template <int SQRT>
 __global__ void __launch_bounds__(256) pair_generic_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int mask_dtype,
