@@ -547,7 +547,7 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     if (slots * WPT > kMaxWarps) slots = kMaxWarps / WPT;
     // Measured on B200 (profiles/r1g_k1_sweep_v6_cells.json): with two warps per tile, four tile buffers
     // (8 warps, 147 KB) sustain 6.1-6.3 TB/s on the distance + mask kernels, five or six buffers 3-8 % less.
-    if (WPT == 2 && kind_has_f32<KIND>() && kind_has_u8<KIND>() && slots > 4) slots = 4;
+    if (WPT == 2 && kind_has_f32<KIND>() && slots > 4) slots = 4;
     if (slots_override > 0 && slots_override <= kMaxSmem / per_slot && slots_override * WPT <= kMaxWarps)
         slots = slots_override;
     if (slots < 1) {

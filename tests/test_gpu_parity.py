@@ -641,3 +641,33 @@ def test_host_buffer_pipeline_matches_the_device_api(native_lib):
     with pytest.raises(ValueError):
         pipe.run(xyz.cuda(), mask, out)
     pipe.close()
+
+
+def test_config5_shape_chunked_streaming_is_bit_identical(native_lib):
+    """BASELINE config 5 (L = 384, A = 15) is streamed through the GPU in batch chunks; chunking must not change a bit,
+    and shards computed independently (as on 2 or 8 GPUs) must reassemble to the unsharded result."""
+    from protstruc_b200.sharding import shard_bounds
+
+    B, L, A = 6, 384, 15
+    g = torch.Generator(device=DEV).manual_seed(5)
+    xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
+    mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
+    xyz = torch.where(mask[..., None], xyz, torch.full_like(xyz, float("nan")))
+    whole = ps.StructureBatch.from_xyz(xyz, mask).inter_residue_geometry()
+    dist_w, mask_w = ps.StructureBatch.from_xyz(xyz, mask).pairwise_distance_matrix()
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            a, b = shard_bounds(B, world, rank)
+            sb = ps.StructureBatch.from_xyz(xyz[a:b], mask[a:b])
+            parts.append((sb.inter_residue_geometry(), sb.pairwise_distance_matrix()))
+        for key in ("omega", "theta", "phi", "d_ca", "d_no_mask"):
+            joined = torch.cat([p[0][key] for p in parts])
+            assert torch.equal(torch.nan_to_num(joined.float(), nan=-7.0), torch.nan_to_num(whole[key].float(), nan=-7.0)), key
+        assert torch.equal(torch.nan_to_num(torch.cat([p[1][0] for p in parts]), nan=-7.0), torch.nan_to_num(dist_w, nan=-7.0))
+        assert torch.equal(torch.cat([p[1][1] for p in parts]), mask_w)
+    # exact structure of the output: symmetric, zero diagonal, NaN exactly where an atom is missing
+    d0 = dist_w[0]
+    assert torch.equal(torch.nan_to_num(d0, nan=-7.0), torch.nan_to_num(d0.permute(1, 0, 3, 2), nan=-7.0))
+    expect_nan = ~(mask[0][:, None, :, None] & mask[0][None, :, None, :])
+    assert torch.equal(torch.isnan(d0), expect_nan)
