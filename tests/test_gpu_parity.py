@@ -671,3 +671,36 @@ def test_config5_shape_chunked_streaming_is_bit_identical(native_lib):
     assert torch.equal(torch.nan_to_num(d0, nan=-7.0), torch.nan_to_num(d0.permute(1, 0, 3, 2), nan=-7.0))
     expect_nan = ~(mask[0][:, None, :, None] & mask[0][None, :, None, :])
     assert torch.equal(torch.isnan(d0), expect_nan)
+
+
+@pytest.mark.parametrize("B,L", [(1, 32), (1, 33), (3, 37), (2, 45), (1, 229), (7, 40)])
+def test_fused_kernel_never_writes_outside_its_outputs(native_lib, B, L):
+    """Guard bands around every output of the fused kernel (tail tiles, odd L, ragged strips): the sentinel bytes
+    before and after each buffer must survive, and the payload must equal the unguarded call."""
+    A, guard = 15, 4096
+    xyz, mask, _ = H.synthetic_batch(B * 100 + L, B, L, A, "bool")
+    x, m = xyz.to(DEV), mask.to(DEV)
+    n_pairs, n_elems = B * L * L, B * L * L * A * A
+
+    def guarded(nbytes):
+        buf = torch.full((guard + nbytes + guard,), 0xA5, dtype=torch.uint8, device=DEV)
+        return buf, buf[guard:guard + nbytes]
+
+    bufs = {name: guarded(n) for name, n in (("dist", n_elems * 4), ("mask", n_elems), ("omega", n_pairs * 4),
+                                             ("theta", n_pairs * 4), ("phi", n_pairs * 4))}
+    ptr = {k: v[1].data_ptr() for k, v in bufs.items()}
+    assert all(p % 16 == 0 for p in ptr.values())
+    rc = native_lib.ps_inter_residue_geometry(x.data_ptr(), m.data_ptr(), 0, ptr["dist"], ptr["mask"], ptr["omega"],
+                                              ptr["theta"], ptr["phi"], B, L, A, torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "ps_inter_residue_geometry")
+    torch.cuda.synchronize()
+    for name, (buf, view) in bufs.items():
+        assert bool((buf[:guard] == 0xA5).all()) and bool((buf[-guard:] == 0xA5).all()), f"{name}: guard band overwritten"
+    ref = ps.StructureBatch.from_xyz(xyz, mask).inter_residue_geometry()
+    dist_ref, mask_ref = ps.StructureBatch.from_xyz(xyz, mask).pairwise_distance_matrix()
+    got_dist = bufs["dist"][1].view(torch.float32).view(B, L, L, A, A)
+    assert torch.equal(torch.nan_to_num(got_dist, nan=-3.0), torch.nan_to_num(dist_ref, nan=-3.0))
+    assert torch.equal(bufs["mask"][1].view(torch.bool).view(B, L, L, A, A), mask_ref)
+    for k in ("omega", "theta", "phi"):
+        got = bufs[k][1].view(torch.float32).view(B, L, L)
+        assert torch.equal(torch.nan_to_num(got, nan=-3.0), torch.nan_to_num(ref[k], nan=-3.0)), k
