@@ -31,6 +31,8 @@
 // Generic kernel (any A, misaligned outputs): one thread per output element, coalesced scalar
 // stores, integer decode per element.  Slower (issue-bound) but shape-agnostic.
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ps {
@@ -138,6 +140,20 @@ __device__ __forceinline__ uint32_t load_mask_bits(const uint8_t* __restrict__ m
 //     (one shuffle) and written by the lower lane only.
 // Lane stride is 56.25 words: start words floor(56.25*l) hit 32 distinct banks -> conflict free.
 // ~1.2 issue slots per mask byte instead of 3 for byte-wise stores (which also bank-conflict).
+// Byte-wise mask block for the other atom counts (A != 15): three issue slots per byte and 2-way bank
+// conflicts, acceptable for the secondary fast paths.
+template <int A>
+__device__ __forceinline__ void write_mask_block_bytes(uint8_t* __restrict__ tile_bytes, int lane,
+                                                       uint32_t mi_bits, uint32_t mj_bits) {
+    uint8_t* dst = tile_bytes + lane * (A * A);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const uint32_t row = ((mi_bits >> a) & 1u) ? mj_bits : 0u;
+#pragma unroll
+        for (int c = 0; c < A; ++c) dst[a * A + c] = static_cast<uint8_t>((row >> c) & 1u);
+    }
+}
+
 template <int A>
 __device__ __forceinline__ void write_mask_block(uint32_t* __restrict__ tile_words, int lane,
                                                  uint32_t mi_bits, uint32_t mj_bits) {
@@ -199,8 +215,15 @@ __device__ __forceinline__ void tile_sync(int slot) {
     }
 }
 
-constexpr int kStageFloats = 96;  // two residues of A*3 = 45 floats, padded
-constexpr int kStageBytesPerWarp = 2 * kStageFloats * 4;  // double buffered
+// Staging area of one warp: two residues of A*3 floats, rounded up to whole 32-float rows, double buffered.
+template <int A>
+__host__ __device__ constexpr int stage_floats() {
+    return (2 * A * 3 + 31) / 32 * 32;
+}
+template <int A>
+__host__ __device__ constexpr int stage_bytes_per_warp() {
+    return 2 * stage_floats<A>() * 4;
+}
 
 // WPT = warps per tile.  WPT = 1: one warp computes the whole tile.  WPT = 2: two warps share the tile
 // buffer — warp 0 takes the first rows and the angle triple, warp 1 the remaining rows and the mask block — which
@@ -216,7 +239,10 @@ constexpr int kStageBytesPerWarp = 2 * kStageFloats * 4;  // double buffered
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_tiles_kernel(const PairDistParams p) {
     using G = TileGeom<A>;
-    static_assert(2 * A * 3 <= kStageFloats, "staging area too small");
+    static_assert(A >= 1 && 2 * A <= 32, "the mask ballot holds two residues of at most 16 atoms");
+    constexpr int kStageFloats = stage_floats<A>();
+    constexpr int kStageRows = kStageFloats / 32;
+    constexpr int kStageBytesPerWarp = stage_bytes_per_warp<A>();
     constexpr int NP = (A + 1) / 2;  // f32x2 packs per coordinate
     // Row split between the two warps of a tile, balanced against their extra duties: the angle triple
     // (warp 0, ~300 issue slots per tile) and the mask block (warp 1, ~255) versus ~80 per row.
@@ -276,18 +302,21 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
         return first_pair / p.L;
     };
 
-    // Residue-i prefetch registers: floats lane, lane+32, lane+64 of the 2-residue block, one mask byte.
-    float pf0 = 0.f, pf1 = 0.f, pf2 = 0.f;
+    // Residue-i prefetch registers: floats lane, lane+32, ... of the 2-residue block, one mask byte.
+    float pf[kStageRows];
+#pragma unroll
+    for (int k = 0; k < kStageRows; ++k) pf[k] = 0.f;
     uint32_t pf_mask_ballot = 0;
     auto prefetch_issue = [&](long long t) {
         const long long r0 = first_row_of(t);
         const long long last_float = p.num_rows * (A * 3) - 1;
         if (kNeedsXyz) {
-            const long long base = r0 * (A * 3);
-            const long long i0 = base + lane, i1 = base + lane + 32, i2 = base + lane + 64;
-            pf0 = __ldg(p.xyz + (i0 < last_float ? i0 : last_float));
-            pf1 = __ldg(p.xyz + (i1 < last_float ? i1 : last_float));
-            pf2 = __ldg(p.xyz + (i2 < last_float ? i2 : last_float));
+            const long long base = r0 * (A * 3) + lane;
+#pragma unroll
+            for (int k = 0; k < kStageRows; ++k) {
+                const long long idx = base + 32 * k;
+                pf[k] = __ldg(p.xyz + (idx < last_float ? idx : last_float));
+            }
         }
         if (kind_has_u8<KIND>()) {
             const uint8_t* am = static_cast<const uint8_t*>(p.atom_mask);
@@ -299,9 +328,8 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     };
     auto prefetch_commit = [&](float* buf) {
         if (kNeedsXyz) {
-            buf[lane] = pf0;
-            buf[lane + 32] = pf1;
-            if (lane + 64 < kStageFloats) buf[lane + 64] = pf2;
+#pragma unroll
+            for (int k = 0; k < kStageRows; ++k) buf[lane + 32 * k] = pf[k];
         }
     };
 
@@ -426,7 +454,12 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                 for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
             }
         }
-        if (does_mask) write_mask_block<A>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
+        if (does_mask) {
+            if (A == 15)
+                write_mask_block<15>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
+            else
+                write_mask_block_bytes<A>(tile_u8, lane, mi_bits, mj_bits);
+        }
 
         if (does_angles) {
             // trRosetta triple of this lane's pair, reference definitions
@@ -540,7 +573,7 @@ __global__ void __launch_bounds__(256) pair_generic_kernel(
 
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t stream) {
-    constexpr int per_slot = warp_smem_bytes<A, KIND>() + WPT * kStageBytesPerWarp;
+    constexpr int per_slot = warp_smem_bytes<A, KIND>() + WPT * stage_bytes_per_warp<A>();
     constexpr int kMaxSmem = 227 * 1024;
     constexpr int kMaxWarps = (WPT == 1) ? 8 : 12;
     int slots = kMaxSmem / per_slot;
@@ -618,6 +651,47 @@ int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, floa
     return check_launch("pair_generic_kernel");
 }
 
+// Kernel selection for one atom count.  A = 15 carries every tuning variant; the other staged atom counts
+// (5 = backbone + CB, 10, 14 = atom14) are built for the default configuration only.
+template <int A>
+int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, bool want_angles, int sqrt_id,
+                   int slots_override, int wpt, cudaStream_t stream) {
+    constexpr bool kAllVariants = (A == 15);
+    if (!kAllVariants) {
+        sqrt_id = kSqrtApproxFtz;
+        wpt = kDefaultWarpsPerTile;
+    }
+    auto dist_kind = [&](auto kind_tag, bool angles) -> int {
+        constexpr int KIND = decltype(kind_tag)::value;
+        if constexpr (kAllVariants) {
+            return angles ? launch_tiles_sqrt<A, KIND, true>(p, sqrt_id, slots_override, wpt, stream)
+                          : launch_tiles_sqrt<A, KIND, false>(p, sqrt_id, slots_override, wpt, stream);
+        } else {
+            return angles
+                       ? launch_tiles_wpt<A, KIND, kSqrtApproxFtz, true, kDefaultWarpsPerTile>(p, slots_override, stream)
+                       : launch_tiles_wpt<A, KIND, kSqrtApproxFtz, false, kDefaultWarpsPerTile>(p, slots_override, stream);
+        }
+    };
+    if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
+        if (p.dist && dist_mask) return dist_kind(std::integral_constant<int, kDistBoolMask>{}, want_angles);
+        if (p.dist) return dist_kind(std::integral_constant<int, kDistOnly>{}, want_angles);
+        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
+        return launch_tiles_wpt<A, kBoolMaskOnly, kSqrtApproxFtz, false, 1>(p, slots_override, stream);
+    }
+    // fp32 mask: distances (+angles) first, then the mask product through the same tile path.
+    if (p.dist) {
+        const int rc = dist_kind(std::integral_constant<int, kDistOnly>{}, want_angles);
+        if (rc != PS_OK) return rc;
+    } else {
+        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
+    }
+    PairDistParams pm = p;
+    pm.dist = static_cast<float*>(dist_mask);
+    pm.mask = nullptr;
+    pm.omega = pm.theta = pm.phi = nullptr;
+    return launch_tiles_wpt<A, kF32MaskOnly, kSqrtApproxFtz, false, 1>(pm, slots_override, stream);
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -650,7 +724,8 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     const int wpt = ((variant >> 9) & 1) ? (3 - kDefaultWarpsPerTile) : kDefaultWarpsPerTile;
 
     // the staged kernel needs L >= 32 (a tile of 32 pairs then touches at most two residue-i rows)
-    const bool fast = (A == 15) && (L >= kTilePairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
+    const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14);
+    const bool fast = staged_atom_count && (L >= kTilePairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
         int rc = launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
         if (rc != PS_OK || !want_angles) return rc;
@@ -680,34 +755,16 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
 
-    if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
-        if (dist && dist_mask) {
-            return want_angles
-                       ? launch_tiles_sqrt<15, kDistBoolMask, true>(p, sqrt_id, warps_override, wpt, stream)
-                       : launch_tiles_sqrt<15, kDistBoolMask, false>(p, sqrt_id, warps_override, wpt, stream);
-        }
-        if (dist) {
-            return want_angles
-                       ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, wpt, stream)
-                       : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, wpt, stream);
-        }
-        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
-        return launch_tiles<15, kBoolMaskOnly, kSqrtApproxFtz, false>(p, warps_override, 1, stream);
+    switch (A) {
+        case 5:
+            return dispatch_tiles<5>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+        case 10:
+            return dispatch_tiles<10>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+        case 14:
+            return dispatch_tiles<14>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+        default:
+            return dispatch_tiles<15>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
     }
-    // fp32 mask: distances (+angles) first, then the mask product through the same tile path.
-    if (dist) {
-        int rc = want_angles
-                     ? launch_tiles_sqrt<15, kDistOnly, true>(p, sqrt_id, warps_override, wpt, stream)
-                     : launch_tiles_sqrt<15, kDistOnly, false>(p, sqrt_id, warps_override, wpt, stream);
-        if (rc != PS_OK) return rc;
-    } else {
-        PS_REQUIRE(!want_angles, PS_ERR_NULL_POINTER, "fused angles need the distance output");
-    }
-    PairDistParams pm = p;
-    pm.dist = static_cast<float*>(dist_mask);
-    pm.mask = nullptr;
-    pm.omega = pm.theta = pm.phi = nullptr;
-    return launch_tiles<15, kF32MaskOnly, kSqrtApproxFtz, false>(pm, warps_override, 1, stream);
 }
 
 }  // namespace ps

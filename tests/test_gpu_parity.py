@@ -75,7 +75,8 @@ def test_pairwise_distance_matrix_real_structure(native_lib):
 
 @pytest.mark.parametrize("B,L,A,kind", [(3, 37, 15, "bool"), (1, 1, 15, "bool"), (2, 2, 15, "float"),
                                         (1, 130, 15, "bool"), (2, 19, 10, "bool"), (1, 6, 37, "float"),
-                                        (5, 16, 15, "bool")])
+                                        (5, 16, 15, "bool"), (2, 40, 5, "bool"), (2, 33, 10, "float"),
+                                        (1, 64, 14, "bool"), (3, 35, 5, "float"), (2, 32, 16, "bool")])
 def test_pairwise_distance_matrix_vs_oracle(native_lib, B, L, A, kind):
     xyz, mask, chain_idx = H.synthetic_batch(100 + L, B, L, A, kind)
     sb = ps.StructureBatch.from_xyz(xyz, mask)
@@ -704,3 +705,37 @@ def test_fused_kernel_never_writes_outside_its_outputs(native_lib, B, L):
     for k in ("omega", "theta", "phi"):
         got = bufs[k][1].view(torch.float32).view(B, L, L)
         assert torch.equal(torch.nan_to_num(got, nan=-3.0), torch.nan_to_num(ref[k], nan=-3.0)), k
+
+
+@pytest.mark.parametrize("B,L,A", [(2, 48, 5), (1, 37, 14), (2, 33, 10)])
+def test_staged_kernels_for_other_atom_counts(native_lib, B, L, A):
+    """A = 5 (backbone + CB), 10 and 14 (atom14) run the staged TMA-store kernel too: fused features vs the oracle,
+    bit-identical to the generic kernel, guard bands intact."""
+    xyz, mask, _ = H.synthetic_batch(500 + A, B, L, A, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    out = sb.inter_residue_geometry()
+    ro, rt, rp = orc.trrosetta_angles(xyz)
+    H.assert_angles_close(out["omega"], ro, angle_conditioning(xyz, "omega"), "omega", all_finite_tol=2e-6)
+    H.assert_angles_close(out["theta"], rt, angle_conditioning(xyz, "theta"), "theta", all_finite_tol=2e-6)
+    H.assert_angles_close(out["phi"], rp, angle_conditioning(xyz, "phi"), "phi", circular=False)
+    rd, rm = orc.pair_distances(xyz, mask)
+    H.assert_distances_close(out["d_ca"], rd[:, :, :, 1, 1], "d_ca")
+    assert torch.equal(out["d_no_mask"].cpu(), rm[:, :, :, 0, 3])
+    x, m = xyz.to(DEV), mask.to(DEV)
+    n = B * L * L * A * A
+    results = []
+    for variant in (0, 1 << 8):  # staged, generic
+        guard = 1024
+        dbuf = torch.full((guard + n * 4 + guard,), 0x5A, dtype=torch.uint8, device=DEV)
+        mbuf = torch.full((guard + n + guard,), 0x5A, dtype=torch.uint8, device=DEV)
+        rc = native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, dbuf[guard:].data_ptr(), mbuf[guard:].data_ptr(),
+                                             B, L, A, variant, torch.cuda.current_stream().cuda_stream)
+        _cabi.check(rc, "ps_pair_dist_mask_ex")
+        torch.cuda.synchronize()
+        for buf in (dbuf, mbuf):
+            assert bool((buf[:guard] == 0x5A).all()) and bool((buf[-guard:] == 0x5A).all())
+        results.append((dbuf[guard:guard + n * 4].view(torch.float32).clone(), mbuf[guard:guard + n].clone()))
+    assert torch.equal(torch.nan_to_num(results[0][0], nan=-2.0), torch.nan_to_num(results[1][0], nan=-2.0))
+    assert torch.equal(results[0][1], results[1][1])
+    H.assert_distances_close(results[0][0].view(B, L, L, A, A), rd)
+    assert torch.equal(results[0][1].view(torch.bool).view(B, L, L, A, A).cpu(), rm)

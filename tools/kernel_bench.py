@@ -133,6 +133,19 @@ def main():
                                 structures_per_s=B / (best / 1e3)))
     del dist, dmask
 
+    # ---- staged kernel at other atom counts (backbone + CB, atom14)
+    for (B, L, A) in ((128, 512, 5), (16, 512, 14)):
+        xyz, mask = inputs(B, L, A)
+        dist = torch.empty(B, L, L, A, A, device=DEV)
+        dmask = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
+
+        def run_other(xyz=xyz, mask=mask, dist=dist, dmask=dmask, B=B, L=L, A=A):
+            _cabi.check(lib.ps_pair_dist_mask(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(), B, L, A, s), "kA")
+        best, med = time_call(run_other)
+        out["results"].append(entry(f"K1 dist+boolmask B{B} L{L} A{A} (staged kernel, other atom count)", best, med,
+                                    B * (L * L * A * A * 5 + L * A * 13), peak))
+        del dist, dmask
+
     # ---- config 3: 256 x 512 backbone (A=5), omega/theta/phi
     B, L, A = 256, 512, 5
     xyz, _ = inputs(B, L, A, nan_masked=False)  # config 3: backbone slots, all valid
