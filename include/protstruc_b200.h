@@ -259,11 +259,14 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * Tuning hook for K1 (benchmarks / profiling only; not part of the drop-in surface).
  * variant bit-field: bits 0-1 sqrt mode (0 = sqrt.approx.ftz.f32 [default], 1 = sqrt.approx.f32,
  * 2 = sqrt.rn.f32); bits 4-7 tile buffers per CTA override (0 = default); bit 8 = force generic kernel;
- * bit 9 = use the non-default number of warps per tile.
+ * bit 9 = use the non-default number of warps per tile; bit 10 = diagnostic "stores only" (no arithmetic,
+ * output content undefined: measures the memory-system ceiling of the kernel's write pattern).
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,
                          int B, int L, int A, int variant, void* stream);
+/* Diagnostic store ceiling: plain 128-bit stores of a non-uniform pattern over n floats (n % 4 == 0). */
+int ps_debug_fill_pattern(float* out, int64_t n, int blocks_per_sm, void* stream);
 /* Same hook for the fused kernel (ps_inter_residue_geometry with a variant bit-field). */
 int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                                  float* dist, void* dist_mask,

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ps_host_pipeline_destroy": (c_int, [c_void_p]),
     "ps_host_inter_residue_geometry": (c_int, [c_void_p, _fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp]),
     "ps_host_pipeline_launches": (c_int64, [c_void_p]),
+    "ps_debug_fill_pattern": (c_int, [_fp, c_int64, c_int, c_void_p]),
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),

@@ -32,6 +32,7 @@ int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStre
 int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float*, float*, cudaStream_t);
 int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
                       cudaStream_t);
+int debug_fill_pattern_impl(float*, long long, int, cudaStream_t);
 struct HostPipeline;
 int host_pipeline_create_impl(int, int, int, HostPipeline**);
 int host_pipeline_destroy_impl(HostPipeline*);
@@ -240,6 +241,10 @@ int ps_host_inter_residue_geometry(void* pipeline, const float* xyz, const uint8
 
 int64_t ps_host_pipeline_launches(void* pipeline) {
     return ps::host_pipeline_launches_impl(static_cast<const ps::HostPipeline*>(pipeline));
+}
+
+int ps_debug_fill_pattern(float* out, int64_t n, int blocks_per_sm, void* stream) {
+    return ps::debug_fill_pattern_impl(out, n, blocks_per_sm, PS_STREAM(stream));
 }
 
 int ps_diffuse(const float* x, const float* beta, const float* noise, uint64_t seed, uint64_t step,

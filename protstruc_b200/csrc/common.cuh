@@ -75,71 +75,8 @@ __device__ __forceinline__ V3 div3(V3 a, float s) {
     return V3{__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)};
 }
 
-__device__ __forceinline__ bool has_nan3(V3 a) { return (a.x != a.x) | (a.y != a.y) | (a.z != a.z); }
-
-// Missing atoms are NaN coordinates in the reference's tensors (protstruc/pdb.py:133-135) and every
-// NaN input coordinate makes the angle NaN (each cross / dot product mixes all three components).
-// Returning NaN up front is therefore exact, and it keeps NaN-carrying lanes out of the slow paths of
-// the IEEE division / square root / atan2f / acosf sequences (a 25 % hit on the fused kernel with half
-// of the atoms missing).  The cheap probe is a plain sum; only when it is NaN (a NaN, or +inf and -inf
-// together) are the coordinates inspected one by one, so infinities still take the full computation.
-__device__ __forceinline__ bool any_nan_coordinate(V3 a, V3 b, V3 c) {
-    const float probe = ((a.x + a.y) + (a.z + b.x)) + ((b.y + b.z) + (c.x + c.y)) + c.z;
-    if (probe == probe) return false;
-    return has_nan3(a) || has_nan3(b) || has_nan3(c);
-}
-
-// geometry.dihedral (protstruc/geometry.py:110-124).
-__device__ __forceinline__ float dihedral4(V3 a, V3 b, V3 c, V3 d) {
-    if (any_nan_coordinate(a, b, c) || has_nan3(d)) return __int_as_float(0x7fc00000);
-    const V3 b0 = sub3(a, b);
-    const V3 b1 = sub3(c, b);
-    const V3 b2 = sub3(d, c);
-    const V3 n1 = cross3(b0, b1);
-    const V3 n2 = cross3(b2, b1);
-    const V3 m = cross3(n1, n2);
-    const float x = dot3(n1, n2);
-    const float y = __fdiv_rn(dot3(m, b1), norm3(b1));
-    return atan2f(y, x);
-}
-
-// geometry.angle (protstruc/geometry.py:64-71); no clamp, exactly like the reference.
-__device__ __forceinline__ float angle3(V3 a, V3 b, V3 c) {
-    if (any_nan_coordinate(a, b, c)) return __int_as_float(0x7fc00000);
-    const V3 ba = sub3(a, b);
-    const V3 bc = sub3(c, b);
-    const float cosine = __fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc)));
-    return acosf(cosine);
-}
-
-// Virtual CB from N, CA, C (protstruc/geometry.py:217-221):
-//   b = CA - N, c = C - CA, a = b x c;  CB = -0.58273431 a + 0.56802827 b - 0.54067466 c + CA
-// evaluated left to right with separately rounded ops as the torch expression does.
-__device__ __forceinline__ V3 virtual_cb(V3 n, V3 ca, V3 c) {
-    const V3 vb = sub3(ca, n);
-    const V3 vc = sub3(c, ca);
-    const V3 va = cross3(vb, vc);
-    V3 r;
-    r.x = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.x), __fmul_rn(0.56802827f, vb.x)),
-                              __fmul_rn(0.54067466f, vc.x)), ca.x);
-    r.y = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.y), __fmul_rn(0.56802827f, vb.y)),
-                              __fmul_rn(0.54067466f, vc.y)), ca.y);
-    r.z = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.z), __fmul_rn(0.56802827f, vb.z)),
-                              __fmul_rn(0.54067466f, vc.z)), ca.z);
-    return r;
-}
-
-// ---------------------------------------------------------------- tuned trRosetta triple
-// omega / theta / phi of one residue pair for the two hot kernels (K2f and the fused K1).  Same
-// formulas and the same non-contracted cross / dot products as dihedral4 / angle3 above — so exact
-// cancellations (diagonal pairs, zero-padded residues) and NaN placement are unchanged — but the final
-// scalar steps use single-MUFU primitives refined to ~1 ulp instead of the IEEE division / sqrt /
-// libdevice atan2f sequences (which cost more than the geometry itself):
-//   * y = (m.b1) / |b1|  ->  (m.b1) * rsqrt(b1.b1), one Newton step on the MUFU.RSQ seed;
-//   * atan2 -> min/max quotient by MUFU.RCP + one Newton step, degree-15 odd minimax polynomial on
-//     [0, 1] (max error 7e-9 before rounding), octant fix-ups; zeros, infinities, NaN and out-of-range
-//     magnitudes fall back to atan2f, so atan2(+-0, -0) = +-pi etc. keep their IEEE values.
-// Measured deviation from the reference after this change: see profiles/*parity_report*.json.
+// Single-MUFU primitives refined to ~1 ulp, used for the last scalar steps of the dihedral (see the note at
+// "tuned trRosetta triple" below).
 __device__ __forceinline__ float rcp_mufu(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -179,6 +116,73 @@ __device__ __forceinline__ float atan2_tuned(float y, float x) {
     return copysignf(a, y);
 }
 
+__device__ __forceinline__ bool has_nan3(V3 a) { return (a.x != a.x) | (a.y != a.y) | (a.z != a.z); }
+
+// Missing atoms are NaN coordinates in the reference's tensors (protstruc/pdb.py:133-135) and every
+// NaN input coordinate makes the angle NaN (each cross / dot product mixes all three components).
+// Returning NaN up front is therefore exact, and it keeps NaN-carrying lanes out of the slow paths of
+// the IEEE division / square root / atan2f / acosf sequences (a 25 % hit on the fused kernel with half
+// of the atoms missing).  The cheap probe is a plain sum; only when it is NaN (a NaN, or +inf and -inf
+// together) are the coordinates inspected one by one, so infinities still take the full computation.
+__device__ __forceinline__ bool any_nan_coordinate(V3 a, V3 b, V3 c) {
+    const float probe = ((a.x + a.y) + (a.z + b.x)) + ((b.y + b.z) + (c.x + c.y)) + c.z;
+    if (probe == probe) return false;
+    return has_nan3(a) || has_nan3(b) || has_nan3(c);
+}
+
+// geometry.dihedral (protstruc/geometry.py:110-124).
+__device__ __forceinline__ float dihedral4(V3 a, V3 b, V3 c, V3 d) {
+    if (any_nan_coordinate(a, b, c) || has_nan3(d)) return __int_as_float(0x7fc00000);
+    const V3 b0 = sub3(a, b);
+    const V3 b1 = sub3(c, b);
+    const V3 b2 = sub3(d, c);
+    const V3 n1 = cross3(b0, b1);
+    const V3 n2 = cross3(b2, b1);
+    const V3 m = cross3(n1, n2);
+    const float x = dot3(n1, n2);
+    // (m.b1) / |b1| and atan2 with the tuned primitives: same result to ~1 ulp as the IEEE division / sqrt /
+    // libdevice atan2f sequence at a third of the issue slots (special values fall back to atan2f)
+    const float y = __fmul_rn(dot3(m, b1), rsqrt_refined(dot3(b1, b1)));
+    return atan2_tuned(y, x);
+}
+
+// geometry.angle (protstruc/geometry.py:64-71); no clamp, exactly like the reference.
+__device__ __forceinline__ float angle3(V3 a, V3 b, V3 c) {
+    if (any_nan_coordinate(a, b, c)) return __int_as_float(0x7fc00000);
+    const V3 ba = sub3(a, b);
+    const V3 bc = sub3(c, b);
+    const float cosine = __fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc)));
+    return acosf(cosine);
+}
+
+// Virtual CB from N, CA, C (protstruc/geometry.py:217-221):
+//   b = CA - N, c = C - CA, a = b x c;  CB = -0.58273431 a + 0.56802827 b - 0.54067466 c + CA
+// evaluated left to right with separately rounded ops as the torch expression does.
+__device__ __forceinline__ V3 virtual_cb(V3 n, V3 ca, V3 c) {
+    const V3 vb = sub3(ca, n);
+    const V3 vc = sub3(c, ca);
+    const V3 va = cross3(vb, vc);
+    V3 r;
+    r.x = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.x), __fmul_rn(0.56802827f, vb.x)),
+                              __fmul_rn(0.54067466f, vc.x)), ca.x);
+    r.y = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.y), __fmul_rn(0.56802827f, vb.y)),
+                              __fmul_rn(0.54067466f, vc.y)), ca.y);
+    r.z = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(-0.58273431f, va.z), __fmul_rn(0.56802827f, vb.z)),
+                              __fmul_rn(0.54067466f, vc.z)), ca.z);
+    return r;
+}
+
+// ---------------------------------------------------------------- tuned trRosetta triple
+// omega / theta / phi of one residue pair for the two hot kernels (K2f and the fused K1).  Same
+// formulas and the same non-contracted cross / dot products as dihedral4 / angle3 above — so exact
+// cancellations (diagonal pairs, zero-padded residues) and NaN placement are unchanged — but the final
+// scalar steps use single-MUFU primitives refined to ~1 ulp instead of the IEEE division / sqrt /
+// libdevice atan2f sequences (which cost more than the geometry itself):
+//   * y = (m.b1) / |b1|  ->  (m.b1) * rsqrt(b1.b1), one Newton step on the MUFU.RSQ seed;
+//   * atan2 -> min/max quotient by MUFU.RCP + one Newton step, degree-15 odd minimax polynomial on
+//     [0, 1] (max error 7e-9 before rounding), octant fix-ups; zeros, infinities, NaN and out-of-range
+//     magnitudes fall back to atan2f, so atan2(+-0, -0) = +-pi etc. keep their IEEE values.
+// Measured deviation from the reference after this change: see profiles/*parity_report*.json.
 __device__ __forceinline__ bool atom_has_nan(V3 a) {
     const float probe = (a.x + a.y) + a.z;
     return (probe != probe) && has_nan3(a);

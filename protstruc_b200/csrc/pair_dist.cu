@@ -116,6 +116,10 @@ struct PairDistParams {
     // few contiguous fronts in HBM instead of ~900 scattered streams.
     long long chunk_members;  // C
     long long num_cells;      // S * ceil(M / C)
+    long long active_workers; // tile buffers that take part (<= gridDim.x * buffers per CTA)
+    int lockstep;             // 1: strips mapped 1:1 to workers (linear sweep of the output), see launch code
+    int stores_only;          // diagnostic: skip the arithmetic, only issue the tile stores (measures the
+                              // memory-system ceiling of this write pattern; output content is undefined)
 };
 
 // Gather the A mask bytes of one residue into a bit field (bit a = mask[a] != 0).
@@ -270,11 +274,13 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 
     // Work partition: the linear order u = (cell * C + step) over (chunk, strip) cells is cut into equal
     // contiguous ranges, one per tile buffer of the persistent grid (balanced to +-1 position).
-    const long long workers = static_cast<long long>(gridDim.x) * slots_per_cta;
-    const long long worker = static_cast<long long>(blockIdx.x) * slots_per_cta + slot;
+    const long long workers = p.active_workers;
+    // consecutive buffers of the grid sit on different SMs, so neighbouring strips are written by different SMs
+    const long long worker = static_cast<long long>(slot) * gridDim.x + blockIdx.x;
     const long long positions = p.num_cells * p.chunk_members;
     long long u = positions / workers * worker + (positions % workers) * worker / workers;
-    const long long u_end = positions / workers * (worker + 1) + (positions % workers) * (worker + 1) / workers;
+    long long u_end = positions / workers * (worker + 1) + (positions % workers) * (worker + 1) / workers;
+    if (worker >= workers) u = u_end = 0;
     long long cell = u / p.chunk_members;
     long long step = u - cell * p.chunk_members;
     long long strip = cell % p.strip_stride;
@@ -401,7 +407,9 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 
         float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
 
-        if (kNeedsXyz) {
+        if (p.stores_only) {
+            // diagnostic path: nothing is computed
+        } else if (kNeedsXyz) {
             // Rows (atoms a of residue i) are processed in groups of kRowsPerGroup; the staged coordinates
             // of the next group are read (broadcast LDS) before the current group is computed.
             constexpr int kRowsPerGroup = 3;
@@ -454,14 +462,14 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                 for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
             }
         }
-        if (does_mask) {
+        if (does_mask && !p.stores_only) {
             if (A == 15)
                 write_mask_block<15>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
             else
                 write_mask_block_bytes<A>(tile_u8, lane, mi_bits, mj_bits);
         }
 
-        if (does_angles) {
+        if (does_angles && !p.stores_only) {
             // trRosetta triple of this lane's pair, reference definitions
             // (protstruc/protstruc.py:810-815): real CB in slot 4.
             const V3 n_i{xi[0], xi[1], xi[2]}, ca_i{xi[3], xi[4], xi[5]}, cb_i{xi[12], xi[13], xi[14]};
@@ -598,11 +606,25 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     if (ctas > sms) ctas = sms;
     PairDistParams q = p;
     const long long workers = ctas * slots;
-    long long chunks_per_strip = (workers + q.strip_stride / 2) / q.strip_stride;  // ~ one cell per worker
-    if (chunks_per_strip < 1) chunks_per_strip = 1;
-    if (chunks_per_strip > q.strip_members) chunks_per_strip = q.strip_members;
-    q.chunk_members = (q.strip_members + chunks_per_strip - 1) / chunks_per_strip;
-    q.num_cells = q.strip_stride * ((q.strip_members + q.chunk_members - 1) / q.chunk_members);
+    q.active_workers = workers;
+    // Lockstep schedule: widen the strip stride to S' = S * floor(workers / S) (still a multiple of S, so
+    // residue j is still reused) and give every strip to one worker.  All workers then advance member by
+    // member together and the stores of the whole GPU sweep the output linearly, S' adjacent tiles at a time —
+    // the access pattern HBM likes best.  Used when at most 6 % of the workers would be left without a strip.
+    const long long wide = q.strip_stride * (workers / q.strip_stride);
+    if (q.lockstep && wide > 0 && (workers - wide) * 100 <= workers * 6 && q.num_tiles >= 4 * wide) {
+        q.strip_stride = wide;
+        q.strip_members = (q.num_tiles + wide - 1) / wide;
+        q.chunk_members = q.strip_members;
+        q.num_cells = wide;
+        q.active_workers = wide;
+    } else {
+        long long chunks_per_strip = (workers + q.strip_stride / 2) / q.strip_stride;  // ~ one cell per worker
+        if (chunks_per_strip < 1) chunks_per_strip = 1;
+        if (chunks_per_strip > q.strip_members) chunks_per_strip = q.strip_members;
+        q.chunk_members = (q.strip_members + chunks_per_strip - 1) / chunks_per_strip;
+        q.num_cells = q.strip_stride * ((q.strip_members + q.chunk_members - 1) / q.chunk_members);
+    }
     kernel<<<static_cast<unsigned>(ctas), slots * WPT * 32, smem, stream>>>(q);
     return check_launch("pair_tiles_kernel");
 }
@@ -699,6 +721,25 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
                           float* theta, float* phi, cudaStream_t stream);  // pair_angles.cu
 
+// Diagnostic: plain 128-bit stores of a non-uniform pattern, linear sweep (what a copy kernel's write side
+// does).  Gives the store ceiling of the memory system for comparison with the TMA bulk-store path.
+__global__ void __launch_bounds__(256) debug_fill_pattern_kernel(float4* __restrict__ out, long long n4) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float v = static_cast<float>(i & 0xFFFFF);
+        out[i] = make_float4(v, v + 0.25f, v + 0.5f, v + 0.75f);
+    }
+}
+
+int debug_fill_pattern_impl(float* out, long long n, int blocks_per_sm, cudaStream_t stream) {
+    PS_REQUIRE(out != nullptr && n > 0 && (n & 3) == 0, PS_ERR_BAD_SHAPE, "debug_fill_pattern: n=%lld", n);
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    if (blocks_per_sm < 1) blocks_per_sm = 8;
+    debug_fill_pattern_kernel<<<sms * blocks_per_sm, 256, 0, stream>>>(reinterpret_cast<float4*>(out), n / 4);
+    return check_launch("debug_fill_pattern_kernel");
+}
+
 // Host entry used by the C-ABI wrappers (cabi.cu).
 int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                         void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
@@ -754,6 +795,9 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.strip_members = (p.num_tiles + p.strip_stride - 1) / p.strip_stride;
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
+    p.stores_only = (variant >> 10) & 1;
+    p.lockstep = (variant >> 11) & 1;
+    p.active_workers = 0;
 
     switch (A) {
         case 5:

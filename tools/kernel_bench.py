@@ -79,6 +79,8 @@ def main():
     nbytes = B * (L * L * A * A * 5 + L * A * 13)
     variants = {"sqrt.approx.ftz (default)": 0, "sqrt.approx": 1, "sqrt.rn": 2, "generic kernel": 1 << 8}
     variants["1 warp per tile (6 warps/SM)"] = 1 << 9
+    variants["DIAGNOSTIC stores only (no arithmetic)"] = 1 << 10
+    variants["DIAGNOSTIC stores only, 6 tile buffers"] = (1 << 10) | (6 << 4)
     if not args.quick:
         for w in (3, 5, 6):
             variants[f"default, {w} tile buffers/CTA"] = w << 4
