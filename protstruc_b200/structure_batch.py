@@ -184,6 +184,12 @@ class StructureBatch:
         return cls(xyz, mask, _always_tensor(chain_idx), chain_ids, seq, _always_tensor(residue_idx), device=dev,
                    **kwargs)
 
+    @classmethod
+    def from_dihedrals(cls, dihedrals, chain_idx=None, chain_ids=None, **kwargs):
+        """Present for API compatibility: the reference's method is an unimplemented stub that returns None
+        (reference protstruc.py:321-339)."""
+        return None
+
     # ------------------------------------------------------------------------------------- getters
     def get_batch_size(self) -> int:
         return self.batch_size

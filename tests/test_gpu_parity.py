@@ -739,3 +739,40 @@ def test_staged_kernels_for_other_atom_counts(native_lib, B, L, A):
     assert torch.equal(results[0][1], results[1][1])
     H.assert_distances_close(results[0][0].view(B, L, L, A, A), rd)
     assert torch.equal(results[0][1].view(torch.bool).view(B, L, L, A, A).cpu(), rm)
+
+
+def test_randomised_shapes_against_the_oracle(native_lib):
+    """Seeded sweep over odd shapes (tail tiles, L around the 32-pair tile size, every staged atom count and the
+    generic path, bool and float masks, ragged lengths): every feature family vs the CPU oracle."""
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 31, 15), (1, 32, 15), (2, 34, 15), (3, 63, 15), (2, 65, 15), (1, 96, 15), (4, 50, 5), (2, 41, 10),
+              (1, 77, 14), (2, 20, 15), (3, 9, 7), (1, 36, 12)]
+    for idx, (B, L, A) in enumerate(shapes):
+        kind = "float" if idx % 3 == 2 else "bool"
+        xyz, mask, chain_idx = H.synthetic_batch(int(rng.integers(1 << 30)), B, L, A, kind)
+        ids = [["A", "B"]] * B
+        sb = ps.StructureBatch.from_xyz(xyz, mask, chain_idx, ids)
+        tag = f"B={B} L={L} A={A} {kind}"
+        dist, dist_mask = sb.pairwise_distance_matrix()
+        rd, rm = orc.pair_distances(xyz, mask)
+        H.assert_distances_close(dist, rd, f"dist {tag}")
+        assert dist_mask.dtype == rm.dtype and torch.equal(dist_mask.cpu(), rm), tag
+        if A >= 5:
+            out = sb.inter_residue_geometry()
+            ro, rt, rp = orc.trrosetta_angles(xyz)
+            H.assert_angles_close(out["omega"], ro, angle_conditioning(xyz, "omega"), f"omega {tag}", all_finite_tol=2e-6)
+            H.assert_angles_close(out["theta"], rt, angle_conditioning(xyz, "theta"), f"theta {tag}", all_finite_tol=2e-6)
+            H.assert_angles_close(out["phi"], rp, angle_conditioning(xyz, "phi"), f"phi {tag}", circular=False)
+            H.assert_distances_close(out["d_cb"], rd[:, :, :, 4, 4], f"d_cb {tag}")
+        dih, dmask = sb.backbone_dihedrals()
+        rdi, rdm = orc.backbone_dihedrals(xyz, chain_idx, mask.bool().any(-1))
+        assert torch.equal(dmask.cpu(), rdm), tag
+        H.assert_same_nan(dih, rdi, f"dihedrals {tag}")
+        assert H.circular_diff(torch.nan_to_num(dih.cpu()), torch.nan_to_num(rdi)).max().item() <= 2e-6, tag
+        com = sb.center_of_mass()
+        assert torch.allclose(com.cpu(), orc.center_of_mass(xyz), rtol=1e-5, atol=1e-4, equal_nan=True), tag
+        sb.standardize()
+        rx, mu, sd = orc.standardize_per_structure(xyz, mask)
+        assert torch.allclose(sb.mu.cpu(), mu, rtol=1e-5, atol=1e-5, equal_nan=True), tag
+        assert torch.allclose(sb.std.cpu(), sd, rtol=1e-5, atol=1e-6, equal_nan=True), tag
+        assert torch.allclose(sb.get_xyz().cpu(), rx, rtol=1e-4, atol=1e-5, equal_nan=True), tag
