@@ -188,6 +188,12 @@ __device__ __forceinline__ bool atom_has_nan(V3 a) {
     return (probe != probe) && has_nan3(a);
 }
 
+// Note on packed arithmetic: evaluating two pairs per thread on the FADD2 / FMUL2 pipe would halve the issue
+// slots of the cross / dot products, but ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
+// explicit .rn modifiers and with -fmad=false (checked on sm_100a), which breaks the exact cancellations the
+// reference relies on (a x a = 0 on the diagonal).  The geometry therefore stays on scalar, individually
+// rounded operations.
+//
 // Everything of the triple that depends on residue i only (hoisted out of the j loop by K2f).
 struct TripleRowSide {
     V3 cb;        // CB_i
