@@ -45,7 +45,14 @@ namespace ps {
 
 namespace {
 
-constexpr int kTilePairs = 32;  // pairs per tile (= lanes)
+constexpr int kTilePairs = 32;  // pairs per tile per pass over the lanes (tile = 32 * Q pairs)
+
+// Pairs per lane.  With few atoms per residue a 32-pair tile is only a few KB and the per-tile bookkeeping
+// dominates, so small residues take several pairs per lane (lane l owns pairs l, l + 32, ... of the tile).
+template <int A>
+__host__ __device__ constexpr int pairs_per_lane() {
+    return A <= 6 ? 4 : (A <= 10 ? 2 : 1);
+}
 constexpr int kDefaultWarpsPerTile = 2;  // see pair_tiles_kernel; variant bit 9 selects the other value
 
 // Default is the single-instruction MUFU.SQRT (sqrt.approx.ftz.f32): relative error <= 2^-23, sqrt(0) = 0,
@@ -79,8 +86,9 @@ enum OutKind {
 
 template <int A>
 struct TileGeom {
+    static constexpr int kPairs = kTilePairs * pairs_per_lane<A>();
     static constexpr int kElemsPerPair = A * A;
-    static constexpr int kTileElems = kTilePairs * A * A;
+    static constexpr int kTileElems = kPairs * A * A;
     static constexpr int kDistBytes = kTileElems * 4;
     static constexpr int kMaskBytes = kTileElems;
     static_assert(kDistBytes % 16 == 0 && kMaskBytes % 16 == 0, "tile must be 16-B granular");
@@ -249,6 +257,7 @@ __host__ __device__ constexpr int stage_bytes_per_warp() {
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_tiles_kernel(const PairDistParams p) {
     using G = TileGeom<A>;
+    constexpr int Q = pairs_per_lane<A>();
     static_assert(A >= 1 && 2 * A <= 32, "the mask ballot holds two residues of at most 16 atoms");
     constexpr int kStageFloats = stage_floats<A>();
     constexpr int kStageRows = kStageFloats / 32;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     };
     // first residue-i row a tile touches
     auto first_row_of = [&](long long t) -> long long {
-        const long long first_pair = t * kTilePairs;
+        const long long first_pair = t * G::kPairs;
         if (p.num_pairs <= 0xFFFFFFFFll) return static_cast<unsigned>(first_pair) / static_cast<unsigned>(p.L);
         return first_pair / p.L;
     };
@@ -345,11 +354,16 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
         }
     };
 
-    // Residue j of this lane: A atoms in registers, SoA, packed two atoms per 64-bit register pair.
-    float2 xj[NP], yj[NP], zj[NP];
-    float mjf[A];  // fp32 mask row (kF32MaskOnly)
-    uint32_t mj_bits = 0;
-    long long loaded_res_j = -1;
+    // Residue j of each of this lane's Q pairs: A atoms in registers, SoA, packed two atoms per 64-bit pair.
+    float2 xj[Q][NP], yj[Q][NP], zj[Q][NP];
+    float mjf[Q][A];  // fp32 mask row (kF32MaskOnly)
+    uint32_t mj_bits[Q];
+    long long loaded_res_j[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        mj_bits[q] = 0;
+        loaded_res_j[q] = -1;
+    }
 
     long long tile = next_tile();
     int parity = 0;
@@ -365,59 +379,84 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
         if (upcoming >= 0) prefetch_issue(upcoming);  // consumed after this tile's rows
 
         const float* __restrict__ xi_stage = stage + parity * kStageFloats;
-        const long long pair0 = tile * kTilePairs;
-        long long pair = pair0 + lane;
-        if (pair >= p.num_pairs) pair = p.num_pairs - 1;  // tail lanes recompute the last pair
-        // pair -> (row = b*L + i, j); 32-bit division whenever the pair count allows it
-        unsigned row, j;
-        if (p.num_pairs <= 0xFFFFFFFFll) {
-            const unsigned pr = static_cast<unsigned>(pair);
-            row = pr / static_cast<unsigned>(p.L);
-            j = pr - row * static_cast<unsigned>(p.L);
-        } else {
-            row = static_cast<unsigned>(pair / p.L);
-            j = static_cast<unsigned>(pair - static_cast<long long>(row) * p.L);
+        const long long pair0 = tile * G::kPairs;
+        // lane l owns pairs pair0 + l + 32 q; pair -> (row = b*L + i, j) with one division, the others follow
+        long long pair[Q];
+        unsigned row[Q];
+        long long res_j[Q];
+        int which[Q];  // 0 or 1: which of the two staged residues the pair uses (lane 0, q 0 holds the first row)
+        {
+            long long p0 = pair0 + lane;
+            if (p0 >= p.num_pairs) p0 = p.num_pairs - 1;  // tail lanes recompute the last pair
+            unsigned r0, j0;
+            if (p.num_pairs <= 0xFFFFFFFFll) {  // 32-bit division whenever the pair count allows it
+                const unsigned pr = static_cast<unsigned>(p0);
+                r0 = pr / static_cast<unsigned>(p.L);
+                j0 = pr - r0 * static_cast<unsigned>(p.L);
+            } else {
+                r0 = static_cast<unsigned>(p0 / p.L);
+                j0 = static_cast<unsigned>(p0 - static_cast<long long>(r0) * p.L);
+            }
+            const unsigned first_row = __shfl_sync(0xffffffffu, r0, 0);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                long long pq = pair0 + lane + kTilePairs * q;
+                unsigned rq = r0, jq = j0 + kTilePairs * q;
+                if (jq >= static_cast<unsigned>(p.L)) {  // L >= 32 Q: at most one wrap inside a tile
+                    jq -= p.L;
+                    ++rq;
+                }
+                if (pq >= p.num_pairs) {
+                    pq = p.num_pairs - 1;
+                    rq = static_cast<unsigned>(p.num_rows - 1);
+                    jq = p.L - 1;
+                }
+                pair[q] = pq;
+                row[q] = rq;
+                res_j[q] = static_cast<long long>(rq - rq % static_cast<unsigned>(p.L)) + jq;
+                which[q] = static_cast<int>(rq - first_row);
+            }
         }
-        const unsigned i = row % static_cast<unsigned>(p.L);
-        const long long res_i = row;
-        const long long res_j = static_cast<long long>(row - i) + j;
-        // 0 or 1: which of the two staged residues this lane's pair uses (lane 0 holds the first row)
-        const int which = static_cast<int>(row - __shfl_sync(0xffffffffu, row, 0));
-        const float* __restrict__ xi = xi_stage + which * (A * 3);
-        const float* __restrict__ xj_ptr = p.xyz + res_j * (A * 3);
 
         // Reload residue j only when the strip (or the structure) changed; warp-uniform decision.
-        if (!__all_sync(0xffffffffu, res_j == loaded_res_j)) {
-            loaded_res_j = res_j;
-            if (kNeedsXyz) {
+        bool same_j = true;
 #pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                    const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
-                    xj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 0), __ldg(xj_ptr + 3 * c1 + 0));
-                    yj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 1), __ldg(xj_ptr + 3 * c1 + 1));
-                    zj[k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
+        for (int q = 0; q < Q; ++q) same_j = same_j && (res_j[q] == loaded_res_j[q]);
+        if (!__all_sync(0xffffffffu, same_j)) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                loaded_res_j[q] = res_j[q];
+                const float* __restrict__ xj_ptr = p.xyz + res_j[q] * (A * 3);
+                if (kNeedsXyz) {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const int c0 = 2 * k, c1 = (2 * k + 1 < A) ? 2 * k + 1 : 2 * k;
+                        xj[q][k] = make_float2(__ldg(xj_ptr + 3 * c0 + 0), __ldg(xj_ptr + 3 * c1 + 0));
+                        yj[q][k] = make_float2(__ldg(xj_ptr + 3 * c0 + 1), __ldg(xj_ptr + 3 * c1 + 1));
+                        zj[q][k] = make_float2(__ldg(xj_ptr + 3 * c0 + 2), __ldg(xj_ptr + 3 * c1 + 2));
+                    }
+                }
+                if (does_mask)
+                    mj_bits[q] = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_j[q] * A);
+                if (KIND == kF32MaskOnly) {
+                    const float* am = static_cast<const float*>(p.atom_mask);
+#pragma unroll
+                    for (int c = 0; c < A; ++c) mjf[q][c] = __ldg(am + res_j[q] * A + c);
                 }
             }
-            if (does_mask) mj_bits = load_mask_bits<A>(static_cast<const uint8_t*>(p.atom_mask) + res_j * A);
-            if (KIND == kF32MaskOnly) {
-                const float* am = static_cast<const float*>(p.atom_mask);
-#pragma unroll
-                for (int c = 0; c < A; ++c) mjf[c] = __ldg(am + res_j * A + c);
-            }
         }
-        const uint32_t mi_bits = (mask_ballot >> (which * A)) & ((1u << A) - 1u);
 
         // The previous tile of this buffer must have left shared memory before it is overwritten.
         if (is_issuer) bulk_wait_read_all();
         tile_sync<WPT>(slot);
 
-        float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
-
         if (p.stores_only) {
             // diagnostic path: nothing is computed
-        } else if (kNeedsXyz) {
+        } else if (kNeedsXyz && Q == 1) {
             // Rows (atoms a of residue i) are processed in groups of kRowsPerGroup; the staged coordinates
             // of the next group are read (broadcast LDS) before the current group is computed.
+            const float* __restrict__ xi = xi_stage + which[0] * (A * 3);
+            float* my_f32 = tile_f32 + lane * G::kElemsPerPair;
             constexpr int kRowsPerGroup = 3;
             float cur[kRowsPerGroup][3], nxt[kRowsPerGroup][3];
 #pragma unroll
@@ -443,9 +482,9 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                         float* out_row = my_f32 + a * A;
 #pragma unroll
                         for (int k = 0; k < NP; ++k) {
-                            const float2 dx = __fadd2_rn(xj[k], nx);
-                            const float2 dy = __fadd2_rn(yj[k], ny);
-                            const float2 dz = __fadd2_rn(zj[k], nz);
+                            const float2 dx = __fadd2_rn(xj[0][k], nx);
+                            const float2 dy = __fadd2_rn(yj[0][k], ny);
+                            const float2 dz = __fadd2_rn(zj[0][k], nz);
                             float2 s = __fmul2_rn(dx, dx);
                             s = __ffma2_rn(dy, dy, s);
                             s = __ffma2_rn(dz, dz, s);
@@ -459,35 +498,72 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
 #pragma unroll
                     for (int k = 0; k < 3; ++k) cur[r][k] = nxt[r][k];
             }
+        } else if (kNeedsXyz) {
+            // several pairs per lane (small residues): the Q independent pairs provide the instruction-level
+            // parallelism, so the rows are read straight from the staging area
+#pragma unroll 1
+            for (int a = row_begin; a < row_end; ++a) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float* __restrict__ xi = xi_stage + which[q] * (A * 3) + 3 * a;
+                    const float2 nx = make_float2(-xi[0], -xi[0]);
+                    const float2 ny = make_float2(-xi[1], -xi[1]);
+                    const float2 nz = make_float2(-xi[2], -xi[2]);
+                    float* out_row = tile_f32 + (lane + kTilePairs * q) * G::kElemsPerPair + a * A;
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float2 dx = __fadd2_rn(xj[q][k], nx);
+                        const float2 dy = __fadd2_rn(yj[q][k], ny);
+                        const float2 dz = __fadd2_rn(zj[q][k], nz);
+                        float2 s = __fmul2_rn(dx, dx);
+                        s = __ffma2_rn(dy, dy, s);
+                        s = __ffma2_rn(dz, dz, s);
+                        out_row[2 * k] = sqrt_mode<SQRT>(s.x);
+                        if (2 * k + 1 < A) out_row[2 * k + 1] = sqrt_mode<SQRT>(s.y);
+                    }
+                }
+            }
         } else if (KIND == kF32MaskOnly) {
             const float* am = static_cast<const float*>(p.atom_mask);
 #pragma unroll 1
             for (int a = row_begin; a < row_end; ++a) {
-                const float mi = __ldg(am + res_i * A + a);
 #pragma unroll
-                for (int c = 0; c < A; ++c) my_f32[a * A + c] = __fmul_rn(mi, mjf[c]);
+                for (int q = 0; q < Q; ++q) {
+                    const float mi = __ldg(am + static_cast<long long>(row[q]) * A + a);
+                    float* out_row = tile_f32 + (lane + kTilePairs * q) * G::kElemsPerPair + a * A;
+#pragma unroll
+                    for (int c = 0; c < A; ++c) out_row[c] = __fmul_rn(mi, mjf[q][c]);
+                }
             }
         }
         if (does_mask && !p.stores_only) {
-            if (A == 15)
-                write_mask_block<15>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits);
-            else
-                write_mask_block_bytes<A>(tile_u8, lane, mi_bits, mj_bits);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const uint32_t mi_bits = (mask_ballot >> (which[q] * A)) & ((1u << A) - 1u);
+                if (A == 15)
+                    write_mask_block<15>(reinterpret_cast<uint32_t*>(tile_u8), lane, mi_bits, mj_bits[q]);
+                else
+                    write_mask_block_bytes<A>(tile_u8, lane + kTilePairs * q, mi_bits, mj_bits[q]);
+            }
         }
 
         if (does_angles && !p.stores_only) {
-            // trRosetta triple of this lane's pair, reference definitions
+            // trRosetta triple of this lane's pairs, reference definitions
             // (protstruc/protstruc.py:810-815): real CB in slot 4.
-            const V3 n_i{xi[0], xi[1], xi[2]}, ca_i{xi[3], xi[4], xi[5]}, cb_i{xi[12], xi[13], xi[14]};
-            const V3 ca_j{xj[0].y, yj[0].y, zj[0].y};  // atom 1 = second half of pack 0
-            const V3 cb_j{xj[2].x, yj[2].x, zj[2].x};  // atom 4 = first half of pack 2
-            if (pair0 + lane < p.num_pairs) {
-                float w, t, f;
-                trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, p.omega != nullptr,
-                                 p.theta != nullptr, p.phi != nullptr, w, t, f);
-                if (p.omega) p.omega[pair] = w;
-                if (p.theta) p.theta[pair] = t;
-                if (p.phi) p.phi[pair] = f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float* __restrict__ xi = xi_stage + which[q] * (A * 3);
+                const V3 n_i{xi[0], xi[1], xi[2]}, ca_i{xi[3], xi[4], xi[5]}, cb_i{xi[12], xi[13], xi[14]};
+                const V3 ca_j{xj[q][0].y, yj[q][0].y, zj[q][0].y};  // atom 1 = second half of pack 0
+                const V3 cb_j{xj[q][2].x, yj[q][2].x, zj[q][2].x};  // atom 4 = first half of pack 2
+                if (pair0 + lane + kTilePairs * q < p.num_pairs) {
+                    float w, t, f;
+                    trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, p.omega != nullptr,
+                                     p.theta != nullptr, p.phi != nullptr, w, t, f);
+                    if (p.omega) p.omega[pair[q]] = w;
+                    if (p.theta) p.theta[pair[q]] = t;
+                    if (p.phi) p.phi[pair[q]] = f;
+                }
             }
         }
 
@@ -495,7 +571,7 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
         if (upcoming >= 0) prefetch_commit(stage + (parity ^ 1) * kStageFloats);
 
         const long long elem0 = pair0 * G::kElemsPerPair;
-        if (pair0 + kTilePairs <= p.num_pairs) {
+        if (pair0 + G::kPairs <= p.num_pairs) {
             // Full tile: hand it to the TMA engine.
             fence_proxy_async_smem();
             tile_sync<WPT>(slot);
@@ -770,9 +846,10 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     const bool force_generic = (variant >> 8) & 1;
     const int wpt = ((variant >> 9) & 1) ? (3 - kDefaultWarpsPerTile) : kDefaultWarpsPerTile;
 
-    // the staged kernel needs L >= 32 (a tile of 32 pairs then touches at most two residue-i rows)
+    // the staged kernel needs L >= pairs per tile (a tile then touches at most two residue-i rows)
     const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14);
-    const bool fast = staged_atom_count && (L >= kTilePairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
+    const int tile_pairs = kTilePairs * (A <= 6 ? 4 : (A <= 10 ? 2 : 1));  // = TileGeom<A>::kPairs
+    const bool fast = staged_atom_count && (L >= tile_pairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
         int rc = launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
         if (rc != PS_OK || !want_angles) return rc;
@@ -790,8 +867,8 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.L = L;
     p.num_rows = static_cast<long long>(L) * B;
     p.num_pairs = static_cast<long long>(L) * L * B;
-    p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
-    int g = L, h = kTilePairs;  // gcd(L, 32)
+    p.num_tiles = (p.num_pairs + tile_pairs - 1) / tile_pairs;
+    int g = L, h = tile_pairs;  // gcd(L, pairs per tile)
     while (h != 0) {
         const int r = g % h;
         g = h;

@@ -17,7 +17,7 @@ namespace ps {
 
 namespace {
 
-constexpr int kStatsThreads = 512;
+constexpr int kStatsMaxThreads = 512;
 
 // torch.nan_to_num(x, nan=0.0): NaN -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX.
 __device__ __forceinline__ float nan_to_num0(float v) {
@@ -59,10 +59,10 @@ __device__ __forceinline__ float mask_value(const void* __restrict__ m, long lon
 }
 
 template <int MASK_DTYPE>
-__global__ void __launch_bounds__(kStatsThreads) masked_stats_kernel(
+__global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
     float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
-    __shared__ double scratch[kStatsThreads / 32][4];
+    __shared__ double scratch[kStatsMaxThreads / 32][4];
     const long long b = blockIdx.x;
     const float* __restrict__ x = xyz + b * atoms_per_struct * 3;
     const long long m0 = b * atoms_per_struct;
@@ -199,12 +199,15 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
     PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
                "masked_stats: structure too large (L*A*3 >= 2^31)");
     const int atoms = L * A;
+    // one CTA per structure; ~8 atoms per thread keeps the three block-wide reductions cheap relative to the
+    // streaming work while many CTAs stay resident per SM for small structures
+    int threads = ((atoms + 7) / 8 + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > kStatsMaxThreads) threads = kStatsMaxThreads;
     if (mask_dtype == PS_MASK_BOOL)
-        masked_stats_kernel<PS_MASK_BOOL><<<B, kStatsThreads, 0, stream>>>(xyz, atom_mask, atoms, mu,
-                                                                           sd, xyz_out);
+        masked_stats_kernel<PS_MASK_BOOL><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
     else if (mask_dtype == PS_MASK_F32)
-        masked_stats_kernel<PS_MASK_F32><<<B, kStatsThreads, 0, stream>>>(xyz, atom_mask, atoms, mu,
-                                                                          sd, xyz_out);
+        masked_stats_kernel<PS_MASK_F32><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
     else {
         set_error("masked_stats: unknown mask_dtype %d", mask_dtype);
         return PS_ERR_BAD_DTYPE;

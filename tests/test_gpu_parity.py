@@ -76,7 +76,9 @@ def test_pairwise_distance_matrix_real_structure(native_lib):
 @pytest.mark.parametrize("B,L,A,kind", [(3, 37, 15, "bool"), (1, 1, 15, "bool"), (2, 2, 15, "float"),
                                         (1, 130, 15, "bool"), (2, 19, 10, "bool"), (1, 6, 37, "float"),
                                         (5, 16, 15, "bool"), (2, 40, 5, "bool"), (2, 33, 10, "float"),
-                                        (1, 64, 14, "bool"), (3, 35, 5, "float"), (2, 32, 16, "bool")])
+                                        (1, 64, 14, "bool"), (3, 35, 5, "float"), (2, 32, 16, "bool"),
+                                        (2, 128, 5, "bool"), (1, 131, 5, "float"), (1, 64, 10, "bool"),
+                                        (2, 67, 10, "float"), (3, 150, 5, "bool")])
 def test_pairwise_distance_matrix_vs_oracle(native_lib, B, L, A, kind):
     xyz, mask, chain_idx = H.synthetic_batch(100 + L, B, L, A, kind)
     sb = ps.StructureBatch.from_xyz(xyz, mask)
@@ -707,7 +709,7 @@ def test_fused_kernel_never_writes_outside_its_outputs(native_lib, B, L):
         assert torch.equal(torch.nan_to_num(got, nan=-3.0), torch.nan_to_num(ref[k], nan=-3.0)), k
 
 
-@pytest.mark.parametrize("B,L,A", [(2, 48, 5), (1, 37, 14), (2, 33, 10)])
+@pytest.mark.parametrize("B,L,A", [(2, 48, 5), (1, 37, 14), (2, 33, 10), (2, 140, 5), (1, 129, 5), (2, 70, 10)])
 def test_staged_kernels_for_other_atom_counts(native_lib, B, L, A):
     """A = 5 (backbone + CB), 10 and 14 (atom14) run the staged TMA-store kernel too: fused features vs the oracle,
     bit-identical to the generic kernel, guard bands intact."""
@@ -746,7 +748,7 @@ def test_randomised_shapes_against_the_oracle(native_lib):
     generic path, bool and float masks, ragged lengths): every feature family vs the CPU oracle."""
     rng = np.random.default_rng(2024)
     shapes = [(1, 31, 15), (1, 32, 15), (2, 34, 15), (3, 63, 15), (2, 65, 15), (1, 96, 15), (4, 50, 5), (2, 41, 10),
-              (1, 77, 14), (2, 20, 15), (3, 9, 7), (1, 36, 12)]
+              (1, 77, 14), (2, 20, 15), (3, 9, 7), (1, 36, 12), (2, 127, 5), (2, 133, 5), (3, 66, 10), (1, 200, 5)]
     for idx, (B, L, A) in enumerate(shapes):
         kind = "float" if idx % 3 == 2 else "bool"
         xyz, mask, chain_idx = H.synthetic_batch(int(rng.integers(1 << 30)), B, L, A, kind)
