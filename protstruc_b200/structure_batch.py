@@ -203,8 +203,10 @@ class StructureBatch:
     def get_local_xyz(self) -> torch.Tensor:
         """Coordinates of every atom in its residue's backbone frame: R^T x minus the residue's (global)
         CA, exactly the expression of the reference (protstruc.py:347-362).  (B, L, A, 3)."""
-        lib = self._lib()
         B, L, A = self._dims()
+        if self._is_empty():
+            return torch.empty_like(self.xyz)
+        lib = self._lib()
         if A <= int(ATOM.C):
             raise IndexError(f"index {int(ATOM.C)} is out of bounds for dimension 2 with size {A}")
         out = torch.empty_like(self.xyz)
@@ -269,6 +271,10 @@ class StructureBatch:
             )
         return _cabi.load()
 
+    def _is_empty(self) -> bool:
+        """No structures or no residues: every feature is an empty tensor and nothing is launched."""
+        return self.batch_size == 0 or self.n_residues == 0 or self.max_n_atoms_per_residue == 0
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.xyz.device).cuda_stream
 
@@ -287,11 +293,14 @@ class StructureBatch:
 
         Returns `dist` (B, L, L, A, A) fp32 — NOT masked, NaN coordinates give NaN distances — and
         `dist_mask` of the same shape and of `atom_mask`'s dtype (bool stays bool)."""
-        lib = self._lib()
         if self.atom_mask is None:
             raise TypeError("'NoneType' object is not subscriptable (pairwise_distance_matrix needs atom_mask)")
         B, L, A = self._dims()
         dev = self.xyz.device
+        if self._is_empty():
+            return (torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev),
+                    torch.empty(B, L, L, A, A, dtype=self.atom_mask.dtype, device=dev))
+        lib = self._lib()
         mask, code = self._mask_for_kernel(self.atom_mask)
         dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
         dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
@@ -313,12 +322,14 @@ class StructureBatch:
         si, sj = self._slots(atoms_i, atoms_j)
         if len(si) + len(sj) != need:
             raise ValueError(f"expected {need} atoms in total, got {len(si)} + {len(sj)}")
-        lib = self._lib()
         B, L, A = self._dims()
+        out = torch.empty(B, L, L, dtype=torch.float32, device=self.xyz.device)
+        if self._is_empty():
+            return out
+        lib = self._lib()
         for s in si + sj:
             if s >= A:
                 raise IndexError(f"index {s} is out of bounds for dimension 2 with size {A}")
-        out = torch.empty(B, L, L, dtype=torch.float32, device=self.xyz.device)
         with torch.cuda.device(self.xyz.device):
             rc = lib.ps_pair_angles(self.xyz.data_ptr(), B, L, A, _cabi.int_array(si), len(si),
                                     _cabi.int_array(sj), len(sj), kind, out.data_ptr(), self._stream())
@@ -339,12 +350,14 @@ class StructureBatch:
         """omega, theta, phi exactly as inter_residue_geometry defines them, in one pass
         (reference protstruc.py:810-815).  `virtual_cb=True` recomputes CB from N, CA, C with the
         ideal-geometry coefficients (reference geometry.py:217-221) instead of reading slot 4."""
-        lib = self._lib()
         B, L, A = self._dims()
         dev = self.xyz.device
         omega = torch.empty(B, L, L, dtype=torch.float32, device=dev)
         theta = torch.empty_like(omega)
         phi = torch.empty_like(omega)
+        if self._is_empty():
+            return omega, theta, phi
+        lib = self._lib()
         with torch.cuda.device(dev):
             rc = lib.ps_trrosetta_angles(self.xyz.data_ptr(), B, L, A, int(bool(virtual_cb)),
                                          omega.data_ptr(), theta.data_ptr(), phi.data_ptr(), self._stream())
@@ -355,10 +368,16 @@ class StructureBatch:
         """trRosetta-style inter-residue geometry (reference protstruc.py:790-817): d_ca, d_cb, d_no
         (strided views of the full distance tensor, with masks) and omega / theta / phi, produced by
         ONE fused kernel launch."""
-        lib = self._lib()
         if self.atom_mask is None:
             raise TypeError("'NoneType' object is not subscriptable (inter_residue_geometry needs atom_mask)")
         B, L, A = self._dims()
+        if self._is_empty():
+            e = lambda dt: torch.empty(B, L, L, dtype=dt, device=self.xyz.device)  # noqa: E731
+            md = self.atom_mask.dtype
+            return {"d_ca": e(torch.float32), "d_ca_mask": e(md), "d_cb": e(torch.float32), "d_cb_mask": e(md),
+                    "d_no": e(torch.float32), "d_no_mask": e(md), "omega": e(torch.float32),
+                    "theta": e(torch.float32), "phi": e(torch.float32)}
+        lib = self._lib()
         if A <= int(ATOM.CB):
             raise IndexError(f"index {int(ATOM.CB)} is out of bounds for dimension 2 with size {A}")
         dev = self.xyz.device
@@ -388,9 +407,13 @@ class StructureBatch:
         return ret
 
     def _backbone(self, want_dihedrals: bool, frame_slots: Optional[Tuple[int, int, int]]):
-        lib = self._lib()
         B, L, A = self._dims()
         dev = self.xyz.device
+        if self._is_empty():
+            return (torch.empty(B, L, 3, dtype=torch.float32, device=dev) if want_dihedrals else None,
+                    torch.empty(B, L, 3, dtype=torch.bool, device=dev) if want_dihedrals else None,
+                    torch.empty(B, L, 3, 3, dtype=torch.float32, device=dev) if frame_slots is not None else None)
+        lib = self._lib()
         dihedrals = dihedral_mask = frames = None
         rm_ptr = ch_ptr = dh_ptr = dm_ptr = fr_ptr = None
         keep = []
@@ -525,8 +548,10 @@ class StructureBatch:
     def center_of_mass(self) -> torch.Tensor:
         """NaN-skipping mean of the CA coordinates over ALL residues, (B, 3); not mask-aware, like
         the reference (protstruc.py:746-757)."""
-        lib = self._lib()
         B, L, A = self._dims()
+        if self._is_empty():  # nanmean over nothing
+            return torch.full((B, 3), float("nan"), dtype=torch.float32, device=self.xyz.device)
+        lib = self._lib()
         if A <= int(ATOM.CA):
             raise IndexError(f"index {int(ATOM.CA)} is out of bounds for dimension 2 with size {A}")
         out = torch.empty(B, 3, dtype=torch.float32, device=self.xyz.device)

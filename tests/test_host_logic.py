@@ -229,3 +229,21 @@ def test_native_pdb_ingest_matches_the_python_restatement_on_the_reference_files
     g = H.load_golden("real_1a6v_HL")
     one = ps.StructureBatch.from_pdb("/root/reference/tests/1a6v_HL.pdb", device="cpu")
     assert np.array_equal(one.get_atom_mask().numpy(), g["atom_mask"])
+
+
+def test_empty_batches_give_empty_features_without_a_launch():
+    """No structures / no residues: shapes and dtypes of the reference's (empty) results, nothing is launched,
+    so this works without a GPU."""
+    for B, L in ((0, 10), (3, 0)):
+        sb = ps.StructureBatch.from_xyz(torch.zeros(B, L, 15, 3), torch.zeros(B, L, 15, dtype=torch.bool), device="cpu")
+        dist, dist_mask = sb.pairwise_distance_matrix()
+        assert tuple(dist.shape) == (B, L, L, 15, 15) and dist.dtype == torch.float32 and dist_mask.dtype == torch.bool
+        feats = sb.inter_residue_geometry()
+        assert tuple(feats["omega"].shape) == (B, L, L) and feats["d_ca_mask"].dtype == torch.bool
+        dih, dmask = sb.backbone_dihedrals()
+        assert tuple(dih.shape) == (B, L, 3) and dmask.dtype == torch.bool
+        assert tuple(sb.backbone_orientations().shape) == (B, L, 3, 3)
+        assert tuple(sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"]).shape) == (B, L, L)
+        assert tuple(sb.get_local_xyz().shape) == (B, L, 15, 3)
+        com = sb.center_of_mass()
+        assert tuple(com.shape) == (B, 3) and bool(torch.isnan(com).all())
