@@ -778,3 +778,49 @@ def test_randomised_shapes_against_the_oracle(native_lib):
         assert torch.allclose(sb.mu.cpu(), mu, rtol=1e-5, atol=1e-5, equal_nan=True), tag
         assert torch.allclose(sb.std.cpu(), sd, rtol=1e-5, atol=1e-6, equal_nan=True), tag
         assert torch.allclose(sb.get_xyz().cpu(), rx, rtol=1e-4, atol=1e-5, equal_nan=True), tag
+
+
+def test_exact_symmetries_at_baseline_config3_size(native_lib):
+    """BASELINE config 3 at full size (256 x 512 backbone slots, 67 M pairs): properties that hold bit for bit.
+    Mirroring x negates every cross product exactly, so dihedrals change sign and planar angles / distances do not;
+    reversing the residue order permutes the pair axes."""
+    B, L, A = 256, 512, 5
+    g = torch.Generator(device=DEV).manual_seed(3)
+    xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
+    mask = torch.ones(B, L, A, dtype=torch.bool, device=DEV)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    omega, theta, phi = sb.trrosetta_angles()
+    assert bool(torch.isfinite(omega).all()) and bool((omega.abs() <= math.pi).all())
+    assert bool((phi[~torch.isnan(phi)] >= 0).all()) and bool((phi[~torch.isnan(phi)] <= math.pi).all())
+    eye = torch.eye(L, dtype=torch.bool, device=DEV)
+    assert bool((omega[:, eye] == 0).all()) and bool((theta[:, eye] == 0).all()) and bool(torch.isnan(phi[:, eye]).all())
+    mirrored = xyz * torch.tensor([-1.0, 1.0, 1.0], device=DEV)
+    mo, mt, mp = ps.StructureBatch.from_xyz(mirrored, mask).trrosetta_angles()
+    assert torch.equal(mo, -omega) and torch.equal(mt, -theta)
+    assert torch.equal(torch.nan_to_num(mp, nan=-1.0), torch.nan_to_num(phi, nan=-1.0))
+    flipped = torch.flip(xyz, dims=[1])
+    fo, ft, fp = ps.StructureBatch.from_xyz(flipped, mask).trrosetta_angles()
+    assert torch.equal(torch.flip(fo, dims=[1, 2]), omega) and torch.equal(torch.flip(ft, dims=[1, 2]), theta)
+    assert torch.equal(torch.nan_to_num(torch.flip(fp, dims=[1, 2]), nan=-1.0), torch.nan_to_num(phi, nan=-1.0))
+    # the generic single-feature kernels agree with the fused one (a few ulp) at this size as well
+    go = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
+    assert H.circular_diff(go[:8].cpu(), omega[:8].cpu()).max().item() <= 1e-6
+    del mo, mt, mp, fo, ft, fp, go
+
+
+def test_exact_symmetries_of_the_distance_tensor_under_mirror_and_reversal(native_lib):
+    B, L, A = 8, 256, 15
+    g = torch.Generator(device=DEV).manual_seed(22)
+    xyz = 10.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)
+    mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
+    d, m = ps.StructureBatch.from_xyz(xyz, mask).pairwise_distance_matrix()
+    dm, mm = ps.StructureBatch.from_xyz(xyz * torch.tensor([1.0, -1.0, 1.0], device=DEV), mask).pairwise_distance_matrix()
+    assert torch.equal(dm, d) and torch.equal(mm, m)
+    df, mf = ps.StructureBatch.from_xyz(torch.flip(xyz, dims=[1]), torch.flip(mask, dims=[1])).pairwise_distance_matrix()
+    assert torch.equal(torch.flip(df, dims=[1, 2]), d) and torch.equal(torch.flip(mf, dims=[1, 2]), m)
+    # translation by a power of two that keeps every coordinate exactly representable changes nothing either
+    shifted = (xyz.double() + 64.0).float()
+    exact = (shifted.double() - 64.0).float() == xyz
+    if bool(exact.all()):
+        ds, _ = ps.StructureBatch.from_xyz(shifted, mask).pairwise_distance_matrix()
+        assert torch.equal(ds, d)
