@@ -796,7 +796,13 @@ def test_exact_symmetries_at_baseline_config3_size(native_lib):
     assert bool((omega[:, eye] == 0).all()) and bool((theta[:, eye] == 0).all()) and bool(torch.isnan(phi[:, eye]).all())
     mirrored = xyz * torch.tensor([-1.0, 1.0, 1.0], device=DEV)
     mo, mt, mp = ps.StructureBatch.from_xyz(mirrored, mask).trrosetta_angles()
-    assert torch.equal(mo, -omega) and torch.equal(mt, -theta)
+    # ... except on the branch cut: a sine that cancels to +0 stays +0 under the mirror (a - a = +0 either way), so
+    # atan2(+0, x < 0) = +pi in both; only such entries (|angle| == fp32 pi, a handful in 67 M) may keep their sign
+    pi32 = torch.tensor(math.pi, dtype=torch.float32, device=DEV)
+    for mirrored_angle, angle in ((mo, omega), (mt, theta)):
+        off = mirrored_angle != -angle
+        assert int(off.sum()) <= 8 and bool((angle[off].abs() == pi32).all())
+        assert torch.equal(mirrored_angle[off], angle[off])
     assert torch.equal(torch.nan_to_num(mp, nan=-1.0), torch.nan_to_num(phi, nan=-1.0))
     flipped = torch.flip(xyz, dims=[1])
     fo, ft, fp = ps.StructureBatch.from_xyz(flipped, mask).trrosetta_angles()
