@@ -55,9 +55,10 @@ int ps_device_sm_count(int device);       /* >0, or negative ps_status          
  *   dist_mask[b,i,j,a,c] = atom_mask[b,i,a] * atom_mask[b,j,c]            (dtype of atom_mask)
  * xyz (B,L,A,3) f32; atom_mask (B,L,A) of mask_dtype; dist (B,L,L,A,A) f32;
  * dist_mask (B,L,L,A,A) of mask_dtype.  atom_mask/dist_mask may both be NULL
- * (distances only).  dist may be NULL (mask only).  Output pointers must be
- * 16-byte aligned for the staged fast path (A == 15); otherwise a generic
- * kernel is used.
+ * (distances only).  dist may be NULL (mask only).  Any A, L and (naturally
+ * aligned) output pointers are accepted: A in {5, 10, 14, 15} with 16-byte
+ * aligned outputs takes the staged kernel, every other case the any-A tile
+ * kernel (plain stores instead of TMA bulk stores where alignment forbids them).
  */
 int ps_pair_dist_mask(const float* xyz, const void* atom_mask, int mask_dtype,
                       float* dist, void* dist_mask,
@@ -258,9 +259,12 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
 /*
  * Tuning hook for K1 (benchmarks / profiling only; not part of the drop-in surface).
  * variant bit-field: bits 0-1 sqrt mode (0 = sqrt.approx.ftz.f32 [default], 1 = sqrt.approx.f32,
- * 2 = sqrt.rn.f32); bits 4-7 tile buffers per CTA override (0 = default); bit 8 = force generic kernel;
- * bit 9 = use the non-default number of warps per tile; bit 10 = diagnostic "stores only" (no arithmetic,
- * output content undefined: measures the memory-system ceiling of the kernel's write pattern).
+ * 2 = sqrt.rn.f32); bits 4-7 tile buffers per CTA override (0 = default); bit 8 = keep the staged kernel out
+ * (any-A tile kernel); bit 9 = use the non-default number of warps per tile; bit 10 = diagnostic "stores only"
+ * (no arithmetic, output content undefined: measures the memory-system ceiling of the kernel's write pattern);
+ * bit 11 = lockstep schedule; bit 12 = with bit 8: row kernel only (the fallback for atom counts whose tile does
+ * not fit in shared memory); bits 16-23 = any-A tile kernel: pairs per tile in units of its alignment quantum
+ * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA.
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,

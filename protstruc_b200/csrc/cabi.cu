@@ -138,8 +138,8 @@ int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_
         ps::set_error("inter_residue_geometry: all inputs and outputs are required");
         return PS_ERR_NULL_POINTER;
     }
-    // A == 15 and L >= 32: one fused launch; otherwise the generic distance kernel followed by the
-    // fused angle kernel (decided inside pair_dist_mask_impl)
+    // staged atom counts (5, 10, 14, 15) with L >= pairs per tile: one fused launch; otherwise the any-A tile
+    // kernel followed by the fused angle kernel (decided inside pair_dist_mask_impl)
     return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, B,
                                    L, A, 0, PS_STREAM(stream));
 }

@@ -547,6 +547,7 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
             }
         }
 
+        if constexpr (ANGLES && A >= 5) {
         if (does_angles && !p.stores_only) {
             // trRosetta triple of this lane's pairs, reference definitions
             // (protstruc/protstruc.py:810-815): real CB in slot 4.
@@ -565,6 +566,7 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
                     if (p.phi) p.phi[pair[q]] = f;
                 }
             }
+        }
         }
 
         // Park the prefetched residue-i data of the upcoming tile in the other staging buffer.
@@ -601,64 +603,237 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
     __syncwarp();
 }
 
-// ------------------------------------------------------------------ generic fallback
-// Any A, any L, any pointer alignment.  A block walks chunks of whole pair blocks; within a chunk thread t
-// owns output element t (so every warp store is one contiguous 128-B line) and derives (pair, a, c) with
-// 32-bit arithmetic whenever the pair count allows it.  Coordinates and mask bytes come from L1 (eight small
-// loads per element), which keeps this kernel far from the HBM roof (measured 0.74 TB/s on the bench shape) —
-// the price of shape generality; A = 15 with L >= 32 never takes this path.
-template <int SQRT>
-__global__ void __launch_bounds__(256) pair_generic_kernel(
-    const float* __restrict__ xyz, const void* __restrict__ atom_mask, int mask_dtype,
-    float* __restrict__ dist, void* __restrict__ dist_mask, int L, int A, long long num_pairs) {
-    const unsigned AA = static_cast<unsigned>(A) * A;
-    const unsigned pairs_per_chunk = AA >= 256 ? 1u : 256u / AA;
-    const unsigned chunk_elems = pairs_per_chunk * AA;
-    const long long num_chunks = (num_pairs + pairs_per_chunk - 1) / pairs_per_chunk;
-    for (long long chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-        const long long pair0 = chunk * pairs_per_chunk;
-        for (unsigned f = threadIdx.x; f < chunk_elems; f += blockDim.x) {
-            const unsigned pl = f / AA;
-            const unsigned r = f - pl * AA;
-            const long long pair = pair0 + pl;
-            if (pair >= num_pairs) break;
-            const unsigned a = r / A;
-            const unsigned c = r - a * A;
-            long long res_i;  // b*L + i
-            unsigned j, i;
-            if (num_pairs <= 0xFFFFFFFFll) {  // 32-bit decode whenever the pair count allows it
-                const unsigned row = static_cast<unsigned>(pair) / static_cast<unsigned>(L);
-                j = static_cast<unsigned>(pair) - row * static_cast<unsigned>(L);
-                i = row % static_cast<unsigned>(L);
-                res_i = row;
-            } else {
-                res_i = pair / L;
-                j = static_cast<unsigned>(pair - res_i * L);
-                i = static_cast<unsigned>(res_i % L);
+// ------------------------------------------------------------------ any-shape row kernel
+// Any A, any L, any pointer alignment.  The unit of work is one residue-i row (b, i) restricted to a range of
+// residues j: its outputs are ONE contiguous run of (j1 - j0) * A * A elements.  Thread u of the unit owns the
+// column (j, c) = divmod(u, A) — residue j's atom c stays in registers (three strided loads that hit L1/L2: the
+// residues of structure b are re-read by every row of b) — and walks the A atoms of residue i, which the CTA
+// staged once per unit as float4 (x, y, z, mask) in shared memory and every lane reads with one broadcast
+// LDS.128.  No integer division in the element loop; the stores of a warp for one atom a are a few A-element
+// segments that the following iterations extend, so every 128-B line leaves L2 complete.
+enum RowMaskKind { kRowNoMask = 0, kRowBoolMask = 1, kRowF32Mask = 2 };
+
+template <int SQRT, bool HAS_DIST, int MASK>
+__global__ void __launch_bounds__(256) pair_rows_kernel(
+    const float* __restrict__ xyz, const void* __restrict__ atom_mask, float* __restrict__ dist,
+    void* __restrict__ dist_mask, int L, int A, long long num_rows, int parts, int cols_per_part) {
+    extern __shared__ float4 row_stage[];  // 2 x A entries, double buffered across units
+    const long long AA = static_cast<long long>(A) * A;
+    const long long num_units = num_rows * parts;
+    int buf = 0;
+    for (long long unit = blockIdx.x; unit < num_units; unit += gridDim.x, buf ^= 1) {
+        const unsigned row = static_cast<unsigned>(unit / parts);  // b * L + i  (< 2^31, checked by the host)
+        const int part = static_cast<int>(unit - static_cast<long long>(row) * parts);
+        const unsigned i = row % static_cast<unsigned>(L);
+        const long long first_residue = static_cast<long long>(row - i);  // b * L
+        float4* xi = row_stage + buf * A;
+        for (int a = threadIdx.x; a < A; a += blockDim.x) {
+            const float* src = xyz + (static_cast<long long>(row) * A + a) * 3;
+            float m = 0.f;
+            if (MASK == kRowBoolMask)
+                m = __ldg(static_cast<const uint8_t*>(atom_mask) + static_cast<long long>(row) * A + a) != 0 ? 1.f : 0.f;
+            if (MASK == kRowF32Mask) m = __ldg(static_cast<const float*>(atom_mask) + static_cast<long long>(row) * A + a);
+            xi[a] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), m);
+        }
+        __syncthreads();  // one barrier per unit: the other buffer is only rewritten after the next barrier
+        const int col_begin = part * cols_per_part;
+        const int col_end = min(col_begin + cols_per_part, L * A);
+        for (int u = col_begin + threadIdx.x; u < col_end; u += blockDim.x) {
+            const int j = u / A;
+            const int c = u - j * A;
+            const long long atom_j = (first_residue + j) * A + c;
+            float xj = 0.f, yj = 0.f, zj = 0.f;
+            if (HAS_DIST) {
+                xj = __ldg(xyz + atom_j * 3);
+                yj = __ldg(xyz + atom_j * 3 + 1);
+                zj = __ldg(xyz + atom_j * 3 + 2);
             }
-            const long long res_j = res_i - i + j;
-            const long long e = pair * AA + r;
-            if (dist) {
-                const float* pi = xyz + (res_i * A + a) * 3;
-                const float* pj = xyz + (res_j * A + c) * 3;
-                const float dx = __ldg(pj) - __ldg(pi);
-                const float dy = __ldg(pj + 1) - __ldg(pi + 1);
-                const float dz = __ldg(pj + 2) - __ldg(pi + 2);
-                dist[e] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-            }
-            if (dist_mask) {
-                if (mask_dtype == PS_MASK_BOOL) {
-                    const uint8_t* am = static_cast<const uint8_t*>(atom_mask);
-                    const bool v = (__ldg(am + res_i * A + a) != 0) && (__ldg(am + res_j * A + c) != 0);
-                    static_cast<uint8_t*>(dist_mask)[e] = v ? 1 : 0;
-                } else {
-                    const float* am = static_cast<const float*>(atom_mask);
-                    static_cast<float*>(dist_mask)[e] =
-                        __fmul_rn(__ldg(am + res_i * A + a), __ldg(am + res_j * A + c));
+            float mj_f = 0.f;
+            bool mj_b = false;
+            if (MASK == kRowBoolMask) mj_b = __ldg(static_cast<const uint8_t*>(atom_mask) + atom_j) != 0;
+            if (MASK == kRowF32Mask) mj_f = __ldg(static_cast<const float*>(atom_mask) + atom_j);
+            const long long e0 = (static_cast<long long>(row) * L + j) * AA + c;  // element (row, j, a = 0, c)
+            float* dp = HAS_DIST ? dist + e0 : nullptr;
+            uint8_t* mb = MASK == kRowBoolMask ? static_cast<uint8_t*>(dist_mask) + e0 : nullptr;
+            float* mf = MASK == kRowF32Mask ? static_cast<float*>(dist_mask) + e0 : nullptr;
+#pragma unroll 4
+            for (int a = 0; a < A; ++a) {
+                const float4 ri = xi[a];
+                if (HAS_DIST) {
+                    const float dx = xj - ri.x;
+                    const float dy = yj - ri.y;
+                    const float dz = zj - ri.z;
+                    *dp = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                    dp += A;
+                }
+                if (MASK == kRowBoolMask) {
+                    *mb = (mj_b && ri.w != 0.f) ? 1 : 0;
+                    mb += A;
+                }
+                if (MASK == kRowF32Mask) {
+                    *mf = __fmul_rn(ri.w, mj_f);
+                    mf += A;
                 }
             }
         }
     }
+}
+
+template <int SQRT>
+int launch_rows_sqrt(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask,
+                     int L, int A, long long num_rows, int parts, int cols_per_part, unsigned grid, int threads,
+                     cudaStream_t stream) {
+    const size_t smem = 2 * static_cast<size_t>(A) * sizeof(float4);
+#define PS_ROWS(HAS_DIST, MASK)                                                                              \
+    pair_rows_kernel<SQRT, HAS_DIST, MASK><<<grid, threads, smem, stream>>>(xyz, atom_mask, dist, dist_mask, \
+                                                                            L, A, num_rows, parts, cols_per_part)
+    if (dist && !dist_mask) PS_ROWS(true, kRowNoMask);
+    else if (dist && mask_dtype == PS_MASK_BOOL) PS_ROWS(true, kRowBoolMask);
+    else if (dist) PS_ROWS(true, kRowF32Mask);
+    else if (mask_dtype == PS_MASK_BOOL) PS_ROWS(false, kRowBoolMask);
+    else PS_ROWS(false, kRowF32Mask);
+#undef PS_ROWS
+    return check_launch("pair_rows_kernel");
+}
+
+// ------------------------------------------------------------------ any-A tile kernel
+// The staged idea for a run-time atom count: a CTA composes a tile of P consecutive pairs (P * A * A
+// elements, contiguous in both outputs) in shared memory and hands it to the TMA engine as one bulk store per
+// output, so HBM only ever sees whole lines.  Thread u of the tile owns the column (pair, c) = divmod(u, A):
+// atom c of the pair's residue j stays in registers and the A atoms of residue i come from the per-tile staging
+// area as broadcast LDS.128 (x, y, z, mask); a warp's shared-memory stores for one atom a are runs of A
+// consecutive words.  P is a multiple of the quantum that keeps the fp32 tile's size and address 16-B granular
+// (4 / gcd(A*A, 4) pairs); the byte-mask tile takes the engine too whenever its byte range happens to be 16-B
+// granular (always, if P is a multiple of 16 / gcd(A*A, 16)) and coalesced word stores otherwise, as do the last,
+// partial tile and outputs that are not 16-B aligned.
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct ColsParams {
+    const float* __restrict__ xyz;
+    const void* __restrict__ atom_mask;
+    float* __restrict__ out_f32;
+    uint8_t* __restrict__ out_u8;
+    int L;
+    int A;
+    unsigned magic_a;  // ceil(2^32 / A): u / A == umulhi(u, magic_a) for u * A < 2^32
+    int tile_pairs;    // P
+    int bulk_f32;      // f32 output 16-B aligned and P on its quantum: tiles leave through the TMA engine
+    int bulk_u8;       // byte output 16-B aligned: tiles whose byte range is 16-B granular leave through the engine
+    long long num_pairs;
+    long long num_tiles;
+};
+
+__host__ __device__ constexpr int round_up16(int v) { return (v + 15) & ~15; }
+
+template <int KIND, int SQRT>
+__global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
+    extern __shared__ __align__(128) unsigned char cols_smem[];
+    constexpr bool kF32 = kind_has_f32<KIND>();
+    constexpr bool kU8 = kind_has_u8<KIND>();
+    constexpr bool kXyz = (KIND == kDistBoolMask || KIND == kDistOnly);
+    constexpr bool kMaskIn = (KIND != kDistOnly);
+    const int A = p.A, L = p.L, P = p.tile_pairs;
+    const int AA = A * A;
+    float* tile_f32 = reinterpret_cast<float*>(cols_smem);
+    uint8_t* tile_u8 = cols_smem + (kF32 ? round_up16(P * AA * 4) : 0);
+    float4* xi = reinterpret_cast<float4*>(tile_u8 + (kU8 ? round_up16(P * AA) : 0));
+    const int tid = threadIdx.x;
+    const bool few_rows = P <= L;  // a tile then touches at most two residue-i rows
+
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const long long pair0 = t * P;
+        const long long left = p.num_pairs - pair0;
+        const int np = left < P ? static_cast<int>(left) : P;
+        const long long row0 = pair0 / L;  // b * L + i of the first pair
+        const int j_first = static_cast<int>(pair0 - row0 * L);
+        const int nrows = (j_first + np - 1) / L + 1;
+        const long long b0 = row0 / L;
+        const int i0 = static_cast<int>(row0 - b0 * L);
+        // the engine must have read the previous tile before anyone overwrites it
+        if ((p.bulk_f32 || p.bulk_u8) && tid == 0) bulk_wait_read_all();
+        for (int k = tid; k < nrows * A; k += blockDim.x) {
+            const long long atom = row0 * A + k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kXyz) {
+                v.x = __ldg(p.xyz + atom * 3);
+                v.y = __ldg(p.xyz + atom * 3 + 1);
+                v.z = __ldg(p.xyz + atom * 3 + 2);
+            }
+            if (KIND == kF32MaskOnly) v.w = __ldg(static_cast<const float*>(p.atom_mask) + atom);
+            else if (kMaskIn) v.w = __ldg(static_cast<const uint8_t*>(p.atom_mask) + atom) != 0 ? 1.f : 0.f;
+            xi[k] = v;
+        }
+        __syncthreads();
+
+        for (int u = tid; u < np * A; u += blockDim.x) {
+            const int pl = A == 1 ? u : static_cast<int>(__umulhi(static_cast<unsigned>(u), p.magic_a));
+            const int c = u - pl * A;
+            const int rel = j_first + pl;
+            int r, j, db;
+            if (few_rows) {
+                r = rel >= L ? 1 : 0;
+                j = rel - (r ? L : 0);
+                db = (i0 + r) >= L ? 1 : 0;
+            } else {
+                r = rel / L;
+                j = rel - r * L;
+                db = (i0 + r) / L;
+            }
+            const long long atom_j = ((b0 + db) * L + j) * A + c;
+            float xj = 0.f, yj = 0.f, zj = 0.f, mj = 0.f;
+            if (kXyz) {
+                xj = __ldg(p.xyz + atom_j * 3);
+                yj = __ldg(p.xyz + atom_j * 3 + 1);
+                zj = __ldg(p.xyz + atom_j * 3 + 2);
+            }
+            if (KIND == kF32MaskOnly) mj = __ldg(static_cast<const float*>(p.atom_mask) + atom_j);
+            else if (kMaskIn) mj = __ldg(static_cast<const uint8_t*>(p.atom_mask) + atom_j) != 0 ? 1.f : 0.f;
+            const float4* __restrict__ ri = xi + r * A;
+            const int off = pl * AA + c;
+            float* of = tile_f32 + off;
+            uint8_t* ob = tile_u8 + off;
+#pragma unroll 4
+            for (int a = 0; a < A; ++a) {
+                const float4 v = ri[a];
+                if (kXyz) {
+                    const float dx = xj - v.x;
+                    const float dy = yj - v.y;
+                    const float dz = zj - v.z;
+                    of[a * A] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                }
+                if (KIND == kF32MaskOnly) of[a * A] = __fmul_rn(v.w, mj);
+                if (kU8) ob[a * A] = (mj != 0.f && v.w != 0.f) ? 1 : 0;
+            }
+        }
+
+        const long long elem0 = pair0 * AA;
+        const int n = np * AA;
+        const bool f32_bulk = kF32 && p.bulk_f32 && ((n & 3) == 0);
+        const bool u8_bulk = kU8 && p.bulk_u8 && ((elem0 & 15) == 0) && ((n & 15) == 0);
+        if (f32_bulk || u8_bulk) fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0 && (f32_bulk || u8_bulk)) {
+            if (f32_bulk) bulk_store_s2g(p.out_f32 + elem0, tile_f32, static_cast<uint32_t>(n) * 4u);
+            if (u8_bulk) bulk_store_s2g(p.out_u8 + elem0, tile_u8, static_cast<uint32_t>(n));
+            bulk_commit();
+        }
+        // plain coalesced stores for whatever the engine cannot take (the barrier after the next tile's staging
+        // keeps the tile intact until every thread is done reading it)
+        if (kF32 && !f32_bulk)
+            for (int e = tid; e < n; e += blockDim.x) p.out_f32[elem0 + e] = tile_f32[e];
+        if (kU8 && !u8_bulk) {
+            uint8_t* dst = p.out_u8 + elem0;
+            if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+                const int words = n >> 2;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(tile_u8);
+                for (int e = tid; e < words; e += blockDim.x) reinterpret_cast<uint32_t*>(dst)[e] = src[e];
+                for (int e = 4 * words + tid; e < n; e += blockDim.x) dst[e] = tile_u8[e];
+            } else {
+                for (int e = tid; e < n; e += blockDim.x) dst[e] = tile_u8[e];
+            }
+        }
+    }
+    if ((p.bulk_f32 || p.bulk_u8) && tid == 0) bulk_wait_all();  // shared memory must outlive the last bulk read
 }
 
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
@@ -734,29 +909,177 @@ int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int slots_overr
     }
 }
 
-int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
-                   void* dist_mask, int B, int L, int A, int sqrt_mode_id, cudaStream_t stream) {
+template <int KIND>
+int launch_cols_kind(const ColsParams& p, int sqrt_mode_id, unsigned grid, int threads, size_t smem, cudaStream_t stream) {
+#define PS_COLS(SQRT)                                                                                              \
+    do {                                                                                                           \
+        auto kernel = pair_cols_kernel<KIND, SQRT>;                                                                \
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_cols_kernel)");                   \
+        kernel<<<grid, threads, smem, stream>>>(p);                                                                \
+    } while (0)
+    if (KIND == kDistBoolMask || KIND == kDistOnly) {
+        if (sqrt_mode_id == kSqrtRn) PS_COLS(kSqrtRn);
+        else if (sqrt_mode_id == kSqrtApprox) PS_COLS(kSqrtApprox);
+        else PS_COLS(kSqrtApproxFtz);
+    } else {
+        PS_COLS(kSqrtApproxFtz);
+    }
+#undef PS_COLS
+    return check_launch("pair_cols_kernel");
+}
+
+// Picks the tile (pairs per tile, threads per CTA) for one output kind and launches.  Returns PS_OK + launched =
+// false when no tile of this atom count fits in shared memory (the caller then uses the row kernel).
+// `tune`: bits 0-7 pairs per tile in units of the quantum (0 = choose), bit 8 = 128 threads per CTA.
+int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f32, void* out_u8, int B, int L, int A,
+                int sqrt_mode_id, int tune, bool* launched, cudaStream_t stream) {
+    *launched = false;
+    const long long AA = static_cast<long long>(A) * A;
+    const bool f32 = kind != kBoolMaskOnly, u8 = (kind == kDistBoolMask || kind == kBoolMaskOnly);
+    const long long bytes_per_pair = AA * ((f32 ? 4 : 0) + (u8 ? 1 : 0));
+    auto gcd = [](long long a, long long b) { while (b) { const long long r = a % b; a = b; b = r; } return a; };
+    const long long q_f32 = 4 / gcd(AA, 4), q_u8 = 16 / gcd(AA, 16);  // pairs that keep a tile 16-B granular
+    const bool f32_aligned = f32 && aligned16(out_f32), u8_aligned = u8 && aligned16(out_u8);
+    const long long step = f32 ? (f32_aligned ? q_f32 : 1) : (u8_aligned ? q_u8 : 1);
+    const long long kBudget = 56 * 1024, kSmemPerSm = 225 * 1024, kSmemCap = 200 * 1024;
     const long long num_pairs = static_cast<long long>(B) * L * L;
+    auto smem_for = [&](long long pairs) -> long long {
+        const long long max_rows = (pairs + L - 2) / L + 2;  // residue-i rows a tile can touch
+        return (f32 ? round_up16(static_cast<int>(pairs * AA * 4)) : 0) + (u8 ? round_up16(static_cast<int>(pairs * AA)) : 0) +
+               max_rows * A * static_cast<long long>(sizeof(float4));
+    };
+    if (step * bytes_per_pair > kSmemCap || smem_for(step) > kSmemCap) return PS_OK;  // row kernel
+    // Candidates: multiples of `step` up to the budget.  Score = lane utilisation of the column loop x how close
+    // the resident warps come to 48 per SM (latency hiding), with a small preference for tiles whose byte mask
+    // can take the bulk path and against tiles so small that per-tile overhead shows.
+    long long best_pairs = step;
+    int best_threads = 256;
+    double best_score = -1.0;
+    for (long long pairs = step; pairs == step || pairs * bytes_per_pair <= kBudget; pairs += step) {
+        if (pairs > step && pairs - step >= num_pairs) break;
+        const long long smem = smem_for(pairs);
+        if (smem > kSmemCap) break;
+        for (int threads : {256, 128}) {
+            const long long cols = pairs * A;
+            const long long passes = (cols + threads - 1) / threads;
+            long long ctas = kSmemPerSm / (smem + 1024);
+            if (ctas > 2048 / threads) ctas = 2048 / threads;
+            if (ctas > 32) ctas = 32;
+            const double warps = static_cast<double>(ctas * threads / 32);
+            double score = static_cast<double>(cols) / static_cast<double>(passes * threads);
+            score *= warps >= 48.0 ? 1.0 : warps / 48.0;
+            if (pairs * bytes_per_pair < 8 * 1024) score *= 0.85;
+            if (u8 && u8_aligned && pairs % q_u8 == 0) score *= 1.05;
+            if (score > best_score + 1e-9 || (score > best_score - 1e-9 && pairs > best_pairs)) {
+                best_score = score;
+                best_pairs = pairs;
+                best_threads = threads;
+            }
+        }
+    }
+    if ((tune & 0xFF) > 0 && smem_for((tune & 0xFF) * step) <= kSmemCap) best_pairs = (tune & 0xFF) * step;
+    if (tune & 0x100) best_threads = 128;
+    if (tune & 0x200) best_threads = 256;
+    PS_REQUIRE(best_pairs * A < (1ll << 24), PS_ERR_BAD_SHAPE, "pair_dist_mask: tile of %lld pairs x %d atoms", best_pairs, A);
+    ColsParams p;
+    p.xyz = xyz;
+    p.atom_mask = atom_mask;
+    p.out_f32 = out_f32;
+    p.out_u8 = static_cast<uint8_t*>(out_u8);
+    p.L = L;
+    p.A = A;
+    p.magic_a = static_cast<unsigned>(((1ull << 32) + A - 1) / A);
+    p.tile_pairs = static_cast<int>(best_pairs);
+    p.bulk_f32 = (f32_aligned && best_pairs % q_f32 == 0) ? 1 : 0;
+    p.bulk_u8 = u8_aligned ? 1 : 0;
+    p.num_pairs = num_pairs;
+    p.num_tiles = (num_pairs + best_pairs - 1) / best_pairs;
+    const size_t smem = static_cast<size_t>(smem_for(best_pairs));
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
-    const long long AA = static_cast<long long>(A) * A;
-    const long long pairs_per_chunk = AA >= 256 ? 1 : 256 / AA;
-    long long blocks = (num_pairs + pairs_per_chunk - 1) / pairs_per_chunk;
-    const long long cap = static_cast<long long>(sms) * 32;
+    long long per_sm = kSmemPerSm / static_cast<long long>(smem + 1024);
+    if (per_sm > 2048 / best_threads) per_sm = 2048 / best_threads;
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = p.num_tiles;
+    if (blocks > per_sm * sms) blocks = per_sm * sms;
+    const unsigned grid = static_cast<unsigned>(blocks);
+    *launched = true;
+    switch (kind) {
+        case kDistBoolMask: return launch_cols_kind<kDistBoolMask>(p, sqrt_mode_id, grid, best_threads, smem, stream);
+        case kDistOnly: return launch_cols_kind<kDistOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
+        case kF32MaskOnly: return launch_cols_kind<kF32MaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
+        default: return launch_cols_kind<kBoolMaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
+    }
+}
+
+// Any shape: the any-A tile kernel, one launch per f32 output (as the staged path does for fp32 masks); the row
+// kernel when a tile of this atom count cannot fit in shared memory.
+int launch_any_shape(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask,
+                     int B, int L, int A, int sqrt_mode_id, bool rows_only, int tune, cudaStream_t stream);
+
+int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                   void* dist_mask, int B, int L, int A, int sqrt_mode_id, cudaStream_t stream) {
+    PS_REQUIRE(A <= 1024, PS_ERR_BAD_SHAPE, "pair_dist_mask: A=%d atoms per residue exceed 1024", A);
+    PS_REQUIRE(static_cast<long long>(L) * A < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "pair_dist_mask: L*A=%lld exceeds 2^31", static_cast<long long>(L) * A);
+    const long long num_rows = static_cast<long long>(B) * L;
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    const int cols = L * A;  // (j, c) columns of one row
+    const int threads = cols >= 256 ? 256 : (cols + 31) / 32 * 32;
+    // Rows are cut into parts (ranges of columns) when there are too few rows to balance the SMs; a part keeps at
+    // least two passes of the block so the staging of residue i stays amortised.
+    const long long want_units = static_cast<long long>(sms) * 8 * 4;
+    int parts = 1;
+    if (num_rows < want_units) {
+        const long long max_parts = cols / (2 * threads) > 0 ? cols / (2 * threads) : 1;
+        const long long need = (want_units + num_rows - 1) / num_rows;
+        parts = static_cast<int>(need < max_parts ? need : max_parts);
+    }
+    const int cols_per_part = (cols + parts - 1) / parts;
+    parts = (cols + cols_per_part - 1) / cols_per_part;
+    long long blocks = num_rows * parts;
+    const long long cap = static_cast<long long>(sms) * 8;
     if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
     const unsigned grid = static_cast<unsigned>(blocks);
     if (sqrt_mode_id == kSqrtRn)
-        pair_generic_kernel<kSqrtRn><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
-    else if (sqrt_mode_id == kSqrtApprox)
-        pair_generic_kernel<kSqrtApprox><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
-    else
-        pair_generic_kernel<kSqrtApproxFtz><<<grid, 256, 0, stream>>>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_pairs);
-    return check_launch("pair_generic_kernel");
+        return launch_rows_sqrt<kSqrtRn>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_rows, parts,
+                                         cols_per_part, grid, threads, stream);
+    if (sqrt_mode_id == kSqrtApprox)
+        return launch_rows_sqrt<kSqrtApprox>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_rows, parts,
+                                             cols_per_part, grid, threads, stream);
+    return launch_rows_sqrt<kSqrtApproxFtz>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_rows, parts,
+                                            cols_per_part, grid, threads, stream);
+}
+
+int launch_any_shape(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask,
+                     int B, int L, int A, int sqrt_mode_id, bool rows_only, int tune, cudaStream_t stream) {
+    const bool tiles_possible = !rows_only && A <= 128 && static_cast<long long>(L) * L < (1ll << 31);
+    if (tiles_possible) {
+        bool launched = false;
+        int rc = PS_OK;
+        if (dist_mask == nullptr || mask_dtype == PS_MASK_BOOL) {
+            const int kind = dist ? (dist_mask ? kDistBoolMask : kDistOnly) : kBoolMaskOnly;
+            rc = launch_cols(xyz, atom_mask, kind, dist, dist_mask, B, L, A, sqrt_mode_id, tune, &launched, stream);
+            if (rc != PS_OK || launched) return rc;
+        } else {
+            bool first = true, second = false;
+            if (dist) rc = launch_cols(xyz, atom_mask, kDistOnly, dist, nullptr, B, L, A, sqrt_mode_id, tune, &first, stream);
+            if (rc != PS_OK) return rc;
+            if (first) {
+                rc = launch_cols(xyz, atom_mask, kF32MaskOnly, static_cast<float*>(dist_mask), nullptr, B, L, A,
+                                 sqrt_mode_id, tune, &second, stream);
+                if (rc != PS_OK || second) return rc;
+                // (same atom count, same footprint per element: if the first fitted, so does the second)
+            }
+        }
+    }
+    return launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_mode_id, stream);
 }
 
 // Kernel selection for one atom count.  A = 15 carries every tuning variant; the other staged atom counts
-// (5 = backbone + CB, 10, 14 = atom14) are built for the default configuration only.
+// (4 = backbone, 5 = backbone + CB, 10, 14 = atom14) are built for the default configuration only.
 template <int A>
 int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, bool want_angles, int sqrt_id,
                    int slots_override, int wpt, cudaStream_t stream) {
@@ -770,10 +1093,12 @@ int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, boo
         if constexpr (kAllVariants) {
             return angles ? launch_tiles_sqrt<A, KIND, true>(p, sqrt_id, slots_override, wpt, stream)
                           : launch_tiles_sqrt<A, KIND, false>(p, sqrt_id, slots_override, wpt, stream);
-        } else {
+        } else if constexpr (A >= 5) {
             return angles
                        ? launch_tiles_wpt<A, KIND, kSqrtApproxFtz, true, kDefaultWarpsPerTile>(p, slots_override, stream)
                        : launch_tiles_wpt<A, KIND, kSqrtApproxFtz, false, kDefaultWarpsPerTile>(p, slots_override, stream);
+        } else {  // no CB slot: the caller has already rejected angle requests
+            return launch_tiles_wpt<A, KIND, kSqrtApproxFtz, false, kDefaultWarpsPerTile>(p, slots_override, stream);
         }
     };
     if (mask_dtype == PS_MASK_BOOL || dist_mask == nullptr) {
@@ -795,8 +1120,6 @@ int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, boo
     pm.omega = pm.theta = pm.phi = nullptr;
     return launch_tiles_wpt<A, kF32MaskOnly, kSqrtApproxFtz, false, 1>(pm, slots_override, stream);
 }
-
-bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
@@ -847,11 +1170,12 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     const int wpt = ((variant >> 9) & 1) ? (3 - kDefaultWarpsPerTile) : kDefaultWarpsPerTile;
 
     // the staged kernel needs L >= pairs per tile (a tile then touches at most two residue-i rows)
-    const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14);
+    const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14) || (A == 4);
     const int tile_pairs = kTilePairs * (A <= 6 ? 4 : (A <= 10 ? 2 : 1));  // = TileGeom<A>::kPairs
     const bool fast = staged_atom_count && (L >= tile_pairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
-        int rc = launch_generic(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, stream);
+        const bool rows_only = (variant >> 12) & 1;
+        int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0x3FF, stream);
         if (rc != PS_OK || !want_angles) return rc;
         return trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, stream);
     }
@@ -883,6 +1207,8 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.active_workers = 0;
 
     switch (A) {
+        case 4:
+            return dispatch_tiles<4>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
         case 5:
             return dispatch_tiles<5>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
         case 10:

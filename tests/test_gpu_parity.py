@@ -743,6 +743,74 @@ def test_staged_kernels_for_other_atom_counts(native_lib, B, L, A):
     assert torch.equal(results[0][1].view(torch.bool).view(B, L, L, A, A).cpu(), rm)
 
 
+@pytest.mark.parametrize("B,L,A", [(2, 20, 25), (1, 9, 37), (3, 50, 4), (2, 64, 3), (5, 3, 6), (1, 1, 7), (2, 33, 16),
+                                   (1, 130, 8), (2, 2, 1), (1, 7, 53), (1, 40, 15), (2, 17, 15), (1, 130, 3), (2, 128, 4),
+                                   (1, 141, 4), (1, 12, 130)])
+def test_any_shape_distance_kernels(native_lib, B, L, A):
+    """Atom counts / lengths the staged kernel does not cover: the any-A tile kernel (TMA bulk stores), its
+    plain-store flavour for outputs that are not 16-B aligned, and the row kernel (variant bit 12) — every output
+    kind, bit-identical to each other, within the distance tolerance of the oracle, guard bands intact."""
+    xyz, mask, _ = H.synthetic_batch(900 + 7 * A + L, B, L, A, "bool")
+    rd, rm = orc.pair_distances(xyz, mask)
+    fmask = mask.float() * torch.rand(B, L, A, generator=torch.Generator().manual_seed(A))  # non-trivial fp32 mask
+    _, rfm = orc.pair_distances(xyz, fmask)
+    x, m, fm = xyz.to(DEV), mask.to(DEV), fmask.to(DEV).contiguous()
+    n = B * L * L * A * A
+    s = torch.cuda.current_stream().cuda_stream
+    guard = 256
+
+    def run(variant, shift, mask_dtype, want_dist, want_mask):
+        """shift = byte offset of the outputs inside 256-B aligned buffers (4 = only fp32-aligned)."""
+        item = 4 if mask_dtype == 1 else 1
+        dbuf = torch.full((guard + n * 4 + guard,), 0x3C, dtype=torch.uint8, device=DEV)
+        mbuf = torch.full((guard + n * item + guard,), 0x3C, dtype=torch.uint8, device=DEV)
+        dptr = dbuf[guard + shift - 16:].data_ptr() if want_dist else 0
+        mshift = shift if mask_dtype == 1 else (shift + 1 if shift else 0)  # byte masks may sit on any address
+        mptr = mbuf[guard + mshift - 16:].data_ptr() if want_mask else 0
+        am = (fm if mask_dtype == 1 else m).data_ptr() if want_mask else 0
+        rc = native_lib.ps_pair_dist_mask_ex(x.data_ptr(), am, mask_dtype, dptr, mptr, B, L, A, variant, s)
+        _cabi.check(rc, "ps_pair_dist_mask_ex")
+        torch.cuda.synchronize()
+        d0, m0 = guard + shift - 16, guard + mshift - 16
+        out = {}
+        if want_dist:
+            assert bool((dbuf[:d0] == 0x3C).all()) and bool((dbuf[d0 + n * 4:] == 0x3C).all()), "dist guard band"
+            out["dist"] = dbuf[d0:d0 + n * 4].clone().view(torch.float32).view(B, L, L, A, A)
+        else:
+            assert bool((dbuf == 0x3C).all())
+        if want_mask:
+            assert bool((mbuf[:m0] == 0x3C).all()) and bool((mbuf[m0 + n * item:] == 0x3C).all()), "mask guard band"
+            raw = mbuf[m0:m0 + n * item].clone()
+            out["mask"] = (raw.view(torch.float32) if mask_dtype == 1 else raw.view(torch.bool)).view(B, L, L, A, A)
+        else:
+            assert bool((mbuf == 0x3C).all())
+        return out
+
+    force = 1 << 8  # keep the staged kernel out even for A = 15
+    base = run(force, 16, 0, True, True)
+    H.assert_distances_close(base["dist"], rd)
+    assert torch.equal(base["mask"].cpu(), rm)
+    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-2.0), torch.nan_to_num(b, nan=-2.0))  # noqa: E731
+    for variant in (force, force | (1 << 12)):
+        for shift in (16, 20):
+            both = run(variant, shift, 0, True, True)
+            assert same(both["dist"], base["dist"]) and torch.equal(both["mask"], base["mask"]), (variant, shift)
+            assert same(run(variant, shift, 0, True, False)["dist"], base["dist"]), (variant, shift)
+            assert torch.equal(run(variant, shift, 0, False, True)["mask"], base["mask"]), (variant, shift)
+            f = run(variant, shift, 1, True, True)
+            assert same(f["dist"], base["dist"]) and torch.equal(f["mask"].cpu(), rfm), (variant, shift)
+            assert torch.equal(run(variant, shift, 1, False, True)["mask"].cpu(), rfm), (variant, shift)
+    # whatever the default dispatch picks for this shape (staged kernel for A = 3 / 4 / 15 when L allows) agrees
+    for mask_dtype in (0, 1):
+        d = run(0, 16, mask_dtype, True, True)
+        assert same(d["dist"], base["dist"])
+        assert torch.equal(d["mask"].cpu(), rfm if mask_dtype else rm)
+    assert torch.equal(run(0, 16, 0, False, True)["mask"], base["mask"])
+    # IEEE square root flavour through the same kernels
+    ieee = run(force | 2, 16, 0, True, False)["dist"]
+    H.assert_distances_close(ieee, rd)
+
+
 def test_randomised_shapes_against_the_oracle(native_lib):
     """Seeded sweep over odd shapes (tail tiles, L around the 32-pair tile size, every staged atom count and the
     generic path, bool and float masks, ragged lengths): every feature family vs the CPU oracle."""

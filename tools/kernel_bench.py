@@ -77,7 +77,7 @@ def main():
     om = torch.empty(B, L, L, device=DEV)
     th, ph = torch.empty_like(om), torch.empty_like(om)
     nbytes = B * (L * L * A * A * 5 + L * A * 13)
-    variants = {"sqrt.approx.ftz (default)": 0, "sqrt.approx": 1, "sqrt.rn": 2, "generic kernel": 1 << 8}
+    variants = {"sqrt.approx.ftz (default)": 0, "sqrt.approx": 1, "sqrt.rn": 2, "any-A tile kernel": 1 << 8, "row kernel": (1 << 8) | (1 << 12)}
     variants["1 warp per tile (6 warps/SM)"] = 1 << 9
     variants["DIAGNOSTIC stores only (no arithmetic)"] = 1 << 10
     variants["DIAGNOSTIC stores only, 6 tile buffers"] = (1 << 10) | (6 << 4)
