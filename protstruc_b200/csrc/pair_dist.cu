@@ -739,28 +739,46 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
     float4* xi = reinterpret_cast<float4*>(tile_u8 + (kU8 ? round_up16(P * AA) : 0));
     const int tid = threadIdx.x;
     const bool few_rows = P <= L;  // a tile then touches at most two residue-i rows
+    const bool any_bulk = p.bulk_f32 || p.bulk_u8;
 
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const long long pair0 = t * P;
+    // Tile coordinates are carried from tile to tile (the grid stride is a fixed number of pairs), so the only
+    // integer divisions of the kernel happen once per CTA: pair0 = (b0 * L + i0) * L + j_first.
+    long long pair0 = static_cast<long long>(blockIdx.x) * P;
+    int j_first, i0;
+    long long b0;
+    {
+        const long long row0 = pair0 / L;
+        j_first = static_cast<int>(pair0 - row0 * L);
+        b0 = row0 / L;
+        i0 = static_cast<int>(row0 - b0 * L);
+    }
+    const long long stride_pairs = static_cast<long long>(gridDim.x) * P;
+    const long long stride_rows = stride_pairs / L;
+    const int stride_j = static_cast<int>(stride_pairs - stride_rows * L);
+    const long long stride_b = stride_rows / L;
+    const int stride_i = static_cast<int>(stride_rows - stride_b * L);
+
+    for (; pair0 < p.num_pairs; pair0 += stride_pairs) {
         const long long left = p.num_pairs - pair0;
         const int np = left < P ? static_cast<int>(left) : P;
-        const long long row0 = pair0 / L;  // b * L + i of the first pair
-        const int j_first = static_cast<int>(pair0 - row0 * L);
-        const int nrows = (j_first + np - 1) / L + 1;
-        const long long b0 = row0 / L;
-        const int i0 = static_cast<int>(row0 - b0 * L);
+        const int last_rel = j_first + np - 1;
+        const int nrows = few_rows ? (last_rel >= L ? 2 : 1) : last_rel / L + 1;
+        const long long structure_atom0 = b0 * L * A;  // first atom of structure b0
+        const float* __restrict__ xb = p.xyz + structure_atom0 * 3;
+        const uint8_t* __restrict__ mb8 = static_cast<const uint8_t*>(p.atom_mask) + structure_atom0;
+        const float* __restrict__ mbf = static_cast<const float*>(p.atom_mask) + structure_atom0;
         // the engine must have read the previous tile before anyone overwrites it
-        if ((p.bulk_f32 || p.bulk_u8) && tid == 0) bulk_wait_read_all();
+        if (any_bulk && tid == 0) bulk_wait_read_all();
         for (int k = tid; k < nrows * A; k += blockDim.x) {
-            const long long atom = row0 * A + k;
+            const int atom = i0 * A + k;  // relative to structure b0 (rows may run into structure b0 + 1)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (kXyz) {
-                v.x = __ldg(p.xyz + atom * 3);
-                v.y = __ldg(p.xyz + atom * 3 + 1);
-                v.z = __ldg(p.xyz + atom * 3 + 2);
+                v.x = __ldg(xb + atom * 3);
+                v.y = __ldg(xb + atom * 3 + 1);
+                v.z = __ldg(xb + atom * 3 + 2);
             }
-            if (KIND == kF32MaskOnly) v.w = __ldg(static_cast<const float*>(p.atom_mask) + atom);
-            else if (kMaskIn) v.w = __ldg(static_cast<const uint8_t*>(p.atom_mask) + atom) != 0 ? 1.f : 0.f;
+            if (KIND == kF32MaskOnly) v.w = __ldg(mbf + atom);
+            else if (kMaskIn) v.w = __ldg(mb8 + atom) != 0 ? 1.f : 0.f;
             xi[k] = v;
         }
         __syncthreads();
@@ -779,15 +797,15 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
                 j = rel - r * L;
                 db = (i0 + r) / L;
             }
-            const long long atom_j = ((b0 + db) * L + j) * A + c;
+            const int atom_j = (db * L + j) * A + c;  // relative to structure b0; < (P / L + 2) * L * A (host-checked)
             float xj = 0.f, yj = 0.f, zj = 0.f, mj = 0.f;
             if (kXyz) {
-                xj = __ldg(p.xyz + atom_j * 3);
-                yj = __ldg(p.xyz + atom_j * 3 + 1);
-                zj = __ldg(p.xyz + atom_j * 3 + 2);
+                xj = __ldg(xb + atom_j * 3);
+                yj = __ldg(xb + atom_j * 3 + 1);
+                zj = __ldg(xb + atom_j * 3 + 2);
             }
-            if (KIND == kF32MaskOnly) mj = __ldg(static_cast<const float*>(p.atom_mask) + atom_j);
-            else if (kMaskIn) mj = __ldg(static_cast<const uint8_t*>(p.atom_mask) + atom_j) != 0 ? 1.f : 0.f;
+            if (KIND == kF32MaskOnly) mj = __ldg(mbf + atom_j);
+            else if (kMaskIn) mj = __ldg(mb8 + atom_j) != 0 ? 1.f : 0.f;
             const float4* __restrict__ ri = xi + r * A;
             const int off = pl * AA + c;
             float* of = tile_f32 + off;
@@ -806,6 +824,16 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
             }
         }
 
+        // coordinates of the tile this CTA takes next
+        {
+            j_first += stride_j;
+            const int carry_j = j_first >= L ? 1 : 0;
+            j_first -= carry_j ? L : 0;
+            i0 += stride_i + carry_j;
+            const int carry_i = i0 >= L ? 1 : 0;
+            i0 -= carry_i ? L : 0;
+            b0 += stride_b + carry_i;
+        }
         const long long elem0 = pair0 * AA;
         const int n = np * AA;
         const bool f32_bulk = kF32 && p.bulk_f32 && ((n & 3) == 0);
@@ -950,9 +978,11 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
                max_rows * A * static_cast<long long>(sizeof(float4));
     };
     if (step * bytes_per_pair > kSmemCap || smem_for(step) > kSmemCap) return PS_OK;  // row kernel
-    // Candidates: multiples of `step` up to the budget.  Score = lane utilisation of the column loop x how close
-    // the resident warps come to 48 per SM (latency hiding), with a small preference for tiles whose byte mask
-    // can take the bulk path and against tiles so small that per-tile overhead shows.
+    // Candidates: multiples of `step` up to the budget, 128 or 256 threads.  Score = issue efficiency at the
+    // resident warp count / issue slots per element, both fitted to the sweep in
+    // profiles/r1r_any_shape_tile_sweep.json: a warp spends ~kPerTile slots per tile and ~kPerColumn per column
+    // besides ~kPerElement per element, and the SM needs ~32 resident warps to keep issuing.
+    const double kPerTile = 60.0, kPerColumn = 20.0, kPerElement = f32 ? (u8 ? 14.0 : 11.0) : 6.0;
     long long best_pairs = step;
     int best_threads = 256;
     double best_score = -1.0;
@@ -967,11 +997,13 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
             if (ctas > 2048 / threads) ctas = 2048 / threads;
             if (ctas > 32) ctas = 32;
             const double warps = static_cast<double>(ctas * threads / 32);
-            double score = static_cast<double>(cols) / static_cast<double>(passes * threads);
-            score *= warps >= 48.0 ? 1.0 : warps / 48.0;
-            if (pairs * bytes_per_pair < 8 * 1024) score *= 0.85;
-            if (u8 && u8_aligned && pairs % q_u8 == 0) score *= 1.05;
-            if (score > best_score + 1e-9 || (score > best_score - 1e-9 && pairs > best_pairs)) {
+            const double slots_per_element = (threads / 32) * (kPerTile + passes * (kPerColumn + kPerElement * A)) /
+                                             static_cast<double>(pairs * AA);
+            double efficiency = 0.4 + 0.6 * warps / 32.0;
+            if (efficiency > 1.0) efficiency = 1.0;
+            double score = efficiency / slots_per_element;
+            if (u8 && u8_aligned && pairs % q_u8 == 0) score *= 1.03;  // byte mask leaves through the engine too
+            if (score > best_score) {
                 best_score = score;
                 best_pairs = pairs;
                 best_threads = threads;
