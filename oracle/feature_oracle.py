@@ -346,15 +346,16 @@ def philox4x32_10(ctr: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
 
 def philox_normal(n: int, seed: int, step: int, elem_offset: int = 0) -> np.ndarray:
     """float64 evaluation of the N(0,1) stream the K5 kernels define: group g = e // 4 (+offset/4),
-    counter (g_lo, g_hi, step_lo, step_hi), key = seed; Box-Muller on (r0, r1) and (r2, r3)."""
+    counter (g_lo, g_hi, step_lo, step_hi), key = seed; uniforms from the top 23 bits of each word;
+    Box-Muller on (r0, r1) and (r2, r3)."""
     groups = (n + 3) // 4
     g = np.arange(groups, dtype=np.uint64) + np.uint64(elem_offset // 4)
     ctr = np.stack([
         (g & np.uint64(0xFFFFFFFF)).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
         np.full(groups, step & 0xFFFFFFFF, dtype=np.uint32), np.full(groups, (step >> 32) & 0xFFFFFFFF, dtype=np.uint32),
     ], axis=1)
-    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)).astype(np.float64)
-    u = r * 2.0**-32 + 2.0**-33
+    r = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    u = ((r >> np.uint32(9)).astype(np.float64) + 0.5) * 2.0**-23  # top 23 bits, centred: u in (0, 1)
     rad_a = np.sqrt(-2.0 * np.log(u[:, 0]))
     rad_b = np.sqrt(-2.0 * np.log(u[:, 2]))
     ang_a = 2.0 * np.pi * u[:, 1]

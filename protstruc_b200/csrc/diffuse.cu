@@ -31,27 +31,53 @@ struct U4 {
     uint32_t x, y, z, w;
 };
 
-__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+// The ten round keys depend on the seed only; the kernels expand them once per thread (twenty
+// registers) instead of bumping them inside every call.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint32_t a = static_cast<uint32_t>(seed), b = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        k.k0[r] = a;
+        k.k1[r] = b;
+        // opaque to the optimiser, which would otherwise re-derive every key from the seed inside the step loop
+        asm volatile("" : "+r"(k.k0[r]), "+r"(k.k1[r]));
+        a += kPhiloxW0;
+        b += kPhiloxW1;
+    }
+    return k;
+}
+
+__device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKeys& k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
-        c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
-        k0 += kPhiloxW0;
-        k1 += kPhiloxW1;
+        c = U4{hi1 ^ c.y ^ k.k0[r], lo1, hi0 ^ c.w ^ k.k1[r], lo0};
     }
     return c;
 }
 
-// Two uniforms -> two N(0,1) (Box-Muller).  u1 in (0,1], angle 2*pi*u2 in (0, 2*pi].  The generator is
-// the ALU bottleneck of the fused T-step kernel, so the transcendental steps are the single-MUFU
-// intrinsics: __logf (abs error 2^-21.4 on [0.5, 2]), MUFU.SQRT, and __sincosf on the angle shifted into
-// (-pi, pi] (abs error 2^-21.4 there); sin(t - pi) = -sin t, so the stream definition
-// z = (r sin 2*pi*u2, r cos 2*pi*u2) is unchanged.  Deviation from an fp64 evaluation of the same stream
-// is < 1e-5 for 99.9 % of the samples (tests/test_gpu_parity.py).
+// Two random words -> two N(0,1) (Box-Muller).  The generator is the bottleneck of the fused T-step kernel and
+// the quarter-rate XU pipe (MUFU, I2F) its scarcest resource, so
+//  * the uniforms are built without an int->float conversion: the top 23 bits of the word become the mantissa of
+//    a float in [1, 2); u = f - (1 - 2^-24) = (k + 1/2) * 2^-23 in (0, 1), exact in fp32 (LOP3/SHF + one FADD);
+//  * the transcendental steps are the single-MUFU intrinsics: __logf (abs error 2^-21.4 on [0.5, 2]), MUFU.SQRT,
+//    and __sincosf on the angle shifted into (-pi, pi) (abs error 2^-21.4 there); sin(t - pi) = -sin t, so the
+//    stream definition z = (r sin 2*pi*u2, r cos 2*pi*u2) is unchanged.
+// Deviation from an fp64 evaluation of the same stream is < 1e-5 for 99.9 % of the samples
+// (tests/test_gpu_parity.py).  23-bit uniforms bound |z| by sqrt(-2 ln 2^-24) = 5.77.
+__device__ __forceinline__ float unit_open(uint32_t word) {
+    return __fsub_rn(__uint_as_float((word >> 9) | 0x3F800000u), 0.99999994f);
+}
+
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-    const float u1 = fmaf(static_cast<float>(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-    const float u2 = fmaf(static_cast<float>(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float u1 = unit_open(a);
+    const float u2 = unit_open(b);
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
     float s, c;
@@ -59,10 +85,10 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     return make_float2(-r * s, -r * c);
 }
 
-__device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t seed, float (&z)[4]) {
+__device__ __forceinline__ void normal4(uint64_t group, uint64_t step, const PhiloxKeys& keys, float (&z)[4]) {
     const U4 ctr{static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32),
                  static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32)};
-    const U4 r = philox4x32_10(ctr, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const U4 r = philox4x32_10(ctr, keys);
     const float2 a = box_muller(r.x, r.y);
     const float2 b = box_muller(r.z, r.w);
     z[0] = a.x;
@@ -91,18 +117,44 @@ __global__ void __launch_bounds__(256) diffuse_noise_kernel(const float* __restr
     }
 }
 
-// Philox variant: one thread per group of 4 consecutive elements, T steps in registers.
-// betas is (T, B).
+// Philox variant: one thread per group of 4 consecutive elements, T steps in registers.  betas is (T, B).
+// A CTA takes blocks of 256 consecutive groups (1024 elements); such a block touches at most kTableSlots
+// structures when per_b >= 1024 / (kTableSlots - 1), and then the CTA first tabulates (sqrt(1 - beta), sqrt(beta))
+// of those structures for all T steps in shared memory — a few IEEE square roots per thread instead of 2 T —
+// and the step loop reads them with one broadcast LDS.64.  Smaller structures take the roots in the loop.
+constexpr int kTableSlots = 2;
+
 __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ betas, int T,
                                                              int B, uint64_t seed, uint64_t step0,
                                                              uint64_t group_offset, long long per_b,
-                                                             long long total,
+                                                             long long total, int use_table,
                                                              float* __restrict__ out) {
+    extern __shared__ float2 schedule[];  // [T][kTableSlots] when use_table
+    const PhiloxKeys keys = philox_keys(seed);
     const long long groups = (total + 3) / 4;
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
-         g += stride) {
+    const long long num_blocks = (groups + blockDim.x - 1) / blockDim.x;
+    for (long long blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
+        const long long g = blk * blockDim.x + threadIdx.x;
+        int b_lo = 0, nb = 0;
+        if (use_table) {  // structures this block of 1024 elements touches
+            const long long block_e0 = blk * blockDim.x * 4;
+            long long block_e1 = block_e0 + static_cast<long long>(blockDim.x) * 4 - 1;
+            if (block_e1 > total - 1) block_e1 = total - 1;
+            b_lo = static_cast<int>(block_e0 / per_b);
+            nb = static_cast<int>(block_e1 / per_b) - b_lo + 1;
+        }
+        const bool table = use_table && nb <= kTableSlots;  // block-uniform
+        if (table) {
+            __syncthreads();  // the previous block's readers are done
+            for (int idx = threadIdx.x; idx < T * nb; idx += blockDim.x) {
+                const int t = idx / nb, slot = idx - t * nb;
+                const float bt = __ldg(betas + static_cast<long long>(t) * B + b_lo + slot);
+                schedule[t * kTableSlots + slot] = make_float2(__fsqrt_rn(__fsub_rn(1.0f, bt)), __fsqrt_rn(bt));
+            }
+            __syncthreads();
+        }
+        if (g >= groups) continue;
         const long long e0 = g * 4;
         float v[4];
         int bidx[4];
@@ -111,14 +163,24 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
             const long long e = e0 + k;
             const bool ok = e < total;
             v[k] = ok ? x[e] : 0.f;
-            bidx[k] = ok ? static_cast<int>(e / per_b) : 0;
+            bidx[k] = ok ? static_cast<int>(e / per_b) : b_lo;
         }
         const bool same_b = bidx[0] == bidx[3];
         for (int t = 0; t < T; ++t) {
             float z[4];
-            normal4(static_cast<uint64_t>(g) + group_offset, step0 + static_cast<uint64_t>(t), seed, z);
+            normal4(static_cast<uint64_t>(g) + group_offset, step0 + static_cast<uint64_t>(t), keys, z);
             const float* __restrict__ bt_row = betas + static_cast<long long>(t) * B;
-            if (same_b) {
+            if (table && same_b) {
+                const float2 ab = schedule[t * kTableSlots + (bidx[0] - b_lo)];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = diffuse_one(v[k], z[k], ab.x, ab.y);
+            } else if (table) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 ab = schedule[t * kTableSlots + (bidx[k] - b_lo)];
+                    v[k] = diffuse_one(v[k], z[k], ab.x, ab.y);
+                }
+            } else if (same_b) {
                 const float bt = __ldg(bt_row + bidx[0]);
                 const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
                 const float sb = __fsqrt_rn(bt);
@@ -141,12 +203,13 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, long long n,
                                                             uint64_t seed, uint64_t step,
                                                             uint64_t group_offset) {
+    const PhiloxKeys keys = philox_keys(seed);
     const long long groups = (n + 3) / 4;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
          g += stride) {
         float z[4];
-        normal4(static_cast<uint64_t>(g) + group_offset, step, seed, z);
+        normal4(static_cast<uint64_t>(g) + group_offset, step, keys, z);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (g * 4 + k < n) out[g * 4 + k] = z[k];
@@ -185,8 +248,11 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
     }
     int rc = grid_for((total + 3) / 4, &grid);
     if (rc != PS_OK) return rc;
-    diffuse_philox_kernel<<<grid, 256, 0, stream>>>(x, betas, T, B, seed, step0, elem_offset / 4,
-                                                    per_b, total, out);
+    // schedule table: worth it from a handful of steps on, as long as it fits the default 48 KB of shared memory
+    const size_t table_bytes = static_cast<size_t>(T) * kTableSlots * sizeof(float2);
+    const int use_table = (T >= 4 && table_bytes <= 40 * 1024 && per_b >= 1024 / (kTableSlots - 1)) ? 1 : 0;
+    diffuse_philox_kernel<<<grid, 256, use_table ? table_bytes : 0, stream>>>(x, betas, T, B, seed, step0, elem_offset / 4,
+                                                                              per_b, total, use_table, out);
     return check_launch("diffuse_philox_kernel");
 }
 
