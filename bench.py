@@ -274,12 +274,12 @@ def main():
     torch.cuda.synchronize()
     fill_gbs = 3 * dist_t.numel() * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9
     # DRAM bytes per launch from the committed `ncu --set full` capture of this command
-    # (profiles/r1i_k1_final_ncu_summary.txt: dram__bytes_write 4.711673 GB + dram__bytes_read 4.99 MB at 16 structures)
-    traffic = (4.711673e9 + 4.99456e6) * B / 16 if B == 16 else None
+    # (profiles/r1t_k1_ncu_summary.txt: dram__bytes_write 4.709095 GB + dram__bytes_read 4.61696 MB at 16 structures)
+    traffic = (4.709095e9 + 4.61696e6) * B / 16 if B == 16 else None
     roofline = {
         "bound": "hbm", "kernel": "pair_tiles_kernel<15, dist+boolmask, angles> (fused inter_residue_geometry)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": traffic, "traffic_source": "profiles/r1i_k1_final_ncu_summary.txt (ncu --set full, per launch)",
+        "traffic": traffic, "traffic_source": "profiles/r1t_k1_ncu_summary.txt (ncu --set full, per launch)",
         "algorithmic_bytes_per_launch": B * BYTES_PER_STRUCT,
         "avg_launch_ms": avg_launch_ms, "best_launch_ms": min(per_launch_ms),
         "fill_ceiling_gbs": fill_gbs,
