@@ -6,6 +6,7 @@ nothing torch-typed crosses this boundary (raw device pointers, ints, a cudaStre
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import threading
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p, POINTER
@@ -110,6 +111,18 @@ def load(path: Path | None = None) -> ctypes.CDLL:
 
 def last_error() -> str:
     return load().ps_last_error_string().decode("utf-8", "replace")
+
+
+_NO_SWITCH = contextlib.nullcontext()
+
+
+def on_device(device):
+    """Context that makes `device` the current CUDA device for a launch; free when it already is (the
+    usual case — `torch.cuda.device` costs ~10 us of driver calls per entry even then)."""
+    import torch
+
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    return _NO_SWITCH if torch.cuda.current_device() == index else torch.cuda.device(index)
 
 
 def check(rc: int, what: str) -> None:

@@ -96,7 +96,7 @@ def angle(a: ArrayLike, b: ArrayLike, c: ArrayLike, to_degree: bool = False):
     (pa, pb, pc), lead = _points(tensors)
     n = pa.shape[0]
     out = torch.empty(n, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _cabi.on_device(dev):
         rc = _cabi.load().ps_geom_angle(pa.data_ptr(), pb.data_ptr(), pc.data_ptr(), n,
                                         int(bool(to_degree)), out.data_ptr(), _stream(dev))
     _cabi.check(rc, "ps_geom_angle")
@@ -110,7 +110,7 @@ def dihedral(a: ArrayLike, b: ArrayLike, c: ArrayLike, d: ArrayLike, to_degree: 
     (pa, pb, pc, pd), lead = _points(tensors)
     n = pa.shape[0]
     out = torch.empty(n, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _cabi.on_device(dev):
         rc = _cabi.load().ps_geom_dihedral(pa.data_ptr(), pb.data_ptr(), pc.data_ptr(), pd.data_ptr(),
                                            n, int(bool(to_degree)), out.data_ptr(), _stream(dev))
     _cabi.check(rc, "ps_geom_dihedral")
@@ -125,7 +125,7 @@ def gram_schmidt(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Ten
     (pa, pb, pc), lead = _points(tensors)
     n = pa.shape[0]
     out = torch.empty(n, 3, 3, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _cabi.on_device(dev):
         rc = _cabi.load().ps_geom_gram_schmidt(pa.data_ptr(), pb.data_ptr(), pc.data_ptr(), n,
                                                out.data_ptr(), _stream(dev))
     _cabi.check(rc, "ps_geom_gram_schmidt")

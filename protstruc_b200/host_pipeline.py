@@ -25,7 +25,7 @@ class HostFeaturePipeline:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.chunk, self.L, self.A = chunk, L, A
         handle = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             _cabi.check(self.lib.ps_host_pipeline_create(chunk, L, A, ctypes.byref(handle)), "ps_host_pipeline_create")
         self._handle = handle
 
@@ -73,7 +73,7 @@ class HostFeaturePipeline:
             t = out[name]
             if t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.shape[0] < B:
                 raise ValueError(f"out[{name!r}] must be a contiguous CPU {dt} tensor with at least {B} rows")
-        with torch.cuda.device(self.device):
+        with _cabi.on_device(self.device):
             rc = self.lib.ps_host_inter_residue_geometry(
                 self._handle, xyz_host.data_ptr(), mask_host.data_ptr(), B, out["dist"].data_ptr(),
                 out["dist_mask"].data_ptr(), out["omega"].data_ptr(), out["theta"].data_ptr(), out["phi"].data_ptr())

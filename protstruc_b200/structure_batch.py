@@ -177,7 +177,7 @@ class StructureBatch:
         ideal = constants.ideal_backbone(include_cb).to(dev).contiguous()
         xyz = torch.empty(B, L, A, 3, dtype=torch.float32, device=dev)
         mask = torch.empty(B, L, A, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_frames_to_backbone(rot.data_ptr(), tr.data_ptr(), ideal.data_ptr(), ideal.shape[0], B, L, A,
                                            xyz.data_ptr(), mask.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(rc, "ps_frames_to_backbone")
@@ -210,7 +210,7 @@ class StructureBatch:
         if A <= int(ATOM.C):
             raise IndexError(f"index {int(ATOM.C)} is out of bounds for dimension 2 with size {A}")
         out = torch.empty_like(self.xyz)
-        with torch.cuda.device(self.xyz.device):
+        with _cabi.on_device(self.xyz.device):
             rc = lib.ps_local_xyz(self.xyz.data_ptr(), B, L, A, int(ATOM.N), int(ATOM.CA), int(ATOM.C), int(ATOM.CA),
                                   out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_local_xyz")
@@ -304,7 +304,7 @@ class StructureBatch:
         mask, code = self._mask_for_kernel(self.atom_mask)
         dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
         dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_pair_dist_mask(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
                                        dist_mask.data_ptr(), B, L, A, self._stream())
         _cabi.check(rc, "ps_pair_dist_mask")
@@ -330,7 +330,7 @@ class StructureBatch:
         for s in si + sj:
             if s >= A:
                 raise IndexError(f"index {s} is out of bounds for dimension 2 with size {A}")
-        with torch.cuda.device(self.xyz.device):
+        with _cabi.on_device(self.xyz.device):
             rc = lib.ps_pair_angles(self.xyz.data_ptr(), B, L, A, _cabi.int_array(si), len(si),
                                     _cabi.int_array(sj), len(sj), kind, out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_pair_angles")
@@ -358,7 +358,7 @@ class StructureBatch:
         if self._is_empty():
             return omega, theta, phi
         lib = self._lib()
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_trrosetta_angles(self.xyz.data_ptr(), B, L, A, int(bool(virtual_cb)),
                                          omega.data_ptr(), theta.data_ptr(), phi.data_ptr(), self._stream())
         _cabi.check(rc, "ps_trrosetta_angles")
@@ -387,7 +387,7 @@ class StructureBatch:
         omega = torch.empty(B, L, L, dtype=torch.float32, device=dev)
         theta = torch.empty_like(omega)
         phi = torch.empty_like(omega)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_inter_residue_geometry(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
                                                dist_mask.data_ptr(), omega.data_ptr(), theta.data_ptr(),
                                                phi.data_ptr(), B, L, A, self._stream())
@@ -431,7 +431,7 @@ class StructureBatch:
             a1, a2, a3 = frame_slots
             frames = torch.empty(B, L, 3, 3, dtype=torch.float32, device=dev)
             fr_ptr = frames.data_ptr()
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_backbone(self.xyz.data_ptr(), rm_ptr, ch_ptr, B, L, A, a1, a2, a3, dh_ptr, dm_ptr,
                                  fr_ptr, self._stream())
         _cabi.check(rc, "ps_backbone")
@@ -478,7 +478,7 @@ class StructureBatch:
         view = translation.expand(self.xyz.shape)  # raises like torch's `+=` if the shapes do not broadcast
         sb, sl, sa, _ = view.stride()
         B, L, A = self._dims()
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_translate_bcast(self.xyz.data_ptr(), view.data_ptr(), sb, sl, sa, B, L, A, self.xyz.data_ptr(),
                                         self._stream())
         _cabi.check(rc, "ps_translate_bcast")
@@ -495,7 +495,7 @@ class StructureBatch:
         rot = rotation.to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
         B, L, A = self._dims()
         out = torch.empty_like(self.xyz)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_rotate(self.xyz.data_ptr(), rot.data_ptr(), rot.shape[0], B, L, A, out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_rotate")
         self.xyz = out
@@ -523,7 +523,7 @@ class StructureBatch:
         mu = torch.empty(B, 3, dtype=torch.float32, device=dev)
         sd = torch.empty(B, 3, dtype=torch.float32, device=dev)
         out = torch.empty_like(self.xyz)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_masked_stats(self.xyz.data_ptr(), mask.data_ptr(), code, B, L, A, mu.data_ptr(),
                                      sd.data_ptr(), out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_masked_stats")
@@ -538,7 +538,7 @@ class StructureBatch:
         lib = self._lib()
         B, L, A = self._dims()
         out = torch.empty_like(self.xyz)
-        with torch.cuda.device(self.xyz.device):
+        with _cabi.on_device(self.xyz.device):
             rc = lib.ps_scale_shift(self.xyz.data_ptr(), self.std.data_ptr(), self.mu.data_ptr(), B, L, A,
                                     out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_scale_shift")
@@ -555,7 +555,7 @@ class StructureBatch:
         if A <= int(ATOM.CA):
             raise IndexError(f"index {int(ATOM.CA)} is out of bounds for dimension 2 with size {A}")
         out = torch.empty(B, 3, dtype=torch.float32, device=self.xyz.device)
-        with torch.cuda.device(self.xyz.device):
+        with _cabi.on_device(self.xyz.device):
             rc = lib.ps_center_of_mass(self.xyz.data_ptr(), B, L, A, int(ATOM.CA), out.data_ptr(), self._stream())
         _cabi.check(rc, "ps_center_of_mass")
         return out
@@ -577,7 +577,7 @@ class StructureBatch:
         dev = self.xyz.device
         B, L, A = self._dims()
         translation = (center.to(device=dev, dtype=torch.float32) - self.center_of_mass()).contiguous()
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_translate(self.xyz.data_ptr(), translation.data_ptr(), translation.shape[0], B, L, A,
                                   self.xyz.data_ptr(), self._stream())
         _cabi.check(rc, "ps_translate")
@@ -602,7 +602,7 @@ class StructureBatch:
         tgt = target.get_xyz().to(device=dev, dtype=torch.float32).contiguous()
         rot = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
         tr = torch.empty(B, 3, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_kabsch(self.xyz.data_ptr(), tgt.data_ptr(), mask.data_ptr(), tgt.shape[0], B, L * A,
                                rot.data_ptr(), tr.data_ptr(), self._stream())
         _cabi.check(rc, "ps_kabsch")
@@ -628,7 +628,7 @@ class StructureBatch:
         valid_u8 = valid.to(torch.uint8).contiguous()
         scratch = torch.empty(L, dtype=torch.float32, device=dev)
         out = torch.empty(L, dtype=torch.bool, device=dev)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_topk_nearest_residue_mask(self.xyz.data_ptr(), valid_u8.data_ptr(), query.data_ptr(),
                                                   query.shape[0], L, A, int(ATOM.CA), k_eff, scratch.data_ptr(),
                                                   out.data_ptr(), self._stream())
@@ -672,12 +672,12 @@ class StructureBatch:
             if noise.shape != self.xyz.shape:
                 raise ValueError(f"`noise` must have shape {tuple(self.xyz.shape)}, got {tuple(noise.shape)}")
             z = noise.to(device=dev, dtype=torch.float32).contiguous()
-            with torch.cuda.device(dev):
+            with _cabi.on_device(dev):
                 rc = lib.ps_diffuse(self.xyz.data_ptr(), beta.data_ptr(), z.data_ptr(), 0, 0, 0, out.data_ptr(),
                                     B, per_b, self._stream())
         else:
             seed, step = _philox.reserve(1, generator)
-            with torch.cuda.device(dev):
+            with _cabi.on_device(dev):
                 rc = lib.ps_diffuse(self.xyz.data_ptr(), beta.data_ptr(), None, seed, step,
                                     self._noise_elem_offset, out.data_ptr(), B, per_b, self._stream())
         _cabi.check(rc, "ps_diffuse")
@@ -697,7 +697,7 @@ class StructureBatch:
             return
         out = torch.empty_like(self.xyz)
         seed, step0 = _philox.reserve(T, generator)
-        with torch.cuda.device(dev):
+        with _cabi.on_device(dev):
             rc = lib.ps_diffuse_steps(self.xyz.data_ptr(), betas.data_ptr(), T, seed, step0,
                                       self._noise_elem_offset, out.data_ptr(), B, L * A * 3, self._stream())
         _cabi.check(rc, "ps_diffuse_steps")
