@@ -181,7 +181,7 @@ def main():
 
     import protstruc_b200 as ps
     from protstruc_b200 import _cabi
-    from protstruc_b200.host_pipeline import HostFeaturePipeline
+    from protstruc_b200.host_pipeline import HostFeaturePipeline, bind_host_thread_near_gpu
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
@@ -235,6 +235,8 @@ def main():
 
     # ---------------------------------------------------------------- end-to-end arm (`e2e`)
     Be = args.e2e_batch
+    all_cpus = os.sched_getaffinity(0)
+    host_cpus = bind_host_thread_near_gpu(dev.index)  # host buffers next to this GPU's PCIe link (multi-rank runs)
     pipe = HostFeaturePipeline(chunk=2, L=L_RES, A=N_ATOM, device=dev)
     xyz_h = xyz[:Be].cpu().pin_memory()
     mask_h = mask[:Be].cpu().pin_memory()
@@ -254,6 +256,7 @@ def main():
     same = torch.equal(torch.nan_to_num(out_h["dist"][0, :4, :4]), torch.nan_to_num(dist_t[0, :4, :4].cpu()))
     if not same:
         raise SystemExit("end-to-end host result differs from the device result")
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline below uses every core again
 
     if rank != 0:
         if world > 1:
@@ -305,6 +308,7 @@ def main():
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(Be),
                 "d2h_bytes_per_step": pipe.d2h_bytes(Be), "steps": args.e2e_steps, "batch": Be,
+                "host_cpus": "all" if host_cpus is None else f"{len(host_cpus)} local to the GPU (NVML affinity)",
                 "api": "C-ABI ps_host_inter_residue_geometry via protstruc_b200.host_pipeline.HostFeaturePipeline.run "
                        "(pinned host in, pinned host out, chunks double-buffered on two streams)"},
         "gpu_launches": args.steps, "clocks": clocks, "impl": "ours",
