@@ -247,3 +247,17 @@ def test_empty_batches_give_empty_features_without_a_launch():
         assert tuple(sb.get_local_xyz().shape) == (B, L, 15, 3)
         com = sb.center_of_mass()
         assert tuple(com.shape) == (B, 3) and bool(torch.isnan(com).all())
+
+
+def test_numa_binding_helper_is_a_no_op_without_a_gpu_and_never_raises():
+    """`bind_host_thread_near_gpu` is opt-in plumbing for multi-rank host streaming: without CUDA / NVML (this
+    container) it must leave the affinity alone and return None."""
+    import os
+
+    from protstruc_b200.host_pipeline import bind_host_thread_near_gpu
+
+    before = os.sched_getaffinity(0)
+    assert bind_host_thread_near_gpu(0) is None or torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
