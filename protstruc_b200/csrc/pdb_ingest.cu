@@ -92,39 +92,147 @@ void field(const char* line, int line_len, int begin, int end, char* out, int ou
     out[n] = '\0';
 }
 
-int type_index(const char* resname) {
-    for (int t = 0; t < 20; ++t)
-        if (strcmp(kTypes[t].name, resname) == 0) return t;
-    return -1;
+// Names are at most four characters: they are compared as packed 32-bit keys (first character in the low byte).
+uint32_t pack_name(const char* s) {
+    uint32_t key = 0;
+    for (int k = 0; k < 4 && s[k]; ++k) key |= static_cast<uint32_t>(static_cast<unsigned char>(s[k])) << (8 * k);
+    return key;
+}
+// Key of the trimmed text in columns [begin, end) (end - begin <= 4); 0 when blank.  Returns false when the
+// trimmed text has an inner blank (never a valid name).
+bool pack_columns(const char* line, int begin, int end, uint32_t* key) {
+    while (begin < end && line[begin] == ' ') ++begin;
+    while (end > begin && (line[end - 1] == ' ' || line[end - 1] == '\r')) --end;
+    uint32_t k = 0;
+    for (int c = begin; c < end; ++c) {
+        if (line[c] == ' ') return false;
+        k |= static_cast<uint32_t>(static_cast<unsigned char>(line[c])) << (8 * (c - begin));
+    }
+    *key = k;
+    return true;
 }
 
-void substitute(char* resname) {
-    if (type_index(resname) >= 0) return;
-    for (const Substitution& s : kSubstitutions) {
-        const char* p = s.sources;
-        while (*p) {
-            if (strncmp(p, resname, 3) == 0 && (p[3] == ' ' || p[3] == '\0') && strlen(resname) == 3) {
-                strcpy(resname, s.target);
-                return;
-            }
-            while (*p && *p != ' ') ++p;
-            while (*p == ' ') ++p;
+// Lookup tables built once (thread-safe function-local static): residue name -> type (standard names and the
+// substitution table folded in), the set of heavy-atom names, and the packed slot names of every type.
+struct Tables {
+    static constexpr int kResBits = 10, kAtomBits = 8;
+    uint32_t res_key[1 << kResBits];
+    int8_t res_type[1 << kResBits];
+    uint32_t atom_key[1 << kAtomBits];
+    uint32_t slot_key[20][kSlots];
+
+    static uint32_t hash(uint32_t key, int bits) { return (key * 2654435761u) >> (32 - bits); }
+
+    void add_residue(uint32_t key, int type) {
+        uint32_t h = hash(key, kResBits);
+        while (res_key[h] != 0 && res_key[h] != key) h = (h + 1) & ((1u << kResBits) - 1);
+        if (res_key[h] == 0) {  // first entry wins, like the linear scans this replaces
+            res_key[h] = key;
+            res_type[h] = static_cast<int8_t>(type);
         }
     }
-}
-
-bool is_heavy_atom_name(const char* name) {
-    if (!*name) return false;
-    for (int t = 0; t < 20; ++t)
+    Tables() {
+        memset(res_key, 0, sizeof res_key);
+        memset(res_type, -1, sizeof res_type);
+        memset(atom_key, 0, sizeof atom_key);
+        for (int t = 0; t < 20; ++t) add_residue(pack_name(kTypes[t].name), t);
+        for (const Substitution& sub : kSubstitutions) {
+            int target = -1;
+            for (int t = 0; t < 20; ++t)
+                if (strcmp(kTypes[t].name, sub.target) == 0) target = t;
+            const char* p = sub.sources;
+            while (*p) {
+                char name[4] = {p[0], p[1], p[2], '\0'};
+                add_residue(pack_name(name), target);
+                p += 3;
+                while (*p == ' ') ++p;
+            }
+        }
+        for (int t = 0; t < 20; ++t)
+            for (int a = 0; a < kSlots; ++a) {
+                const uint32_t key = pack_name(kTypes[t].atoms[a]);
+                slot_key[t][a] = key;
+                if (key == 0) continue;
+                uint32_t h = hash(key, kAtomBits);
+                while (atom_key[h] != 0 && atom_key[h] != key) h = (h + 1) & ((1u << kAtomBits) - 1);
+                atom_key[h] = key;
+            }
+    }
+    // Type of a residue name after substitution (-1: not one of the 20 amino acids).
+    int residue_type(uint32_t key) const {
+        if (key == 0) return -1;
+        uint32_t h = hash(key, kResBits);
+        while (res_key[h] != 0) {
+            if (res_key[h] == key) return res_type[h];
+            h = (h + 1) & ((1u << kResBits) - 1);
+        }
+        return -1;
+    }
+    bool is_heavy_atom(uint32_t key) const {
+        if (key == 0) return false;
+        uint32_t h = hash(key, kAtomBits);
+        while (atom_key[h] != 0) {
+            if (atom_key[h] == key) return true;
+            h = (h + 1) & ((1u << kAtomBits) - 1);
+        }
+        return false;
+    }
+    int slot_of(int type, uint32_t key) const {
         for (int a = 0; a < kSlots; ++a)
-            if (strcmp(kTypes[t].atoms[a], name) == 0) return true;
-    return false;
+            if (slot_key[type][a] == key) return a;
+        return -1;
+    }
+};
+
+const Tables& tables() {
+    static const Tables t;
+    return t;
 }
 
-int slot_of(int type, const char* atom) {
-    for (int a = 0; a < kSlots; ++a)
-        if (strcmp(kTypes[type].atoms[a], atom) == 0) return a;
-    return -1;
+// Integer in columns [begin, end) with atoi semantics (leading blanks, optional sign, digits until anything else).
+int parse_int(const char* line, int begin, int end) {
+    while (begin < end && line[begin] == ' ') ++begin;
+    bool negative = false;
+    if (begin < end && (line[begin] == '-' || line[begin] == '+')) negative = line[begin++] == '-';
+    int v = 0;
+    while (begin < end && line[begin] >= '0' && line[begin] <= '9') v = v * 10 + (line[begin++] - '0');
+    return negative ? -v : v;
+}
+
+// Fixed-point coordinate field ("%8.3f").  digits / 10^decimals with both operands exact in double is the
+// correctly rounded double of the decimal text, i.e. what strtod returns; anything that is not plain
+// [sign]digits[.digits] goes to strtod itself.
+float parse_coordinate(const char* line, int line_len, int begin, int end) {
+    static const double kPow10[10] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
+    if (end > line_len) end = line_len;
+    int c = begin;
+    while (c < end && line[c] == ' ') ++c;
+    int stop = end;
+    while (stop > c && (line[stop - 1] == ' ' || line[stop - 1] == '\r')) --stop;
+    int q = c;
+    bool negative = false;
+    if (q < stop && (line[q] == '-' || line[q] == '+')) negative = line[q++] == '-';
+    long long mantissa = 0;
+    int digits = 0, decimals = 0;
+    while (q < stop && line[q] >= '0' && line[q] <= '9') {
+        mantissa = mantissa * 10 + (line[q++] - '0');
+        ++digits;
+    }
+    if (q < stop && line[q] == '.') {
+        ++q;
+        while (q < stop && line[q] >= '0' && line[q] <= '9') {
+            mantissa = mantissa * 10 + (line[q++] - '0');
+            ++digits;
+            ++decimals;
+        }
+    }
+    if (q == stop && digits > 0 && digits <= 15 && decimals <= 9) {
+        const double v = static_cast<double>(mantissa) / kPow10[decimals];
+        return static_cast<float>(negative ? -v : v);
+    }
+    char text[16];
+    field(line, line_len, begin, end, text, sizeof text);
+    return static_cast<float>(strtod(text, nullptr));
 }
 
 struct Sink {
@@ -164,10 +272,11 @@ struct Sink {
 };
 
 int parse(const char* text, long long len, Sink& sink) {
+    const Tables& tb = tables();
     bool seen_model = false, in_first_model = true;
     // identity of the residue currently being filled
     bool have_residue = false;
-    char cur_chain = 0, cur_ins = 0, cur_name[4] = "";
+    char cur_chain = 0, cur_ins = 0;
     int cur_number = 0, cur_type = -1, cur_row = -1;
     char first_altloc = 0;
     // gap bookkeeping (reference pdb.py:92-121)
@@ -195,20 +304,18 @@ int parse(const char* text, long long len, Sink& sink) {
         if (strncmp(line, "ATOM  ", 6) != 0 && strncmp(line, "HETATM", 6) != 0) continue;
         if (line_len < 54) continue;
 
-        char atom[8], resname[8], num[8], coord[16];
-        field(line, line_len, 12, 16, atom, sizeof atom);
-        field(line, line_len, 17, 20, resname, sizeof resname);
-        substitute(resname);
-        const int type = type_index(resname);
-        if (type < 0 || !is_heavy_atom_name(atom)) continue;
+        uint32_t atom_key = 0, res_key = 0;
+        if (!pack_columns(line, 12, 16, &atom_key) || !pack_columns(line, 17, 20, &res_key)) continue;
+        const int type = tb.residue_type(res_key);
+        if (type < 0 || !tb.is_heavy_atom(atom_key)) continue;
         const char altloc = line[16] == ' ' ? 0 : line[16];
         const char chain = line[21];
         const char ins = line[26] == ' ' ? 0 : line[26];
-        field(line, line_len, 22, 26, num, sizeof num);
-        const int number = atoi(num);
+        const int number = parse_int(line, 22, 26);
 
+        // (after substitution a residue name is one of the 20 standard ones, so comparing types compares names)
         const bool same = have_residue && chain == cur_chain && number == cur_number && ins == cur_ins &&
-                          strcmp(resname, cur_name) == 0;
+                          type == cur_type;
         if (!same) {
             // a new residue starts: fill numbering gaps inside the chain with UNK rows first
             if (!have_chain || gap_chain != chain) {
@@ -227,7 +334,6 @@ int parse(const char* text, long long len, Sink& sink) {
             cur_chain = chain;
             cur_number = number;
             cur_ins = ins;
-            strcpy(cur_name, resname);
             cur_type = type;
             first_altloc = 0;
         }
@@ -235,13 +341,10 @@ int parse(const char* text, long long len, Sink& sink) {
             if (!first_altloc) first_altloc = altloc;
             if (altloc != first_altloc) continue;
         }
-        const int slot = slot_of(cur_type, atom);
+        const int slot = tb.slot_of(cur_type, atom_key);
         if (slot < 0 || cur_row < 0) continue;
         float* dst = sink.xyz + (static_cast<long long>(cur_row) * kSlots + slot) * 3;
-        for (int k = 0; k < 3; ++k) {
-            field(line, line_len, 30 + 8 * k, 38 + 8 * k, coord, sizeof coord);
-            dst[k] = static_cast<float>(strtod(coord, nullptr));
-        }
+        for (int k = 0; k < 3; ++k) dst[k] = parse_coordinate(line, line_len, 30 + 8 * k, 38 + 8 * k);
         sink.mask[cur_row * kSlots + slot] = 1;
     }
     return sink.rows;

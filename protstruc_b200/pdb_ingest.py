@@ -26,29 +26,41 @@ def read_pdb_arrays(path) -> Dict[str, object]:
     lib = _cabi.load()
     text = Path(path).read_bytes()
     n = ctypes.c_int(0)
-    _cabi.check(lib.ps_host_pdb_parse(text, len(text), 0, None, None, None, None, None, None, None, ctypes.byref(n)),
-                "ps_host_pdb_parse")
-    L = n.value
-    xyz = np.empty((L, N_SLOTS, 3), dtype=np.float32)
-    mask = np.empty((L, N_SLOTS), dtype=np.uint8)
-    chain_idx = np.empty(L, dtype=np.int32)
-    resseq = np.empty(L, dtype=np.int32)
-    chain_id = np.empty(L, dtype="S1")
-    icode = np.empty(L, dtype="S1")
-    aa1 = np.empty(L, dtype="S1")
-    if L:
+    # One parse in the common case: PDB lines are 81 bytes and an all-atom file has ~8 ATOM lines per residue, so
+    # one row per four lines is a generous first guess; files with long numbering gaps (UNK placeholder rows) or
+    # CA-only traces trigger the second call.
+    capacity = len(text) // (81 * 4) + 64
+    while True:
+        xyz = np.empty((capacity, N_SLOTS, 3), dtype=np.float32)
+        mask = np.empty((capacity, N_SLOTS), dtype=np.uint8)
+        chain_idx = np.empty(capacity, dtype=np.int32)
+        resseq = np.empty(capacity, dtype=np.int32)
+        chain_id = np.empty(capacity, dtype="S1")
+        icode = np.empty(capacity, dtype="S1")
+        aa1 = np.empty(capacity, dtype="S1")
         ptr = lambda a: a.ctypes.data  # noqa: E731
-        _cabi.check(lib.ps_host_pdb_parse(text, len(text), L, ptr(xyz), ptr(mask), ptr(chain_idx), ptr(chain_id),
-                                          ptr(resseq), ptr(icode), ptr(aa1), ctypes.byref(n)), "ps_host_pdb_parse")
-    chain_chars = [c.decode() for c in chain_id]
-    chain_ids: List[str] = []
-    for c in chain_chars:
-        if c not in chain_ids:
-            chain_ids.append(c)
-    letters = "".join(c.decode() for c in aa1)
-    seq = {cid: "".join(ch for ch, c in zip(letters, chain_chars) if c == cid) for cid in chain_ids}
-    return {"xyz": xyz, "atom_mask": mask.astype(bool), "chain_idx": chain_idx, "chain_ids": chain_ids, "seq": seq,
-            "residue_number": resseq, "insertion_code": [c.decode().strip("\x00") for c in icode], "one_letter": letters}
+        rc = lib.ps_host_pdb_parse(text, len(text), capacity, ptr(xyz), ptr(mask), ptr(chain_idx), ptr(chain_id),
+                                   ptr(resseq), ptr(icode), ptr(aa1), ctypes.byref(n))
+        if n.value <= capacity:
+            _cabi.check(rc, "ps_host_pdb_parse")
+            break
+        capacity = n.value  # the row count is reported even when the rows did not fit
+    L = n.value
+    xyz, mask, chain_idx, resseq = xyz[:L], mask[:L], chain_idx[:L], resseq[:L]
+    chain_id, icode, aa1 = chain_id[:L], icode[:L], aa1[:L]
+    # per-residue characters as flat strings (one decode each instead of a Python loop over residues)
+    chain_chars = chain_id.tobytes().decode("latin-1")
+    letters = aa1.tobytes().decode("latin-1")
+    chain_ids: List[str] = list(dict.fromkeys(chain_chars))  # order of first appearance
+    if len(chain_ids) == 1:
+        seq = {chain_ids[0]: letters}
+    else:
+        codes = np.frombuffer(chain_id.tobytes(), dtype=np.uint8)
+        letter_codes = np.frombuffer(aa1.tobytes(), dtype=np.uint8)
+        seq = {cid: letter_codes[codes == ord(cid)].tobytes().decode("latin-1") for cid in chain_ids}
+    return {"xyz": xyz, "atom_mask": mask.view(np.bool_), "chain_idx": chain_idx, "chain_ids": chain_ids, "seq": seq,
+            "residue_number": resseq, "insertion_code": ["" if ch == "\x00" else ch for ch in icode.tobytes().decode("latin-1")],
+            "one_letter": letters}
 
 
 def read_pdb_batch(paths: Sequence, max_workers: int = 8) -> Dict[str, object]:
