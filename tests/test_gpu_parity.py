@@ -811,6 +811,39 @@ def test_any_shape_distance_kernels(native_lib, B, L, A):
     H.assert_distances_close(ieee, rd)
 
 
+def test_random_shapes_of_the_distance_tensor_against_a_device_side_check(native_lib):
+    """60 seeded random (B, L, A) — tile boundaries fall everywhere relative to residue rows and structures — through
+    the default dispatch and the any-A tile kernel with forced small / large tiles.  The check is evaluated with
+    torch on the device (same subtraction, fp32 sum of squares in the kernel's order is within 1 ulp of it), masks
+    exact; the any-A tile kernel must be bit-identical across tile sizes."""
+    rng = np.random.default_rng(77)
+    s = torch.cuda.current_stream().cuda_stream
+    for case in range(60):
+        A = int(rng.choice([1, 2, 3, 4, 5, 6, 7, 9, 11, 12, 13, 15, 16, 17, 21, 25, 30, 37, 40]))
+        L = int(rng.integers(1, 70 if A > 20 else 150))
+        B = int(rng.integers(1, 5))
+        g = torch.Generator(device=DEV).manual_seed(1000 + case)
+        xyz = (20.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)).contiguous()
+        mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.6
+        diff = xyz[:, :, None, :, None, :] - xyz[:, None, :, None, :, :]
+        want = torch.sqrt((diff * diff).sum(-1))
+        want_mask = mask[:, :, None, :, None] & mask[:, None, :, None, :]
+        outs = []
+        for variant in (0, 1 << 8, (1 << 8) | (1 << 16) | (1 << 24), (1 << 8) | (40 << 16) | (1 << 25)):
+            d = torch.full((B, L, L, A, A), -1.0, device=DEV)
+            m = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+            rc = native_lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr(), 0, d.data_ptr(), m.data_ptr(), B, L, A,
+                                                 variant, s)
+            _cabi.check(rc, "ps_pair_dist_mask_ex")
+            tag = f"case {case}: B={B} L={L} A={A} variant={variant:#x}"
+            assert torch.equal(m, want_mask), tag
+            err = (d - want).abs()
+            assert bool((err <= 4e-7 * want + 1e-30).all()), f"{tag}: max err {err.max().item()}"
+            outs.append(d)
+        assert torch.equal(outs[1], outs[2]) and torch.equal(outs[1], outs[3]), f"case {case}: tile size changed the result"
+        assert torch.equal(outs[0], outs[1]), f"case {case}: default dispatch differs from the any-A tile kernel"
+
+
 def test_randomised_shapes_against_the_oracle(native_lib):
     """Seeded sweep over odd shapes (tail tiles, L around the 32-pair tile size, every staged atom count and the
     generic path, bool and float masks, ragged lengths): every feature family vs the CPU oracle."""
