@@ -844,6 +844,32 @@ def test_random_shapes_of_the_distance_tensor_against_a_device_side_check(native
         assert torch.equal(outs[0], outs[1]), f"case {case}: default dispatch differs from the any-A tile kernel"
 
 
+@pytest.mark.parametrize("A", [15, 16])
+def test_more_than_2_31_output_elements(native_lib, A):
+    """One structure of 3100 residues: 2.16 G (A = 15, staged kernel) / 2.46 G (A = 16, any-A tile kernel) output
+    elements, i.e. element offsets beyond 32 bits.  Sampled residue rows (first, last, around the 2^31-element
+    boundary) are checked against a device-side evaluation; the mask exactly."""
+    B, L = 1, 3100
+    g = torch.Generator(device=DEV).manual_seed(31)
+    xyz = (30.0 * torch.randn(B, L, A, 3, device=DEV, generator=g)).contiguous()
+    mask = torch.rand(B, L, A, device=DEV, generator=g) < 0.5
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    dist, dist_mask = sb.pairwise_distance_matrix()
+    assert dist.numel() > 2 ** 31
+    boundary_row = (2 ** 31) // (L * A * A)
+    rows = sorted({0, 1, 17, boundary_row - 1, boundary_row, boundary_row + 1, L // 2, L - 2, L - 1})
+    for i in rows:
+        diff = xyz[0, i, None, :, None, :] - xyz[0, :, None, :, :]          # (L, A, A, 3)
+        want = torch.sqrt((diff * diff).sum(-1))
+        got = dist[0, i]
+        assert bool(((got - want).abs() <= 4e-7 * want + 1e-30).all()), f"row {i}"
+        assert torch.equal(dist_mask[0, i], mask[0, i, None, :, None] & mask[0, :, None, :]), f"mask row {i}"
+    # every element was written (the buffer is torch.empty): the diagonal blocks hold exact zeros, nothing is NaN
+    assert bool((dist[0, torch.arange(L), torch.arange(L)].diagonal(dim1=-2, dim2=-1) == 0).all())
+    assert not bool(torch.isnan(dist[0, ::97]).any())
+    del dist, dist_mask
+
+
 def test_randomised_shapes_against_the_oracle(native_lib):
     """Seeded sweep over odd shapes (tail tiles, L around the 32-pair tile size, every staged atom count and the
     generic path, bool and float masks, ragged lengths): every feature family vs the CPU oracle."""
