@@ -95,8 +95,9 @@ int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
  * K1+K2f — the full pairwise feature set in ONE kernel: distance matrix, pair mask
  * and omega/theta/phi.  Replaces StructureBatch.inter_residue_geometry
  * (protstruc/protstruc.py:790-817); d_ca/d_cb/d_no are views of `dist` taken by the caller.
- * Requires A >= 5.  mask_dtype must be PS_MASK_BOOL for the single-kernel path
- * (PS_MASK_F32 runs the distance/mask/angle kernels back to back on `stream`).
+ * Requires A >= 5.  One launch when A is a staged atom count (5, 10, 14, 15), L is at least the
+ * pairs per tile (128, 64, 32, 32), the outputs are 16-byte aligned and mask_dtype is PS_MASK_BOOL;
+ * otherwise the distance / mask / angle kernels run back to back on `stream` with identical results.
  */
 int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_dtype,
                               float* dist, void* dist_mask,
