@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) backbone_kernel(
     long long total) {
     const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (r >= total) return;
-    const int l = static_cast<int>(r % L);
+    const int l = static_cast<int>(r - index_div(r, L, total <= 0xFFFFFFFFll) * L);
     const float* __restrict__ x = xyz + r * A * 3;
 
     if (dihedrals) {
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) local_xyz_kernel(const float* __restrict_
                                                         float* __restrict__ out) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const long long r = t / A;
+    const long long r = index_div(t, A, total <= 0xFFFFFFFFll);
     const float* __restrict__ x = xyz + r * A * 3;
     const Frame f = gram_schmidt_frame(ld3(x + a1 * 3), ld3(x + a2 * 3), ld3(x + a3 * 3));
     const V3 p = ld3(xyz + t * 3);
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256) rotate_kernel(const float* __restrict__ x
                                                      float* __restrict__ out) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const float* __restrict__ m = rot + (rot_rows == 1 ? 0 : (t / atoms_per_struct) * 9);
+    const float* __restrict__ m =
+        rot + (rot_rows == 1 ? 0 : index_div(t, atoms_per_struct, total <= 0xFFFFFFFFll) * 9);
     const V3 p = ld3(xyz + t * 3);
     out[t * 3 + 0] = dot3(V3{__ldg(m + 0), __ldg(m + 1), __ldg(m + 2)}, p);
     out[t * 3 + 1] = dot3(V3{__ldg(m + 3), __ldg(m + 4), __ldg(m + 5)}, p);
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(256) frames_to_backbone_kernel(
     float* __restrict__ atom_mask) {
     const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    const long long r = t / A;
+    const long long r = index_div(t, A, total <= 0xFFFFFFFFll);
     const int a = static_cast<int>(t - r * A);
     V3 o{0.f, 0.f, 0.f};
     float m = 0.f;
@@ -186,17 +187,36 @@ __global__ void __launch_bounds__(256) frames_to_backbone_kernel(
 __global__ void __launch_bounds__(256) translate_bcast_kernel(const float* __restrict__ xyz,
                                                               const float* __restrict__ tr,
                                                               long long sb, long long sl, long long sa,
-                                                              int L, int A, long long total,
+                                                              int B, int A, int per_b,
                                                               float* __restrict__ out) {
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const long long atom = t / 3;
-    const int k = static_cast<int>(t - atom * 3);
-    const long long res = atom / A;
-    const int a = static_cast<int>(atom - res * A);
-    const long long b = res / L;
-    const int l = static_cast<int>(res - b * L);
-    out[t] = __fadd_rn(xyz[t], __ldg(tr + b * sb + l * sl + a * sa + k));
+    // 2-D grid: blockIdx.y walks the structures, x the structure's floats; (l, a, axis) from the 32-bit offset
+    // inside the structure with one 32-bit division
+    const unsigned row = static_cast<unsigned>(A) * 3u;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* __restrict__ xb = xyz + static_cast<long long>(b) * per_b;
+        float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
+        const float* __restrict__ tb = tr + b * sb;
+        const unsigned n = static_cast<unsigned>(per_b), step = gridDim.x * blockDim.x;
+        for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * step) {
+            float v[4], w[4];  // four independent load pairs in flight per thread
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned e = e0 + u * step;
+                v[u] = w[u] = 0.f;
+                if (e < n) {
+                    const unsigned l = e / row;
+                    const unsigned r = e - l * row;
+                    const unsigned a = r / 3u;
+                    const unsigned k = r - a * 3u;
+                    v[u] = xb[e];
+                    w[u] = __ldg(tb + l * sl + a * sa + k);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * step < n) ob[e0 + u * step] = __fadd_rn(v[u], w[u]);
+        }
+    }
 }
 
 unsigned blocks_for(long long n) { return static_cast<unsigned>((n + 255) / 256); }
@@ -270,8 +290,13 @@ int translate_bcast_impl(const float* xyz, const float* tr, long long sb, long l
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "translate: B=%d L=%d A=%d must be > 0", B, L, A);
     PS_REQUIRE(xyz && tr && out, PS_ERR_NULL_POINTER, "translate: NULL pointer");
     PS_REQUIRE(sb >= 0 && sl >= 0 && sa >= 0, PS_ERR_BAD_SHAPE, "translate: negative stride");
-    const long long total = static_cast<long long>(B) * L * A * 3;
-    translate_bcast_kernel<<<blocks_for(total), 256, 0, stream>>>(xyz, tr, sb, sl, sa, L, A, total, out);
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "translate: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
+    const int per_b = L * A * 3;
+    int gx = (per_b + 1023) / 1024;
+    if (gx > 64) gx = 64;
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(B < 65535 ? B : 65535), 1);
+    translate_bcast_kernel<<<grid, 256, 0, stream>>>(xyz, tr, sb, sl, sa, B, A, per_b, out);
     return check_launch("translate_bcast_kernel");
 }
 

@@ -252,6 +252,13 @@ __device__ __forceinline__ void trrosetta_triple(const TripleRowSide& r, V3 ca_j
     }
 }
 
+// n / d for a non-negative 64-bit index and a positive 32-bit divisor: the 32-bit instruction sequence whenever
+// the caller knows (uniformly) that the index range fits — an emulated 64-bit division costs ~120 issue slots.
+__device__ __forceinline__ long long index_div(long long n, long long d, bool fits_32_bits) {
+    if (fits_32_bits) return static_cast<unsigned>(n) / static_cast<unsigned>(d);
+    return n / d;
+}
+
 // ---------------------------------------------------------------- bulk async copy (TMA engine)
 // smem -> global bulk copy, tracked by the per-thread bulk async-group.
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {

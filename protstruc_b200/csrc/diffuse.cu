@@ -101,19 +101,31 @@ __device__ __forceinline__ float diffuse_one(float x, float z, float sa, float s
     return __fadd_rn(__fmul_rn(sa, x), __fmul_rn(z, sb));
 }
 
-// Injected-noise variant: purely elementwise.
+// Injected-noise variant: purely elementwise.  2-D grid: blockIdx.y walks the structures (one beta, two IEEE
+// square roots per thread and structure), x the structure's floats, fully coalesced.
 __global__ void __launch_bounds__(256) diffuse_noise_kernel(const float* __restrict__ x,
                                                             const float* __restrict__ beta,
                                                             const float* __restrict__ noise,
-                                                            long long per_b, long long total,
+                                                            long long per_b, int B,
                                                             float* __restrict__ out) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += stride) {
-        const float bt = __ldg(beta + e / per_b);
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float bt = __ldg(beta + b);
         const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
         const float sb = __fsqrt_rn(bt);
-        out[e] = diffuse_one(x[e], __ldg(noise + e), sa, sb);
+        const long long base = b * per_b;
+        const long long step = static_cast<long long>(gridDim.x) * blockDim.x;
+        for (long long e0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e0 < per_b; e0 += 4 * step) {
+            float v[4], z[4];  // four independent load pairs in flight per thread
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long e = e0 + u * step;
+                v[u] = e < per_b ? x[base + e] : 0.f;
+                z[u] = e < per_b ? __ldg(noise + base + e) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * step < per_b) out[base + e0 + u * step] = diffuse_one(v[u], z[u], sa, sb);
+        }
     }
 }
 
@@ -158,12 +170,25 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
         const long long e0 = g * 4;
         float v[4];
         int bidx[4];
+        // structure of each of the four elements: ONE division per thread (32-bit whenever the element count
+        // allows), then the group either stays inside the structure or steps over its end
+        long long b0, rem0;
+        if (total <= 0xFFFFFFFFll && per_b <= 0xFFFFFFFFll) {
+            const unsigned q = static_cast<unsigned>(e0) / static_cast<unsigned>(per_b);
+            b0 = q;
+            rem0 = static_cast<unsigned>(e0) - q * static_cast<unsigned>(per_b);
+        } else {
+            b0 = e0 / per_b;
+            rem0 = e0 - b0 * per_b;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long e = e0 + k;
             const bool ok = e < total;
             v[k] = ok ? x[e] : 0.f;
-            bidx[k] = ok ? static_cast<int>(e / per_b) : b_lo;
+            long long bk = b0 + (rem0 + k >= per_b ? 1 : 0);
+            if (per_b < 4) bk = e / per_b;  // degenerate structures of fewer than four floats
+            bidx[k] = ok ? static_cast<int>(bk) : static_cast<int>(b0);
         }
         const bool same_b = bidx[0] == bidx[3];
         for (int t = 0; t < T; ++t) {
@@ -241,9 +266,10 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
     int grid = 0;
     if (noise) {
         PS_REQUIRE(T == 1, PS_ERR_BAD_SHAPE, "diffuse: injected noise supports a single step");
-        int rc = grid_for(total, &grid);
-        if (rc != PS_OK) return rc;
-        diffuse_noise_kernel<<<grid, 256, 0, stream>>>(x, betas, noise, per_b, total, out);
+        long long gx = (per_b + 1023) / 1024;
+        if (gx > 32) gx = 32;
+        const dim3 grid2(static_cast<unsigned>(gx), static_cast<unsigned>(B < 65535 ? B : 65535), 1);
+        diffuse_noise_kernel<<<grid2, 256, 0, stream>>>(x, betas, noise, per_b, B, out);
         return check_launch("diffuse_noise_kernel");
     }
     int rc = grid_for((total + 3) / 4, &grid);

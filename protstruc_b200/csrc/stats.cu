@@ -115,33 +115,64 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
     }
 }
 
+// The per-structure elementwise maps run on a 2-D grid: blockIdx.y walks the structures, blockIdx.x / threadIdx.x
+// the structure's L*A*3 floats with fully coalesced scalar accesses.  The axis of an element is its 32-bit offset
+// inside the structure mod 3 (a multiply-shift); no per-element 64-bit division.
+
+// Four independent loads per thread are issued before the first use (kUnroll), so a thread keeps 4 x 128 B per
+// warp in flight instead of one dependent load -> store chain.
+constexpr int kUnroll = 4;
+
 // out = x * scale[b, axis] + shift[b, axis]  (unstandardize) — two rounded ops.
 __global__ void __launch_bounds__(256) scale_shift_kernel(const float* __restrict__ x,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift,
-                                                          long long per_b, long long total,
-                                                          float* __restrict__ out) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += stride) {
-        const long long b = e / per_b;
-        const int k = static_cast<int>((e - b * per_b) % 3);
-        out[e] = __fadd_rn(__fmul_rn(x[e], __ldg(scale + b * 3 + k)), __ldg(shift + b * 3 + k));
+                                                          int per_b, int B, float* __restrict__ out) {
+    const unsigned n = static_cast<unsigned>(per_b), step = gridDim.x * blockDim.x;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* __restrict__ xb = x + static_cast<long long>(b) * per_b;
+        float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
+        const float sc0 = __ldg(scale + b * 3), sc1 = __ldg(scale + b * 3 + 1), sc2 = __ldg(scale + b * 3 + 2);
+        const float sh0 = __ldg(shift + b * 3), sh1 = __ldg(shift + b * 3 + 1), sh2 = __ldg(shift + b * 3 + 2);
+        for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += kUnroll * step) {
+            float v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) v[u] = e0 + u * step < n ? xb[e0 + u * step] : 0.f;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned e = e0 + u * step;
+                if (e >= n) break;
+                const unsigned k = e % 3u;
+                const float sc = k == 0 ? sc0 : (k == 1 ? sc1 : sc2);
+                const float sh = k == 0 ? sh0 : (k == 1 ? sh1 : sh2);
+                ob[e] = __fadd_rn(__fmul_rn(v[u], sc), sh);
+            }
+        }
     }
 }
 
 // out = x + t[b or 0, axis]
 __global__ void __launch_bounds__(256) translate_kernel(const float* __restrict__ x,
                                                         const float* __restrict__ t, int t_rows,
-                                                        long long per_b, long long total,
-                                                        float* __restrict__ out) {
-    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-         e += stride) {
-        const long long b = e / per_b;
-        const int k = static_cast<int>((e - b * per_b) % 3);
-        const long long row = t_rows == 1 ? 0 : b;
-        out[e] = __fadd_rn(x[e], __ldg(t + row * 3 + k));
+                                                        int per_b, int B, float* __restrict__ out) {
+    const unsigned n = static_cast<unsigned>(per_b), step = gridDim.x * blockDim.x;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float* __restrict__ xb = x + static_cast<long long>(b) * per_b;
+        float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
+        const float* __restrict__ tb = t + (t_rows == 1 ? 0 : b * 3);
+        const float t0 = __ldg(tb), t1 = __ldg(tb + 1), t2 = __ldg(tb + 2);
+        for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += kUnroll * step) {
+            float v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) v[u] = e0 + u * step < n ? xb[e0 + u * step] : 0.f;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const unsigned e = e0 + u * step;
+                if (e >= n) break;
+                const unsigned k = e % 3u;
+                ob[e] = __fadd_rn(v[u], k == 0 ? t0 : (k == 1 ? t1 : t2));
+            }
+        }
     }
 }
 
@@ -178,15 +209,13 @@ __global__ void __launch_bounds__(128) center_of_mass_kernel(const float* __rest
     }
 }
 
-int elementwise_grid(long long total, int* grid) {
-    const int sms = sm_count_for_current_device();
-    if (sms < 0) return sms;
-    long long g = (total + 255) / 256;
-    const long long cap = static_cast<long long>(sms) * 16;
-    if (g > cap) g = cap;
-    if (g < 1) g = 1;
-    *grid = static_cast<int>(g);
-    return PS_OK;
+// Grid of the per-structure elementwise kernels: y = structures (capped, the kernel loops), x = enough CTAs of 256
+// threads that a thread handles about four elements of its structure.
+dim3 per_structure_grid(int per_b, int B) {
+    int gx = (per_b + 1023) / 1024;
+    if (gx < 1) gx = 1;
+    if (gx > 32) gx = 32;
+    return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(B < 65535 ? B : 65535), 1);
 }
 
 }  // namespace
@@ -220,12 +249,10 @@ int scale_shift_impl(const float* xyz, const float* scale, const float* shift, i
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "scale_shift: B=%d L=%d A=%d must be > 0",
                B, L, A);
     PS_REQUIRE(xyz && scale && shift && xyz_out, PS_ERR_NULL_POINTER, "scale_shift: NULL pointer");
-    const long long per_b = static_cast<long long>(L) * A * 3;
-    const long long total = per_b * B;
-    int grid = 0;
-    int rc = elementwise_grid(total, &grid);
-    if (rc != PS_OK) return rc;
-    scale_shift_kernel<<<grid, 256, 0, stream>>>(xyz, scale, shift, per_b, total, xyz_out);
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "scale_shift: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
+    const int per_b = L * A * 3;
+    scale_shift_kernel<<<per_structure_grid(per_b, B), 256, 0, stream>>>(xyz, scale, shift, per_b, B, xyz_out);
     return check_launch("scale_shift_kernel");
 }
 
@@ -236,12 +263,10 @@ int translate_impl(const float* xyz, const float* t, int t_rows, int B, int L, i
     PS_REQUIRE(xyz && t && xyz_out, PS_ERR_NULL_POINTER, "translate: NULL pointer");
     PS_REQUIRE(t_rows == 1 || t_rows == B, PS_ERR_BAD_SHAPE, "translate: t_rows=%d must be 1 or B=%d",
                t_rows, B);
-    const long long per_b = static_cast<long long>(L) * A * 3;
-    const long long total = per_b * B;
-    int grid = 0;
-    int rc = elementwise_grid(total, &grid);
-    if (rc != PS_OK) return rc;
-    translate_kernel<<<grid, 256, 0, stream>>>(xyz, t, t_rows, per_b, total, xyz_out);
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "translate: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
+    const int per_b = L * A * 3;
+    translate_kernel<<<per_structure_grid(per_b, B), 256, 0, stream>>>(xyz, t, t_rows, per_b, B, xyz_out);
     return check_launch("translate_kernel");
 }
 
