@@ -62,6 +62,20 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, const PhiloxKeys& k) {
     return c;
 }
 
+// Same function with the round keys bumped on the fly (uniform-datapath adds): cheaper when a thread makes a
+// single call, as in the one-step kernel.
+__device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c.x), lo0 = kPhiloxM0 * c.x;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c.z), lo1 = kPhiloxM1 * c.z;
+        c = U4{hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0};
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return c;
+}
+
 // Two random words -> two N(0,1) (Box-Muller).  The generator is the bottleneck of the fused T-step kernel and
 // the quarter-rate XU pipe (MUFU, I2F) its scarcest resource, so
 //  * the uniforms are built without an int->float conversion: the top 23 bits of the word become the mantissa of
@@ -89,6 +103,18 @@ __device__ __forceinline__ void normal4(uint64_t group, uint64_t step, const Phi
     const U4 ctr{static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32),
                  static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32)};
     const U4 r = philox4x32_10(ctr, keys);
+    const float2 a = box_muller(r.x, r.y);
+    const float2 b = box_muller(r.z, r.w);
+    z[0] = a.x;
+    z[1] = a.y;
+    z[2] = b.x;
+    z[3] = b.y;
+}
+
+__device__ __forceinline__ void normal4(uint64_t group, uint64_t step, uint64_t seed, float (&z)[4]) {
+    const U4 ctr{static_cast<uint32_t>(group), static_cast<uint32_t>(group >> 32),
+                 static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32)};
+    const U4 r = philox4x32_10(ctr, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     const float2 a = box_muller(r.x, r.y);
     const float2 b = box_muller(r.z, r.w);
     z[0] = a.x;
@@ -225,6 +251,36 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
     }
 }
 
+// One step (what a caller of the reference's diffuse_xyz does T times): the lean form of the kernel above — one
+// group of four elements per thread, no schedule table, no key expansion; the same stream and the same arithmetic,
+// so T calls of it equal one T-step launch bit for bit.
+__global__ void __launch_bounds__(256) diffuse_philox_step_kernel(const float* __restrict__ x,
+                                                                  const float* __restrict__ beta, uint64_t seed,
+                                                                  uint64_t step, uint64_t group_offset,
+                                                                  long long per_b, long long total,
+                                                                  float* __restrict__ out) {
+    const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long e0 = g * 4;
+    if (e0 >= total) return;
+    const bool fits_32_bits = total <= 0xFFFFFFFFll && per_b <= 0xFFFFFFFFll;
+    const long long b0 = index_div(e0, per_b, fits_32_bits);
+    const long long rem0 = e0 - b0 * per_b;
+    float z[4];
+    normal4(static_cast<uint64_t>(g) + group_offset, step, seed, z);
+    if (rem0 + 3 < per_b && e0 + 3 < total) {  // the whole group lies in structure b0 (the common case)
+        const float bt = __ldg(beta + b0);
+        const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
+        const float sb = __fsqrt_rn(bt);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[e0 + k] = diffuse_one(x[e0 + k], z[k], sa, sb);
+    } else {
+        for (int k = 0; k < 4 && e0 + k < total; ++k) {
+            const float bt = __ldg(beta + (e0 + k) / per_b);
+            out[e0 + k] = diffuse_one(x[e0 + k], z[k], __fsqrt_rn(__fsub_rn(1.0f, bt)), __fsqrt_rn(bt));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, long long n,
                                                             uint64_t seed, uint64_t step,
                                                             uint64_t group_offset) {
@@ -271,6 +327,13 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
         const dim3 grid2(static_cast<unsigned>(gx), static_cast<unsigned>(B < 65535 ? B : 65535), 1);
         diffuse_noise_kernel<<<grid2, 256, 0, stream>>>(x, betas, noise, per_b, B, out);
         return check_launch("diffuse_noise_kernel");
+    }
+    if (T == 1) {
+        const long long groups = (total + 3) / 4;
+        PS_REQUIRE((groups + 255) / 256 < (1ll << 31), PS_ERR_BAD_SHAPE, "diffuse: %lld elements", total);
+        diffuse_philox_step_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(
+            x, betas, seed, step0, elem_offset / 4, per_b, total, out);
+        return check_launch("diffuse_philox_step_kernel");
     }
     int rc = grid_for((total + 3) / 4, &grid);
     if (rc != PS_OK) return rc;
