@@ -26,29 +26,36 @@ struct SlotList {
     int n;
 };
 
-template <int KIND>
+// NI = how many of the points come from residue i (the first NI of the list).  It is a template parameter so that
+// the points of residue i — and everything dihedral4 / angle3 derive from them alone (b0 for NI >= 2; b1, the normal
+// n1 and 1 / |b1| for NI >= 3) — are loop invariants the compiler hoists out of the j loop, and so that the point
+// array is indexed with compile-time constants only.
+template <int KIND, int NI>
 __global__ void __launch_bounds__(256) pair_angles_kernel(const float* __restrict__ xyz,
                                                           float* __restrict__ out, int L, int A,
                                                           SlotList sl, long long rows) {
+    constexpr int N = KIND == PS_ANGLE_DIHEDRAL ? 4 : 3;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const long long b = row / L;
         const float* __restrict__ xi = xyz + row * A * 3;
         const float* __restrict__ xb = xyz + b * L * A * 3;
+        float* __restrict__ out_row = out + row * L;
         V3 pt[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (k < sl.n && !sl.from_j[k]) pt[k] = ld3(xi + sl.s[k] * 3);
-        for (int j = threadIdx.x; j < L; j += blockDim.x) {
-            const float* __restrict__ xj = xb + static_cast<long long>(j) * A * 3;
+        for (int k = 0; k < N; ++k) pt[k] = V3{0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < sl.n && sl.from_j[k]) pt[k] = ld3(xj + sl.s[k] * 3);
+        for (int k = 0; k < NI; ++k) pt[k] = ld3(xi + sl.s[k] * 3);
+        const int stride = A * 3;
+        for (int j = threadIdx.x; j < L; j += blockDim.x) {
+            const float* __restrict__ xj = xb + j * stride;
+#pragma unroll
+            for (int k = NI; k < N; ++k) pt[k] = ld3(xj + sl.s[k] * 3);
             float v;
             if (KIND == PS_ANGLE_DIHEDRAL)
                 v = dihedral4(pt[0], pt[1], pt[2], pt[3]);
             else
                 v = angle3(pt[0], pt[1], pt[2]);
-            out[row * L + j] = v;
+            out_row[j] = v;
         }
     }
 }
@@ -133,10 +140,27 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
     int rc = grid_for_rows(rows, &grid);
     if (rc != PS_OK) return rc;
     const int threads = threads_for_L(L);
-    if (kind == PS_ANGLE_DIHEDRAL)
-        pair_angles_kernel<PS_ANGLE_DIHEDRAL><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows);
-    else
-        pair_angles_kernel<PS_ANGLE_PLANAR><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows);
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "pair_angles: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
+#define PS_PAIR_ANGLES(KIND, NI) \
+    pair_angles_kernel<KIND, NI><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows)
+    if (kind == PS_ANGLE_DIHEDRAL) {
+        switch (n_i) {
+            case 0: PS_PAIR_ANGLES(PS_ANGLE_DIHEDRAL, 0); break;
+            case 1: PS_PAIR_ANGLES(PS_ANGLE_DIHEDRAL, 1); break;
+            case 2: PS_PAIR_ANGLES(PS_ANGLE_DIHEDRAL, 2); break;
+            case 3: PS_PAIR_ANGLES(PS_ANGLE_DIHEDRAL, 3); break;
+            default: PS_PAIR_ANGLES(PS_ANGLE_DIHEDRAL, 4); break;
+        }
+    } else {
+        switch (n_i) {
+            case 0: PS_PAIR_ANGLES(PS_ANGLE_PLANAR, 0); break;
+            case 1: PS_PAIR_ANGLES(PS_ANGLE_PLANAR, 1); break;
+            case 2: PS_PAIR_ANGLES(PS_ANGLE_PLANAR, 2); break;
+            default: PS_PAIR_ANGLES(PS_ANGLE_PLANAR, 3); break;
+        }
+    }
+#undef PS_PAIR_ANGLES
     return check_launch("pair_angles_kernel");
 }
 
