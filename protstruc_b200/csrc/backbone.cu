@@ -123,21 +123,41 @@ __global__ void __launch_bounds__(256) geom_gram_schmidt_kernel(const float* __r
 // ---- rigid-frame family ---------------------------------------------------------
 // get_local_xyz (protstruc/protstruc.py:347-362): local = R^T x - CA, with R the residue's Gram-Schmidt
 // frame and CA the residue's GLOBAL alpha-carbon (the reference subtracts it after rotating; kept).
-// One thread per (residue, atom); the frame is recomputed per thread from three L1-resident atoms.
+// A CTA takes kLocalResidues residues: their frames (and CA) are computed once, one thread per residue, and parked
+// in shared memory; then one thread per (residue, atom) applies them.  (The first version recomputed the
+// Gram-Schmidt frame in every atom thread: A-fold redundant square roots and divisions, issue-bound.)
+constexpr int kLocalResidues = 64;
+
 __global__ void __launch_bounds__(256) local_xyz_kernel(const float* __restrict__ xyz, int A, int a1,
-                                                        int a2, int a3, int ca_slot, long long total,
+                                                        int a2, int a3, int ca_slot, long long num_residues,
                                                         float* __restrict__ out) {
-    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const long long r = index_div(t, A, total <= 0xFFFFFFFFll);
-    const float* __restrict__ x = xyz + r * A * 3;
-    const Frame f = gram_schmidt_frame(ld3(x + a1 * 3), ld3(x + a2 * 3), ld3(x + a3 * 3));
-    const V3 p = ld3(xyz + t * 3);
-    const V3 ca = ld3(x + ca_slot * 3);
-    // einsum("bnaji,bnaj->bnai"): out_i = sum_j R[j][i] x_j = e_i . x
-    out[t * 3 + 0] = __fsub_rn(dot3(f.e1, p), ca.x);
-    out[t * 3 + 1] = __fsub_rn(dot3(f.e2, p), ca.y);
-    out[t * 3 + 2] = __fsub_rn(dot3(f.e3, p), ca.z);
+    __shared__ float frame[kLocalResidues][12];  // e1, e2, e3, CA
+    const long long r0 = static_cast<long long>(blockIdx.x) * kLocalResidues;
+    const long long left = num_residues - r0;
+    const int nres = left < kLocalResidues ? static_cast<int>(left) : kLocalResidues;
+    if (threadIdx.x < nres) {
+        const float* __restrict__ x = xyz + (r0 + threadIdx.x) * A * 3;
+        const Frame f = gram_schmidt_frame(ld3(x + a1 * 3), ld3(x + a2 * 3), ld3(x + a3 * 3));
+        const V3 ca = ld3(x + ca_slot * 3);
+        float* dst = frame[threadIdx.x];
+        dst[0] = f.e1.x; dst[1] = f.e1.y; dst[2] = f.e1.z;
+        dst[3] = f.e2.x; dst[4] = f.e2.y; dst[5] = f.e2.z;
+        dst[6] = f.e3.x; dst[7] = f.e3.y; dst[8] = f.e3.z;
+        dst[9] = ca.x; dst[10] = ca.y; dst[11] = ca.z;
+    }
+    __syncthreads();
+    const float* __restrict__ xin = xyz + r0 * A * 3;
+    float* __restrict__ xout = out + r0 * A * 3;
+    const int atoms = nres * A;
+    for (int t = threadIdx.x; t < atoms; t += blockDim.x) {
+        const int r = t / A;
+        const float* fr = frame[r];
+        const V3 p = ld3(xin + t * 3);
+        // einsum("bnaji,bnaj->bnai"): out_i = sum_j R[j][i] x_j = e_i . x
+        xout[t * 3 + 0] = __fsub_rn(dot3(V3{fr[0], fr[1], fr[2]}, p), fr[9]);
+        xout[t * 3 + 1] = __fsub_rn(dot3(V3{fr[3], fr[4], fr[5]}, p), fr[10]);
+        xout[t * 3 + 2] = __fsub_rn(dot3(V3{fr[6], fr[7], fr[8]}, p), fr[11]);
+    }
 }
 
 // rotate (protstruc/protstruc.py:681-694): x' = R_b x with one (3,3) matrix per structure (or one for all).
@@ -254,8 +274,10 @@ int local_xyz_impl(const float* xyz, int B, int L, int A, int a1, int a2, int a3
     PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "local_xyz: NULL pointer");
     PS_REQUIRE(a1 >= 0 && a1 < A && a2 >= 0 && a2 < A && a3 >= 0 && a3 < A && ca_slot >= 0 && ca_slot < A,
                PS_ERR_BAD_SLOT, "local_xyz: slot outside [0,%d)", A);
-    const long long total = static_cast<long long>(B) * L * A;
-    local_xyz_kernel<<<blocks_for(total), 256, 0, stream>>>(xyz, A, a1, a2, a3, ca_slot, total, out);
+    const long long residues = static_cast<long long>(B) * L;
+    const long long blocks = (residues + kLocalResidues - 1) / kLocalResidues;
+    PS_REQUIRE(blocks < (1ll << 31), PS_ERR_BAD_SHAPE, "local_xyz: %lld residues", residues);
+    local_xyz_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(xyz, A, a1, a2, a3, ca_slot, residues, out);
     return check_launch("local_xyz_kernel");
 }
 
