@@ -83,38 +83,36 @@ __device__ void jacobi_eigen3(double (&a)[3][3], double (&V)[3][3], double (&w)[
 __global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
     const float* __restrict__ src, const float* __restrict__ dst, const uint8_t* __restrict__ mask,
     int dst_rows, int n_atoms, float* __restrict__ rot, float* __restrict__ trans) {
-    __shared__ double scratch[kKabschThreads / 32][9];
+    __shared__ double scratch[kKabschThreads / 32][16];
     const long long b = blockIdx.x;
     const float* __restrict__ a = src + b * n_atoms * 3;
     const float* __restrict__ t = dst + (dst_rows == 1 ? 0 : b) * static_cast<long long>(n_atoms) * 3;
     const uint8_t* __restrict__ m = mask + b * n_atoms;
 
-    // pass 1: centroids of the selected atoms (reference: a.mean(dim=-2), b.mean(dim=-2))
-    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // ONE pass over the selected atoms: first moments (centroids, reference: a.mean(dim=-2), b.mean(dim=-2)) and
+    // the raw second moments sum a_i b_j, all in fp64, so that the centred covariance
+    //   H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j = sum a_i b_j - n ca_i cb_j
+    // loses nothing that matters (|x| ~ 1e2, n ~ 1e4: the subtraction cancels ~4 of fp64's 16 digits).
+    double s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int k = threadIdx.x; k < n_atoms; k += blockDim.x) {
         if (__ldg(m + k)) {
-            s[0] += __ldg(a + 3 * k + 0); s[1] += __ldg(a + 3 * k + 1); s[2] += __ldg(a + 3 * k + 2);
-            s[3] += __ldg(t + 3 * k + 0); s[4] += __ldg(t + 3 * k + 1); s[5] += __ldg(t + 3 * k + 2);
+            const double ax = __ldg(a + 3 * k + 0), ay = __ldg(a + 3 * k + 1), az = __ldg(a + 3 * k + 2);
+            const double bx = __ldg(t + 3 * k + 0), by = __ldg(t + 3 * k + 1), bz = __ldg(t + 3 * k + 2);
+            s[0] += ax; s[1] += ay; s[2] += az;
+            s[3] += bx; s[4] += by; s[5] += bz;
             s[6] += 1.0;
+            s[7] += ax * bx; s[8] += ax * by; s[9] += ax * bz;
+            s[10] += ay * bx; s[11] += ay * by; s[12] += ay * bz;
+            s[13] += az * bx; s[14] += az * by; s[15] += az * bz;
         }
     }
-    block_sum<9>(s, scratch);
+    block_sum<16>(s, scratch);
     const double cnt = s[6];
     const double ca[3] = {s[0] / cnt, s[1] / cnt, s[2] / cnt};
     const double cb[3] = {s[3] / cnt, s[4] / cnt, s[5] / cnt};
-
-    // pass 2: H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j
-    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = threadIdx.x; k < n_atoms; k += blockDim.x) {
-        if (__ldg(m + k)) {
-            const double ax = __ldg(a + 3 * k + 0) - ca[0], ay = __ldg(a + 3 * k + 1) - ca[1], az = __ldg(a + 3 * k + 2) - ca[2];
-            const double bx = __ldg(t + 3 * k + 0) - cb[0], by = __ldg(t + 3 * k + 1) - cb[1], bz = __ldg(t + 3 * k + 2) - cb[2];
-            h[0] += ax * bx; h[1] += ax * by; h[2] += ax * bz;
-            h[3] += ay * bx; h[4] += ay * by; h[5] += ay * bz;
-            h[6] += az * bx; h[7] += az * by; h[8] += az * bz;
-        }
-    }
-    block_sum<9>(h, scratch);
+    double h[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) h[i * 3 + j] = s[7 + i * 3 + j] - cnt * ca[i] * cb[j];
 
     if (threadIdx.x == 0) {
         double H[3][3] = {{h[0], h[1], h[2]}, {h[3], h[4], h[5]}, {h[6], h[7], h[8]}};
