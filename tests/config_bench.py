@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Times the five BASELINE.json configurations through the public API (run on the GPU box).
 
-    python tools/config_bench.py [--no-cpu] > gpurun_out/config_bench.json
-    python -m torch.distributed.run --nproc-per-node N ... tools/config_bench.py --only c5   # sharded config 5
+    python tests/config_bench.py [--no-cpu] > gpurun_out/config_bench.json
+    python -m torch.distributed.run --nproc-per-node N ... tests/config_bench.py --only c5   # sharded config 5
 
 Every GPU number is CUDA-event time of the façade call(s) with inputs resident; every CPU number is the oracle
 port (same ATen/numpy ops as the reference) on a bounded sample of the same workload, normalised per structure.

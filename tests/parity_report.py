@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Measures the deviation of the CUDA path from the reference golden vectors (run on the GPU box).
 
-    python tools/parity_report.py > gpurun_out/parity_report.json
+    python tests/parity_report.py > gpurun_out/parity_report.json
 
 For every golden case: max |dist - ref| (abs and rel), max circular deviation of omega/theta/phi and of
 the backbone dihedrals over ALL finite entries and over the well-conditioned ones (min sin >= 0.1),
