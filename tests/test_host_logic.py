@@ -101,6 +101,10 @@ def test_product_package_never_imports_the_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         text = f.read_text()
         assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+    # the measurement scripts under tools/ do not import it either (those that need the checker live in tests/)
+    for f in (pkg.parent / "tools").glob("*.py"):
+        text = f.read_text()
+        assert "from oracle" not in text and "import oracle" not in text, f"{f} imports the oracle"
 
 
 def test_atom_vocabulary():
