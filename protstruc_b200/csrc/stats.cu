@@ -5,11 +5,17 @@
 // (:662-679, 759-788).
 //
 // Roofline: HBM read + write of the (B,L,A,3) coordinates (25 B per atom with a bool mask).
-// One CTA per structure: pass 1 (masked sum, count) and pass 2 (masked squared deviation) read the
-// structure's coordinates, which stay in L1/L2 (92 KB at L=512), pass 3 writes the normalised
-// coordinates, so HBM sees one read and one write.  Warp-shuffle + shared-memory block reductions;
+// One thread-block CLUSTER per structure (1, 2, 4 or 8 CTAs, chosen so that a CTA keeps >= ~1k atoms): every CTA
+// reduces its contiguous share of the atoms, parks the partial sums in its shared memory and, after a cluster
+// barrier, reads the partials of all its peers through distributed shared memory (summed in rank order, so every
+// CTA holds the same totals).  Pass 1 (masked sum, count) and pass 2 (masked squared deviation) read the CTA's
+// share, which stays in L1/L2, pass 3 writes the normalised coordinates, so HBM sees one read and one write.
+// A few large structures (the bench shape: 16 x 7680 atoms) thus occupy 128 CTAs instead of 16.
+// Warp-shuffle + shared-memory block reductions;
 // partial sums are accumulated in fp64 (the reference sums in fp32 with ATen's cascade summation —
 // both are well inside the 1e-5 relative parity tolerance, fp64 is simply the more exact of the two).
+
+#include <cooperative_groups.h>
 
 #include "common.cuh"
 
@@ -58,25 +64,69 @@ __device__ __forceinline__ float mask_value(const void* __restrict__ m, long lon
     return __ldg(static_cast<const float*>(m) + idx);
 }
 
-template <int MASK_DTYPE>
+// Totals of 4 doubles over the cluster: own partial -> shared memory, cluster barrier, read every rank's partial
+// through distributed shared memory in rank order.  `slot` must differ between the two uses inside one kernel
+// (a peer may still be reading the previous slot).
+__device__ __forceinline__ void cluster_sum4(double (&v)[4], double (*exchange)[4], int slot) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned ranks = cluster.num_blocks();
+    if (ranks == 1) return;
+    if (threadIdx.x < 4) exchange[slot][threadIdx.x] = v[threadIdx.x];
+    cluster.sync();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = 0.0;
+    for (unsigned r = 0; r < ranks; ++r) {
+        const double* peer = cluster.map_shared_rank(&exchange[slot][0], r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += peer[k];
+    }
+}
+
+// CLUSTER = false is the plain one-CTA-per-structure kernel (the common case: many structures); CLUSTER = true
+// is launched with a cluster dimension > 1 for a few large structures and also unrolls the atom loops (the loads of
+// kStatsUnroll atoms are issued before the first use: with few CTAs in flight, latency is what there is to hide).
+template <int MASK_DTYPE, bool CLUSTER>
 __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
     float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
+    namespace cg = cooperative_groups;
+    constexpr int kStatsUnroll = CLUSTER ? 4 : 1;
     __shared__ double scratch[kStatsMaxThreads / 32][4];
-    const long long b = blockIdx.x;
+    __shared__ double exchange[CLUSTER ? 2 : 1][4];
+    const int ranks = CLUSTER ? static_cast<int>(cg::this_cluster().num_blocks()) : 1;
+    const int rank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+    const long long b = blockIdx.x / ranks;
     const float* __restrict__ x = xyz + b * atoms_per_struct * 3;
     const long long m0 = b * atoms_per_struct;
+    // this CTA's contiguous share of the structure's atoms
+    const int share = (atoms_per_struct + ranks - 1) / ranks;
+    const int t_begin = rank * share;
+    const int t_end = t_begin + share < atoms_per_struct ? t_begin + share : atoms_per_struct;
 
     // pass 1: sum(nan_to_num(x * m)) per axis, sum(m)
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
-        const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
-        acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 0), m)));
-        acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 1), m)));
-        acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 2), m)));
-        acc[3] += static_cast<double>(m);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
+        float m[kStatsUnroll], c[kStatsUnroll][3];
+#pragma unroll
+        for (int u = 0; u < kStatsUnroll; ++u) {
+            const int t = t0 + u * blockDim.x;
+            const bool ok = t < t_end;
+            m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kStatsUnroll; ++u) {
+            if (t0 + u * blockDim.x >= t_end) break;
+            acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][0], m[u])));
+            acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][1], m[u])));
+            acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][2], m[u])));
+            acc[3] += static_cast<double>(m[u]);
+        }
     }
     block_sum4(acc, scratch);
+    if (CLUSTER) cluster_sum4(acc, exchange, 0);
     const float count = static_cast<float>(acc[3]);
     float mu[3];
 #pragma unroll
@@ -84,35 +134,60 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
 
     // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
     double dev[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
-        const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
+    for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
+        float m[kStatsUnroll], c[kStatsUnroll][3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float d = __fsub_rn(nan_to_num0(__ldg(x + 3 * t + k)), mu[k]);
-            dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m));
+        for (int u = 0; u < kStatsUnroll; ++u) {
+            const int t = t0 + u * blockDim.x;
+            const bool ok = t < t_end;
+            m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kStatsUnroll; ++u) {
+            if (t0 + u * blockDim.x >= t_end) break;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float d = __fsub_rn(nan_to_num0(c[u][k]), mu[k]);
+                dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m[u]));
+            }
         }
     }
     block_sum4(dev, scratch);
+    if (CLUSTER) cluster_sum4(dev, exchange, 1);
     float sd[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) sd[k] = __fsqrt_rn(__fdiv_rn(static_cast<float>(dev[k]), count));
 
-    if (threadIdx.x < 3) {
+    if (rank == 0 && threadIdx.x < 3) {
         mu_out[b * 3 + threadIdx.x] = mu[threadIdx.x];
         sd_out[b * 3 + threadIdx.x] = sd[threadIdx.x];
     }
 
-    // pass 3: (x - mu) / sd on every atom (masked or not, NaN stays NaN)
+    // pass 3: (x - mu) / sd on every atom of the share (masked or not, NaN stays NaN)
     if (xyz_out) {
         float* __restrict__ o = xyz_out + b * atoms_per_struct * 3;
-        const int n = atoms_per_struct * 3;
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            const int k = e % 3;
-            const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
-            const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
-            o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+        for (int e0 = t_begin * 3 + threadIdx.x; e0 < t_end * 3; e0 += kStatsUnroll * blockDim.x) {
+            float v[kStatsUnroll];
+#pragma unroll
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                const int e = e0 + u * blockDim.x;
+                v[u] = e < t_end * 3 ? x[e] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                const int e = e0 + u * blockDim.x;
+                if (e >= t_end * 3) break;
+                const int k = e % 3;
+                const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
+                const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
+                o[e] = __fdiv_rn(__fsub_rn(v[u], m), s);
+            }
         }
     }
+    // a CTA's shared memory must stay valid until every peer has read its partial sums
+    if (CLUSTER) cg::this_cluster().sync();
 }
 
 // The per-structure elementwise maps run on a 2-D grid: blockIdx.y walks the structures, blockIdx.x / threadIdx.x
@@ -228,19 +303,46 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
     PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
                "masked_stats: structure too large (L*A*3 >= 2^31)");
     const int atoms = L * A;
-    // one CTA per structure; ~8 atoms per thread keeps the three block-wide reductions cheap relative to the
-    // streaming work while many CTAs stay resident per SM for small structures
-    int threads = ((atoms + 7) / 8 + 31) / 32 * 32;
+    PS_REQUIRE(mask_dtype == PS_MASK_BOOL || mask_dtype == PS_MASK_F32, PS_ERR_BAD_DTYPE,
+               "masked_stats: unknown mask_dtype %d", mask_dtype);
+    // One cluster per structure.  Cluster size: enough CTAs that the GPU is busy when there are few structures, but
+    // at least ~1k atoms per CTA so that the block / cluster reductions stay cheap relative to the streaming work.
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    int ranks = 1;
+    while (ranks < 8 && static_cast<long long>(B) * ranks * 2 <= sms && atoms / (ranks * 2) >= 1024) ranks *= 2;
+    const int share = (atoms + ranks - 1) / ranks;
+    // ~8 atoms per thread (two unrolled iterations); many CTAs stay resident per SM for small structures
+    int threads = ((share + 7) / 8 + 31) / 32 * 32;
     if (threads < 64) threads = 64;
     if (threads > kStatsMaxThreads) threads = kStatsMaxThreads;
-    if (mask_dtype == PS_MASK_BOOL)
-        masked_stats_kernel<PS_MASK_BOOL><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
-    else if (mask_dtype == PS_MASK_F32)
-        masked_stats_kernel<PS_MASK_F32><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
-    else {
-        set_error("masked_stats: unknown mask_dtype %d", mask_dtype);
-        return PS_ERR_BAD_DTYPE;
+    PS_REQUIRE(static_cast<long long>(B) * ranks < (1ll << 31), PS_ERR_BAD_SHAPE, "masked_stats: B=%d too large", B);
+
+    if (ranks == 1) {  // no cluster: the ordinary launch path
+        if (mask_dtype == PS_MASK_BOOL)
+            masked_stats_kernel<PS_MASK_BOOL, false><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
+        else
+            masked_stats_kernel<PS_MASK_F32, false><<<B, threads, 0, stream>>>(xyz, atom_mask, atoms, mu, sd, xyz_out);
+        return check_launch("masked_stats_kernel");
     }
+    cudaLaunchConfig_t config = {};
+    config.gridDim = dim3(static_cast<unsigned>(B) * ranks, 1, 1);
+    config.blockDim = dim3(threads, 1, 1);
+    config.dynamicSmemBytes = 0;
+    config.stream = stream;
+    cudaLaunchAttribute attribute[1];
+    attribute[0].id = cudaLaunchAttributeClusterDimension;
+    attribute[0].val.clusterDim.x = ranks;
+    attribute[0].val.clusterDim.y = 1;
+    attribute[0].val.clusterDim.z = 1;
+    config.attrs = attribute;
+    config.numAttrs = 1;
+    cudaError_t err;
+    if (mask_dtype == PS_MASK_BOOL)
+        err = cudaLaunchKernelEx(&config, masked_stats_kernel<PS_MASK_BOOL, true>, xyz, atom_mask, atoms, mu, sd, xyz_out);
+    else
+        err = cudaLaunchKernelEx(&config, masked_stats_kernel<PS_MASK_F32, true>, xyz, atom_mask, atoms, mu, sd, xyz_out);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaLaunchKernelEx(masked_stats_kernel)");
     return check_launch("masked_stats_kernel");
 }
 

@@ -355,6 +355,29 @@ def test_standardize_statistics_vs_oracle_config4_slice(native_lib):
     assert not bool(torch.isnan(valid).any())  # reference tests/test_StructureBatch.py:218-226
 
 
+@pytest.mark.parametrize("B,L,kind", [(2, 2101, "bool"), (3, 701, "float"), (1, 4097, "bool"), (5, 300, "bool")])
+def test_standardize_few_large_structures_take_the_cluster_path(native_lib, B, L, kind):
+    """Few, large structures: every structure is reduced by a thread-block cluster (2 - 8 CTAs exchanging partial
+    sums through distributed shared memory); shares are uneven on purpose (atom counts not divisible by the cluster
+    size).  Same statistics and coordinates as the oracle, and the same as the C-ABI call writing in place."""
+    xyz, mask, _ = H.synthetic_batch(90 + L, B, L, 15, kind)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    sb.standardize()
+    ref_xyz, mu, sd = orc.standardize_per_structure(xyz, mask)
+    assert torch.allclose(sb.mu.cpu(), mu, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(sb.std.cpu(), sd, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sb.get_xyz().cpu(), ref_xyz, rtol=1e-4, atol=1e-5, equal_nan=True)
+    # in place (xyz_out aliases xyz): a CTA only ever reads the share it later overwrites
+    x = xyz.to(DEV).contiguous()
+    m = (mask.float() if kind == "float" else mask).to(DEV).contiguous()
+    mu_d, sd_d = torch.empty(B, 3, device=DEV), torch.empty(B, 3, device=DEV)
+    rc = native_lib.ps_masked_stats(x.data_ptr(), m.data_ptr(), 1 if kind == "float" else 0, B, L, 15, mu_d.data_ptr(),
+                                    sd_d.data_ptr(), x.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "ps_masked_stats")
+    assert torch.equal(mu_d, sb.mu.reshape(B, 3)) and torch.equal(sd_d, sb.std.reshape(B, 3))
+    assert torch.equal(torch.nan_to_num(x, nan=-3.0), torch.nan_to_num(sb.get_xyz(), nan=-3.0))
+
+
 # ------------------------------------------------------------------------------ K5 diffusion
 @pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
 def test_diffuse_xyz_is_bit_exact_given_the_noise(native_lib, name):
