@@ -106,23 +106,33 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
 
     // pass 1: sum(nan_to_num(x * m)) per axis, sum(m)
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
-        float m[kStatsUnroll], c[kStatsUnroll][3];
-#pragma unroll
-        for (int u = 0; u < kStatsUnroll; ++u) {
-            const int t = t0 + u * blockDim.x;
-            const bool ok = t < t_end;
-            m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
+    if constexpr (!CLUSTER) {
+        for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
+            const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
+            acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 0), m)));
+            acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 1), m)));
+            acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(__ldg(x + 3 * t + 2), m)));
+            acc[3] += static_cast<double>(m);
         }
+    } else {
+        for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
+            float m[kStatsUnroll], c[kStatsUnroll][3];
 #pragma unroll
-        for (int u = 0; u < kStatsUnroll; ++u) {
-            if (t0 + u * blockDim.x >= t_end) break;
-            acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][0], m[u])));
-            acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][1], m[u])));
-            acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][2], m[u])));
-            acc[3] += static_cast<double>(m[u]);
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                const int t = t0 + u * blockDim.x;
+                const bool ok = t < t_end;
+                m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                if (t0 + u * blockDim.x >= t_end) break;
+                acc[0] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][0], m[u])));
+                acc[1] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][1], m[u])));
+                acc[2] += static_cast<double>(nan_to_num0(__fmul_rn(c[u][2], m[u])));
+                acc[3] += static_cast<double>(m[u]);
+            }
         }
     }
     block_sum4(acc, scratch);
@@ -134,23 +144,34 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
 
     // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
     double dev[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
-        float m[kStatsUnroll], c[kStatsUnroll][3];
-#pragma unroll
-        for (int u = 0; u < kStatsUnroll; ++u) {
-            const int t = t0 + u * blockDim.x;
-            const bool ok = t < t_end;
-            m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < kStatsUnroll; ++u) {
-            if (t0 + u * blockDim.x >= t_end) break;
+    if constexpr (!CLUSTER) {
+        for (int t = threadIdx.x; t < atoms_per_struct; t += blockDim.x) {
+            const float m = mask_value<MASK_DTYPE>(atom_mask, m0 + t);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float d = __fsub_rn(nan_to_num0(c[u][k]), mu[k]);
-                dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m[u]));
+                const float d = __fsub_rn(nan_to_num0(__ldg(x + 3 * t + k)), mu[k]);
+                dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m));
+            }
+        }
+    } else {
+        for (int t0 = t_begin + threadIdx.x; t0 < t_end; t0 += kStatsUnroll * blockDim.x) {
+            float m[kStatsUnroll], c[kStatsUnroll][3];
+#pragma unroll
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                const int t = t0 + u * blockDim.x;
+                const bool ok = t < t_end;
+                m[u] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + t) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) c[u][k] = ok ? __ldg(x + 3 * t + k) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kStatsUnroll; ++u) {
+                if (t0 + u * blockDim.x >= t_end) break;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float d = __fsub_rn(nan_to_num0(c[u][k]), mu[k]);
+                    dev[k] += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m[u]));
+                }
             }
         }
     }
@@ -168,21 +189,31 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
     // pass 3: (x - mu) / sd on every atom of the share (masked or not, NaN stays NaN)
     if (xyz_out) {
         float* __restrict__ o = xyz_out + b * atoms_per_struct * 3;
-        for (int e0 = t_begin * 3 + threadIdx.x; e0 < t_end * 3; e0 += kStatsUnroll * blockDim.x) {
-            float v[kStatsUnroll];
-#pragma unroll
-            for (int u = 0; u < kStatsUnroll; ++u) {
-                const int e = e0 + u * blockDim.x;
-                v[u] = e < t_end * 3 ? x[e] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < kStatsUnroll; ++u) {
-                const int e = e0 + u * blockDim.x;
-                if (e >= t_end * 3) break;
+        if constexpr (!CLUSTER) {
+            const int n = atoms_per_struct * 3;
+            for (int e = threadIdx.x; e < n; e += blockDim.x) {
                 const int k = e % 3;
                 const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
                 const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
-                o[e] = __fdiv_rn(__fsub_rn(v[u], m), s);
+                o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+            }
+        } else {
+            for (int e0 = t_begin * 3 + threadIdx.x; e0 < t_end * 3; e0 += kStatsUnroll * blockDim.x) {
+                float v[kStatsUnroll];
+#pragma unroll
+                for (int u = 0; u < kStatsUnroll; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    v[u] = e < t_end * 3 ? x[e] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < kStatsUnroll; ++u) {
+                    const int e = e0 + u * blockDim.x;
+                    if (e >= t_end * 3) break;
+                    const int k = e % 3;
+                    const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
+                    const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
+                    o[e] = __fdiv_rn(__fsub_rn(v[u], m), s);
+                }
             }
         }
     }
