@@ -768,7 +768,7 @@ def test_staged_kernels_for_other_atom_counts(native_lib, B, L, A):
 
 @pytest.mark.parametrize("B,L,A", [(2, 20, 25), (1, 9, 37), (3, 50, 4), (2, 64, 3), (5, 3, 6), (1, 1, 7), (2, 33, 16),
                                    (1, 130, 8), (2, 2, 1), (1, 7, 53), (1, 40, 15), (2, 17, 15), (1, 130, 3), (2, 128, 4),
-                                   (1, 141, 4), (1, 12, 130)])
+                                   (1, 141, 4), (1, 12, 130), (1, 5, 64), (1, 4, 100), (1, 3, 128), (1, 3, 129)])
 def test_any_shape_distance_kernels(native_lib, B, L, A):
     """Atom counts / lengths the staged kernel does not cover: the any-A tile kernel (TMA bulk stores), its
     plain-store flavour for outputs that are not 16-B aligned, and the row kernel (variant bit 12) — every output
