@@ -25,12 +25,13 @@ namespace {
 
 constexpr int kStatsMaxThreads = 512;
 
-// torch.nan_to_num(x, nan=0.0): NaN -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX.
+// torch.nan_to_num(x, nan=0.0): NaN -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX.  One compare on the common (finite)
+// path: |v| <= FLT_MAX is false for infinities and for NaN.
 __device__ __forceinline__ float nan_to_num0(float v) {
+    constexpr float kMax = 3.4028234663852886e38f;
+    if (fabsf(v) <= kMax) return v;
     if (v != v) return 0.f;
-    if (v == __int_as_float(0x7f800000)) return 3.4028234663852886e38f;
-    if (v == __int_as_float(0xff800000)) return -3.4028234663852886e38f;
-    return v;
+    return v > 0.f ? kMax : -kMax;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -191,11 +192,20 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
         float* __restrict__ o = xyz_out + b * atoms_per_struct * 3;
         if constexpr (!CLUSTER) {
             const int n = atoms_per_struct * 3;
-            for (int e = threadIdx.x; e < n; e += blockDim.x) {
-                const int k = e % 3;
+            if (blockDim.x % 3 == 0) {
+                // the host launches a multiple of 96 threads: a thread's elements all lie on ONE axis, so its mean
+                // and deviation are picked once, outside the loop
+                const int k = threadIdx.x % 3;
                 const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
                 const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
-                o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+                for (int e = threadIdx.x; e < n; e += blockDim.x) o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+            } else {
+                for (int e = threadIdx.x; e < n; e += blockDim.x) {
+                    const int k = e % 3;
+                    const float m = k == 0 ? mu[0] : (k == 1 ? mu[1] : mu[2]);
+                    const float s = k == 0 ? sd[0] : (k == 1 ? sd[1] : sd[2]);
+                    o[e] = __fdiv_rn(__fsub_rn(x[e], m), s);
+                }
             }
         } else {
             for (int e0 = t_begin * 3 + threadIdx.x; e0 < t_end * 3; e0 += kStatsUnroll * blockDim.x) {
@@ -344,9 +354,10 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
     while (ranks < 8 && static_cast<long long>(B) * ranks * 2 <= sms && atoms / (ranks * 2) >= 1024) ranks *= 2;
     const int share = (atoms + ranks - 1) / ranks;
     // ~8 atoms per thread (two unrolled iterations); many CTAs stay resident per SM for small structures
-    int threads = ((share + 7) / 8 + 31) / 32 * 32;
-    if (threads < 64) threads = 64;
-    if (threads > kStatsMaxThreads) threads = kStatsMaxThreads;
+    // (a multiple of 96 = 3 x 32: whole warps, and every thread of the normalisation pass stays on one axis)
+    int threads = ((share + 7) / 8 + 95) / 96 * 96;
+    if (threads < 96) threads = 96;
+    if (threads > 480) threads = 480;
     PS_REQUIRE(static_cast<long long>(B) * ranks < (1ll << 31), PS_ERR_BAD_SHAPE, "masked_stats: B=%d too large", B);
 
     if (ranks == 1) {  // no cluster: the ordinary launch path
