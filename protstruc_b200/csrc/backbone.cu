@@ -204,14 +204,19 @@ __global__ void __launch_bounds__(256) frames_to_backbone_kernel(
 
 // translate (protstruc/protstruc.py:662-679): x += t with a broadcastable translation given by its
 // element strides over (structure, residue, atom); stride 0 = broadcast.
+// FAST: the residue index comes from a multiply-high by a host-computed reciprocal of the row length (exact while
+// e * row < 2^32) and the translation offset is 32-bit arithmetic; the general flavour divides and uses 64-bit
+// strides.
+template <bool FAST>
 __global__ void __launch_bounds__(256) translate_bcast_kernel(const float* __restrict__ xyz,
                                                               const float* __restrict__ tr,
                                                               long long sb, long long sl, long long sa,
-                                                              int B, int A, int per_b,
+                                                              int B, int A, int per_b, unsigned row_magic,
                                                               float* __restrict__ out) {
     // 2-D grid: blockIdx.y walks the structures, x the structure's floats; (l, a, axis) from the 32-bit offset
-    // inside the structure with one 32-bit division
+    // inside the structure
     const unsigned row = static_cast<unsigned>(A) * 3u;
+    const unsigned sl32 = static_cast<unsigned>(sl), sa32 = static_cast<unsigned>(sa);
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float* __restrict__ xb = xyz + static_cast<long long>(b) * per_b;
         float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
@@ -224,12 +229,12 @@ __global__ void __launch_bounds__(256) translate_bcast_kernel(const float* __res
                 const unsigned e = e0 + u * step;
                 v[u] = w[u] = 0.f;
                 if (e < n) {
-                    const unsigned l = e / row;
+                    const unsigned l = FAST ? __umulhi(e, row_magic) : e / row;
                     const unsigned r = e - l * row;
                     const unsigned a = r / 3u;
                     const unsigned k = r - a * 3u;
                     v[u] = xb[e];
-                    w[u] = __ldg(tb + l * sl + a * sa + k);
+                    w[u] = FAST ? __ldg(tb + (l * sl32 + a * sa32 + k)) : __ldg(tb + l * sl + a * sa + k);
                 }
             }
 #pragma unroll
@@ -318,7 +323,14 @@ int translate_bcast_impl(const float* xyz, const float* tr, long long sb, long l
     int gx = (per_b + 1023) / 1024;
     if (gx > 64) gx = 64;
     const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(B < 65535 ? B : 65535), 1);
-    translate_bcast_kernel<<<grid, 256, 0, stream>>>(xyz, tr, sb, sl, sa, B, A, per_b, out);
+    const unsigned long long row = static_cast<unsigned long long>(A) * 3ull;
+    const bool fast = static_cast<unsigned long long>(per_b) * row < (1ull << 32) &&
+                      static_cast<long long>(L - 1) * sl + static_cast<long long>(A - 1) * sa + 2 < (1ll << 31);
+    const unsigned row_magic = static_cast<unsigned>(((1ull << 32) + row - 1) / row);
+    if (fast && row > 1)
+        translate_bcast_kernel<true><<<grid, 256, 0, stream>>>(xyz, tr, sb, sl, sa, B, A, per_b, row_magic, out);
+    else
+        translate_bcast_kernel<false><<<grid, 256, 0, stream>>>(xyz, tr, sb, sl, sa, B, A, per_b, 0u, out);
     return check_launch("translate_bcast_kernel");
 }
 
