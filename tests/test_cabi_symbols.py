@@ -67,3 +67,31 @@ def test_status_codes_are_mapped_to_exceptions(native_lib):
     with pytest.raises(_cabi.NativeLibraryError, match="PS_ERR_BAD_SHAPE"):
         _cabi.check(-1, "unit test")
     _cabi.check(0, "unit test")
+
+
+def test_argument_validation_happens_before_any_cuda_call(native_lib):
+    """Every entry point validates shapes / pointers / codes first and reports through the status code and the
+    thread-local message — no launch, so this runs without a GPU (compute calls would need one)."""
+    lib = native_lib
+    null = None
+    fake = 4096  # a non-NULL pointer value that is never dereferenced: validation fails first
+
+    def message():
+        return lib.ps_last_error_string().decode()
+
+    assert lib.ps_pair_dist_mask(fake, fake, 0, fake, fake, 0, 8, 15, null) == -1 and "must be > 0" in message()
+    assert lib.ps_pair_dist_mask(null, fake, 0, fake, fake, 1, 8, 15, null) == -2 and "xyz is NULL" in message()
+    assert lib.ps_pair_dist_mask(fake, fake, 7, fake, fake, 1, 8, 15, null) == -3 and "mask_dtype" in message()
+    assert lib.ps_pair_dist_mask(fake, null, 0, fake, fake, 1, 8, 15, null) == -2  # mask in without mask out
+    assert lib.ps_pair_dist_mask(fake, null, 0, null, null, 1, 8, 15, null) == -2 and "nothing to compute" in message()
+    # the trRosetta triple needs the CB slot
+    assert lib.ps_inter_residue_geometry(fake, fake, 0, fake, fake, fake, fake, fake, 1, 8, 4, null) == -1
+    assert "CB slot" in message()
+    assert lib.ps_center_of_mass(fake, 1, 8, 15, 15, fake, null) == -4 and "slot 15" in message()
+    assert lib.ps_translate(fake, fake, 3, 2, 8, 15, fake, null) == -1 and "t_rows" in message()
+    assert lib.ps_rotate(fake, fake, 1, 1, 8, 15, fake, null) == -5  # in-place rotation is refused
+    assert lib.ps_diffuse(fake, fake, null, 1, 0, 2, fake, 1, 360, null) == -5 and "multiple of 4" in message()
+    slots = _cabi.int_array([0, 1, 2])
+    assert lib.ps_pair_angles(fake, 1, 8, 15, slots, 3, slots, 3, 0, fake, null) == -1 and "needs 4 atoms" in message()
+    bad = _cabi.int_array([0, 1, 99])
+    assert lib.ps_pair_angles(fake, 1, 8, 15, bad, 3, slots, 1, 0, fake, null) == -4 and "slot 99" in message()
