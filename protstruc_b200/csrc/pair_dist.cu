@@ -131,7 +131,7 @@ struct PairDistParams {
     long long chunk_members;  // C
     long long num_cells;      // S * ceil(M / C)
     long long active_workers; // tile buffers that take part (<= gridDim.x * buffers per CTA)
-    int lockstep;             // 1: strips mapped 1:1 to workers (linear sweep of the output), see launch code
+    int lockstep;             // strips mapped 1:1 to workers (linear sweep of the output): 0 auto, 1 on, 2 off
     int stores_only;          // diagnostic: skip the arithmetic, only issue the tile stores (measures the
                               // memory-system ceiling of this write pattern; output content is undefined)
 };
@@ -896,8 +896,17 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     // residue j is still reused) and give every strip to one worker.  All workers then advance member by
     // member together and the stores of the whole GPU sweep the output linearly, S' adjacent tiles at a time —
     // the access pattern HBM likes best.  Used when at most 6 % of the workers would be left without a strip.
+    //
+    // It pays when a worker stays inside one structure for several steps (residue j is reloaded whenever the
+    // structure changes): measured on B200 (profiles/r1_lockstep_by_length.txt), distances + mask gain 5-8 % at
+    // L = 256 / 384 / 1024 and lose 22 % at L = 128; the fused kernel gains 5-8 % at L = 512 / 1024 and loses 6 %
+    // at L = 256.  Default: on when a structure holds at least 3 (fused: 6) such wide rows of tiles.
+    // q.lockstep: 0 = this default, 1 = forced on, 2 = forced off (tuning hook).
     const long long wide = q.strip_stride * (workers / q.strip_stride);
-    if (q.lockstep && wide > 0 && (workers - wide) * 100 <= workers * 6 && q.num_tiles >= 4 * wide) {
+    const long long tiles_per_structure = static_cast<long long>(p.L) * p.L / TileGeom<A>::kPairs;
+    const bool automatic = tiles_per_structure >= (ANGLES ? 6 : 3) * wide;
+    const bool want_lockstep = q.lockstep == 1 || (q.lockstep == 0 && automatic);
+    if (want_lockstep && wide > 0 && (workers - wide) * 100 <= workers * 6 && q.num_tiles >= 4 * wide) {
         q.strip_stride = wide;
         q.strip_members = (q.num_tiles + wide - 1) / wide;
         q.chunk_members = q.strip_members;
@@ -1235,7 +1244,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
     p.stores_only = (variant >> 10) & 1;
-    p.lockstep = (variant >> 11) & 1;
+    p.lockstep = ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
     p.active_workers = 0;
 
     switch (A) {
