@@ -263,8 +263,8 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * 2 = sqrt.rn.f32); bits 4-7 tile buffers per CTA override (0 = default); bit 8 = keep the staged kernel out
  * (any-A tile kernel); bit 9 = use the non-default number of warps per tile; bit 10 = diagnostic "stores only"
  * (no arithmetic, output content undefined: measures the memory-system ceiling of the kernel's write pattern);
- * bit 11 = force the lockstep schedule, bit 13 = force the cell schedule (default: chosen by length); bit 12 = with
- * bit 8: row kernel only (the fallback for atom counts whose tile does
+ * bit 11 = force the lockstep schedule, bit 13 = force the cell schedule (default: chosen by length), bit 14 = lockstep
+ * even with up to 35 % idle tile buffers; bit 12 = with bit 8: row kernel only (the fallback for atom counts whose tile does
  * not fit in shared memory); bits 16-23 = any-A tile kernel: pairs per tile in units of its alignment quantum
  * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA.
  */

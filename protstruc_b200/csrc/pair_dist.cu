@@ -895,18 +895,25 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     // Lockstep schedule: widen the strip stride to S' = S * floor(workers / S) (still a multiple of S, so
     // residue j is still reused) and give every strip to one worker.  All workers then advance member by
     // member together and the stores of the whole GPU sweep the output linearly, S' adjacent tiles at a time —
-    // the access pattern HBM likes best.  Used when at most 6 % of the workers would be left without a strip.
+    // the access pattern HBM likes best.
     //
     // It pays when a worker stays inside one structure for several steps (residue j is reloaded whenever the
-    // structure changes): measured on B200 (profiles/r1_lockstep_by_length.txt), distances + mask gain 5-8 % at
-    // L = 256 / 384 / 1024 and lose 22 % at L = 128; the fused kernel gains 5-8 % at L = 512 / 1024 and loses 6 %
-    // at L = 256.  Default: on when a structure holds at least 3 (fused: 6) such wide rows of tiles.
-    // q.lockstep: 0 = this default, 1 = forced on, 2 = forced off (tuning hook).
+    // structure changes) and as long as few tile buffers are left without a strip.  Measured on B200
+    // (profiles/r1_lockstep_by_length.txt): distances + mask gain 3-8 % at L = 256 / 384 / 1024 and at L = 250 / 300 /
+    // 350 / 500 / 510 (11-16 % of the buffers idle), lose 22 % at L = 128 and 6 % at L = 229 (23 % idle).  The fused
+    // kernel, which needs every warp for the angle triple, gains 2-7 % at L = 512 / 1024, is inconsistent at
+    // L = 384 (+2 % with 28 structures per launch, -6 % with 128) and loses at L = 256 and whenever buffers idle.
+    // Default: on when a structure holds at least 1.9 (fused: 12) such wide rows of tiles and at most 16 %
+    // (fused: 6 %) of the buffers idle.
+    // q.lockstep: 0 = this default, 1 = forced on (same idle limit), 2 = forced off, 3 = forced on with up to 35 % idle
+    // buffers (tuning hooks).
     const long long wide = q.strip_stride * (workers / q.strip_stride);
     const long long tiles_per_structure = static_cast<long long>(p.L) * p.L / TileGeom<A>::kPairs;
-    const bool automatic = tiles_per_structure >= (ANGLES ? 6 : 3) * wide;
-    const bool want_lockstep = q.lockstep == 1 || (q.lockstep == 0 && automatic);
-    if (want_lockstep && wide > 0 && (workers - wide) * 100 <= workers * 6 && q.num_tiles >= 4 * wide) {
+    const bool automatic = tiles_per_structure * 10 >= (ANGLES ? 120 : 19) * wide;
+    const long long idle_pct_allowed = q.lockstep == 3 ? 35 : (ANGLES ? 6 : 16);
+    const bool forced = q.lockstep == 1 || q.lockstep == 3;
+    if ((forced || (q.lockstep == 0 && automatic)) && wide > 0 && (workers - wide) * 100 <= workers * idle_pct_allowed &&
+        q.num_tiles >= 4 * wide) {
         q.strip_stride = wide;
         q.strip_members = (q.num_tiles + wide - 1) / wide;
         q.chunk_members = q.strip_members;
@@ -1244,7 +1251,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
     p.stores_only = (variant >> 10) & 1;
-    p.lockstep = ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
+    p.lockstep = ((variant >> 14) & 1) ? 3 : ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
     p.active_workers = 0;
 
     switch (A) {
