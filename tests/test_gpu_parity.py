@@ -116,6 +116,38 @@ def test_distance_kernel_variants_agree(native_lib):
     assert torch.equal(outs[1][0], base), "non-ftz variant differs on normal-range inputs"
 
 
+@pytest.mark.parametrize("B,L", [(8, 256), (6, 250), (5, 190), (3, 384)])
+def test_tile_schedules_write_the_same_bytes(native_lib, B, L):
+    """The cell schedule, the lock-step schedule (default for long structures) and its relaxed flavour only change
+    WHICH tile buffer writes a tile and when: every output byte must be identical, for the distance + mask kernel and
+    for the fused kernel, including the angle tensors."""
+    A = 15
+    xyz, mask, _ = H.synthetic_batch(600 + L, B, L, A, "bool")
+    x, m = xyz.to(DEV), mask.to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for variant in (0, 1 << 13, 1 << 11, 1 << 14):
+        d = torch.full((B, L, L, A, A), -1.0, device=DEV)
+        dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
+                                                    variant, s), "ps_pair_dist_mask_ex")
+        fd = torch.full((B, L, L, A, A), -1.0, device=DEV)
+        fm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        angles = [torch.full((B, L, L), -9.0, device=DEV) for _ in range(3)]
+        _cabi.check(native_lib.ps_inter_residue_geometry_ex(x.data_ptr(), m.data_ptr(), 0, fd.data_ptr(), fm.data_ptr(),
+                                                            angles[0].data_ptr(), angles[1].data_ptr(),
+                                                            angles[2].data_ptr(), B, L, A, variant, s), "fused")
+        outs.append([d, dm, fd, fm] + angles)
+    torch.cuda.synchronize()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(torch.nan_to_num(a.float(), nan=-5.0), torch.nan_to_num(b.float(), nan=-5.0))
+    assert torch.equal(torch.nan_to_num(outs[0][0], nan=-5.0), torch.nan_to_num(outs[0][2], nan=-5.0))
+    rd, rm = orc.pair_distances(xyz, mask)
+    H.assert_distances_close(outs[0][0], rd)
+    assert torch.equal(outs[0][1].cpu(), rm)
+
+
 def test_distance_properties_at_baseline_config2(native_lib):
     """BASELINE config 2 (64 x 256 x 15, 3.8 GB of distances): size-independent properties."""
     B, L, A = 64, 256, 15
