@@ -384,9 +384,7 @@ class StructureBatch:
         mask, code = self._mask_for_kernel(self.atom_mask)
         dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
         dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
-        omega = torch.empty(B, L, L, dtype=torch.float32, device=dev)
-        theta = torch.empty_like(omega)
-        phi = torch.empty_like(omega)
+        omega, theta, phi = torch.empty(3, B, L, L, dtype=torch.float32, device=dev).unbind(0)  # one allocation
         with _cabi.on_device(dev):
             rc = lib.ps_inter_residue_geometry(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
                                                dist_mask.data_ptr(), omega.data_ptr(), theta.data_ptr(),
@@ -394,17 +392,19 @@ class StructureBatch:
         _cabi.check(rc, "ps_inter_residue_geometry")
         if dist_mask.dtype != self.atom_mask.dtype:
             dist_mask = dist_mask.to(self.atom_mask.dtype)
-        ret = {}
-        ret["d_ca"] = dist[:, :, :, ATOM.CA, ATOM.CA]
-        ret["d_ca_mask"] = dist_mask[:, :, :, ATOM.CA, ATOM.CA]
-        ret["d_cb"] = dist[:, :, :, ATOM.CB, ATOM.CB]
-        ret["d_cb_mask"] = dist_mask[:, :, :, ATOM.CB, ATOM.CB]
-        ret["d_no"] = dist[:, :, :, ATOM.N, ATOM.O]
-        ret["d_no_mask"] = dist_mask[:, :, :, ATOM.N, ATOM.O]
-        ret["omega"] = omega
-        ret["theta"] = theta
-        ret["phi"] = phi
-        return ret
+        # strided (B, L, L) views of the full tensors, like the reference's dist[:, :, :, a, c] (one as_strided each:
+        # this method is latency-critical for single small structures)
+        block = A * A
+        shape, strides = (B, L, L), (L * L * block, L * block, block)
+
+        def pick(t: torch.Tensor, a: int, c: int) -> torch.Tensor:
+            return t.as_strided(shape, strides, a * A + c)
+
+        n, ca, cb, o = int(ATOM.N), int(ATOM.CA), int(ATOM.CB), int(ATOM.O)
+        return {"d_ca": pick(dist, ca, ca), "d_ca_mask": pick(dist_mask, ca, ca),
+                "d_cb": pick(dist, cb, cb), "d_cb_mask": pick(dist_mask, cb, cb),
+                "d_no": pick(dist, n, o), "d_no_mask": pick(dist_mask, n, o),
+                "omega": omega, "theta": theta, "phi": phi}
 
     def _backbone(self, want_dihedrals: bool, frame_slots: Optional[Tuple[int, int, int]]):
         B, L, A = self._dims()
