@@ -910,7 +910,8 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
     const long long wide = q.strip_stride * (workers / q.strip_stride);
     const long long tiles_per_structure = static_cast<long long>(p.L) * p.L / TileGeom<A>::kPairs;
     // (measured for A = 15 only; the other staged atom counts keep the cell schedule: A = 5 loses 17 % with lock-step)
-    const bool automatic = A == 15 && tiles_per_structure * 10 >= (ANGLES ? 120 : 19) * wide;
+    // (and for the kinds that write an fp32 tensor; the byte-mask-only kind was not measured)
+    const bool automatic = A == 15 && KIND != kBoolMaskOnly && tiles_per_structure * 10 >= (ANGLES ? 120 : 19) * wide;
     const long long idle_pct_allowed = q.lockstep == 3 ? 35 : (ANGLES ? 6 : 16);
     const bool forced = q.lockstep == 1 || q.lockstep == 3;
     if ((forced || (q.lockstep == 0 && automatic)) && wide > 0 && (workers - wide) * 100 <= workers * idle_pct_allowed &&
