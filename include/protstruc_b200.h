@@ -219,10 +219,10 @@ int64_t ps_host_pipeline_launches(void* pipeline);  /* fused-kernel launches iss
  * (protstruc/protstruc.py:864-878):
  *   out = fl( fl(sqrt(1-beta_b) * x) + fl(z * sqrt(beta_b)) )     (no FMA contraction)
  * noise != NULL: z is read from `noise` (bit-matches the reference given the same z).
- * noise == NULL: z ~ N(0,1) from Philox4x32-10 keyed by `seed`; the counter of element e is
- *   (e / 4 + elem_offset / 4, step) so the stream does not depend on the launch shape or
- *   on how the batch is sharded across GPUs (elem_offset = first global element of this shard,
- *   must be a multiple of 4).
+ * noise == NULL: z ~ N(0,1) from Philox4x32-10 keyed by `seed`; with g = e + elem_offset the GLOBAL
+ *   index of local element e, the element takes output lane (g & 3) of the counter (g >> 2, step), so
+ *   the stream does not depend on the launch shape or on how the batch is sharded across GPUs
+ *   (elem_offset = first global element of this shard; ANY value, not only multiples of 4).
  * x, out: `B * per_b` f32 elements (per_b = L*A*3); beta (B,) f32.  out may alias x.
  */
 int ps_diffuse(const float* x, const float* beta, const float* noise,
@@ -271,6 +271,13 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,
                          int B, int L, int A, int variant, void* stream);
+/*
+ * What the most recent K1 launch of the calling host thread chose (tests assert on it that a shape took the path its
+ * parity claim is about).  out[0..n) of: path (0 staged tile kernel, 1 any-A tile kernel, 2 row kernel), lock-step
+ * schedule (0/1), CTAs, tile buffers of the grid, tile buffers taking part, strip stride in tiles, pairs per tile,
+ * kernel launches of the call.
+ */
+int ps_pair_dist_last_plan(int64_t* out, int n);
 /* Diagnostic store ceiling: plain 128-bit stores of a non-uniform pattern over n floats (n % 4 == 0). */
 int ps_debug_fill_pattern(float* out, int64_t n, int blocks_per_sm, void* stream);
 /* Same hook for the fused kernel (ps_inter_residue_geometry with a variant bit-field). */

@@ -345,11 +345,13 @@ def philox4x32_10(ctr: np.ndarray, key: Tuple[int, int]) -> np.ndarray:
 
 
 def philox_normal(n: int, seed: int, step: int, elem_offset: int = 0) -> np.ndarray:
-    """float64 evaluation of the N(0,1) stream the K5 kernels define: group g = e // 4 (+offset/4),
-    counter (g_lo, g_hi, step_lo, step_hi), key = seed; uniforms from the top 23 bits of each word;
-    Box-Muller on (r0, r1) and (r2, r3)."""
-    groups = (n + 3) // 4
-    g = np.arange(groups, dtype=np.uint64) + np.uint64(elem_offset // 4)
+    """float64 evaluation of the N(0,1) stream the K5 kernels define: element e (global index
+    e + elem_offset, ANY offset) takes lane (global & 3) of the counter (global >> 2 as lo/hi words,
+    step_lo, step_hi), key = seed; uniforms from the top 23 bits of each word; Box-Muller on (r0, r1)
+    and (r2, r3)."""
+    shift = elem_offset & 3
+    groups = (n + shift + 3) // 4
+    g = np.arange(groups, dtype=np.uint64) + np.uint64(elem_offset >> 2)
     ctr = np.stack([
         (g & np.uint64(0xFFFFFFFF)).astype(np.uint32), (g >> np.uint64(32)).astype(np.uint32),
         np.full(groups, step & 0xFFFFFFFF, dtype=np.uint32), np.full(groups, (step >> 32) & 0xFFFFFFFF, dtype=np.uint32),
@@ -361,4 +363,4 @@ def philox_normal(n: int, seed: int, step: int, elem_offset: int = 0) -> np.ndar
     ang_a = 2.0 * np.pi * u[:, 1]
     ang_b = 2.0 * np.pi * u[:, 3]
     z = np.stack([rad_a * np.sin(ang_a), rad_a * np.cos(ang_a), rad_b * np.sin(ang_b), rad_b * np.cos(ang_b)], axis=1)
-    return z.reshape(-1)[:n]
+    return z.reshape(-1)[shift:shift + n]

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ps_host_pipeline_destroy": (c_int, [c_void_p]),
     "ps_host_inter_residue_geometry": (c_int, [c_void_p, _fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp]),
     "ps_host_pipeline_launches": (c_int64, [c_void_p]),
+    "ps_pair_dist_last_plan": (c_int, [POINTER(c_int64), c_int]),
     "ps_debug_fill_pattern": (c_int, [_fp, c_int64, c_int, c_void_p]),
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
@@ -130,6 +131,16 @@ def check(rc: int, what: str) -> None:
     if rc == 0:
         return
     raise NativeLibraryError(f"{what} failed with {STATUS_NAMES.get(rc, rc)}: {last_error()}")
+
+
+PLAN_FIELDS = ("path", "lockstep", "ctas", "tile_buffers", "active_buffers", "strip_stride", "tile_pairs", "launches")
+
+
+def last_pair_dist_plan() -> dict:
+    """What the most recent K1 launch of this thread chose (ps_pair_dist_last_plan)."""
+    out = (c_int64 * len(PLAN_FIELDS))()
+    check(load().ps_pair_dist_last_plan(out, len(PLAN_FIELDS)), "ps_pair_dist_last_plan")
+    return dict(zip(PLAN_FIELDS, (int(v) for v in out)))
 
 
 def int_array(values):

@@ -132,11 +132,33 @@ __global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
             u0[i] = H[i][0] * v0[0] + H[i][1] * v0[1] + H[i][2] * v0[2];
             u1[i] = H[i][0] * v1[0] + H[i][1] * v1[1] + H[i][2] * v1[2];
         }
+        // Rank-deficient selections (reference: torch.linalg.svd still returns a proper rotation, geometry.py:470-478):
+        //   no atom selected                      -> identity motion;
+        //   H = 0 (one atom, coincident points)   -> identity rotation, translation between the centroids;
+        //   rank 1 (collinear atoms)              -> the second singular pair is any unit vector orthogonal to the
+        //                                            first on either side (the rotation about the line is free).
         const double n0 = sqrt(u0[0] * u0[0] + u0[1] * u0[1] + u0[2] * u0[2]);
+        if (!(cnt > 0.0) || !(n0 > 0.0)) {
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) rot[b * 9 + i * 3 + j] = i == j ? 1.f : 0.f;
+                trans[b * 3 + i] = cnt > 0.0 ? static_cast<float>(cb[i] - ca[i]) : 0.f;
+            }
+            return;
+        }
         for (int i = 0; i < 3; ++i) u0[i] /= n0;
         const double p = u1[0] * u0[0] + u1[1] * u0[1] + u1[2] * u0[2];
         for (int i = 0; i < 3; ++i) u1[i] -= p * u0[i];
-        const double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        if (!(n1 > 1e-9 * n0)) {
+            int k = 0;  // the coordinate axis least aligned with u0
+            if (fabs(u0[1]) < fabs(u0[k])) k = 1;
+            if (fabs(u0[2]) < fabs(u0[k])) k = 2;
+            const double e[3] = {k == 0 ? 1.0 : 0.0, k == 1 ? 1.0 : 0.0, k == 2 ? 1.0 : 0.0};
+            u1[0] = u0[1] * e[2] - u0[2] * e[1];
+            u1[1] = u0[2] * e[0] - u0[0] * e[2];
+            u1[2] = u0[0] * e[1] - u0[1] * e[0];
+            n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+        }
         for (int i = 0; i < 3; ++i) u1[i] /= n1;
         const double v2[3] = {v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0]};
         const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};

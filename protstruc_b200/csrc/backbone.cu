@@ -208,18 +208,20 @@ __global__ void __launch_bounds__(256) frames_to_backbone_kernel(
 // e * row < 2^32) and the translation offset is 32-bit arithmetic; the general flavour divides and uses 64-bit
 // strides.
 template <bool FAST>
-__global__ void __launch_bounds__(256) translate_bcast_kernel(const float* __restrict__ xyz,
+// xyz and out may be the SAME buffer (StructureBatch.translate works in place like the reference's `+=`), so neither
+// is declared __restrict__: every thread reads an element before it writes that same element and touches no other.
+__global__ void __launch_bounds__(256) translate_bcast_kernel(const float* xyz,
                                                               const float* __restrict__ tr,
                                                               long long sb, long long sl, long long sa,
                                                               int B, int A, int per_b, unsigned row_magic,
-                                                              float* __restrict__ out) {
+                                                              float* out) {
     // 2-D grid: blockIdx.y walks the structures, x the structure's floats; (l, a, axis) from the 32-bit offset
     // inside the structure
     const unsigned row = static_cast<unsigned>(A) * 3u;
     const unsigned sl32 = static_cast<unsigned>(sl), sa32 = static_cast<unsigned>(sa);
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
-        const float* __restrict__ xb = xyz + static_cast<long long>(b) * per_b;
-        float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
+        const float* xb = xyz + static_cast<long long>(b) * per_b;
+        float* ob = out + static_cast<long long>(b) * per_b;
         const float* __restrict__ tb = tr + b * sb;
         const unsigned n = static_cast<unsigned>(per_b), step = gridDim.x * blockDim.x;
         for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * step) {

@@ -33,6 +33,7 @@ int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float
 int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
                       cudaStream_t);
 int debug_fill_pattern_impl(float*, long long, int, cudaStream_t);
+int pair_dist_last_plan_impl(long long*, int);
 struct HostPipeline;
 int host_pipeline_create_impl(int, int, int, HostPipeline**);
 int host_pipeline_destroy_impl(HostPipeline*);
@@ -241,6 +242,10 @@ int ps_host_inter_residue_geometry(void* pipeline, const float* xyz, const uint8
 
 int64_t ps_host_pipeline_launches(void* pipeline) {
     return ps::host_pipeline_launches_impl(static_cast<const ps::HostPipeline*>(pipeline));
+}
+
+int ps_pair_dist_last_plan(int64_t* out, int n) {
+    return ps::pair_dist_last_plan_impl(reinterpret_cast<long long*>(out), n);
 }
 
 int ps_debug_fill_pattern(float* out, int64_t n, int blocks_per_sm, void* stream) {

@@ -62,9 +62,13 @@ __device__ __forceinline__ float dot3(V3 a, V3 b) {
     return __fadd_rn(__fadd_rn(acc, __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
 }
 
-// x.norm(dim=-1): IEEE sqrt of the sum of squares.
+// x.norm(dim=-1) / torch.norm(x, dim=-1): IEEE sqrt of the sum of squares.  ATen's CPU vector-norm kernel
+// accumulates the squares with fused multiply-adds — fma(z, z, fma(y, y, x * x)) — for every shape the reference
+// uses it on (probed on 1e6 random vectors and on (n, 3) ... (B, L, L, 3) shapes: bit-identical to this chain,
+// 10 % one-ulp mismatches against the separately rounded sum).  The last ulp matters where a quotient by a
+// product of norms is fed to an unclamped arccos (geometry.py:64-71): it decides which collinear triples are NaN.
 __device__ __forceinline__ float norm3(V3 a) {
-    return __fsqrt_rn(dot3(a, a));
+    return __fsqrt_rn(__fmaf_rn(a.z, a.z, __fmaf_rn(a.y, a.y, __fmul_rn(a.x, a.x))));
 }
 
 __device__ __forceinline__ V3 scale3(V3 a, float s) {
@@ -202,6 +206,7 @@ struct TripleRowSide {
     V3 tn1;       // (N_i - CA_i) x (CB_i - CA_i)   (theta's n1)
     float inv_tb1_norm;  // 1 / |CB_i - CA_i|
     float inv_ba_norm;   // 1 / |CA_i - CB_i|
+    float ba_norm;       // |CA_i - CB_i|  (phi's exact sequence near |cos| = 1)
     bool nan_ca_cb;      // CA_i or CB_i missing
     bool nan_n;          // N_i missing
 };
@@ -213,7 +218,8 @@ __device__ __forceinline__ TripleRowSide triple_row_side(V3 n_i, V3 ca_i, V3 cb_
     r.tb1 = sub3(cb_i, ca_i);
     r.tn1 = cross3(sub3(n_i, ca_i), r.tb1);
     r.inv_tb1_norm = __frcp_rn(norm3(r.tb1));
-    r.inv_ba_norm = __frcp_rn(norm3(r.b0));
+    r.ba_norm = norm3(r.b0);
+    r.inv_ba_norm = __frcp_rn(r.ba_norm);
     r.nan_ca_cb = atom_has_nan(ca_i) || atom_has_nan(cb_i);
     r.nan_n = atom_has_nan(n_i);
     return r;
@@ -247,7 +253,17 @@ __device__ __forceinline__ void trrosetta_triple(const TripleRowSide& r, V3 ca_j
         theta = atan2_tuned(y, x);
     }
     if (want_phi && !(r.nan_ca_cb || nan_cb_j)) {
-        const float cosine = __fmul_rn(__fmul_rn(dot3(r.b0, bc), r.inv_ba_norm), rsqrt_refined(dot3(bc, bc)));
+        // cos = (ba.bc) / (|ba| |bc|) without a clamp (reference geometry.py:64-71): acos of 1.0000001 is NaN,
+        // so WHERE the rounded quotient exceeds 1 is part of the contract.  Away from |cos| = 1 the quotient is
+        // formed with the hoisted 1/|ba| and one refined MUFU.RSQ (<= 3 ulp from the reference's value, i.e.
+        // <= 4e-6 rad at sin >= 0.045); within 1e-3 of +-1 — and for anything non-finite (the diagonal's 0/0,
+        // zero-padded residues, |bc|^2 below the ftz threshold) — the reference's exact op sequence is issued:
+        // ATen's norms (norm3), their rounded product, IEEE division.  NaN placement is then the reference's
+        // bit for bit (tests: adversarial collinear triples).
+        const float d = dot3(r.b0, bc);
+        const float bc2 = dot3(bc, bc);
+        float cosine = __fmul_rn(__fmul_rn(d, r.inv_ba_norm), rsqrt_refined(bc2));
+        if (!(fabsf(cosine) <= 0.999f)) cosine = __fdiv_rn(d, __fmul_rn(r.ba_norm, norm3(bc)));
         phi = acosf(cosine);
     }
 }

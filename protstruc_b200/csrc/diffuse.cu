@@ -5,11 +5,13 @@
 // which the reference evaluates as three separately rounded fp32 ops (no FMA); __fmul_rn /
 // __fadd_rn below pin that rounding so that, given the same noise tensor, results are bit-equal.
 //
-// Random numbers: counter-based Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.  The counter
-// of a group of four consecutive elements is (global_group_index, step), the key is the seed, so
-// the stream is a pure function of (seed, step, global element index): independent of the launch
-// shape, of the number of GPUs the batch is sharded over, and identical between the single-step
-// kernel and the fused multi-step kernel.
+// Random numbers: counter-based Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.  Element e of
+// the GLOBAL (unsharded) tensor takes output lane (e & 3) of the counter (e >> 2, step); the key is
+// the seed.  The stream is therefore a pure function of (seed, step, global element index):
+// independent of the launch shape and identical between the single-step kernel and the fused
+// multi-step kernel.  A shard may start at ANY global element (elem_offset need not be a multiple
+// of 4): thread g of a launch owns global group (elem_offset >> 2) + g, i.e. the local elements
+// 4 g - (elem_offset & 3) + k, k = 0..3, so the result never depends on the number of GPUs.
 //
 // Roofline: single step = HBM/L2 read + write of 4 B per element (the noise is never
 // materialised); the 300-step schedule of BASELINE config 4 (23.6 MB of state) is launch/L2-bound
@@ -165,19 +167,20 @@ constexpr int kTableSlots = 2;
 __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __restrict__ x,
                                                              const float* __restrict__ betas, int T,
                                                              int B, uint64_t seed, uint64_t step0,
-                                                             uint64_t group_offset, long long per_b,
+                                                             uint64_t group_offset, int shift, long long per_b,
                                                              long long total, int use_table,
                                                              float* __restrict__ out) {
     extern __shared__ float2 schedule[];  // [T][kTableSlots] when use_table
     const PhiloxKeys keys = philox_keys(seed);
-    const long long groups = (total + 3) / 4;
+    const long long groups = (total + shift + 3) / 4;
     const long long num_blocks = (groups + blockDim.x - 1) / blockDim.x;
     for (long long blk = blockIdx.x; blk < num_blocks; blk += gridDim.x) {
         const long long g = blk * blockDim.x + threadIdx.x;
         int b_lo = 0, nb = 0;
         if (use_table) {  // structures this block of 1024 elements touches
-            const long long block_e0 = blk * blockDim.x * 4;
+            long long block_e0 = blk * blockDim.x * 4 - shift;
             long long block_e1 = block_e0 + static_cast<long long>(blockDim.x) * 4 - 1;
+            if (block_e0 < 0) block_e0 = 0;
             if (block_e1 > total - 1) block_e1 = total - 1;
             b_lo = static_cast<int>(block_e0 / per_b);
             nb = static_cast<int>(block_e1 / per_b) - b_lo + 1;
@@ -193,27 +196,28 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
             __syncthreads();
         }
         if (g >= groups) continue;
-        const long long e0 = g * 4;
+        const long long e0 = g * 4 - shift;  // first local element of the group (negative only for g = 0)
+        const long long e0c = e0 < 0 ? 0 : e0;
         float v[4];
         int bidx[4];
         // structure of each of the four elements: ONE division per thread (32-bit whenever the element count
         // allows), then the group either stays inside the structure or steps over its end
         long long b0, rem0;
         if (total <= 0xFFFFFFFFll && per_b <= 0xFFFFFFFFll) {
-            const unsigned q = static_cast<unsigned>(e0) / static_cast<unsigned>(per_b);
+            const unsigned q = static_cast<unsigned>(e0c) / static_cast<unsigned>(per_b);
             b0 = q;
-            rem0 = static_cast<unsigned>(e0) - q * static_cast<unsigned>(per_b);
+            rem0 = static_cast<unsigned>(e0c) - q * static_cast<unsigned>(per_b);
         } else {
-            b0 = e0 / per_b;
-            rem0 = e0 - b0 * per_b;
+            b0 = e0c / per_b;
+            rem0 = e0c - b0 * per_b;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long e = e0 + k;
-            const bool ok = e < total;
+            const bool ok = e >= 0 && e < total;
             v[k] = ok ? x[e] : 0.f;
-            long long bk = b0 + (rem0 + k >= per_b ? 1 : 0);
-            if (per_b < 4) bk = e / per_b;  // degenerate structures of fewer than four floats
+            long long bk = b0 + (rem0 + (e - e0c) >= per_b ? 1 : 0);
+            if (per_b < 4 && ok) bk = e / per_b;  // degenerate structures of fewer than four floats
             bidx[k] = ok ? static_cast<int>(bk) : static_cast<int>(b0);
         }
         const bool same_b = bidx[0] == bidx[3];
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (e0 + k < total) out[e0 + k] = v[k];
+            if (e0 + k >= 0 && e0 + k < total) out[e0 + k] = v[k];
     }
 }
 
@@ -256,17 +260,24 @@ __global__ void __launch_bounds__(256) diffuse_philox_kernel(const float* __rest
 // so T calls of it equal one T-step launch bit for bit.
 __global__ void __launch_bounds__(256) diffuse_philox_step_kernel(const float* __restrict__ x,
                                                                   const float* __restrict__ beta, uint64_t seed,
-                                                                  uint64_t step, uint64_t group_offset,
+                                                                  uint64_t step, uint64_t group_offset, int shift,
                                                                   long long per_b, long long total,
                                                                   float* __restrict__ out) {
     const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long e0 = g * 4;
+    const long long e0 = g * 4 - shift;
     if (e0 >= total) return;
+    float z[4];
+    normal4(static_cast<uint64_t>(g) + group_offset, step, seed, z);
+    if (e0 < 0) {  // the first group of a shard that starts inside a group of four
+        for (int k = static_cast<int>(-e0); k < 4 && e0 + k < total; ++k) {
+            const float bt = __ldg(beta + (e0 + k) / per_b);
+            out[e0 + k] = diffuse_one(x[e0 + k], z[k], __fsqrt_rn(__fsub_rn(1.0f, bt)), __fsqrt_rn(bt));
+        }
+        return;
+    }
     const bool fits_32_bits = total <= 0xFFFFFFFFll && per_b <= 0xFFFFFFFFll;
     const long long b0 = index_div(e0, per_b, fits_32_bits);
     const long long rem0 = e0 - b0 * per_b;
-    float z[4];
-    normal4(static_cast<uint64_t>(g) + group_offset, step, seed, z);
     if (rem0 + 3 < per_b && e0 + 3 < total) {  // the whole group lies in structure b0 (the common case)
         const float bt = __ldg(beta + b0);
         const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
@@ -283,17 +294,19 @@ __global__ void __launch_bounds__(256) diffuse_philox_step_kernel(const float* _
 
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, long long n,
                                                             uint64_t seed, uint64_t step,
-                                                            uint64_t group_offset) {
+                                                            uint64_t group_offset, int shift) {
     const PhiloxKeys keys = philox_keys(seed);
-    const long long groups = (n + 3) / 4;
+    const long long groups = (n + shift + 3) / 4;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < groups;
          g += stride) {
         float z[4];
         normal4(static_cast<uint64_t>(g) + group_offset, step, keys, z);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (g * 4 + k < n) out[g * 4 + k] = z[k];
+        for (int k = 0; k < 4; ++k) {
+            const long long e = g * 4 - shift + k;
+            if (e >= 0 && e < n) out[e] = z[k];
+        }
     }
 }
 
@@ -316,8 +329,7 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
     PS_REQUIRE(B > 0 && per_b > 0 && T > 0, PS_ERR_BAD_SHAPE,
                "diffuse: B=%d per_b=%lld T=%d must be > 0", B, per_b, T);
     PS_REQUIRE(x && betas && out, PS_ERR_NULL_POINTER, "diffuse: NULL pointer");
-    PS_REQUIRE((elem_offset & 3u) == 0, PS_ERR_MISALIGNED,
-               "diffuse: elem_offset must be a multiple of 4");
+    const int shift = static_cast<int>(elem_offset & 3u);  // position of the shard's first element in its group
     const long long total = per_b * B;
     int grid = 0;
     if (noise) {
@@ -329,19 +341,19 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
         return check_launch("diffuse_noise_kernel");
     }
     if (T == 1) {
-        const long long groups = (total + 3) / 4;
+        const long long groups = (total + shift + 3) / 4;
         PS_REQUIRE((groups + 255) / 256 < (1ll << 31), PS_ERR_BAD_SHAPE, "diffuse: %lld elements", total);
         diffuse_philox_step_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(
-            x, betas, seed, step0, elem_offset / 4, per_b, total, out);
+            x, betas, seed, step0, elem_offset / 4, shift, per_b, total, out);
         return check_launch("diffuse_philox_step_kernel");
     }
-    int rc = grid_for((total + 3) / 4, &grid);
+    int rc = grid_for((total + shift + 3) / 4, &grid);
     if (rc != PS_OK) return rc;
     // schedule table: worth it from a handful of steps on, as long as it fits the default 48 KB of shared memory
     const size_t table_bytes = static_cast<size_t>(T) * kTableSlots * sizeof(float2);
     const int use_table = (T >= 4 && table_bytes <= 40 * 1024 && per_b >= 1024 / (kTableSlots - 1)) ? 1 : 0;
     diffuse_philox_kernel<<<grid, 256, use_table ? table_bytes : 0, stream>>>(x, betas, T, B, seed, step0, elem_offset / 4,
-                                                                              per_b, total, use_table, out);
+                                                                              shift, per_b, total, use_table, out);
     return check_launch("diffuse_philox_kernel");
 }
 
@@ -350,12 +362,11 @@ int philox_normal_impl(float* out, long long n, uint64_t seed, uint64_t step, ui
     PS_REQUIRE(n >= 0, PS_ERR_BAD_SHAPE, "philox_normal: n=%lld", n);
     if (n == 0) return PS_OK;
     PS_REQUIRE(out, PS_ERR_NULL_POINTER, "philox_normal: out is NULL");
-    PS_REQUIRE((elem_offset & 3u) == 0, PS_ERR_MISALIGNED,
-               "philox_normal: elem_offset must be a multiple of 4");
+    const int shift = static_cast<int>(elem_offset & 3u);
     int grid = 0;
-    int rc = grid_for((n + 3) / 4, &grid);
+    int rc = grid_for((n + shift + 3) / 4, &grid);
     if (rc != PS_OK) return rc;
-    philox_normal_kernel<<<grid, 256, 0, stream>>>(out, n, seed, step, elem_offset / 4);
+    philox_normal_kernel<<<grid, 256, 0, stream>>>(out, n, seed, step, elem_offset / 4, shift);
     return check_launch("philox_normal_kernel");
 }
 

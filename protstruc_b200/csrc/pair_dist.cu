@@ -43,6 +43,20 @@
 
 namespace ps {
 
+// What the most recent pair-distance launch of this host thread chose (ps_pair_dist_last_plan): tests assert on it
+// that a shape took the path — and the tile schedule — its parity claim is about.
+struct PairDistPlan {
+    long long path = -1;          // 0 staged tile kernel, 1 any-A tile kernel, 2 row kernel
+    long long lockstep = 0;       // staged kernel: 1 = linear lock-step sweep, 0 = (chunk, strip) cells
+    long long ctas = 0;
+    long long tile_buffers = 0;   // tile buffers (workers) of the grid
+    long long active_buffers = 0; // buffers that take part
+    long long strip_stride = 0;   // tiles between two members of a strip
+    long long tile_pairs = 0;
+    long long launches = 0;       // kernel launches of the call
+};
+thread_local PairDistPlan g_last_plan;
+
 namespace {
 
 constexpr int kTilePairs = 32;  // pairs per tile per pass over the lanes (tile = 32 * Q pairs)
@@ -928,6 +942,14 @@ int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t s
         q.chunk_members = (q.strip_members + chunks_per_strip - 1) / chunks_per_strip;
         q.num_cells = q.strip_stride * ((q.strip_members + q.chunk_members - 1) / q.chunk_members);
     }
+    g_last_plan.path = 0;
+    g_last_plan.lockstep = (q.num_cells == q.strip_stride && q.chunk_members == q.strip_members && q.active_workers == q.strip_stride) ? 1 : 0;
+    g_last_plan.ctas = ctas;
+    g_last_plan.tile_buffers = workers;
+    g_last_plan.active_buffers = q.active_workers;
+    g_last_plan.strip_stride = q.strip_stride;
+    g_last_plan.tile_pairs = TileGeom<A>::kPairs;
+    ++g_last_plan.launches;
     kernel<<<static_cast<unsigned>(ctas), slots * WPT * 32, smem, stream>>>(q);
     return check_launch("pair_tiles_kernel");
 }
@@ -1055,6 +1077,10 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
     if (blocks > per_sm * sms) blocks = per_sm * sms;
     const unsigned grid = static_cast<unsigned>(blocks);
     *launched = true;
+    g_last_plan.path = 1;
+    g_last_plan.ctas = blocks;
+    g_last_plan.tile_pairs = best_pairs;
+    ++g_last_plan.launches;
     switch (kind) {
         case kDistBoolMask: return launch_cols_kind<kDistBoolMask>(p, sqrt_mode_id, grid, best_threads, smem, stream);
         case kDistOnly: return launch_cols_kind<kDistOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
@@ -1093,6 +1119,9 @@ int launch_generic(const float* xyz, const void* atom_mask, int mask_dtype, floa
     const long long cap = static_cast<long long>(sms) * 8;
     if (blocks > cap) blocks = cap;
     const unsigned grid = static_cast<unsigned>(blocks);
+    g_last_plan.path = 2;
+    g_last_plan.ctas = blocks;
+    ++g_last_plan.launches;
     if (sqrt_mode_id == kSqrtRn)
         return launch_rows_sqrt<kSqrtRn>(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A, num_rows, parts,
                                          cols_per_part, grid, threads, stream);
@@ -1195,6 +1224,15 @@ int debug_fill_pattern_impl(float* out, long long n, int blocks_per_sm, cudaStre
     return check_launch("debug_fill_pattern_kernel");
 }
 
+int pair_dist_last_plan_impl(long long* out, int n) {
+    const long long v[8] = {g_last_plan.path, g_last_plan.lockstep, g_last_plan.ctas, g_last_plan.tile_buffers,
+                            g_last_plan.active_buffers, g_last_plan.strip_stride, g_last_plan.tile_pairs,
+                            g_last_plan.launches};
+    PS_REQUIRE(out != nullptr && n >= 0, PS_ERR_NULL_POINTER, "pair_dist_last_plan: out is NULL");
+    for (int k = 0; k < n && k < 8; ++k) out[k] = v[k];
+    return PS_OK;
+}
+
 // Host entry used by the C-ABI wrappers (cabi.cu).
 int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                         void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
@@ -1210,6 +1248,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
                "pair_dist_mask: unknown mask_dtype %d", mask_dtype);
     PS_REQUIRE(static_cast<long long>(B) * L < (1ll << 31), PS_ERR_BAD_SHAPE,
                "pair_dist_mask: B*L=%lld residues exceed 2^31", static_cast<long long>(B) * L);
+    g_last_plan = PairDistPlan();
     const bool want_angles = omega || theta || phi;
     PS_REQUIRE(!want_angles || A >= 5, PS_ERR_BAD_SHAPE,
                "inter_residue_geometry needs the CB slot (A >= 5), got A=%d", A);
@@ -1227,6 +1266,7 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
         const bool rows_only = (variant >> 12) & 1;
         int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0x3FF, stream);
         if (rc != PS_OK || !want_angles) return rc;
+        ++g_last_plan.launches;
         return trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, stream);
     }
 

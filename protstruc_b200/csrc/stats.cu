@@ -267,14 +267,15 @@ __global__ void __launch_bounds__(256) scale_shift_kernel(const float* __restric
     }
 }
 
-// out = x + t[b or 0, axis]
-__global__ void __launch_bounds__(256) translate_kernel(const float* __restrict__ x,
+// out = x + t[b or 0, axis].  x and out may be the SAME buffer (center_at works in place like the reference's `+=`),
+// so neither is __restrict__: a thread reads an element before it writes that same element and touches no other.
+__global__ void __launch_bounds__(256) translate_kernel(const float* x,
                                                         const float* __restrict__ t, int t_rows,
-                                                        int per_b, int B, float* __restrict__ out) {
+                                                        int per_b, int B, float* out) {
     const unsigned n = static_cast<unsigned>(per_b), step = gridDim.x * blockDim.x;
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
-        const float* __restrict__ xb = x + static_cast<long long>(b) * per_b;
-        float* __restrict__ ob = out + static_cast<long long>(b) * per_b;
+        const float* xb = x + static_cast<long long>(b) * per_b;
+        float* ob = out + static_cast<long long>(b) * per_b;
         const float* __restrict__ tb = t + (t_rows == 1 ? 0 : b * 3);
         const float t0 = __ldg(tb), t1 = __ldg(tb + 1), t2 = __ldg(tb + 2);
         for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n; e0 += kUnroll * step) {

@@ -56,13 +56,9 @@ def shard_structure_batch(xyz, atom_mask=None, chain_idx=None, chain_ids=None, s
         None if seq is None else seq[start:stop],
         device=device,
     )
-    per_structure = int(xyz.shape[1]) * int(xyz.shape[2]) * 3
-    offset = start * per_structure
-    if offset % 4 != 0:
-        # the Philox counter addresses groups of 4 elements; a shard that does not start on a group
-        # boundary cannot reproduce the global stream -> fall back to a per-rank stream
-        offset = ((offset + 3) // 4) * 4 + (rank << 40)
-    sb._noise_elem_offset = offset
+    # first GLOBAL element of this shard: the kernels address the Philox stream per element
+    # (counter = global index >> 2, lane = global index & 3), so any offset reproduces the global stream
+    sb._noise_elem_offset = start * int(xyz.shape[1]) * int(xyz.shape[2]) * 3
     return sb
 
 

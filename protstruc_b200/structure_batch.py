@@ -26,23 +26,47 @@ ArrayLike = Union[np.ndarray, torch.Tensor]
 
 
 # ------------------------------------------------------------------------------------------------
-# RNG stream of diffuse_xyz: (seed, step) of the Philox generator inside the kernels.
+# RNG stream of diffuse_xyz: (key, step) of the Philox generator inside the kernels.
 class _PhiloxStream:
-    """Process-wide counter-based stream: seed follows torch's global seed, `step` advances by one
-    per diffusion step, so consecutive calls never reuse random numbers."""
+    """Derives the (key, step) pair of every diffusion step from the state of a torch generator (the global
+    CPU generator unless `generator=` is given), the way `torch.randn_like` in the reference consumes it
+    (reference protstruc.py:876):
+
+    * the first call on a generator — and the first call after anybody else touched that generator
+      (`torch.manual_seed`, `generator.manual_seed`, any other random draw) — starts a SESSION: 63 random bits
+      are drawn from the generator and become the Philox key, the step counter starts at 0;
+    * while the generator is left alone, later calls continue the session: the step counter advances by the
+      number of diffusion steps taken, so T calls of `diffuse_xyz` and one `diffuse_xyz_steps` of T steps
+      use the same noise.
+
+    Consequences: switching between generators never rewinds either of them (one session per generator
+    object); re-seeding — also with the same seed, also by re-creating a generator — restarts the stream
+    reproducibly; no noise is ever reused without a re-seed."""
+
+    _MAX_SESSIONS = 64
 
     def __init__(self) -> None:
-        self.seed: Optional[int] = None
-        self.step = 0
+        self._sessions: Dict[int, list] = {}  # id(generator) -> [generator, fingerprint, key, step]
+
+    @staticmethod
+    def _fingerprint(generator: torch.Generator) -> int:
+        return hash(generator.get_state().numpy().tobytes())
+
+    def reset(self) -> None:
+        self._sessions.clear()
 
     def reserve(self, n_steps: int, generator: Optional[torch.Generator]) -> Tuple[int, int]:
-        seed = int(generator.initial_seed() if generator is not None else torch.initial_seed())
-        seed &= (1 << 64) - 1
-        if seed != self.seed:
-            self.seed, self.step = seed, 0
-        first = self.step
-        self.step += n_steps
-        return seed, first
+        g = torch.default_generator if generator is None else generator
+        session = self._sessions.get(id(g))
+        if session is None or session[1] != self._fingerprint(g):
+            draw = torch.randint(0, 2 ** 63 - 1, (1,), generator=g, dtype=torch.int64, device=g.device)
+            if len(self._sessions) >= self._MAX_SESSIONS:
+                self._sessions.pop(next(iter(self._sessions)))
+            session = [g, self._fingerprint(g), int(draw.item()), 0]
+            self._sessions[id(g)] = session
+        first = session[3]
+        session[3] += n_steps
+        return session[2], first
 
 
 _philox = _PhiloxStream()
@@ -51,7 +75,7 @@ _philox = _PhiloxStream()
 def manual_seed(seed: int) -> None:
     """Seeds torch's global generator and restarts the diffusion noise stream."""
     torch.manual_seed(seed)
-    _philox.seed, _philox.step = int(seed) & ((1 << 64) - 1), 0
+    _philox.reset()
 
 
 def _always_tensor(x):
@@ -466,16 +490,20 @@ class StructureBatch:
         """In-place translation by (B, L, 3) / (B, 1, 3) or atomwise (B, L, A, 3) tensors
         (reference protstruc.py:662-679).  One broadcast-add kernel; `translation` is read through its
         broadcast strides, nothing is materialised."""
-        lib = self._lib()
         dev = self.xyz.device
         translation = translation.to(device=dev, dtype=torch.float32)
         if not atomwise:
             if translation.ndim != 3:
                 raise ValueError(f"`translation` must have shape (batch, residues, 3), got {tuple(translation.shape)}")
             translation = translation.unsqueeze(-2)
-        if translation.stride(-1) != 1:
-            translation = translation.contiguous()
         view = translation.expand(self.xyz.shape)  # raises like torch's `+=` if the shapes do not broadcast
+        if self._is_empty():
+            return
+        lib = self._lib()
+        if view.stride(-1) != 1:
+            # the kernel reads the three coordinates of a translation vector at unit stride; a broadcast or strided
+            # coordinate axis (e.g. a (B, L, 1) translation) is materialised with its last axis expanded
+            view = translation.expand(translation.shape[:-1] + (3,)).contiguous().expand(self.xyz.shape)
         sb, sl, sa, _ = view.stride()
         B, L, A = self._dims()
         with _cabi.on_device(dev):
@@ -490,6 +518,8 @@ class StructureBatch:
             raise ValueError(f"`rotation` must have shape (batch, 3, 3) or (3, 3), got {tuple(rotation.shape)}")
         if rotation.ndim == 3 and rotation.shape[0] not in (1, self.batch_size):
             raise ValueError(f"`rotation` has {rotation.shape[0]} matrices for {self.batch_size} structures")
+        if self._is_empty():  # nothing to rotate: a no-op like the reference's einsum over no atoms
+            return
         lib = self._lib()
         dev = self.xyz.device
         rot = rotation.to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
@@ -510,8 +540,13 @@ class StructureBatch:
             raise ValueError("Coordinates are already standardized.")
         if self.atom_mask is None:
             raise TypeError("standardize needs an atom_mask")
-        lib = self._lib()
         dev = self.xyz.device
+        if self._is_empty():  # mean / deviation over no atoms: 0 / 0 like the reference
+            self.mu = torch.full((self.batch_size, 3), float("nan"), dtype=torch.float32, device=dev)
+            self.std = self.mu.clone()
+            self._standardized = True
+            return
+        lib = self._lib()
         if atom_mask is not None:
             use = atom_mask.to(dev) * self.atom_mask
         elif residue_mask is not None:
@@ -535,6 +570,9 @@ class StructureBatch:
         """Inverse of `standardize` (reference protstruc.py:736-744)."""
         if not self._standardized:
             raise ValueError("Cannot unstandardize structures that are not standardized.")
+        if self._is_empty():
+            self._standardized = False
+            return
         lib = self._lib()
         B, L, A = self._dims()
         out = torch.empty_like(self.xyz)
@@ -573,6 +611,8 @@ class StructureBatch:
             raise ValueError(f"`center` must have a shape of (batch_size, 3) or (3,), got {center.shape}.")
         if center.ndim == 1:
             center = center.unsqueeze(0)
+        if self._is_empty():
+            return
         lib = self._lib()
         dev = self.xyz.device
         B, L, A = self._dims()
@@ -591,8 +631,10 @@ class StructureBatch:
             raise ValueError("Batch size of the two structures must be the same.")
         if tuple(target.get_xyz().shape[1:]) != tuple(self.xyz.shape[1:]):
             raise ValueError("Source and target must have the same (residues, atoms) layout.")
-        lib = self._lib()
         dev = self.xyz.device
+        if self._is_empty():  # no atoms to superimpose: identity motions, nothing moves
+            return torch.eye(3, dtype=torch.float32, device=dev).repeat(self.batch_size, 1, 1)
+        lib = self._lib()
         if atom_mask is None:
             if self.atom_mask is None or target.get_atom_mask() is None:
                 raise TypeError("align needs atom masks (or an explicit `atom_mask`)")
@@ -617,9 +659,11 @@ class StructureBatch:
         if self.batch_size > 1:
             raise ValueError("get_topk_nearest_residue_mask method is not defined "
                              "for a StructureBatch with batch size > 1.")
-        lib = self._lib()
         dev = self.xyz.device
         B, L, A = self._dims()
+        if self._is_empty():
+            return torch.zeros(1, L, dtype=torch.bool, device=dev)
+        lib = self._lib()
         valid = self.residue_mask[0]
         if mask is not None:
             valid = valid & mask.to(dev)
@@ -660,12 +704,15 @@ class StructureBatch:
         `noise` (extension): inject z explicitly — the result is then bit-identical to the
         reference evaluated with the same z.  Otherwise z comes from the kernel's own Philox
         stream, seeded by `generator` (or torch's global seed)."""
-        lib = self._lib()
         dev = self.xyz.device
         B, L, A = self._dims()
         beta = beta.to(device=dev, dtype=torch.float32).contiguous()
         if beta.shape != (B,):
             raise ValueError(f"`beta` must have shape ({B},), got {tuple(beta.shape)}")
+        if self._is_empty():
+            self.xyz = self.xyz.clone()  # rebinds like the reference, nothing to diffuse
+            return
+        lib = self._lib()
         out = torch.empty_like(self.xyz)
         per_b = L * A * 3
         if noise is not None:
@@ -686,15 +733,15 @@ class StructureBatch:
     def diffuse_xyz_steps(self, betas: torch.Tensor, generator: Optional[torch.Generator] = None) -> None:
         """T diffusion steps fused in one kernel (extension); `betas` is (T, B).  Bit-identical to
         calling `diffuse_xyz(betas[t])` for t = 0..T-1 on the same noise stream."""
-        lib = self._lib()
         dev = self.xyz.device
         B, L, A = self._dims()
         betas = betas.to(device=dev, dtype=torch.float32).contiguous()
         if betas.ndim != 2 or betas.shape[1] != B:
             raise ValueError(f"`betas` must have shape (T, {B}), got {tuple(betas.shape)}")
         T = betas.shape[0]
-        if T == 0:
+        if T == 0 or self._is_empty():
             return
+        lib = self._lib()
         out = torch.empty_like(self.xyz)
         seed, step0 = _philox.reserve(T, generator)
         with _cabi.on_device(dev):

@@ -100,6 +100,20 @@ def pair_points(xyz: torch.Tensor, slots_i, slots_j):
     return torch.cat([pi, pj], dim=-2)
 
 
+def trrosetta_conditioning(xyz: torch.Tensor, which: str) -> torch.Tensor:
+    """min sin(bond angle) of every residue pair for omega / theta / phi as the reference defines them
+    (protstruc.py:810-815): the gate of the 1e-5 rad tolerance ("away from collinear degeneracies")."""
+    N, CA, CB = 0, 1, 4
+    if which == "omega":
+        p = pair_points(xyz, [CA, CB], [CA, CB])
+        return dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+    if which == "theta":
+        p = pair_points(xyz, [N, CA, CB], [CB])
+        return dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+    p = pair_points(xyz, [CA, CB], [CB])
+    return planar_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :])
+
+
 def synthetic_batch(seed: int, B: int, L: int, A: int, mask_kind: str = "bool", nan_masked: bool = True,
                     full_length: bool = False):
     """Same generator family as tests/golden/make_golden.py::synthetic_inputs (protein-like walk)."""

@@ -90,7 +90,8 @@ def test_argument_validation_happens_before_any_cuda_call(native_lib):
     assert lib.ps_center_of_mass(fake, 1, 8, 15, 15, fake, null) == -4 and "slot 15" in message()
     assert lib.ps_translate(fake, fake, 3, 2, 8, 15, fake, null) == -1 and "t_rows" in message()
     assert lib.ps_rotate(fake, fake, 1, 1, 8, 15, fake, null) == -5  # in-place rotation is refused
-    assert lib.ps_diffuse(fake, fake, null, 1, 0, 2, fake, 1, 360, null) == -5 and "multiple of 4" in message()
+    # (elem_offset may be ANY value since round 2: the Philox stream is addressed per element)
+    assert lib.ps_diffuse(fake, fake, null, 1, 0, 2, fake, 0, 360, null) == -1 and "must be > 0" in message()
     slots = _cabi.int_array([0, 1, 2])
     assert lib.ps_pair_angles(fake, 1, 8, 15, slots, 3, slots, 3, 0, fake, null) == -1 and "needs 4 atoms" in message()
     bad = _cabi.int_array([0, 1, 99])

@@ -16,7 +16,8 @@ from protstruc_b200 import _cabi
 from oracle import feature_oracle as orc
 from tests import helpers as H
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device (B200); there is no CPU path")]
 
 SYNTHETIC = ["synthetic_small", "synthetic_floatmask_oddL", "synthetic_A5",
              "synthetic_A25_like_reference_tests", "synthetic_ragged_33"]
@@ -28,16 +29,7 @@ def make_batch(g):
     return ps.StructureBatch.from_xyz(g["xyz"], g["atom_mask"], g["chain_idx"], ids)
 
 
-def angle_conditioning(xyz, which):
-    N, CA, CB = 0, 1, 4
-    if which == "omega":
-        p = H.pair_points(xyz, [CA, CB], [CA, CB])
-        return H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
-    if which == "theta":
-        p = H.pair_points(xyz, [N, CA, CB], [CB])
-        return H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
-    p = H.pair_points(xyz, [CA, CB], [CB])
-    return H.planar_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :])
+angle_conditioning = H.trrosetta_conditioning
 
 
 # ------------------------------------------------------------------------------ K1 distances + mask
@@ -170,6 +162,101 @@ def test_distance_properties_at_baseline_config2(native_lib):
         sub_j = xyz[b, j0:j0 + 6].cpu()
         ref = torch.norm(sub_i[:, None, :, None] - sub_j[None, :, None, :], dim=-1)
         H.assert_distances_close(dist[b, i0:i0 + 6, j0:j0 + 6], ref, "spot block")
+
+
+@pytest.mark.parametrize("L,expect_lockstep", [(512, True), (384, None), (256, None)])
+def test_full_feature_set_at_the_baseline_shapes_vs_oracle(native_lib, L, expect_lockstep):
+    """The shapes the numbers of record are quoted on — L = 512 (the metric shape, bench.py), L = 384 (BASELINE
+    config 5), L = 256 (config 2); A = 15, bool mask, NaN-masked coordinates, ragged lengths, DEFAULT dispatch through
+    the public call — against the CPU oracle (reference protstruc.py:790-817) on the FULL tensors: every distance,
+    every mask byte, omega / theta / phi.  The launch plan is read back so that the test fails if the shape stops
+    taking the fused staged kernel (and, at L = 512, the lock-step schedule the bench runs)."""
+    B, A = 2, 15
+    xyz, mask, _ = H.synthetic_batch(5120 + L, B, L, A, "bool")
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    out = sb.inter_residue_geometry()
+    plan = _cabi.last_pair_dist_plan()
+    assert plan["path"] == 0 and plan["launches"] == 1, plan  # ONE fused launch of the staged tile kernel
+    if expect_lockstep is not None:
+        assert bool(plan["lockstep"]) == expect_lockstep, plan
+    dist, dist_mask = out["d_ca"]._base, out["d_ca_mask"]._base  # the full tensors behind the strided views
+    assert tuple(dist.shape) == (B, L, L, A, A) and dist_mask.dtype == torch.bool
+    for b in range(B):  # one structure at a time: the oracle needs ~1.5 GB per 512-residue structure
+        ref = orc.inter_residue_geometry(xyz[b:b + 1], mask[b:b + 1])
+        rd, rm = orc.pair_distances(xyz[b:b + 1], mask[b:b + 1])
+        H.assert_distances_close(dist[b:b + 1], rd, f"dist[{b}]")
+        assert torch.equal(dist_mask[b:b + 1].cpu(), rm), f"dist_mask[{b}]"
+        del rd, rm
+        for which in ("omega", "theta"):
+            H.assert_angles_close(out[which][b:b + 1], ref[which], angle_conditioning(xyz[b:b + 1], which),
+                                  f"{which}[{b}]", all_finite_tol=2e-6)
+        H.assert_angles_close(out["phi"][b:b + 1], ref["phi"], angle_conditioning(xyz[b:b + 1], "phi"), f"phi[{b}]",
+                              circular=False)
+        for key in ("d_ca", "d_cb", "d_no"):
+            H.assert_distances_close(out[key][b:b + 1], ref[key], key)
+            assert torch.equal(out[key + "_mask"][b:b + 1].cpu(), ref[key + "_mask"])
+    # the separate distance call at the same shape (its own default schedule) writes the same bytes
+    d2, m2 = sb.pairwise_distance_matrix()
+    assert torch.equal(torch.nan_to_num(d2, nan=-5.0), torch.nan_to_num(dist, nan=-5.0)) and torch.equal(m2, dist_mask)
+
+
+def collinear_batch(L: int = 192):
+    """Adversarial input for the unclamped arccos of phi = angle(CA_i, CB_i, CB_j) (reference geometry.py:64-71):
+    every CA and CB of a structure lies on ONE line, so every triple is exactly or nearly collinear and the rounded
+    cosine lands on either side of +-1 — whether an entry is NaN depends on the last ulp of the reference's op
+    sequence.  Structures: axis-aligned line (exactly collinear in fp32), general direction, the same scaled by 100
+    and by 0.01, one-ulp perturbations of the axis-aligned case, and a general line far from the origin."""
+    g = torch.Generator().manual_seed(777)
+    structs = []
+    for kind in ("axis", "general", "big", "small", "ulp", "offset"):
+        d = torch.randn(3, generator=g)
+        if kind in ("axis", "ulp"):
+            d = torch.tensor([0.0, 1.0, 0.0])
+        p0 = 10.0 * torch.randn(3, generator=g) if kind != "offset" else 500.0 + 10.0 * torch.randn(3, generator=g)
+        s_ca = 40.0 * torch.rand(L, generator=g) - 20.0
+        s_cb = s_ca + (0.5 + 2.5 * torch.rand(L, generator=g)) * torch.where(torch.rand(L, generator=g) < 0.5, -1.0, 1.0)
+        x = 1.5 * torch.randn(L, 15, 3, generator=g) + p0
+        x[:, 1] = p0 + s_ca[:, None] * d
+        x[:, 4] = p0 + s_cb[:, None] * d
+        if kind == "big":
+            x = x * 100.0
+        if kind == "small":
+            x = x * 0.01
+        if kind == "ulp":
+            bump = torch.rand(L, 3, generator=g) < 0.3
+            x[:, 4] = torch.where(bump, torch.nextafter(x[:, 4], torch.full_like(x[:, 4], float("inf"))), x[:, 4])
+        structs.append(x)
+    xyz = torch.stack(structs).contiguous()
+    return xyz, torch.ones(xyz.shape[:3], dtype=torch.bool)
+
+
+def test_phi_nan_placement_on_collinear_triples_is_the_references(native_lib):
+    """NaN placement of phi is decided by the last ulp of cos = (ba.bc) / (|ba| |bc|): the fused kernels must issue
+    the reference's exact sequence (ATen norm = FMA chain, rounded product, IEEE division) wherever |cos| is near 1.
+    Checked for the fused K1 (inter_residue_geometry), K2f (trrosetta_angles) and the generic planar kernel against
+    the CPU oracle on ~220 k exactly / nearly collinear triples — the NaN maps must be IDENTICAL and the finite
+    values within 1e-3 rad (arccos near +-1 amplifies one ulp of the cosine to 3.5e-4 rad)."""
+    xyz, mask = collinear_batch()
+    ref = torch.cat([orc.pair_planar_angles(xyz[b:b + 1], [1, 4], [4]) for b in range(xyz.shape[0])])
+    n_nan = int(torch.isnan(ref).sum())
+    off_diag = xyz.shape[0] * xyz.shape[1] * (xyz.shape[1] - 1)
+    assert 0.05 * off_diag < n_nan - xyz.shape[0] * xyz.shape[1] < 0.95 * off_diag, "the input is not adversarial"
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    fused = sb.inter_residue_geometry()
+    assert _cabi.last_pair_dist_plan()["path"] == 0
+    k2f = sb.trrosetta_angles()
+    generic = sb.pairwise_planar_angles(["CA", "CB"], ["CB"])
+    for got, name in ((fused["phi"], "fused K1"), (k2f[2], "K2f"), (generic, "generic planar kernel")):
+        H.assert_same_nan(got, ref, f"phi ({name})")
+        ok = ~torch.isnan(ref)
+        assert (got.cpu()[ok] - ref[ok]).abs().max().item() < 1e-3, name
+    # omega / theta of the same batch are degenerate everywhere (all four points on a line / n2 = 0): only the NaN
+    # maps are comparable
+    ro, rt, _ = [torch.cat(t) for t in zip(*[orc.trrosetta_angles(xyz[b:b + 1]) for b in range(xyz.shape[0])])]
+    H.assert_same_nan(fused["omega"], ro, "omega")
+    H.assert_same_nan(fused["theta"], rt, "theta")
+    H.assert_same_nan(k2f[0], ro, "omega K2f")
+    H.assert_same_nan(k2f[1], rt, "theta K2f")
 
 
 # ------------------------------------------------------------------------------ K2 pairwise angles
@@ -487,6 +574,83 @@ def test_diffusion_distribution_fused_steps_and_shard_invariance(native_lib):
     assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
 
 
+def test_philox_stream_is_addressed_per_element_for_any_shard_offset(native_lib):
+    """north_star / SURVEY 8(e): results independent of the number of GPUs.  L = 229 (the real 1a6v_HL length) gives
+    10,305 floats per structure, so shard offsets are not multiples of 4; the stream is addressed per element
+    (counter = global index >> 2, lane = global index & 3) and every shard reproduces its slice of the global
+    stream bit for bit — for the raw normals, one diffusion step and the fused T-step kernel, on 2, 3 and 5 ranks."""
+    from protstruc_b200.sharding import shard_bounds, shard_structure_batch
+
+    s = torch.cuda.current_stream().cuda_stream
+    n = 50_001
+    full = torch.empty(n, device=DEV)
+    _cabi.check(native_lib.ps_philox_normal(full.data_ptr(), n, 77, 3, 0, s), "ps_philox_normal")
+    for off, cnt in ((1, 17), (2, 4096), (3, 5), (10_305, 10_305), (20_610 + 3, 1), (49_999, 2)):
+        part = torch.full((cnt,), -7.0, device=DEV)
+        _cabi.check(native_lib.ps_philox_normal(part.data_ptr(), cnt, 77, 3, off, s), "ps_philox_normal")
+        assert torch.equal(part, full[off:off + cnt]), (off, cnt)
+    ref = orc.philox_normal(64, seed=77, step=3, elem_offset=10_305)
+    assert np.abs(full[10_305:10_305 + 64].cpu().double().numpy() - ref).max() < 2e-3
+
+    B, L, A, T = 5, 229, 15, 7
+    xyz, mask, _ = H.synthetic_batch(229, B, L, A, "bool", nan_masked=False, full_length=True)
+    betas = orc.cosine_variance_schedule(300)[100:100 + T, None].repeat(1, B).contiguous()
+    ps.manual_seed(4321)
+    whole = ps.StructureBatch.from_xyz(xyz, mask)
+    whole.diffuse_xyz(betas[0])
+    one_step = whole.get_xyz().clone()
+    whole.diffuse_xyz_steps(betas[1:])
+    all_steps = whole.get_xyz()
+    for world in (2, 3, 5):
+        got_one, got_all = [], []
+        for rank in range(world):
+            lo, hi = shard_bounds(B, world, rank)
+            ps.manual_seed(4321)  # every rank seeds alike, as ranks of one job do
+            sb = shard_structure_batch(xyz, mask, rank=rank, world_size=world)
+            assert sb._noise_elem_offset == lo * L * A * 3
+            sb.diffuse_xyz(betas[0, lo:hi])
+            got_one.append(sb.get_xyz().clone())
+            sb.diffuse_xyz_steps(betas[1:, lo:hi])
+            got_all.append(sb.get_xyz())
+        assert torch.equal(torch.cat(got_one), one_step), f"one step differs on {world} ranks"
+        assert torch.equal(torch.cat(got_all), all_steps), f"fused steps differ on {world} ranks"
+
+
+def test_noise_stream_follows_the_generator_state(native_lib):
+    """alternating generators must not rewind each other, and re-seeding (torch.manual_seed, a re-created
+    generator with the same seed) must restart the stream reproducibly — like torch.randn_like in the reference
+    (protstruc.py:876), whose noise is a function of the generator state."""
+    xyz, mask, _ = H.synthetic_batch(8, 2, 40, 15, "bool", nan_masked=False, full_length=True)
+    beta = torch.tensor([0.3, 0.6])
+
+    def step(sb, **kw):
+        sb.diffuse_xyz(beta, **kw)
+        return sb.get_xyz().clone()
+
+    def fresh():
+        return ps.StructureBatch.from_xyz(xyz, mask)
+
+    g1, g2 = torch.Generator().manual_seed(11), torch.Generator().manual_seed(22)
+    a = [step(fresh(), generator=g) for g in (g1, g2, g1, g2)]
+    assert not torch.equal(a[0], a[2]) and not torch.equal(a[1], a[3]), "switching generators replayed noise"
+    assert not torch.equal(a[0], a[1])
+    g1b = torch.Generator().manual_seed(11)  # re-created, same seed: same stream from the start
+    assert torch.equal(step(fresh(), generator=g1b), a[0]) and torch.equal(step(fresh(), generator=g1b), a[2])
+    g1.manual_seed(11)  # re-seeded in place
+    assert torch.equal(step(fresh(), generator=g1), a[0])
+    torch.manual_seed(5)
+    b0, b1 = step(fresh()), step(fresh())
+    assert not torch.equal(b0, b1), "consecutive calls must not reuse noise"
+    torch.manual_seed(5)  # plain torch re-seed (not ps.manual_seed) restarts too
+    assert torch.equal(step(fresh()), b0) and torch.equal(step(fresh()), b1)
+    torch.manual_seed(5)
+    torch.rand(3)  # someone else consumed the generator: a different, but reproducible, stream
+    c0 = step(fresh())
+    torch.manual_seed(5)
+    torch.rand(3)
+    assert torch.equal(step(fresh()), c0) and not torch.equal(c0, b0)
+
+
 # ------------------------------------------------------------------------------ geometry free functions
 def test_geometry_known_answers(native_lib):
     """reference tests/test_geometry.py:10-190 and tests/test_decorator.py type propagation."""
@@ -615,6 +779,78 @@ def test_rigid_frame_family_matches_reference_golden(native_lib):
     assert torch.allclose(rebuilt.backbone_orientations(), sb.backbone_orientations(), atol=1e-5, equal_nan=True)
     assert torch.allclose(rebuilt.backbone_translations()[~torch.isnan(rebuilt.backbone_translations())],
                           sb.backbone_translations()[~torch.isnan(rebuilt.backbone_translations())], atol=1e-5)
+
+
+def test_translate_broadcasts_like_the_reference(native_lib):
+    """every shape torch's `xyz += translation` accepts (protstruc.py:662-679), including a size-1
+    coordinate axis and non-contiguous translations; in place (the tensor object is kept)."""
+    xyz, mask, _ = H.synthetic_batch(31, 3, 21, 15, "bool", nan_masked=False, full_length=True)
+    g = torch.Generator().manual_seed(1)
+    cases = [(torch.randn(3, 21, 3, generator=g), False), (torch.randn(3, 1, 3, generator=g), False),
+             (torch.randn(3, 21, 1, generator=g), False), (torch.randn(1, 1, 1, generator=g), False),
+             (torch.randn(3, 21, 6, generator=g)[:, :, ::2], False), (torch.randn(3, 21, 15, 3, generator=g), True),
+             (torch.randn(3, 21, 15, 1, generator=g), True), (torch.randn(1, 21, 1, 3, generator=g), True)]
+    for tr, atomwise in cases:
+        sb = ps.StructureBatch.from_xyz(xyz, mask)
+        before = sb.get_xyz()
+        sb.translate(tr, atomwise=atomwise)
+        assert sb.get_xyz().data_ptr() == before.data_ptr()
+        ref = xyz + (tr if atomwise else tr.unsqueeze(-2))
+        assert torch.equal(sb.get_xyz().cpu(), ref), (tuple(tr.shape), atomwise)
+    with pytest.raises(RuntimeError):
+        ps.StructureBatch.from_xyz(xyz, mask).translate(torch.zeros(3, 20, 3))
+
+
+def test_align_with_rank_deficient_selections(native_lib):
+    """collinear selections, two-atom and one-atom masks and an empty mask must give a proper rotation
+    (the reference's SVD path does, geometry.py:442-480) and leave no NaN behind."""
+    xyz, mask, _ = H.synthetic_batch(77, 4, 12, 15, "bool", nan_masked=False, full_length=True)
+    g = torch.Generator().manual_seed(3)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    q = q * torch.sign(torch.linalg.det(q))
+    target_xyz = xyz @ q.T + torch.tensor([3.0, -2.0, 5.0])
+    sel = torch.zeros(4, 12, 15, dtype=torch.bool)
+    line = torch.linspace(-5, 5, 12)[:, None] * torch.tensor([1.0, 2.0, -1.0])
+    xyz[0, :, 1] = line  # structure 0: collinear CA atoms selected
+    target_xyz[0, :, 1] = line @ q.T + torch.tensor([3.0, -2.0, 5.0])
+    sel[0, :, 1] = True
+    sel[1, 0, 1] = sel[1, 5, 1] = True  # two atoms
+    sel[2, 3, 1] = True  # one atom
+    # structure 3: nothing selected
+    src = ps.StructureBatch.from_xyz(xyz.clone(), mask)
+    tgt = ps.StructureBatch.from_xyz(target_xyz, mask)
+    rot = src.align(tgt, atom_mask=sel)
+    torch.cuda.synchronize()
+    rot_c, out = rot.cpu().double(), src.get_xyz().cpu()
+    assert bool(torch.isfinite(rot_c).all()) and bool(torch.isfinite(out).all())
+    eye = torch.eye(3, dtype=torch.float64)
+    assert (rot_c @ rot_c.transpose(1, 2) - eye).abs().max().item() < 1e-5
+    assert (torch.linalg.det(rot_c) - 1.0).abs().max().item() < 1e-5
+    for b in (0, 1, 2):  # the selected atoms are superimposed (distances between them allow it exactly)
+        m = sel[b]
+        assert (out[b][m] - target_xyz[b][m]).abs().max().item() < 2e-3, b
+    assert torch.equal(out[3], xyz[3]), "an empty selection must not move the structure"
+
+
+def test_empty_batches_are_no_ops(native_lib):
+    """B == 0 or L == 0 (e.g. residue_masked_select with an all-False mask) never reach the C-ABI."""
+    sb = ps.StructureBatch.from_xyz(torch.zeros(1, 4, 15, 3), torch.ones(1, 4, 15, dtype=torch.bool))
+    empty = sb.residue_masked_select(torch.zeros(1, 4, dtype=torch.bool))
+    assert empty.get_max_n_residues() == 0
+    for e in (empty, ps.StructureBatch.from_xyz(torch.zeros(0, 7, 15, 3), torch.ones(0, 7, 15, dtype=torch.bool))):
+        B, L = e.get_batch_size(), e.get_max_n_residues()
+        e.translate(torch.zeros(B, L, 3))
+        e.rotate(torch.eye(3))
+        e.center_at()
+        e.standardize()
+        assert tuple(e.mu.shape) == (B, 3)
+        e.unstandardize()
+        e.diffuse_xyz(torch.zeros(B))
+        e.diffuse_xyz_steps(torch.zeros(4, B))
+        assert tuple(e.align(e).shape) == (B, 3, 3)
+        assert tuple(e.get_xyz().shape) == (B, L, 15, 3)
+        assert tuple(e.inter_residue_geometry()["omega"].shape) == (B, L, L)
+    assert tuple(empty.get_topk_nearest_residue_mask(torch.zeros(2, 3)).shape) == (1, 0)
 
 
 def test_align_matches_reference_golden(native_lib):

@@ -128,7 +128,37 @@ def test_shard_bounds_partition_the_batch():
     part = sharding.shard_structure_batch(xyz, mask, chain_idx, [["A", "B"]] * 8, rank=1, world_size=4, device="cpu")
     assert part.get_batch_size() == 2 and torch.equal(torch.nan_to_num(part.get_xyz()), torch.nan_to_num(xyz[2:4]))
     assert part._noise_elem_offset == 2 * 16 * 15 * 3
+    # odd structure sizes (L = 229: 10,305 floats) keep the exact global offset: no per-rank fallback stream
+    x229 = torch.zeros(5, 229, 15, 3)
+    offsets = [sharding.shard_structure_batch(x229, rank=r, world_size=3, device="cpu")._noise_elem_offset for r in range(3)]
+    assert offsets == [0, 2 * 10_305, 4 * 10_305]
     assert sharding.shard_structure_batch(xyz[:1], mask[:1], rank=1, world_size=2, device="cpu") is None
+
+
+def test_noise_stream_sessions_follow_the_generator_state():
+    """The (key, step) bookkeeping behind diffuse_xyz (no GPU needed): one session per generator object, continued
+    while nobody else touches the generator, restarted reproducibly by any re-seed."""
+    from protstruc_b200 import structure_batch as sbm
+
+    stream = sbm._PhiloxStream()
+    g1, g2 = torch.Generator().manual_seed(1), torch.Generator().manual_seed(2)
+    a = [stream.reserve(1, g1), stream.reserve(1, g2), stream.reserve(3, g1), stream.reserve(1, g2), stream.reserve(1, g1)]
+    assert a[0][0] == a[2][0] == a[4][0] != a[1][0] == a[3][0]          # one key per generator
+    assert [x[1] for x in a] == [0, 0, 1, 1, 4]                          # steps advance, never rewind
+    assert stream.reserve(2, torch.Generator().manual_seed(1)) == (a[0][0], 0)   # re-created generator, same seed
+    g1.manual_seed(1)
+    assert stream.reserve(1, g1) == (a[0][0], 0)                         # re-seeded in place
+    torch.manual_seed(9)
+    k0 = stream.reserve(300, None)
+    assert stream.reserve(1, None) == (k0[0], 300)
+    torch.rand(1)                                                        # the global generator was used by someone else
+    k1 = stream.reserve(1, None)
+    assert k1[0] != k0[0] and k1[1] == 0
+    torch.manual_seed(9)
+    assert stream.reserve(1, None) == (k0[0], 0)                         # torch.manual_seed restarts the stream
+    sbm.manual_seed(9)
+    assert sbm._philox.reserve(2, None) == (k0[0], 0)
+    assert all(0 <= key < 2 ** 63 for key in (k0[0], k1[0], a[0][0], a[1][0]))
 
 
 def _free_port():
