@@ -90,6 +90,9 @@ int ps_pair_angles(const float* xyz, int B, int L, int A,
  */
 int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
                         float* omega, float* theta, float* phi, void* stream);
+/* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel), 1 = the exact-operation-sequence kernel. */
+int ps_trrosetta_angles_ex(const float* xyz, int B, int L, int A, int virtual_cb,
+                           float* omega, float* theta, float* phi, int variant, void* stream);
 
 /*
  * K1+K2f — the full pairwise feature set in ONE kernel: distance matrix, pair mask
@@ -103,6 +106,17 @@ int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_
                               float* dist, void* dist_mask,
                               float* omega, float* theta, float* phi,
                               int B, int L, int A, void* stream);
+
+/*
+ * The same launch with the COMPACT features gathered on the way: compact is a contiguous (6, B, L, L) f32 buffer that
+ * receives omega, theta, phi and d_ca = dist[..,CA,CA], d_cb = dist[..,CB,CB], d_no = dist[..,N,O] — the (B, L, L)
+ * planes of inter_residue_geometry (protstruc/protstruc.py:801-815) as dense tensors, which is what the optional
+ * multi-GPU exchange all-gathers over NVLink (the reference returns the distance planes as strided views of `dist`;
+ * the fused kernel reads them back from the finished tile in shared memory, 12 extra bytes per residue pair).
+ */
+int ps_inter_residue_geometry_compact(const float* xyz, const void* atom_mask, int mask_dtype,
+                                      float* dist, void* dist_mask, float* compact,
+                                      int B, int L, int A, void* stream);
 
 /*
  * K3 — per-residue backbone features.
@@ -123,10 +137,14 @@ int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chai
  * K4 — masked per-structure, per-axis mean / population std, optionally applied.
  * Replaces StructureBatch.standardize (protstruc/protstruc.py:696-734), with the
  * per-structure broadcast the reference intends.
- *   mu, sd (B,3) f32 out;  xyz_out (B,L,A,3) f32 = (xyz - mu) / sd, may alias xyz, may be NULL.
+ *   mu, sd (B,3) f32 out;  xyz_out (B,L,A,3) f32 = (xyz - mu) / sd, may be NULL; must NOT alias xyz (the kernels
+ *   read xyz through the read-only path).
  */
 int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype,
                     int B, int L, int A, float* mu, float* sd, float* xyz_out, void* stream);
+/* Comparison hook: variant 0 = default (register-resident single-read kernel), 1 = the three-pass kernel of round 1. */
+int ps_masked_stats_ex(const float* xyz, const void* atom_mask, int mask_dtype,
+                       int B, int L, int A, float* mu, float* sd, float* xyz_out, int variant, void* stream);
 
 /*
  * Affine per-structure map used by unstandardize (protstruc/protstruc.py:736-744):

@@ -42,13 +42,16 @@ SIGNATURES = {
     "ps_pair_angles": (c_int, [_fp, c_int, c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), c_int,
                                c_int, _fp, c_void_p]),
     "ps_trrosetta_angles": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_void_p]),
+    "ps_trrosetta_angles_ex": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_int, c_void_p]),
     "ps_inter_residue_geometry": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
                                           c_void_p]),
+    "ps_inter_residue_geometry_compact": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, c_int, c_int, c_int, c_void_p]),
     "ps_inter_residue_geometry_ex": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
                                              c_int, c_void_p]),
     "ps_backbone": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, _fp, _fp, _fp,
                             c_void_p]),
     "ps_masked_stats": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_void_p]),
+    "ps_masked_stats_ex": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_int, c_void_p]),
     "ps_scale_shift": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, _fp, c_void_p]),
     "ps_center_of_mass": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),
     "ps_translate": (c_int, [_fp, _fp, c_int, c_int, c_int, c_int, _fp, c_void_p]),

@@ -19,7 +19,8 @@ namespace ps {
 
 namespace {
 
-constexpr int kKabschThreads = 256;
+constexpr int kKabschThreads = 512;
+constexpr int kKabschUnroll = 4;
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -93,17 +94,37 @@ __global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
     // the raw second moments sum a_i b_j, all in fp64, so that the centred covariance
     //   H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j = sum a_i b_j - n ca_i cb_j
     // loses nothing that matters (|x| ~ 1e2, n ~ 1e4: the subtraction cancels ~4 of fp64's 16 digits).
+    // The loop is latency-bound (one CTA per structure, ~15 atoms per thread): the mask bytes and BOTH coordinate
+    // triples of kKabschUnroll atoms are requested before the first use, unconditionally (an unselected atom's
+    // coordinates are discarded by the select below, so NaN there is harmless).
     double s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = threadIdx.x; k < n_atoms; k += blockDim.x) {
-        if (__ldg(m + k)) {
-            const double ax = __ldg(a + 3 * k + 0), ay = __ldg(a + 3 * k + 1), az = __ldg(a + 3 * k + 2);
-            const double bx = __ldg(t + 3 * k + 0), by = __ldg(t + 3 * k + 1), bz = __ldg(t + 3 * k + 2);
-            s[0] += ax; s[1] += ay; s[2] += az;
-            s[3] += bx; s[4] += by; s[5] += bz;
-            s[6] += 1.0;
-            s[7] += ax * bx; s[8] += ax * by; s[9] += ax * bz;
-            s[10] += ay * bx; s[11] += ay * by; s[12] += ay * bz;
-            s[13] += az * bx; s[14] += az * by; s[15] += az * bz;
+    for (int k0 = threadIdx.x; k0 < n_atoms; k0 += kKabschUnroll * blockDim.x) {
+        float pa[kKabschUnroll][3], pb[kKabschUnroll][3];
+        bool sel[kKabschUnroll];
+#pragma unroll
+        for (int u = 0; u < kKabschUnroll; ++u) {
+            const int k = k0 + u * blockDim.x;
+            const bool in = k < n_atoms;
+            const int kk = in ? k : 0;
+            sel[u] = in && __ldg(m + kk) != 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                pa[u][c] = __ldg(a + 3 * kk + c);
+                pb[u][c] = __ldg(t + 3 * kk + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kKabschUnroll; ++u) {
+            if (sel[u]) {
+                const double ax = pa[u][0], ay = pa[u][1], az = pa[u][2];
+                const double bx = pb[u][0], by = pb[u][1], bz = pb[u][2];
+                s[0] += ax; s[1] += ay; s[2] += az;
+                s[3] += bx; s[4] += by; s[5] += bz;
+                s[6] += 1.0;
+                s[7] += ax * bx; s[8] += ax * by; s[9] += ax * bz;
+                s[10] += ay * bx; s[11] += ay * by; s[12] += ay * bz;
+                s[13] += az * bx; s[14] += az * by; s[15] += az * bz;
+            }
         }
     }
     block_sum<16>(s, scratch);

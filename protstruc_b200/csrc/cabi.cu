@@ -11,9 +11,12 @@ namespace ps {
 // launchers defined in the kernel translation units
 int pair_dist_mask_impl(const float*, const void*, int, float*, void*, float*, float*, float*, int,
                         int, int, int, cudaStream_t);
+int pair_dist_mask_compact_impl(const float*, const void*, int, float*, void*, float*, float*, float*, float*,
+                                float*, float*, int, int, int, int, cudaStream_t);
 int pair_angles_impl(const float*, int, int, int, const int*, int, const int*, int, int, float*,
                      cudaStream_t);
 int trrosetta_angles_impl(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
+int trrosetta_angles_variant_impl(const float*, int, int, int, int, float*, float*, float*, int, cudaStream_t);
 int backbone_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, int, float*,
                   uint8_t*, float*, cudaStream_t);
 int geom_angle_impl(const float*, const float*, const float*, long long, int, float*, cudaStream_t);
@@ -23,6 +26,8 @@ int geom_gram_schmidt_impl(const float*, const float*, const float*, long long, 
                            cudaStream_t);
 int masked_stats_impl(const float*, const void*, int, int, int, int, float*, float*, float*,
                       cudaStream_t);
+int masked_stats_variant_impl(const float*, const void*, int, int, int, int, float*, float*, float*, int,
+                              cudaStream_t);
 int scale_shift_impl(const float*, const float*, const float*, int, int, int, float*, cudaStream_t);
 int translate_impl(const float*, const float*, int, int, int, int, float*, cudaStream_t);
 int center_of_mass_impl(const float*, int, int, int, int, float*, cudaStream_t);
@@ -132,6 +137,11 @@ int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb, f
     return ps::trrosetta_angles_impl(xyz, B, L, A, virtual_cb, omega, theta, phi, PS_STREAM(stream));
 }
 
+int ps_trrosetta_angles_ex(const float* xyz, int B, int L, int A, int virtual_cb, float* omega,
+                           float* theta, float* phi, int variant, void* stream) {
+    return ps::trrosetta_angles_variant_impl(xyz, B, L, A, virtual_cb, omega, theta, phi, variant, PS_STREAM(stream));
+}
+
 int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                               void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
                               int A, void* stream) {
@@ -143,6 +153,22 @@ int ps_inter_residue_geometry(const float* xyz, const void* atom_mask, int mask_
     // kernel followed by the fused angle kernel (decided inside pair_dist_mask_impl)
     return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, B,
                                    L, A, 0, PS_STREAM(stream));
+}
+
+int ps_inter_residue_geometry_compact(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                                      void* dist_mask, float* compact, int B, int L, int A, void* stream) {
+    if (!(compact && dist && dist_mask && atom_mask)) {
+        ps::set_error("inter_residue_geometry_compact: all inputs and outputs are required");
+        return PS_ERR_NULL_POINTER;
+    }
+    if (B <= 0 || L <= 0) {
+        ps::set_error("inter_residue_geometry_compact: B=%d L=%d must be > 0", B, L);
+        return PS_ERR_BAD_SHAPE;
+    }
+    const long long plane = static_cast<long long>(B) * L * L;
+    return ps::pair_dist_mask_compact_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, compact, compact + plane,
+                                           compact + 2 * plane, compact + 3 * plane, compact + 4 * plane,
+                                           compact + 5 * plane, B, L, A, 0, PS_STREAM(stream));
 }
 
 int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
@@ -167,6 +193,12 @@ int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype, int
                     float* mu, float* sd, float* xyz_out, void* stream) {
     return ps::masked_stats_impl(xyz, atom_mask, mask_dtype, B, L, A, mu, sd, xyz_out,
                                  PS_STREAM(stream));
+}
+
+int ps_masked_stats_ex(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
+                       float* mu, float* sd, float* xyz_out, int variant, void* stream) {
+    return ps::masked_stats_variant_impl(xyz, atom_mask, mask_dtype, B, L, A, mu, sd, xyz_out, variant,
+                                         PS_STREAM(stream));
 }
 
 int ps_scale_shift(const float* xyz, const float* scale, const float* shift, int B, int L, int A,

@@ -89,6 +89,231 @@ __global__ void __launch_bounds__(256) trrosetta_kernel(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K2f, second generation: the trRosetta triple on the packed FP32 pipe.
+//
+// The first version (trrosetta_kernel above, kept as the exact-sequence variant and for structures that do not fit in
+// shared memory) issues the reference's operation sequence literally — separately rounded products, cross product of
+// cross products — and was issue-bound at 289 lane-instructions per pair (profiles/r1o_k2f_ncu_summary.txt: 0.20 of
+// the HBM roof).  This version spends the tolerance the contract gives (<= 1e-5 rad where min sin(bond angle) >= 0.1)
+// on a cheaper evaluation of the SAME angles, and keeps the reference's NaN placement and exact special cases:
+//
+//  * a thread owns TWO consecutive residues j, j + 1 of a row and evaluates both pairs at once as f32x2 values: every
+//    subtraction, product and fused multiply-add of the geometry is one FADD2 / FMUL2 / FFMA2 instruction for two
+//    pairs (fused multiply-adds are more accurate than the reference's separately rounded products, never less);
+//  * the sine term needs no third cross product:  (n1 x n2) . b1 = -(n1 . b2) |b1|^2  for n1 = b0 x b1, n2 = b2 x b1,
+//    hence  y = (m . b1) / |b1| = -(n1 . b2) |b1|;
+//  * a CTA stages the structure's CA / CB (real slot 4, or the virtual CB of geometry.py:217-221 evaluated ONCE per
+//    residue with the reference's exact sequence) as structure-of-arrays in shared memory, so residue j arrives as
+//    three conflict-free LDS.64 per atom instead of six strided global loads, and everything that depends on residue i
+//    only (b0, CB_i, the normal n1 of theta, |b0|, 1/|b0|) is computed once per residue, not once per thread;
+//  * atan2 = MUFU.RCP quotient + degree-15 odd minimax polynomial evaluated as FFMA2 for the two pairs, octant
+//    fix-ups; zeros, infinities, NaN and out-of-range magnitudes fall back to atan2f.
+//
+// What keeps the special cases exact (all covered by tests/test_gpu_parity.py):
+//  * zero-padded residues and coincident atoms: a zero operand makes every fused product exactly zero, so x = y = 0
+//    arrives at the atan2f fallback as in the reference (x is given the reference's +0 sign there: ATen's sum starts
+//    from +0); norms are formed as v.v * rsqrt(v.v), which is NaN for v = 0 exactly where the reference divides 0 / 0;
+//  * the diagonal j = i: theta (b2 = CB_i - CB_i = 0) and phi (0 * inf) come out as in the reference by themselves;
+//    omega would see b0 x b0 — exactly zero only with separately rounded products — and is overwritten with its known
+//    value: 0, or NaN if CA_i / CB_i are missing or coincide (0 * 1/|b0|);
+//  * missing atoms (NaN coordinates) propagate through every product and through the select-based min / max of the
+//    atan2 (fminf / fmaxf would drop them);
+//  * phi: within 1e-3 of |cos| = 1 — where the unclamped arccos of the reference turns a last-ulp excess into NaN —
+//    the reference's exact sequence is issued (trrosetta_phi_exact below), as in the fused K1.
+template <typename T>
+__device__ __forceinline__ float2 f2(T v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+struct P3 {  // three f32x2 values: one 3-vector for each of the two pairs of a thread
+    float2 x, y, z;
+};
+__device__ __forceinline__ P3 sub_p3(P3 a, P3 b) {
+    return P3{__fadd2_rn(a.x, neg2(b.x)), __fadd2_rn(a.y, neg2(b.y)), __fadd2_rn(a.z, neg2(b.z))};
+}
+__device__ __forceinline__ P3 cross_p3(P3 a, P3 b) {  // a x b, one FMUL2 + one FFMA2 per component
+    P3 r;
+    r.x = __ffma2_rn(a.y, b.z, neg2(__fmul2_rn(a.z, b.y)));
+    r.y = __ffma2_rn(a.z, b.x, neg2(__fmul2_rn(a.x, b.z)));
+    r.z = __ffma2_rn(a.x, b.y, neg2(__fmul2_rn(a.y, b.x)));
+    return r;
+}
+__device__ __forceinline__ float2 dot_p3(P3 a, P3 b) {
+    return __ffma2_rn(a.z, b.z, __ffma2_rn(a.y, b.y, __fmul2_rn(a.x, b.x)));
+}
+
+// atan2 of two (y, x) pairs at once.
+__device__ __forceinline__ float2 atan2_pair(float2 y, float2 x) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+    const bool sw0 = ay0 > ax0, sw1 = ay1 > ax1;
+    // select-based max / min: a NaN on either side survives in mx or mn (fmaxf / fminf would drop it)
+    const float mx0 = sw0 ? ay0 : ax0, mn0 = sw0 ? ax0 : ay0;
+    const float mx1 = sw1 ? ay1 : ax1, mn1 = sw1 ? ax1 : ay1;
+    const float lo = fminf(mx0, mx1), hi = fmaxf(mx0, mx1);
+    // zeros, denormal-range and huge magnitudes, infinities, NaN (either compare fails, or mn is NaN): IEEE atan2f;
+    // x + 0 turns a -0 cosine term into the reference's +0 (ATen's sum starts from +0)
+    if (!((lo > 1e-30f) & (hi < 1e30f) & (mn0 == mn0) & (mn1 == mn1) & (mx0 == mx0) & (mx1 == mx1)))
+        return make_float2(atan2f(y.x, x.x + 0.0f), atan2f(y.y, x.y + 0.0f));
+    const float2 t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rcp_mufu(mx0), rcp_mufu(mx1)));
+    const float2 s = __fmul2_rn(t, t);
+    float2 p = f2(2.622234402e-03f);
+    p = __ffma2_rn(p, s, f2(-1.513249334e-02f));
+    p = __ffma2_rn(p, s, f2(4.112178832e-02f));
+    p = __ffma2_rn(p, s, f2(-7.366699725e-02f));
+    p = __ffma2_rn(p, s, f2(1.057392880e-01f));
+    p = __ffma2_rn(p, s, f2(-1.418597400e-01f));
+    p = __ffma2_rn(p, s, f2(1.999039650e-01f));
+    p = __ffma2_rn(p, s, f2(-3.333298564e-01f));
+    const float2 a = __ffma2_rn(__fmul2_rn(t, s), p, t);
+    float a0 = a.x, a1 = a.y;
+    if (sw0) a0 = 1.57079637f - a0;
+    if (sw1) a1 = 1.57079637f - a1;
+    if (x.x < 0.f) a0 = 3.14159274f - a0;
+    if (x.y < 0.f) a1 = 3.14159274f - a1;
+    return make_float2(copysignf(a0, y.x), copysignf(a1, y.y));
+}
+
+// phi's cosine by the reference's exact sequence (geometry.py:64-71): separately rounded dot product, ATen norms,
+// rounded product of the norms, IEEE division.
+__device__ __forceinline__ float trrosetta_phi_exact(V3 ba, V3 bc) {
+    return acosf(__fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc))));
+}
+
+// Row-side record of one residue i (floats): b0 = CA - CB (3), CB (3), tn1 = (N - CA) x (CB - CA) (3),
+// |b0| (NaN for b0 = 0), 1 / |b0| (inf for b0 = 0), omega on the diagonal.
+constexpr int kRowRecord = 12;
+
+template <bool VIRTUAL_CB>
+__global__ void __launch_bounds__(256) trrosetta_fast_kernel(const float* __restrict__ xyz, float* __restrict__ omega,
+                                                             float* __restrict__ theta, float* __restrict__ phi, int L,
+                                                             int A, int rows_per_cta, int blocks_per_structure,
+                                                             int vector_stores) {
+    extern __shared__ __align__(16) float fast_smem[];
+    const int Lp = (L + 1) & ~1;  // residues j padded to whole pairs
+    float* const sca_x = fast_smem;
+    float* const sca_y = sca_x + Lp;
+    float* const sca_z = sca_y + Lp;
+    float* const scb_x = sca_z + Lp;
+    float* const scb_y = scb_x + Lp;
+    float* const scb_z = scb_y + Lp;
+    float* const srow = scb_z + Lp;  // rows_per_cta records of kRowRecord floats
+
+    const long long b = blockIdx.x / blocks_per_structure;
+    const int row0 = (blockIdx.x - static_cast<int>(b) * blocks_per_structure) * rows_per_cta;
+    const int nrows = min(rows_per_cta, L - row0);
+    const float* __restrict__ xb = xyz + b * L * A * 3;
+
+    // ---- stage residue j of the whole structure: CA and CB (real or virtual), structure of arrays
+    for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
+        V3 ca{0.f, 0.f, 0.f}, cb{0.f, 0.f, 0.f};
+        if (r < L) {
+            const float* __restrict__ xr = xb + static_cast<long long>(r) * A * 3;
+            ca = ld3(xr + 3);
+            cb = VIRTUAL_CB ? virtual_cb(ld3(xr + 0), ca, ld3(xr + 6)) : ld3(xr + 12);
+        }
+        sca_x[r] = ca.x; sca_y[r] = ca.y; sca_z[r] = ca.z;
+        scb_x[r] = cb.x; scb_y[r] = cb.y; scb_z[r] = cb.z;
+    }
+    __syncthreads();
+    // ---- row-side records of this CTA's residues i
+    for (int k = threadIdx.x; k < nrows; k += blockDim.x) {
+        const int i = row0 + k;
+        const V3 n_i = ld3(xb + static_cast<long long>(i) * A * 3);
+        const V3 ca{sca_x[i], sca_y[i], sca_z[i]}, cb{scb_x[i], scb_y[i], scb_z[i]};
+        const V3 b0 = sub3(ca, cb);                       // omega's b0, phi's ba;  theta's b1 is exactly -b0
+        const V3 u = sub3(n_i, ca);
+        const V3 tb1{-b0.x, -b0.y, -b0.z};
+        V3 tn1;                                           // (N - CA) x (CB - CA), fused
+        tn1.x = fmaf(u.y, tb1.z, -(u.z * tb1.y));
+        tn1.y = fmaf(u.z, tb1.x, -(u.x * tb1.z));
+        tn1.z = fmaf(u.x, tb1.y, -(u.y * tb1.x));
+        const float bb = fmaf(b0.z, b0.z, fmaf(b0.y, b0.y, b0.x * b0.x));
+        const float inv = rsqrt_refined(bb);              // inf * 0 = NaN for bb = 0, NaN for missing atoms
+        float* rec = srow + k * kRowRecord;
+        rec[0] = b0.x; rec[1] = b0.y; rec[2] = b0.z;
+        rec[3] = cb.x; rec[4] = cb.y; rec[5] = cb.z;
+        rec[6] = tn1.x; rec[7] = tn1.y; rec[8] = tn1.z;
+        rec[9] = bb * inv;                                // |b0|, NaN where the reference divides 0 / 0
+        rec[10] = bb == 0.f ? __int_as_float(0x7f800000) : inv;  // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
+        rec[11] = 0.0f * (bb == 0.f ? __int_as_float(0x7f800000) : inv);  // omega[i, i]: 0, or NaN (missing / coincident)
+    }
+    __syncthreads();
+
+    const float2* __restrict__ pca_x = reinterpret_cast<const float2*>(sca_x);
+    const float2* __restrict__ pca_y = reinterpret_cast<const float2*>(sca_y);
+    const float2* __restrict__ pca_z = reinterpret_cast<const float2*>(sca_z);
+    const float2* __restrict__ pcb_x = reinterpret_cast<const float2*>(scb_x);
+    const float2* __restrict__ pcb_y = reinterpret_cast<const float2*>(scb_y);
+    const float2* __restrict__ pcb_z = reinterpret_cast<const float2*>(scb_z);
+    const int npairs = Lp >> 1;
+
+    for (int k = 0; k < nrows; ++k) {
+        const int i = row0 + k;
+        const float* rec = srow + k * kRowRecord;
+        const P3 b0{f2(rec[0]), f2(rec[1]), f2(rec[2])};
+        const P3 cbi{f2(rec[3]), f2(rec[4]), f2(rec[5])};
+        const P3 tn1{f2(rec[6]), f2(rec[7]), f2(rec[8])};
+        const P3 tb1{neg2(b0.x), neg2(b0.y), neg2(b0.z)};
+        const float2 norm_b0 = f2(rec[9]);
+        const float2 inv_b0 = f2(rec[10]);
+        const float diag_omega = rec[11];
+        const long long out_row = (b * L + i) * L;
+        for (int jp = threadIdx.x; jp < npairs; jp += blockDim.x) {
+            const P3 caj{pca_x[jp], pca_y[jp], pca_z[jp]};
+            const P3 cbj{pcb_x[jp], pcb_y[jp], pcb_z[jp]};
+            const P3 bc = sub_p3(cbj, cbi);  // CB_j - CB_i: theta's b2, phi's bc
+            float2 w = f2(0.f), t = f2(0.f), f = f2(0.f);
+            if (omega) {
+                const P3 b1 = sub_p3(caj, cbi);
+                const P3 b2 = sub_p3(cbj, caj);
+                const P3 n1 = cross_p3(b0, b1);
+                const P3 n2 = cross_p3(b2, b1);
+                const float2 x = dot_p3(n1, n2);
+                const float2 sn = dot_p3(n1, b2);
+                const float2 bb = dot_p3(b1, b1);
+                const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
+                w = atan2_pair(neg2(__fmul2_rn(sn, nb1)), x);
+                if (jp == (i >> 1)) {  // the diagonal entry of this row
+                    if (i & 1) w.y = diag_omega; else w.x = diag_omega;
+                }
+            }
+            if (theta) {
+                const P3 n2 = cross_p3(bc, tb1);
+                const float2 x = dot_p3(tn1, n2);
+                const float2 sn = dot_p3(tn1, bc);
+                t = atan2_pair(neg2(__fmul2_rn(sn, norm_b0)), x);
+            }
+            if (phi) {
+                const float2 d = dot_p3(b0, bc);
+                const float2 cc = dot_p3(bc, bc);
+                const float2 c = __fmul2_rn(__fmul2_rn(d, inv_b0), make_float2(rsqrt_refined(cc.x), rsqrt_refined(cc.y)));
+                if ((fabsf(c.x) <= 0.999f) & (fabsf(c.y) <= 0.999f)) {
+                    f = make_float2(acosf(c.x), acosf(c.y));
+                } else {
+                    const V3 ba{rec[0], rec[1], rec[2]};
+                    f.x = fabsf(c.x) <= 0.999f ? acosf(c.x) : trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
+                    f.y = fabsf(c.y) <= 0.999f ? acosf(c.y) : trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
+                }
+            }
+            const int j = 2 * jp;
+            if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
+                if (omega) *reinterpret_cast<float2*>(omega + out_row + j) = w;
+                if (theta) *reinterpret_cast<float2*>(theta + out_row + j) = t;
+                if (phi) *reinterpret_cast<float2*>(phi + out_row + j) = f;
+            } else {
+                if (omega) omega[out_row + j] = w.x;
+                if (theta) theta[out_row + j] = t.x;
+                if (phi) phi[out_row + j] = f.x;
+                if (j + 1 < L) {
+                    if (omega) omega[out_row + j + 1] = w.y;
+                    if (theta) theta[out_row + j + 1] = t.y;
+                    if (phi) phi[out_row + j + 1] = f.y;
+                }
+            }
+        }
+    }
+}
+
 int grid_for_rows(long long rows, int* grid) {
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
@@ -164,8 +389,10 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
     return check_launch("pair_angles_kernel");
 }
 
-int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
-                          float* theta, float* phi, cudaStream_t stream) {
+// variant: 0 = default (the packed kernel whenever the structure fits in shared memory), 1 = the exact-sequence
+// kernel of round 1 (tuning / comparison hook, ps_trrosetta_angles_ex).
+int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
+                                  float* theta, float* phi, int variant, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE,
                "trrosetta_angles: B=%d L=%d A=%d must be > 0", B, L, A);
     PS_REQUIRE(xyz, PS_ERR_NULL_POINTER, "trrosetta_angles: xyz is NULL");
@@ -173,6 +400,37 @@ int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual
     PS_REQUIRE(A >= (use_virtual_cb ? 3 : 5), PS_ERR_BAD_SHAPE,
                "trrosetta_angles: A=%d has no %s slot", A, use_virtual_cb ? "C" : "CB");
     const long long rows = static_cast<long long>(B) * L;
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    // Packed kernel: the structure's CA / CB (6 floats per residue) plus the row records must fit in shared memory.
+    const int Lp = (L + 1) & ~1;
+    // rows per CTA: as many as possible (the staging of the structure is amortised over them) while the grid still
+    // holds >= 2 CTAs per SM; at least 4, at most 32
+    int rows_per_cta = 32;
+    while (rows_per_cta > 4 && rows / rows_per_cta < 2ll * sms) rows_per_cta /= 2;
+    if (rows_per_cta > L) rows_per_cta = L;
+    const size_t smem = (static_cast<size_t>(6) * Lp + static_cast<size_t>(rows_per_cta) * kRowRecord) * sizeof(float);
+    const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
+    const long long ctas = static_cast<long long>(B) * blocks_per_structure;
+    if (variant == 0 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
+        int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread and pass
+        if (threads > 256) threads = 256;
+        auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+        const int vector_stores = (L % 2 == 0) && aligned8(omega) && aligned8(theta) && aligned8(phi);
+        cudaError_t err;
+        if (use_virtual_cb) {
+            err = cudaFuncSetAttribute(trrosetta_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");
+            trrosetta_fast_kernel<true><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(
+                xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);
+        } else {
+            err = cudaFuncSetAttribute(trrosetta_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");
+            trrosetta_fast_kernel<false><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(
+                xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);
+        }
+        return check_launch("trrosetta_fast_kernel");
+    }
     int grid = 0;
     int rc = grid_for_rows(rows, &grid);
     if (rc != PS_OK) return rc;
@@ -182,6 +440,11 @@ int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual
     else
         trrosetta_kernel<false><<<grid, threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
     return check_launch("trrosetta_kernel");
+}
+
+int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
+                          float* theta, float* phi, cudaStream_t stream) {
+    return trrosetta_angles_variant_impl(xyz, B, L, A, use_virtual_cb, omega, theta, phi, 0, stream);
 }
 
 }  // namespace ps

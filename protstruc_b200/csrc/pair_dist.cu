@@ -130,6 +130,9 @@ struct PairDistParams {
     float* __restrict__ omega;   // fused angles (may be null)
     float* __restrict__ theta;
     float* __restrict__ phi;
+    float* __restrict__ d_ca;    // compact (B, L, L) copies of dist[..., CA, CA], [..., CB, CB], [..., N, O] for the
+    float* __restrict__ d_cb;    // optional NVLink gather of compact features (may be null)
+    float* __restrict__ d_no;
     int L;
     long long num_rows;   // B*L residues
     long long num_pairs;  // B*L*L
@@ -606,6 +609,22 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
             if (kind_has_u8<KIND>())
                 for (int e = t; e < n; e += 32 * WPT) p.mask[elem0 + e] = tile_u8[e];
             tile_sync<WPT>(slot);
+        }
+        if constexpr (ANGLES && A >= 5) {
+            // Compact (B, L, L) copies of dist[..., CA, CA], [..., CB, CB], [..., N, O] for the optional gather of
+            // compact features: the tile is complete (barrier above) and stays in shared memory until this buffer's
+            // next tile, so the three values of the lane's pair are read back from it and stored coalesced.
+            if (does_angles && p.d_ca != nullptr && !p.stores_only) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    if (pair0 + lane + kTilePairs * q < p.num_pairs) {
+                        const float* blk = tile_f32 + (lane + kTilePairs * q) * G::kElemsPerPair;
+                        p.d_ca[pair[q]] = blk[1 * A + 1];
+                        p.d_cb[pair[q]] = blk[4 * A + 4];
+                        p.d_no[pair[q]] = blk[0 * A + 3];
+                    }
+                }
+            }
         }
         __syncwarp();  // staging buffer of the upcoming tile is complete
         mask_ballot = pf_mask_ballot;
@@ -1197,13 +1216,14 @@ int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, boo
     pm.dist = static_cast<float*>(dist_mask);
     pm.mask = nullptr;
     pm.omega = pm.theta = pm.phi = nullptr;
+    pm.d_ca = pm.d_cb = pm.d_no = nullptr;
     return launch_tiles_wpt<A, kF32MaskOnly, kSqrtApproxFtz, false, 1>(pm, slots_override, stream);
 }
 
 }  // namespace
 
-int trrosetta_angles_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
-                          float* theta, float* phi, cudaStream_t stream);  // pair_angles.cu
+int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
+                                  float* theta, float* phi, int variant, cudaStream_t stream);  // pair_angles.cu
 
 // Diagnostic: plain 128-bit stores of a non-uniform pattern, linear sweep (what a copy kernel's write side
 // does).  Gives the store ceiling of the memory system for comparison with the TMA bulk-store path.
@@ -1234,9 +1254,35 @@ int pair_dist_last_plan_impl(long long* out, int n) {
 }
 
 // Host entry used by the C-ABI wrappers (cabi.cu).
+int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                                void* dist_mask, float* omega, float* theta, float* phi, float* d_ca, float* d_cb,
+                                float* d_no, int B, int L, int A, int variant, cudaStream_t stream);
+
 int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                         void* dist_mask, float* omega, float* theta, float* phi, int B, int L,
                         int A, int variant, cudaStream_t stream) {
+    return pair_dist_mask_compact_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, nullptr, nullptr,
+                                       nullptr, B, L, A, variant, stream);
+}
+
+// Strided gather of one atom-pair plane of the distance tensor: out[p] = dist[p * A * A + offset] (the compact planes
+// when a shape does not take the fused staged kernel).
+__global__ void __launch_bounds__(256) gather_plane_kernel(const float* __restrict__ dist, long long num_pairs,
+                                                           int block, int off_ca, int off_cb, int off_no,
+                                                           float* __restrict__ d_ca, float* __restrict__ d_cb,
+                                                           float* __restrict__ d_no) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; p < num_pairs; p += stride) {
+        const float* blk = dist + p * block;
+        d_ca[p] = __ldg(blk + off_ca);
+        d_cb[p] = __ldg(blk + off_cb);
+        d_no[p] = __ldg(blk + off_no);
+    }
+}
+
+int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                                void* dist_mask, float* omega, float* theta, float* phi, float* d_ca, float* d_cb,
+                                float* d_no, int B, int L, int A, int variant, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "pair_dist_mask: B=%d L=%d A=%d must be > 0",
                B, L, A);
     PS_REQUIRE(xyz != nullptr, PS_ERR_NULL_POINTER, "pair_dist_mask: xyz is NULL");
@@ -1252,6 +1298,9 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     const bool want_angles = omega || theta || phi;
     PS_REQUIRE(!want_angles || A >= 5, PS_ERR_BAD_SHAPE,
                "inter_residue_geometry needs the CB slot (A >= 5), got A=%d", A);
+    const bool want_compact = d_ca || d_cb || d_no;
+    PS_REQUIRE(!want_compact || (d_ca && d_cb && d_no && want_angles && dist), PS_ERR_NULL_POINTER,
+               "compact distance planes come as a set of three, with the angles and the distance tensor");
 
     const int sqrt_id = variant & 3;
     const int warps_override = (variant >> 4) & 15;  // tile buffers (slots) per CTA
@@ -1267,7 +1316,19 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
         int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0x3FF, stream);
         if (rc != PS_OK || !want_angles) return rc;
         ++g_last_plan.launches;
-        return trrosetta_angles_impl(xyz, B, L, A, 0, omega, theta, phi, stream);
+        // the exact-sequence angle kernel: the same trrosetta_triple the fused tile kernel evaluates, so
+        // inter_residue_geometry returns identical bits whichever way a shape is dispatched
+        rc = trrosetta_angles_variant_impl(xyz, B, L, A, 0, omega, theta, phi, 1, stream);
+        if (rc != PS_OK || !want_compact) return rc;
+        const long long pairs = static_cast<long long>(B) * L * L;
+        const int sms = sm_count_for_current_device();
+        if (sms < 0) return sms;
+        long long blocks = (pairs + 255) / 256;
+        if (blocks > 16ll * sms) blocks = 16ll * sms;
+        ++g_last_plan.launches;
+        gather_plane_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dist, pairs, A * A, 1 * A + 1, 4 * A + 4,
+                                                                              0 * A + 3, d_ca, d_cb, d_no);
+        return check_launch("gather_plane_kernel");
     }
 
     PairDistParams p;
@@ -1278,6 +1339,9 @@ int pair_dist_mask_impl(const float* xyz, const void* atom_mask, int mask_dtype,
     p.omega = omega;
     p.theta = theta;
     p.phi = phi;
+    p.d_ca = d_ca;
+    p.d_cb = d_cb;
+    p.d_no = d_no;
     p.L = L;
     p.num_rows = static_cast<long long>(L) * B;
     p.num_pairs = static_cast<long long>(L) * L * B;

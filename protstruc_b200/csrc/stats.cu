@@ -231,6 +231,91 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_kernel(
     if (CLUSTER) cg::this_cluster().sync();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Register-resident variant (the default whenever a CTA's share of a structure fits in registers).
+//
+// The three-pass kernel above re-reads its share from L1/L2 for the deviation and for the normalisation, and each pass
+// is a chain of dependent scalar loads: ncu showed it latency-bound (issue-active 38 %, top stall long_scoreboard),
+// not instruction-bound.  Here every thread issues ALL of its loads up front — E independent coalesced 32-bit loads of
+// coordinates plus the matching mask loads, i.e. the whole share of the CTA is in flight at once — and keeps the
+// values in registers through mean -> deviation -> normalise, so the structure is read exactly once.
+// Element mapping: thread t owns floats t, t + T, t + 2 T, ... of the share with T a multiple of 3, so all of a
+// thread's elements lie on ONE axis (t % 3): its mean and deviation are scalars, and the atom index of element k is
+// t / 3 + k * T / 3 (no division in the loops).  Works for any alignment and any atom count.
+// Arithmetic per element is unchanged (reference op order, fp64 partial sums).
+template <int MASK_DTYPE, int E, bool CLUSTER>
+__global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_regs_kernel(
+    const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
+    float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
+    namespace cg = cooperative_groups;
+    __shared__ double scratch[kStatsMaxThreads / 32][4];
+    __shared__ double exchange[CLUSTER ? 2 : 1][4];
+    const int ranks = CLUSTER ? static_cast<int>(cg::this_cluster().num_blocks()) : 1;
+    const int rank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+    const long long b = blockIdx.x / ranks;
+    const int share = (atoms_per_struct + ranks - 1) / ranks;  // atoms per CTA
+    const int a_begin = rank * share;
+    const int a_end = a_begin + share < atoms_per_struct ? a_begin + share : atoms_per_struct;
+    const float* __restrict__ x = xyz + (b * atoms_per_struct + a_begin) * 3;
+    const long long m0 = b * atoms_per_struct + a_begin;
+    const int n = (a_end - a_begin) * 3;  // floats of this CTA (may be <= 0 for the last ranks of a short structure)
+    const int T = blockDim.x, axis = threadIdx.x % 3, a0 = threadIdx.x / 3, astep = T / 3;
+
+    float v[E], m[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+        const int e = threadIdx.x + k * T;
+        const bool ok = e < n;
+        v[k] = ok ? __ldg(x + e) : 0.f;
+        m[k] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + a0 + k * astep) : 0.f;
+    }
+    // pass 1: sum(nan_to_num(x * m)) on this thread's axis, sum(m) counted by the axis-0 thread of each atom
+    double s = 0.0, c = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+        s += static_cast<double>(nan_to_num0(__fmul_rn(v[k], m[k])));
+        c += static_cast<double>(m[k]);
+    }
+    double acc[4] = {axis == 0 ? s : 0.0, axis == 1 ? s : 0.0, axis == 2 ? s : 0.0, axis == 0 ? c : 0.0};
+    block_sum4(acc, scratch);
+    if (CLUSTER) cluster_sum4(acc, exchange, 0);
+    const float count = static_cast<float>(acc[3]);
+    float mu[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = __fdiv_rn(static_cast<float>(acc[k]), count);
+    const float my_mu = axis == 0 ? mu[0] : (axis == 1 ? mu[1] : mu[2]);
+
+    // pass 2: sum((nan_to_num(x) - mu)^2 * m)
+    double d2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+        const float d = __fsub_rn(nan_to_num0(v[k]), my_mu);
+        d2 += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m[k]));
+    }
+    double dev[4] = {axis == 0 ? d2 : 0.0, axis == 1 ? d2 : 0.0, axis == 2 ? d2 : 0.0, 0.0};
+    block_sum4(dev, scratch);
+    if (CLUSTER) cluster_sum4(dev, exchange, 1);
+    float sd[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sd[k] = __fsqrt_rn(__fdiv_rn(static_cast<float>(dev[k]), count));
+    if (rank == 0 && threadIdx.x < 3) {
+        mu_out[b * 3 + threadIdx.x] = mu[threadIdx.x];
+        sd_out[b * 3 + threadIdx.x] = sd[threadIdx.x];
+    }
+
+    // pass 3: (x - mu) / sd on every element of the share (masked or not, NaN stays NaN), straight from registers
+    if (xyz_out) {
+        const float my_sd = axis == 0 ? sd[0] : (axis == 1 ? sd[1] : sd[2]);
+        float* __restrict__ o = xyz_out + (b * atoms_per_struct + a_begin) * 3;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+            const int e = threadIdx.x + k * T;
+            if (e < n) o[e] = __fdiv_rn(__fsub_rn(v[k], my_mu), my_sd);
+        }
+    }
+    if (CLUSTER) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
+}
+
 // The per-structure elementwise maps run on a 2-D grid: blockIdx.y walks the structures, blockIdx.x / threadIdx.x
 // the structure's L*A*3 floats with fully coalesced scalar accesses.  The axis of an element is its 32-bit offset
 // inside the structure mod 3 (a multiply-shift); no per-element 64-bit division.
@@ -293,36 +378,59 @@ __global__ void __launch_bounds__(256) translate_kernel(const float* x,
     }
 }
 
-// nanmean over residues of one atom slot: one warp per structure.
-__global__ void __launch_bounds__(128) center_of_mass_kernel(const float* __restrict__ xyz, int B,
-                                                             int L, int A, int slot,
+// nanmean over residues of one atom slot.  One CTA per structure (the first version gave a structure to ONE warp:
+// 6 % of the warp slots busy at 256 structures, every lane a chain of dependent strided loads): a thread issues the
+// three loads of up to kComUnroll residues before the first use, per-thread fp32 NaN-skipping sums go through fp64
+// warp-shuffle / shared-memory reductions.  The loads are strided by the residue (A * 12 B), so a 32-byte sector
+// carries 12 useful bytes: the algorithmic 12 B per residue cost ~32 B of L2 traffic whatever the kernel does.
+constexpr int kComUnroll = 4;
+
+__global__ void __launch_bounds__(256) center_of_mass_kernel(const float* __restrict__ xyz, int L, int A, int slot,
                                                              float* __restrict__ out) {
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp_global >= B) return;
-    const float* __restrict__ x = xyz + static_cast<long long>(warp_global) * L * A * 3 + slot * 3;
-    double s[3] = {0.0, 0.0, 0.0};
-    double n[3] = {0.0, 0.0, 0.0};
-    for (int l = lane; l < L; l += 32) {
+    __shared__ double scratch[8][6];
+    const long long b = blockIdx.x;
+    const float* __restrict__ x = xyz + (b * L * A + slot) * 3;
+    const long long stride = static_cast<long long>(A) * 3;
+    double s[3] = {0.0, 0.0, 0.0}, n[3] = {0.0, 0.0, 0.0};
+    for (int l0 = threadIdx.x; l0 < L; l0 += kComUnroll * blockDim.x) {
+        float v[kComUnroll][3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float v = __ldg(x + static_cast<long long>(l) * A * 3 + k);
-            if (v == v) {
-                s[k] += static_cast<double>(v);
-                n[k] += 1.0;
-            }
+        for (int u = 0; u < kComUnroll; ++u) {
+            const int l = l0 + u * blockDim.x;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) v[u][k] = l < L ? __ldg(x + l * stride + k) : __int_as_float(0x7fc00000);
         }
+#pragma unroll
+        for (int u = 0; u < kComUnroll; ++u)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (v[u][k] == v[u][k]) {
+                    s[k] += static_cast<double>(v[u][k]);
+                    n[k] += 1.0;
+                }
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         s[k] = warp_sum(s[k]);
         n[k] = warp_sum(n[k]);
     }
-    if (lane < 3) {
-        const double sk = lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2]);
-        const double nk = lane == 0 ? n[0] : (lane == 1 ? n[1] : n[2]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            scratch[warp][k] = s[k];
+            scratch[warp][3 + k] = n[k];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double sk = 0.0, nk = 0.0;
+        for (int w = 0; w < nwarps; ++w) {
+            sk += scratch[w][threadIdx.x];
+            nk += scratch[w][3 + threadIdx.x];
+        }
         // torch.nanmean = nansum / count, both in fp32
-        out[warp_global * 3 + lane] = __fdiv_rn(static_cast<float>(sk), static_cast<float>(nk));
+        out[b * 3 + threadIdx.x] = __fdiv_rn(static_cast<float>(sk), static_cast<float>(nk));
     }
 }
 
@@ -337,8 +445,9 @@ dim3 per_structure_grid(int per_b, int B) {
 
 }  // namespace
 
-int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
-                      float* mu, float* sd, float* xyz_out, cudaStream_t stream) {
+// legacy != 0 forces the three-pass kernel of round 1 (comparison hook, ps_masked_stats_ex).
+int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
+                              float* mu, float* sd, float* xyz_out, int legacy, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "masked_stats: B=%d L=%d A=%d must be > 0",
                B, L, A);
     PS_REQUIRE(xyz && atom_mask && mu && sd, PS_ERR_NULL_POINTER, "masked_stats: NULL pointer");
@@ -347,11 +456,65 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
     const int atoms = L * A;
     PS_REQUIRE(mask_dtype == PS_MASK_BOOL || mask_dtype == PS_MASK_F32, PS_ERR_BAD_DTYPE,
                "masked_stats: unknown mask_dtype %d", mask_dtype);
-    // One cluster per structure.  Cluster size: enough CTAs that the GPU is busy when there are few structures, but
-    // at least ~1k atoms per CTA so that the block / cluster reductions stay cheap relative to the streaming work.
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
+    PS_REQUIRE(static_cast<long long>(B) * 8 < (1ll << 31), PS_ERR_BAD_SHAPE, "masked_stats: B=%d too large", B);
+    const bool is_bool = mask_dtype == PS_MASK_BOOL;
+
+    // ---- register-resident kernel: one cluster of `ranks` CTAs per structure, each thread holds E floats.
+    // ranks: split a structure over a thread-block cluster until the grid holds >= 2 CTAs per SM (few structures)
+    // or a CTA's share fits in registers (large structures); a CTA keeps >= 128 atoms.
+    constexpr int kMaxE = 32, kMaxT = 480;
     int ranks = 1;
+    while (ranks < 8 && atoms / (ranks * 2) >= 128 &&
+           (static_cast<long long>(B) * ranks < 2ll * sms || (atoms + ranks - 1) / ranks * 3 > kMaxE * kMaxT))
+        ranks *= 2;
+    const int share_floats = (atoms + ranks - 1) / ranks * 3;
+    if (share_floats <= kMaxE * kMaxT && !legacy) {
+        // threads: a multiple of 96 (whole warps, every thread on one axis), ~8 floats per thread for small shares
+        int threads = (share_floats / 8 + 95) / 96 * 96;
+        if (threads < 96) threads = 96;
+        if (threads > kMaxT) threads = kMaxT;
+        const int need = (share_floats + threads - 1) / threads;
+        cudaLaunchConfig_t config = {};
+        config.gridDim = dim3(static_cast<unsigned>(B) * ranks, 1, 1);
+        config.blockDim = dim3(threads, 1, 1);
+        config.dynamicSmemBytes = 0;
+        config.stream = stream;
+        cudaLaunchAttribute attribute[1];
+        attribute[0].id = cudaLaunchAttributeClusterDimension;
+        attribute[0].val.clusterDim.x = ranks;
+        attribute[0].val.clusterDim.y = 1;
+        attribute[0].val.clusterDim.z = 1;
+        config.attrs = attribute;
+        config.numAttrs = ranks > 1 ? 1 : 0;
+        cudaError_t err = cudaSuccess;
+#define PS_STATS_REGS(E)                                                                                              \
+    do {                                                                                                              \
+        if (ranks > 1)                                                                                                \
+            err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_regs_kernel<PS_MASK_BOOL, E, true>, xyz,        \
+                                               atom_mask, atoms, mu, sd, xyz_out)                                    \
+                          : cudaLaunchKernelEx(&config, masked_stats_regs_kernel<PS_MASK_F32, E, true>, xyz,         \
+                                               atom_mask, atoms, mu, sd, xyz_out);                                   \
+        else                                                                                                          \
+            err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_regs_kernel<PS_MASK_BOOL, E, false>, xyz,       \
+                                               atom_mask, atoms, mu, sd, xyz_out)                                    \
+                          : cudaLaunchKernelEx(&config, masked_stats_regs_kernel<PS_MASK_F32, E, false>, xyz,        \
+                                               atom_mask, atoms, mu, sd, xyz_out);                                   \
+    } while (0)
+        if (need <= 4) PS_STATS_REGS(4);
+        else if (need <= 8) PS_STATS_REGS(8);
+        else if (need <= 12) PS_STATS_REGS(12);
+        else if (need <= 16) PS_STATS_REGS(16);
+        else if (need <= 24) PS_STATS_REGS(24);
+        else PS_STATS_REGS(32);
+#undef PS_STATS_REGS
+        if (err != cudaSuccess) return cuda_fail(err, "cudaLaunchKernelEx(masked_stats_regs_kernel)");
+        return check_launch("masked_stats_regs_kernel");
+    }
+
+    // ---- structures too large for registers even as a cluster of 8 (> 40,960 atoms): the three-pass kernel
+    ranks = 1;
     while (ranks < 8 && static_cast<long long>(B) * ranks * 2 <= sms && atoms / (ranks * 2) >= 1024) ranks *= 2;
     const int share = (atoms + ranks - 1) / ranks;
     // ~8 atoms per thread (two unrolled iterations); many CTAs stay resident per SM for small structures
@@ -359,7 +522,6 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
     int threads = ((share + 7) / 8 + 95) / 96 * 96;
     if (threads < 96) threads = 96;
     if (threads > 480) threads = 480;
-    PS_REQUIRE(static_cast<long long>(B) * ranks < (1ll << 31), PS_ERR_BAD_SHAPE, "masked_stats: B=%d too large", B);
 
     if (ranks == 1) {  // no cluster: the ordinary launch path
         if (mask_dtype == PS_MASK_BOOL)
@@ -387,6 +549,11 @@ int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, i
         err = cudaLaunchKernelEx(&config, masked_stats_kernel<PS_MASK_F32, true>, xyz, atom_mask, atoms, mu, sd, xyz_out);
     if (err != cudaSuccess) return cuda_fail(err, "cudaLaunchKernelEx(masked_stats_kernel)");
     return check_launch("masked_stats_kernel");
+}
+
+int masked_stats_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
+                      float* mu, float* sd, float* xyz_out, cudaStream_t stream) {
+    return masked_stats_variant_impl(xyz, atom_mask, mask_dtype, B, L, A, mu, sd, xyz_out, 0, stream);
 }
 
 int scale_shift_impl(const float* xyz, const float* scale, const float* shift, int B, int L, int A,
@@ -422,9 +589,9 @@ int center_of_mass_impl(const float* xyz, int B, int L, int A, int slot, float* 
     PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "center_of_mass: NULL pointer");
     PS_REQUIRE(slot >= 0 && slot < A, PS_ERR_BAD_SLOT, "center_of_mass: slot %d outside [0,%d)",
                slot, A);
-    const int warps_per_block = 4;
-    const int blocks = (B + warps_per_block - 1) / warps_per_block;
-    center_of_mass_kernel<<<blocks, warps_per_block * 32, 0, stream>>>(xyz, B, L, A, slot, out);
+    int threads = (L + 31) / 32 * 32;  // one residue per thread up to 256 threads, then several
+    if (threads > 256) threads = 256;
+    center_of_mass_kernel<<<B, threads, 0, stream>>>(xyz, L, A, slot, out);
     return check_launch("center_of_mass_kernel");
 }
 

@@ -40,7 +40,9 @@ def shard_structure_batch(xyz, atom_mask=None, chain_idx=None, chain_ids=None, s
     rows: host -> its GPU directly, no scatter collective).  Returns None for an empty shard.
 
     The diffusion noise stream is keyed by the GLOBAL element index, so `diffuse_xyz` on the shards
-    gives exactly what it gives on the unsharded batch, whatever the number of GPUs."""
+    gives exactly what it gives on the unsharded batch, whatever the number of GPUs (any shard offset: the kernels
+    address the stream per element).  The noise key follows the state of torch's generator, like `torch.randn_like`
+    in the reference: ranks of one job must seed alike (`protstruc_b200.manual_seed(s)` on every rank)."""
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
     if world_size is None:
@@ -62,23 +64,66 @@ def shard_structure_batch(xyz, atom_mask=None, chain_idx=None, chain_ids=None, s
     return sb
 
 
-def gather_compact_features(local: Dict[str, torch.Tensor], batch_size: int,
-                            group=None) -> Dict[str, torch.Tensor]:
-    """Optional exchange step: all-gathers per-structure features (leading dimension = local batch)
-    from all ranks, in rank order, so every rank ends up with the (B, ...) tensors.  Uses one
-    `all_gather` per feature on padded equal-size buffers (NCCL needs equal counts); with NCCL the
-    bytes move GPU-to-GPU over NVLink/NVSwitch."""
+class _PendingGather:
+    """Handle of an asynchronous `gather_compact_features`: `wait()` makes the current CUDA stream wait for the
+    collectives and returns the gathered dict."""
+
+    def __init__(self, works, finish):
+        self._works, self._finish = works, finish
+
+    def wait(self) -> Dict[str, torch.Tensor]:
+        for w in self._works:
+            w.wait()
+        return self._finish()
+
+
+def gather_compact_features(local: Dict[str, torch.Tensor], batch_size: int, group=None,
+                            out: Optional[Dict[str, torch.Tensor]] = None, async_op: bool = False):
+    """Optional exchange step: all-gathers per-structure features (leading dimension = this rank's structures) from
+    all ranks in rank order, so every rank ends up with the (B, ...) tensors.
+
+    One `all_gather_into_tensor` per feature, straight from the feature tensor into ONE preallocated
+    (world * shard, ...) output per feature — no staging copy, no list of buffers, no `cat` when the batch divides
+    evenly.  Dense inputs are sent as they are (the fused kernel writes the compact planes densely,
+    `StructureBatch.inter_residue_geometry_compact`); only a strided view is made contiguous first.  With uneven shards
+    the short ranks send a zero-padded copy and the padding rows are dropped from the result (one gather-copy).
+    With NCCL the bytes move GPU-to-GPU over NVLink / NVSwitch.  `async_op=True` returns a handle at once (the
+    collectives run on NCCL's own stream, so the next chunk's kernel overlaps them); call `.wait()` for the result.
+
+    Every rank must call this with the same feature names — also a rank whose shard is EMPTY: pass zero-row
+    tensors of the right trailing shape and dtype (an empty `StructureBatch` returns such tensors), so that it takes
+    part in every collective."""
     if not dist.is_initialized():
-        return dict(local)
+        return _PendingGather([], lambda: dict(local)) if async_op else dict(local)
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     sizes = shard_sizes(batch_size, world)
     biggest = max(sizes)
-    out: Dict[str, torch.Tensor] = {}
+    even = all(n == biggest for n in sizes)
+    works, gathered, keep = [], {}, []
     for name in sorted(local):
-        t = local[name].contiguous()
-        pad = torch.zeros((biggest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[: t.shape[0]] = t
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad, group=group)
-        out[name] = torch.cat([buf[:n] for buf, n in zip(bufs, sizes)], dim=0)
-    return out
+        t = local[name]
+        if t.shape[0] != sizes[rank]:
+            raise ValueError(f"feature {name!r} has {t.shape[0]} structures, this rank's shard has {sizes[rank]}")
+        if not t.is_contiguous():
+            t = t.contiguous()
+        if t.shape[0] != biggest:  # short shard: zero-padded copy (only on uneven batches)
+            pad = torch.zeros((biggest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            pad[: t.shape[0]] = t
+            t = pad
+        target = None if out is None else out.get(name)
+        want = (world * biggest,) + tuple(t.shape[1:])
+        if target is None or tuple(target.shape) != want or target.dtype != t.dtype or not target.is_contiguous():
+            target = torch.empty(want, dtype=t.dtype, device=t.device)
+        works.append(dist.all_gather_into_tensor(target, t, group=group, async_op=True))
+        gathered[name] = target
+        keep.append(t)
+
+    def finish() -> Dict[str, torch.Tensor]:
+        if even:
+            return gathered
+        rows = torch.cat([torch.arange(r * biggest, r * biggest + n) for r, n in enumerate(sizes)])
+        return {name: g.index_select(0, rows.to(g.device)) for name, g in gathered.items()}
+
+    handle = _PendingGather(works, finish)
+    return handle if async_op else handle.wait()

@@ -430,6 +430,38 @@ class StructureBatch:
                 "d_no": pick(dist, n, o), "d_no_mask": pick(dist_mask, n, o),
                 "omega": omega, "theta": theta, "phi": phi}
 
+    def inter_residue_geometry_compact(self, out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """`inter_residue_geometry` with the six (B, L, L) float features as DENSE planes of one contiguous
+        (6, B, L, L) buffer — omega, theta, phi, d_ca, d_cb, d_no — written by the same single fused launch (extension;
+        the reference returns the distance planes as strided views, protstruc.py:801-808).  This is the buffer the
+        optional multi-GPU exchange gathers over NVLink (`sharding.gather_compact_features`).  `out` may supply the
+        buffer (e.g. a slot of a reused ring).  The dict also carries `dist`, `dist_mask` and `compact` (the buffer)."""
+        if self.atom_mask is None:
+            raise TypeError("'NoneType' object is not subscriptable (inter_residue_geometry needs atom_mask)")
+        B, L, A = self._dims()
+        dev = self.xyz.device
+        names = ("omega", "theta", "phi", "d_ca", "d_cb", "d_no")
+        if out is None:
+            out = torch.empty(6, B, L, L, dtype=torch.float32, device=dev)
+        if tuple(out.shape) != (6, B, L, L) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"`out` must be a contiguous float32 tensor of shape (6, {B}, {L}, {L}) on {dev}")
+        mask, code = self._mask_for_kernel(self.atom_mask)
+        dist = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
+        dist_mask = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
+        if not self._is_empty():
+            lib = self._lib()
+            if A <= int(ATOM.CB):
+                raise IndexError(f"index {int(ATOM.CB)} is out of bounds for dimension 2 with size {A}")
+            with _cabi.on_device(dev):
+                rc = lib.ps_inter_residue_geometry_compact(self.xyz.data_ptr(), mask.data_ptr(), code, dist.data_ptr(),
+                                                           dist_mask.data_ptr(), out.data_ptr(), B, L, A, self._stream())
+            _cabi.check(rc, "ps_inter_residue_geometry_compact")
+        if dist_mask.dtype != self.atom_mask.dtype:
+            dist_mask = dist_mask.to(self.atom_mask.dtype)
+        feats = {name: out[k] for k, name in enumerate(names)}
+        feats.update(dist=dist, dist_mask=dist_mask, compact=out)
+        return feats
+
     def _backbone(self, want_dihedrals: bool, frame_slots: Optional[Tuple[int, int, int]]):
         B, L, A = self._dims()
         dev = self.xyz.device

@@ -300,14 +300,28 @@ def test_pairwise_angle_methods_match_reference_golden(native_lib, name):
     H.assert_angles_close(omega, H.t(g["ref_omega"]), angle_conditioning(xyz, "omega"), "omega", all_finite_tol=2e-6)
     H.assert_angles_close(theta, H.t(g["ref_theta"]), angle_conditioning(xyz, "theta"), "theta", all_finite_tol=2e-6)
     H.assert_angles_close(phi, H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi", circular=False)
-    # the fused kernels share the geometry but finish with tuned scalar steps (rsqrt / polynomial atan2):
-    # same NaN map, values within a few ulp of the straightforward IEEE kernel
-    fo, ft, fp = sb.trrosetta_angles()
-    for a, b, tol in ((fo, omega, 1e-6), (ft, theta, 1e-6)):
+    # K2f, exact-sequence variant: shares the geometry with the generic kernel and finishes with tuned scalar steps
+    # (rsqrt / polynomial atan2): same NaN map, values within a few ulp of the straightforward IEEE kernel
+    B, L, A = xyz.shape[:3]
+    s = torch.cuda.current_stream().cuda_stream
+    eo, et, ep = (torch.empty(B, L, L, device=DEV) for _ in range(3))
+    _cabi.check(native_lib.ps_trrosetta_angles_ex(sb.get_xyz().data_ptr(), B, L, A, 0, eo.data_ptr(), et.data_ptr(),
+                                                  ep.data_ptr(), 1, s), "ps_trrosetta_angles_ex")
+    for a, b, tol in ((eo, omega, 1e-6), (et, theta, 1e-6)):
         assert torch.equal(torch.isnan(a), torch.isnan(b))
         assert H.circular_diff(torch.nan_to_num(a).cpu(), torch.nan_to_num(b).cpu()).max().item() <= tol
-    assert torch.equal(torch.isnan(fp), torch.isnan(phi))
-    H.assert_angles_close(fp, phi.cpu(), angle_conditioning(xyz, "phi"), "phi fused vs generic", circular=False)
+    assert torch.equal(torch.isnan(ep), torch.isnan(phi))
+    H.assert_angles_close(ep, phi.cpu(), angle_conditioning(xyz, "phi"), "phi exact K2f vs generic", circular=False)
+    # K2f, default (packed FP32, fused multiply-adds): the contract — NaN placement bit-exact against the REFERENCE,
+    # <= 1e-5 rad where min sin(bond angle) >= 0.1, <= 1e-6 / sin below; diagonal and zero-padded entries exact
+    fo, ft, fp = sb.trrosetta_angles()
+    H.assert_angles_close(fo, H.t(g["ref_omega"]), angle_conditioning(xyz, "omega"), "omega (packed K2f)")
+    H.assert_angles_close(ft, H.t(g["ref_theta"]), angle_conditioning(xyz, "theta"), "theta (packed K2f)")
+    H.assert_angles_close(fp, H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi (packed K2f)", circular=False)
+    eye = torch.eye(L, dtype=torch.bool)
+    for got, ref in ((fo, g["ref_omega"]), (ft, g["ref_theta"])):
+        rd = H.t(ref)[:, eye]
+        assert torch.equal(torch.nan_to_num(got.cpu()[:, eye], nan=-9.0), torch.nan_to_num(rd, nan=-9.0)), "diagonal"
     if name != "real_1a6v_HL":
         gen = sb.pairwise_dihedrals(["n", "ca", "c"], ["N"])  # case-insensitive names
         p = H.pair_points(xyz, [0, 1, 2], [0])
@@ -1261,7 +1275,7 @@ def test_exact_symmetries_at_baseline_config3_size(native_lib):
     assert torch.equal(torch.nan_to_num(torch.flip(fp, dims=[1, 2]), nan=-1.0), torch.nan_to_num(phi, nan=-1.0))
     # the generic single-feature kernels agree with the fused one (a few ulp) at this size as well
     go = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
-    assert H.circular_diff(go[:8].cpu(), omega[:8].cpu()).max().item() <= 1e-6
+    H.assert_angles_close(omega[:2], go[:2].cpu(), angle_conditioning(xyz[:2].cpu(), "omega"), "packed K2f vs generic kernel")
     del mo, mt, mp, fo, ft, fp, go
 
 

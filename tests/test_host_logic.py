@@ -186,8 +186,9 @@ def _gloo_worker(rank, world, port, B, L, result_dir):
         dist.destroy_process_group()
 
 
-def test_world_size_two_gloo_shards_reassemble_to_the_unsharded_result(tmp_path):
-    B, L, world = 5, 12, 2
+@pytest.mark.parametrize("B", [5, 4, 1])  # uneven shards, even shards, an EMPTY shard on rank 1
+def test_world_size_two_gloo_shards_reassemble_to_the_unsharded_result(tmp_path, B):
+    L, world = 12, 2
     mp.spawn(_gloo_worker, args=(world, _free_port(), B, L, str(tmp_path)), nprocs=world, join=True)
     gathered = torch.load(tmp_path / "gathered.pt")
     torch.set_num_threads(1)

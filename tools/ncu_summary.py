@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Condenses an .ncu-rep (read here, without a GPU) into the small text summary kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/k1.ncu-rep > profiles/r1_k1_ncu_summary.txt
+    python tools/ncu_summary.py gpurun_out/k1.ncu-rep [--structures N] > profiles/r2_k1_ncu_summary.txt
+
+`--structures N` records how many structures one profiled launch processed (bench.py scales the DRAM traffic by it).
 """
 import csv
 import io
@@ -38,11 +40,14 @@ KEYS = [
 
 def main():
     rep = sys.argv[1]
+    structures = int(sys.argv[sys.argv.index("--structures") + 1]) if "--structures" in sys.argv else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
     print(f"# ncu summary of {rep} ({len(data)} profiled launch(es)); ncu --set full --clock-control none")
+    if structures is not None:
+        print(f"# structures per launch: {structures}")
     for d in data:
         print(f"\nkernel: {d[col['Kernel Name']]}")
         for k in KEYS:
