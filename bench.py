@@ -47,7 +47,9 @@ sys.path.insert(0, str(REPO))
 N_ATOM = 15
 UNIT = "structures/s"
 FALLBACK_HBM_GBS = 6650.0
-HEADLINE_KERNEL = "pair_tiles_kernel<15, 0, 0, 1, 2>"  # A = 15, dist + bool mask, ftz sqrt, fused angles, 2 warps / tile
+# the fused A = 15 kernel a launch can take (ps_pair_dist_last_plan says which): name as ncu prints it
+KERNEL_NAMES = {1: "pair_sweep_kernel<0, 0, 1>",          # linear sweep: dist + bool mask, ftz sqrt, fused angles
+                0: "pair_tiles_kernel<15, 0, 0, 1, 2>"}   # column strips: A = 15, dist + bool mask, ftz sqrt, angles, 2 warps / tile
 
 WORKLOADS = {
     "m": {"L": 512, "metric": "structures/sec, 512-res x 15-atom pairwise features (dist + mask + omega/theta/phi)",
@@ -133,10 +135,11 @@ def hbm_peak():
 _SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
-def ncu_traffic_per_structure():
+def ncu_traffic_per_structure(launched_kernel: str, allow_stale: bool):
     """DRAM bytes (read + write) per structure of the headline kernel, parsed at run time from the NEWEST committed
     `ncu --set full` summary of it under profiles/ (`*k1*_ncu_summary.txt`).  Fails loudly when that capture is of
-    another kernel than the one this bench launches — a stale constant cannot go unnoticed."""
+    another kernel than the one this bench launched — a stale number cannot go unnoticed (`--allow-stale-profile`
+    turns the failure into `traffic: null` for runs made while a new kernel is being developed)."""
     def order(path: Path):
         m = re.match(r"r(\d+)([a-z]*)_", path.name)
         return (int(m.group(1)), m.group(2)) if m else (0, "")
@@ -147,9 +150,12 @@ def ncu_traffic_per_structure():
     f = files[-1]
     text = f.read_text()
     kernel = re.search(r"^kernel: (.*)$", text, re.M)
-    if kernel is None or HEADLINE_KERNEL not in kernel.group(1):
-        raise SystemExit(f"{f}: the newest K1 ncu summary is of `{kernel.group(1) if kernel else '?'}`, but bench.py "
-                         f"launches `{HEADLINE_KERNEL}` — re-capture the profile (tools/ncu_summary.py)")
+    if kernel is None or launched_kernel not in kernel.group(1):
+        msg = (f"{f}: the newest K1 ncu summary is of `{kernel.group(1) if kernel else '?'}`, but this run launched "
+               f"`{launched_kernel}` — re-capture the profile (tools/ncu_summary.py)")
+        if allow_stale:
+            return None, "STALE PROFILE: " + msg
+        raise SystemExit(msg)
     per_launch = re.search(r"structures per launch: (\d+)", text)
     structures = int(per_launch.group(1)) if per_launch else 16  # the round-1 captures were taken at 16 per launch
     total = 0.0
@@ -244,6 +250,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=96, help="structures timed for the CPU baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-gather", action="store_true", help="also time the optional NVLink gather of compact features")
+    ap.add_argument("--allow-stale-profile", action="store_true",
+                    help="do not fail when the committed ncu capture is of another kernel than the one launched")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -470,18 +478,20 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     fill_gbs = 3 * dist_t.numel() * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9
-    traffic_per_structure, traffic_src = ncu_traffic_per_structure()
+    headline_kernel = KERNEL_NAMES[1 if plan.get("sweep") else 0]
+    traffic_per_structure, traffic_src = ncu_traffic_per_structure(headline_kernel, args.allow_stale_profile)
     if args.workload != "m" and traffic_per_structure is not None:
         traffic_per_structure, traffic_src = None, "no ncu capture at this shape (the committed one is at L = 512)"
     roofline = {
-        "bound": "hbm", "kernel": f"{HEADLINE_KERNEL} (fused inter_residue_geometry)",
+        "bound": "hbm", "kernel": f"{headline_kernel} (fused inter_residue_geometry)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None if traffic_per_structure is None else traffic_per_structure * B, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": B * per_struct, "structures_per_launch": B,
         "avg_launch_ms": avg_launch_ms, "best_step_ms": min(per_step_ms), "launches_per_step": launches_per_step,
         "fill_ceiling_gbs": fill_gbs,
         "schedule": {"lockstep": bool(plan["lockstep"]), "ctas": plan["ctas"], "tile_buffers": plan["tile_buffers"],
-                     "active_buffers": plan["active_buffers"], "path": plan["path"]},
+                     "active_buffers": plan["active_buffers"], "path": plan["path"],
+                     "kernel": "linear sweep (pair_sweep.cu)" if plan.get("sweep") else "column strips (pair_dist.cu)"},
     }
     if plan["path"] != 0 or plan["launches"] != 1:
         raise SystemExit(f"the bench shape did not take ONE launch of the staged fused kernel: {plan}")

@@ -268,6 +268,10 @@ int ps_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t step,
  *   ps_geom_gram_schmidt — geometry.gram_schmidt (:413-439) a,b,c (n,3) → out (n,3,3)
  * to_degree != 0 converts like torch.rad2deg / np.degrees (multiply by 180/pi in fp32).
  */
+/* geometry.dot / norm / unit (protstruc/geometry.py:24-36) on n rows of D components: out (n), (n), (n, D). */
+int ps_geom_dot(const float* x, const float* y, int64_t n, int D, float* out, void* stream);
+int ps_geom_norm(const float* x, int64_t n, int D, float* out, void* stream);
+int ps_geom_unit(const float* x, int64_t n, int D, float* out, void* stream);
 int ps_geom_angle(const float* a, const float* b, const float* c, int64_t n,
                   int to_degree, float* out, void* stream);
 int ps_geom_dihedral(const float* a, const float* b, const float* c, const float* d,
@@ -284,7 +288,9 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * bit 11 = force the lockstep schedule, bit 13 = force the cell schedule (default: chosen by length), bit 14 = lockstep
  * even with up to 35 % idle tile buffers; bit 12 = with bit 8: row kernel only (the fallback for atom counts whose tile does
  * not fit in shared memory); bits 16-23 = any-A tile kernel: pairs per tile in units of its alignment quantum
- * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA.
+ * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA; bit 15 = A = 15: the column-strip kernel of
+ * round 1 instead of the linear-sweep kernel (comparison hook; the environment variable PROTSTRUC_B200_K1 = strip | sweep
+ * does the same for a whole process, bit 27 = sweep regardless of it).
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,
@@ -293,7 +299,7 @@ int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype
  * What the most recent K1 launch of the calling host thread chose (tests assert on it that a shape took the path its
  * parity claim is about).  out[0..n) of: path (0 staged tile kernel, 1 any-A tile kernel, 2 row kernel), lock-step
  * schedule (0/1), CTAs, tile buffers of the grid, tile buffers taking part, strip stride in tiles, pairs per tile,
- * kernel launches of the call.
+ * kernel launches of the call, linear-sweep kernel (1) or column-strip kernel (0).
  */
 int ps_pair_dist_last_plan(int64_t* out, int n);
 /* Diagnostic store ceiling: plain 128-bit stores of a non-uniform pattern over n floats (n % 4 == 0). */

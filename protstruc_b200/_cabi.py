@@ -72,6 +72,9 @@ SIGNATURES = {
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),
     "ps_philox_normal": (c_int, [_fp, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]),
+    "ps_geom_dot": (c_int, [_fp, _fp, c_int64, c_int, _fp, c_void_p]),
+    "ps_geom_norm": (c_int, [_fp, c_int64, c_int, _fp, c_void_p]),
+    "ps_geom_unit": (c_int, [_fp, c_int64, c_int, _fp, c_void_p]),
     "ps_geom_angle": (c_int, [_fp, _fp, _fp, c_int64, c_int, _fp, c_void_p]),
     "ps_geom_dihedral": (c_int, [_fp, _fp, _fp, _fp, c_int64, c_int, _fp, c_void_p]),
     "ps_geom_gram_schmidt": (c_int, [_fp, _fp, _fp, c_int64, _fp, c_void_p]),
@@ -136,7 +139,8 @@ def check(rc: int, what: str) -> None:
     raise NativeLibraryError(f"{what} failed with {STATUS_NAMES.get(rc, rc)}: {last_error()}")
 
 
-PLAN_FIELDS = ("path", "lockstep", "ctas", "tile_buffers", "active_buffers", "strip_stride", "tile_pairs", "launches")
+PLAN_FIELDS = ("path", "lockstep", "ctas", "tile_buffers", "active_buffers", "strip_stride", "tile_pairs", "launches",
+               "sweep")
 
 
 def last_pair_dist_plan() -> dict:

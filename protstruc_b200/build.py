@@ -22,7 +22,7 @@ LIB_PATH = LIB_DIR / "libprotstruc_b200.so"
 STAMP_PATH = LIB_DIR / "libprotstruc_b200.stamp"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 
-SOURCES = ["cabi.cu", "pair_dist.cu", "pair_angles.cu", "backbone.cu", "stats.cu", "diffuse.cu", "align.cu", "pdb_ingest.cu", "host_pipeline.cu"]
+SOURCES = ["cabi.cu", "pair_dist.cu", "pair_sweep.cu", "pair_angles.cu", "backbone.cu", "stats.cu", "diffuse.cu", "align.cu", "pdb_ingest.cu", "host_pipeline.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

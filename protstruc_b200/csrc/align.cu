@@ -238,7 +238,12 @@ int kabsch_impl(const float* src, const float* dst, const uint8_t* mask, int dst
     PS_REQUIRE(B > 0 && n_atoms > 0, PS_ERR_BAD_SHAPE, "kabsch: B=%d atoms=%d must be > 0", B, n_atoms);
     PS_REQUIRE(src && dst && mask && rot && trans, PS_ERR_NULL_POINTER, "kabsch: NULL pointer");
     PS_REQUIRE(dst_rows == 1 || dst_rows == B, PS_ERR_BAD_SHAPE, "kabsch: %d targets for %d structures", dst_rows, B);
-    kabsch_kernel<<<B, kKabschThreads, 0, stream>>>(src, dst, mask, dst_rows, n_atoms, rot, trans);
+    // ~16 atoms per thread: small structures get small CTAs, so that many of the serial 3x3 solves (one thread per
+    // structure, a few microseconds of dependent fp64 arithmetic) run side by side on an SM
+    int threads = (n_atoms / 16 + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    if (threads > kKabschThreads) threads = kKabschThreads;
+    kabsch_kernel<<<B, threads, 0, stream>>>(src, dst, mask, dst_rows, n_atoms, rot, trans);
     return check_launch("kabsch_kernel");
 }
 

@@ -120,6 +120,36 @@ __global__ void __launch_bounds__(256) geom_gram_schmidt_kernel(const float* __r
     store_frame(out + t * 9, gram_schmidt_frame(ld3(pa + t * 3), ld3(pb + t * 3), ld3(pc + t * 3)));
 }
 
+// geometry.dot / norm / unit (protstruc/geometry.py:24-36) on n rows of D components (D = 3 for points; any D works).
+// One thread per row.  dot: separately rounded products added left to right from +0, like ATen's sum over a short last
+// axis; norm: ATen's vector norm, a fused multiply-add chain under an IEEE square root (see norm3 in common.cuh);
+// unit: IEEE division of every component by the norm (0 / 0 = NaN for a zero vector, like the reference).
+// op: 0 = dot(x, y) -> out (n), 1 = norm(x) -> out (n), 2 = unit(x) -> out (n, D).
+__global__ void __launch_bounds__(256) geom_rowwise_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                           long long n, int D, int op, float* __restrict__ out) {
+    const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float* __restrict__ xr = x + t * D;
+    if (op == 0) {
+        const float* __restrict__ yr = y + t * D;
+        float acc = 0.0f;
+        for (int k = 0; k < D; ++k) acc = __fadd_rn(acc, __fmul_rn(__ldg(xr + k), __ldg(yr + k)));
+        out[t] = acc;
+        return;
+    }
+    float ss = 0.0f;
+    for (int k = 0; k < D; ++k) {
+        const float v = __ldg(xr + k);
+        ss = k == 0 ? __fmul_rn(v, v) : __fmaf_rn(v, v, ss);
+    }
+    const float nrm = __fsqrt_rn(ss);
+    if (op == 1) {
+        out[t] = nrm;
+        return;
+    }
+    for (int k = 0; k < D; ++k) out[t * D + k] = __fdiv_rn(__ldg(xr + k), nrm);
+}
+
 // ---- rigid-frame family ---------------------------------------------------------
 // get_local_xyz (protstruc/protstruc.py:347-362): local = R^T x - CA, with R the residue's Gram-Schmidt
 // frame and CA the residue's GLOBAL alpha-carbon (the reference subtracts it after rotating; kept).
@@ -352,6 +382,15 @@ int geom_dihedral_impl(const float* a, const float* b, const float* c, const flo
     PS_REQUIRE(a && b && c && d && out, PS_ERR_NULL_POINTER, "geom_dihedral: NULL pointer");
     geom_dihedral_kernel<<<blocks_for(n), 256, 0, stream>>>(a, b, c, d, n, to_degree, out);
     return check_launch("geom_dihedral_kernel");
+}
+
+int geom_rowwise_impl(const float* x, const float* y, long long n, int D, int op, float* out, cudaStream_t stream) {
+    PS_REQUIRE(n >= 0 && D > 0, PS_ERR_BAD_SHAPE, "geom dot/norm/unit: n=%lld D=%d", n, D);
+    PS_REQUIRE(op >= 0 && op <= 2, PS_ERR_BAD_DTYPE, "geom dot/norm/unit: unknown op %d", op);
+    if (n == 0) return PS_OK;
+    PS_REQUIRE(x && out && (op != 0 || y), PS_ERR_NULL_POINTER, "geom dot/norm/unit: NULL pointer");
+    geom_rowwise_kernel<<<blocks_for(n), 256, 0, stream>>>(x, y, n, D, op, out);
+    return check_launch("geom_rowwise_kernel");
 }
 
 int geom_gram_schmidt_impl(const float* a, const float* b, const float* c, long long n, float* out,

@@ -24,6 +24,7 @@ int geom_dihedral_impl(const float*, const float*, const float*, const float*, l
                        float*, cudaStream_t);
 int geom_gram_schmidt_impl(const float*, const float*, const float*, long long, float*,
                            cudaStream_t);
+int geom_rowwise_impl(const float*, const float*, long long, int, int, float*, cudaStream_t);
 int masked_stats_impl(const float*, const void*, int, int, int, int, float*, float*, float*,
                       cudaStream_t);
 int masked_stats_variant_impl(const float*, const void*, int, int, int, int, float*, float*, float*, int,
@@ -309,6 +310,18 @@ int ps_geom_angle(const float* a, const float* b, const float* c, int64_t n, int
 int ps_geom_dihedral(const float* a, const float* b, const float* c, const float* d, int64_t n,
                      int to_degree, float* out, void* stream) {
     return ps::geom_dihedral_impl(a, b, c, d, n, to_degree, out, PS_STREAM(stream));
+}
+
+int ps_geom_dot(const float* x, const float* y, int64_t n, int D, float* out, void* stream) {
+    return ps::geom_rowwise_impl(x, y, n, D, 0, out, PS_STREAM(stream));
+}
+
+int ps_geom_norm(const float* x, int64_t n, int D, float* out, void* stream) {
+    return ps::geom_rowwise_impl(x, nullptr, n, D, 1, out, PS_STREAM(stream));
+}
+
+int ps_geom_unit(const float* x, int64_t n, int D, float* out, void* stream) {
+    return ps::geom_rowwise_impl(x, nullptr, n, D, 2, out, PS_STREAM(stream));
 }
 
 int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t n, float* out,

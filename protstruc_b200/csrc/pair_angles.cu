@@ -142,18 +142,57 @@ __device__ __forceinline__ float2 dot_p3(P3 a, P3 b) {
     return __ffma2_rn(a.z, b.z, __ffma2_rn(a.y, b.y, __fmul2_rn(a.x, b.x)));
 }
 
+// max / min that PROPAGATE NaN (fmaxf / fminf return the other operand): one FMNMX each, and a missing atom on either
+// side of an atan2 shows up in both of them.
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// atan2 of one (y, x): the scalar twin of the packed evaluation below (same operations in the same order, so a pair's
+// result does not depend on which lane or lane partner evaluated it).  in_range = the caller's range test.
+__device__ __forceinline__ float atan2_single(float y, float x, bool in_range) {
+    if (!in_range) {
+        if ((x != x) | (y != y)) return __int_as_float(0x7fc00000);
+        // zeros, denormal-range and huge magnitudes, infinities: IEEE atan2f; x + 0 turns a -0 cosine term into the
+        // reference's +0 (ATen's sum starts from +0)
+        return atan2f(y, x + 0.0f);
+    }
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool sw = ay > ax;
+    const float mx = max_nan(ax, ay), mn = min_nan(ax, ay);
+    const float t = __fmul_rn(mn, rcp_mufu(mx));
+    const float s = __fmul_rn(t, t);
+    float p = 2.622234402e-03f;
+    p = __fmaf_rn(p, s, -1.513249334e-02f);
+    p = __fmaf_rn(p, s, 4.112178832e-02f);
+    p = __fmaf_rn(p, s, -7.366699725e-02f);
+    p = __fmaf_rn(p, s, 1.057392880e-01f);
+    p = __fmaf_rn(p, s, -1.418597400e-01f);
+    p = __fmaf_rn(p, s, 1.999039650e-01f);
+    p = __fmaf_rn(p, s, -3.333298564e-01f);
+    float a = __fmaf_rn(__fmul_rn(t, s), p, t);
+    if (sw) a = 1.57079637f - a;
+    if (x < 0.f) a = 3.14159274f - a;
+    return copysignf(a, y);
+}
+
 // atan2 of two (y, x) pairs at once.
 __device__ __forceinline__ float2 atan2_pair(float2 y, float2 x) {
     const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
     const bool sw0 = ay0 > ax0, sw1 = ay1 > ax1;
-    // select-based max / min: a NaN on either side survives in mx or mn (fmaxf / fminf would drop it)
-    const float mx0 = sw0 ? ay0 : ax0, mn0 = sw0 ? ax0 : ay0;
-    const float mx1 = sw1 ? ay1 : ax1, mn1 = sw1 ? ax1 : ay1;
-    const float lo = fminf(mx0, mx1), hi = fmaxf(mx0, mx1);
-    // zeros, denormal-range and huge magnitudes, infinities, NaN (either compare fails, or mn is NaN): IEEE atan2f;
-    // x + 0 turns a -0 cosine term into the reference's +0 (ATen's sum starts from +0)
-    if (!((lo > 1e-30f) & (hi < 1e30f) & (mn0 == mn0) & (mn1 == mn1) & (mx0 == mx0) & (mx1 == mx1)))
-        return make_float2(atan2f(y.x, x.x + 0.0f), atan2f(y.y, x.y + 0.0f));
+    const float mx0 = max_nan(ax0, ay0), mn0 = min_nan(ax0, ay0);
+    const float mx1 = max_nan(ax1, ay1), mn1 = min_nan(ax1, ay1);
+    const bool ok0 = (mx0 > 1e-30f) & (mx0 < 1e30f);  // false for zero, huge, infinite and NaN (of either operand)
+    const bool ok1 = (mx1 > 1e-30f) & (mx1 < 1e30f);
+    // a lane out of range (zeros, huge, infinite, NaN — e.g. a missing atom in one of the two pairs): each lane on its own
+    if (!(ok0 & ok1)) return make_float2(atan2_single(y.x, x.x, ok0), atan2_single(y.y, x.y, ok1));
     const float2 t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rcp_mufu(mx0), rcp_mufu(mx1)));
     const float2 s = __fmul2_rn(t, t);
     float2 p = f2(2.622234402e-03f);
@@ -179,29 +218,65 @@ __device__ __forceinline__ float trrosetta_phi_exact(V3 ba, V3 bc) {
     return acosf(__fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc))));
 }
 
-// Row-side record of one residue i (floats): b0 = CA - CB (3), CB (3), tn1 = (N - CA) x (CB - CA) (3),
-// |b0| (NaN for b0 = 0), 1 / |b0| (inf for b0 = 0), omega on the diagonal.
-constexpr int kRowRecord = 12;
+// acos of two cosines at once (|c| <= 1; anything else, NaN included, gives NaN): the classic two-range evaluation —
+// acos(c) = pi/2 - asin(c) for |c| <= 0.56, 2 asin(sqrt((1 - |c|) / 2)) mirrored for c < 0 above — with the odd
+// minimax polynomial of asin on [0, 0.56] (|error| < 3e-7 rad over the whole range) evaluated as FFMA2 for both lanes.
+__device__ __forceinline__ float2 acos_pair(float2 c) {
+    const float a0 = fabsf(c.x), a1 = fabsf(c.y);
+    const bool big0 = a0 > 0.56f, big1 = a1 > 0.56f;
+    const float2 zb = __ffma2_rn(make_float2(a0, a1), f2(-0.5f), f2(0.5f));  // (1 - |c|) / 2; negative for |c| > 1
+    const float2 zs = __fmul2_rn(c, c);
+    const float2 z = make_float2(big0 ? zb.x : zs.x, big1 ? zb.y : zs.y);
+    // sqrt(z) for the upper range: z * rsqrt(z) with one Newton step; z = 0 (|c| = 1) must give 0, z < 0 gives NaN
+    const float r0 = rsqrt_mufu(zb.x), r1 = rsqrt_mufu(zb.y);
+    float2 q = __fmul2_rn(zb, make_float2(r0, r1));
+    q = __ffma2_rn(__ffma2_rn(neg2(q), q, zb), __fmul2_rn(make_float2(r0, r1), f2(0.5f)), q);
+    const float2 s = make_float2(big0 ? (zb.x == 0.f ? 0.f : q.x) : a0, big1 ? (zb.y == 0.f ? 0.f : q.y) : a1);
+    float2 p = f2(3.53822075e-02f);
+    p = __ffma2_rn(p, z, f2(1.69805195e-02f));
+    p = __ffma2_rn(p, z, f2(3.07629332e-02f));
+    p = __ffma2_rn(p, z, f2(4.47094180e-02f));
+    p = __ffma2_rn(p, z, f2(7.49890432e-02f));
+    p = __ffma2_rn(p, z, f2(1.66667074e-01f));
+    const float2 as = __ffma2_rn(__fmul2_rn(s, z), p, s);  // asin(s)
+    float o0, o1;
+    if (big0) o0 = c.x < 0.f ? 3.14159274f - 2.f * as.x : 2.f * as.x; else o0 = 1.57079637f - copysignf(as.x, c.x);
+    if (big1) o1 = c.y < 0.f ? 3.14159274f - 2.f * as.y : 2.f * as.y; else o1 = 1.57079637f - copysignf(as.y, c.y);
+    return make_float2(o0, o1);
+}
 
-template <bool VIRTUAL_CB>
-__global__ void __launch_bounds__(256) trrosetta_fast_kernel(const float* __restrict__ xyz, float* __restrict__ omega,
+// Row-side record of one residue i (16 floats, 64-byte aligned: four broadcast LDS.128 per row): b0 = CA - CB (3),
+// |b0| (NaN for b0 = 0), CB (3), 1 / |b0| (inf for b0 = 0), tn1 = (N - CA) x (CB - CA) (3), omega on the diagonal,
+// flags (1 = CA_i or CB_i missing: the whole row is NaN; 2 = N_i missing: theta of the row is NaN), padding.
+constexpr int kRowRecord = 16;
+
+// Loop order: a thread OWNS pairs of residues j (one pair when L <= 2 * blockDim.x) and walks the CTA's rows with them
+// in registers, so per (row, pair of j) the only memory traffic is the broadcast read of the row record and the three
+// 64-bit stores; nothing that depends on j alone (its coordinates, its NaN flags, the position of the diagonal) is
+// redone per row.  (The first packed version walked j inside a row: with one j-pair per thread and row it re-read the
+// row record, the coordinates and the flags for every pair and spent a quarter of its issue slots on addressing.)
+template <bool VIRTUAL_CB, bool ALL3>
+__global__ void __launch_bounds__(256, 3) trrosetta_fast_kernel(const float* __restrict__ xyz, float* __restrict__ omega,
                                                              float* __restrict__ theta, float* __restrict__ phi, int L,
                                                              int A, int rows_per_cta, int blocks_per_structure,
                                                              int vector_stores) {
     extern __shared__ __align__(16) float fast_smem[];
     const int Lp = (L + 1) & ~1;  // residues j padded to whole pairs
-    float* const sca_x = fast_smem;
+    float* const srow = fast_smem;  // rows_per_cta records of kRowRecord floats (16-byte aligned)
+    float* const sca_x = srow + rows_per_cta * kRowRecord;
     float* const sca_y = sca_x + Lp;
     float* const sca_z = sca_y + Lp;
     float* const scb_x = sca_z + Lp;
     float* const scb_y = scb_x + Lp;
     float* const scb_z = scb_y + Lp;
-    float* const srow = scb_z + Lp;  // rows_per_cta records of kRowRecord floats
+    // per residue j: bit 0 = CB missing (NaN coordinate): all three angles of the pair are NaN
+    unsigned char* const sflag = reinterpret_cast<unsigned char*>(scb_z + Lp);
 
     const long long b = blockIdx.x / blocks_per_structure;
     const int row0 = (blockIdx.x - static_cast<int>(b) * blocks_per_structure) * rows_per_cta;
     const int nrows = min(rows_per_cta, L - row0);
     const float* __restrict__ xb = xyz + b * L * A * 3;
+    const bool want_omega = ALL3 || omega != nullptr, want_theta = ALL3 || theta != nullptr, want_phi = ALL3 || phi != nullptr;
 
     // ---- stage residue j of the whole structure: CA and CB (real or virtual), structure of arrays
     for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
@@ -213,6 +288,7 @@ __global__ void __launch_bounds__(256) trrosetta_fast_kernel(const float* __rest
         }
         sca_x[r] = ca.x; sca_y[r] = ca.y; sca_z[r] = ca.z;
         scb_x[r] = cb.x; scb_y[r] = cb.y; scb_z[r] = cb.z;
+        sflag[r] = atom_has_nan(cb) ? 1 : 0;
     }
     __syncthreads();
     // ---- row-side records of this CTA's residues i
@@ -229,13 +305,16 @@ __global__ void __launch_bounds__(256) trrosetta_fast_kernel(const float* __rest
         tn1.z = fmaf(u.x, tb1.y, -(u.y * tb1.x));
         const float bb = fmaf(b0.z, b0.z, fmaf(b0.y, b0.y, b0.x * b0.x));
         const float inv = rsqrt_refined(bb);              // inf * 0 = NaN for bb = 0, NaN for missing atoms
+        const float inv_or_inf = bb == 0.f ? __int_as_float(0x7f800000) : inv;
         float* rec = srow + k * kRowRecord;
         rec[0] = b0.x; rec[1] = b0.y; rec[2] = b0.z;
-        rec[3] = cb.x; rec[4] = cb.y; rec[5] = cb.z;
-        rec[6] = tn1.x; rec[7] = tn1.y; rec[8] = tn1.z;
-        rec[9] = bb * inv;                                // |b0|, NaN where the reference divides 0 / 0
-        rec[10] = bb == 0.f ? __int_as_float(0x7f800000) : inv;  // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
-        rec[11] = 0.0f * (bb == 0.f ? __int_as_float(0x7f800000) : inv);  // omega[i, i]: 0, or NaN (missing / coincident)
+        rec[3] = bb * inv;                                // |b0|, NaN where the reference divides 0 / 0
+        rec[4] = cb.x; rec[5] = cb.y; rec[6] = cb.z;
+        rec[7] = inv_or_inf;                              // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
+        rec[8] = tn1.x; rec[9] = tn1.y; rec[10] = tn1.z;
+        rec[11] = 0.0f * inv_or_inf;                      // omega[i, i]: 0, or NaN (missing / coincident)
+        rec[12] = __int_as_float((atom_has_nan(ca) || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(n_i) ? 2 : 0));
+        rec[13] = rec[14] = rec[15] = 0.f;
     }
     __syncthreads();
 
@@ -245,69 +324,81 @@ __global__ void __launch_bounds__(256) trrosetta_fast_kernel(const float* __rest
     const float2* __restrict__ pcb_x = reinterpret_cast<const float2*>(scb_x);
     const float2* __restrict__ pcb_y = reinterpret_cast<const float2*>(scb_y);
     const float2* __restrict__ pcb_z = reinterpret_cast<const float2*>(scb_z);
+    const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(srow);
     const int npairs = Lp >> 1;
+    const float2 nan2 = f2(__int_as_float(0x7fc00000));
+    const long long first_out = (b * L + row0) * L;  // element (b, row0, 0) of the outputs
 
-    for (int k = 0; k < nrows; ++k) {
-        const int i = row0 + k;
-        const float* rec = srow + k * kRowRecord;
-        const P3 b0{f2(rec[0]), f2(rec[1]), f2(rec[2])};
-        const P3 cbi{f2(rec[3]), f2(rec[4]), f2(rec[5])};
-        const P3 tn1{f2(rec[6]), f2(rec[7]), f2(rec[8])};
-        const P3 tb1{neg2(b0.x), neg2(b0.y), neg2(b0.z)};
-        const float2 norm_b0 = f2(rec[9]);
-        const float2 inv_b0 = f2(rec[10]);
-        const float diag_omega = rec[11];
-        const long long out_row = (b * L + i) * L;
-        for (int jp = threadIdx.x; jp < npairs; jp += blockDim.x) {
-            const P3 caj{pca_x[jp], pca_y[jp], pca_z[jp]};
-            const P3 cbj{pcb_x[jp], pcb_y[jp], pcb_z[jp]};
-            const P3 bc = sub_p3(cbj, cbi);  // CB_j - CB_i: theta's b2, phi's bc
-            float2 w = f2(0.f), t = f2(0.f), f = f2(0.f);
-            if (omega) {
-                const P3 b1 = sub_p3(caj, cbi);
-                const P3 b2 = sub_p3(cbj, caj);
-                const P3 n1 = cross_p3(b0, b1);
-                const P3 n2 = cross_p3(b2, b1);
-                const float2 x = dot_p3(n1, n2);
-                const float2 sn = dot_p3(n1, b2);
-                const float2 bb = dot_p3(b1, b1);
-                const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
-                w = atan2_pair(neg2(__fmul2_rn(sn, nb1)), x);
-                if (jp == (i >> 1)) {  // the diagonal entry of this row
-                    if (i & 1) w.y = diag_omega; else w.x = diag_omega;
+    for (int jp = threadIdx.x; jp < npairs; jp += blockDim.x) {
+        const P3 caj{pca_x[jp], pca_y[jp], pca_z[jp]};
+        const P3 cbj{pcb_x[jp], pcb_y[jp], pcb_z[jp]};
+        const P3 b2 = sub_p3(cbj, caj);  // omega's b2 = CB_j - CA_j depends on j alone
+        // Missing atoms are NaN coordinates (protstruc/pdb.py:133-135) and make the angle NaN whatever the other atoms
+        // are: such pairs (and rows, below) are answered without arithmetic — with half of the atoms missing that is
+        // 15 of 16 pairs — instead of dragging NaN through the IEEE fall-backs of atan2 / acos.
+        const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jp];
+        const bool nan0 = fl & 0x0001, nan1 = fl & 0x0100;
+        const bool pair_nan = nan0 && nan1;
+        const int j = 2 * jp;
+        const int diag_k = (j >> 1 << 1) - row0;  // row (relative to row0) whose diagonal lies in this pair: j or j + 1
+        long long o = first_out + j;
+        for (int k = 0; k < nrows; ++k, o += L) {
+            const float4 q0 = rows4[4 * k + 0], q1 = rows4[4 * k + 1], q2 = rows4[4 * k + 2], q3 = rows4[4 * k + 3];
+            const int row_flags = __float_as_int(q3.x);
+            float2 w = nan2, t = nan2, f = nan2;
+            if (!((row_flags & 1) || pair_nan)) {
+                const P3 b0{f2(q0.x), f2(q0.y), f2(q0.z)};
+                const P3 cbi{f2(q1.x), f2(q1.y), f2(q1.z)};
+                const P3 bc = sub_p3(cbj, cbi);  // CB_j - CB_i: theta's b2, phi's bc
+                if (want_omega) {
+                    const P3 b1 = sub_p3(caj, cbi);
+                    const P3 n1 = cross_p3(b0, b1);
+                    const P3 n2 = cross_p3(b2, b1);
+                    const float2 x = dot_p3(n1, n2);
+                    const float2 sn = dot_p3(n1, b2);
+                    const float2 bb = dot_p3(b1, b1);
+                    const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
+                    w = atan2_pair(neg2(__fmul2_rn(sn, nb1)), x);
+                    const int dk = k - diag_k;  // 0: lane x is the diagonal entry, 1: lane y
+                    if (dk == 0) w.x = q2.w;
+                    if (dk == 1) w.y = q2.w;
+                }
+                if (want_theta && !(row_flags & 2)) {
+                    const P3 tn1{f2(q2.x), f2(q2.y), f2(q2.z)};
+                    const P3 tb1{f2(-q0.x), f2(-q0.y), f2(-q0.z)};
+                    const P3 n2 = cross_p3(bc, tb1);
+                    const float2 x = dot_p3(tn1, n2);
+                    const float2 sn = dot_p3(tn1, bc);
+                    t = atan2_pair(neg2(__fmul2_rn(sn, f2(q0.w))), x);
+                }
+                if (want_phi) {
+                    const float2 d = dot_p3(b0, bc);
+                    const float2 cc = dot_p3(bc, bc);
+                    float2 r = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
+                    r = __fmul2_rn(r, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), r), r, f2(1.5f)));  // Newton step
+                    const float2 c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), r);
+                    // (a lane whose CB_j is missing is NaN either way and must not drag its partner into the exact path)
+                    const bool ok0 = (fabsf(c.x) <= 0.999f) | nan0, ok1 = (fabsf(c.y) <= 0.999f) | nan1;
+                    f = acos_pair(c);
+                    if (!(ok0 & ok1)) {
+                        const V3 ba{q0.x, q0.y, q0.z};
+                        if (!ok0) f.x = trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
+                        if (!ok1) f.y = trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
+                    }
                 }
             }
-            if (theta) {
-                const P3 n2 = cross_p3(bc, tb1);
-                const float2 x = dot_p3(tn1, n2);
-                const float2 sn = dot_p3(tn1, bc);
-                t = atan2_pair(neg2(__fmul2_rn(sn, norm_b0)), x);
-            }
-            if (phi) {
-                const float2 d = dot_p3(b0, bc);
-                const float2 cc = dot_p3(bc, bc);
-                const float2 c = __fmul2_rn(__fmul2_rn(d, inv_b0), make_float2(rsqrt_refined(cc.x), rsqrt_refined(cc.y)));
-                if ((fabsf(c.x) <= 0.999f) & (fabsf(c.y) <= 0.999f)) {
-                    f = make_float2(acosf(c.x), acosf(c.y));
-                } else {
-                    const V3 ba{rec[0], rec[1], rec[2]};
-                    f.x = fabsf(c.x) <= 0.999f ? acosf(c.x) : trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
-                    f.y = fabsf(c.y) <= 0.999f ? acosf(c.y) : trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
-                }
-            }
-            const int j = 2 * jp;
             if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
-                if (omega) *reinterpret_cast<float2*>(omega + out_row + j) = w;
-                if (theta) *reinterpret_cast<float2*>(theta + out_row + j) = t;
-                if (phi) *reinterpret_cast<float2*>(phi + out_row + j) = f;
+                if (want_omega) *reinterpret_cast<float2*>(omega + o) = w;
+                if (want_theta) *reinterpret_cast<float2*>(theta + o) = t;
+                if (want_phi) *reinterpret_cast<float2*>(phi + o) = f;
             } else {
-                if (omega) omega[out_row + j] = w.x;
-                if (theta) theta[out_row + j] = t.x;
-                if (phi) phi[out_row + j] = f.x;
+                if (want_omega) omega[o] = w.x;
+                if (want_theta) theta[o] = t.x;
+                if (want_phi) phi[o] = f.x;
                 if (j + 1 < L) {
-                    if (omega) omega[out_row + j + 1] = w.y;
-                    if (theta) theta[out_row + j + 1] = t.y;
-                    if (phi) phi[out_row + j + 1] = f.y;
+                    if (want_omega) omega[o + 1] = w.y;
+                    if (want_theta) theta[o + 1] = t.y;
+                    if (want_phi) phi[o + 1] = f.y;
                 }
             }
         }
@@ -405,30 +496,34 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
     // Packed kernel: the structure's CA / CB (6 floats per residue) plus the row records must fit in shared memory.
     const int Lp = (L + 1) & ~1;
     // rows per CTA: as many as possible (the staging of the structure is amortised over them) while the grid still
-    // holds >= 2 CTAs per SM; at least 4, at most 32
-    int rows_per_cta = 32;
+    // holds >= 2 CTAs per SM; at least 4, at most 64
+    int rows_per_cta = 64;
     while (rows_per_cta > 4 && rows / rows_per_cta < 2ll * sms) rows_per_cta /= 2;
     if (rows_per_cta > L) rows_per_cta = L;
-    const size_t smem = (static_cast<size_t>(6) * Lp + static_cast<size_t>(rows_per_cta) * kRowRecord) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(6) * Lp + static_cast<size_t>(rows_per_cta) * kRowRecord) * sizeof(float) +
+                        static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
     if (variant == 0 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
-        int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread and pass
+        int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread (several beyond 512 residues)
         if (threads > 256) threads = 256;
         auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
         const int vector_stores = (L % 2 == 0) && aligned8(omega) && aligned8(theta) && aligned8(phi);
-        cudaError_t err;
+        const bool all3 = omega && theta && phi;
+#define PS_FAST(VCB, ALL)                                                                                             \
+    do {                                                                                                              \
+        cudaError_t err = cudaFuncSetAttribute(trrosetta_fast_kernel<VCB, ALL>,                                       \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);              \
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");                 \
+        trrosetta_fast_kernel<VCB, ALL><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                      \
+            xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);                         \
+    } while (0)
         if (use_virtual_cb) {
-            err = cudaFuncSetAttribute(trrosetta_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");
-            trrosetta_fast_kernel<true><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(
-                xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);
+            if (all3) PS_FAST(true, true); else PS_FAST(true, false);
         } else {
-            err = cudaFuncSetAttribute(trrosetta_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");
-            trrosetta_fast_kernel<false><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(
-                xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);
+            if (all3) PS_FAST(false, true); else PS_FAST(false, false);
         }
+#undef PS_FAST
         return check_launch("trrosetta_fast_kernel");
     }
     int grid = 0;

@@ -58,6 +58,39 @@ __device__ __forceinline__ void block_sum4(double (&v)[4], double (*scratch)[4])
     }
 }
 
+// Block sum for the register-resident kernel, whose threads each hold ONE axis (threadIdx.x % 3) and whose block size
+// is a multiple of 96: lanes l, l + 3, l + 6, ... of a warp share an axis, so four shuffle steps at strides 24, 12, 6, 3
+// leave the three per-axis sums of the warp in lanes 0, 1, 2 (instead of five steps on each of four values); the warps'
+// sums meet in shared memory, four threads add them up, everybody reads the total of ITS axis and the total of `extra`
+// (the atom count, exact in fp32).  scratch: [warps][4] partials followed by one row of totals.
+__device__ __forceinline__ void block_sum_by_axis(double v, float extra, int axis, double (*scratch)[4], double& axis_total,
+                                                  double& extra_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int off = 24; off >= 3; off >>= 1) {
+        const double a = __shfl_down_sync(0xffffffffu, v, off);
+        const float b = __shfl_down_sync(0xffffffffu, extra, off);
+        if (lane + off < 32) {
+            v += a;
+            extra += b;
+        }
+    }
+    __syncthreads();  // scratch reuse across calls
+    if (lane < 3) {
+        scratch[warp][axis] = v;
+        if (axis == 0) scratch[warp][3] = static_cast<double>(extra);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += scratch[w][threadIdx.x];
+        scratch[kStatsMaxThreads / 32][threadIdx.x] = t;
+    }
+    __syncthreads();
+    axis_total = scratch[kStatsMaxThreads / 32][axis];
+    extra_total = scratch[kStatsMaxThreads / 32][3];
+}
+
 template <int MASK_DTYPE>
 __device__ __forceinline__ float mask_value(const void* __restrict__ m, long long idx) {
     if (MASK_DTYPE == PS_MASK_BOOL)
@@ -248,7 +281,7 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_regs_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
     float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
     namespace cg = cooperative_groups;
-    __shared__ double scratch[kStatsMaxThreads / 32][4];
+    __shared__ double scratch[kStatsMaxThreads / 32 + 1][4];
     __shared__ double exchange[CLUSTER ? 2 : 1][4];
     const int ranks = CLUSTER ? static_cast<int>(cg::this_cluster().num_blocks()) : 1;
     const int rank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
@@ -256,62 +289,69 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_regs_kernel(
     const int share = (atoms_per_struct + ranks - 1) / ranks;  // atoms per CTA
     const int a_begin = rank * share;
     const int a_end = a_begin + share < atoms_per_struct ? a_begin + share : atoms_per_struct;
-    const float* __restrict__ x = xyz + (b * atoms_per_struct + a_begin) * 3;
-    const long long m0 = b * atoms_per_struct + a_begin;
     const int n = (a_end - a_begin) * 3;  // floats of this CTA (may be <= 0 for the last ranks of a short structure)
-    const int T = blockDim.x, axis = threadIdx.x % 3, a0 = threadIdx.x / 3, astep = T / 3;
+    const int T = blockDim.x, axis = threadIdx.x % 3, astep = T / 3;
+    // this thread's first element / first atom; element k is T floats (astep atoms) further on
+    const float* __restrict__ x = xyz + (b * atoms_per_struct + a_begin) * 3 + threadIdx.x;
+    const long long m_first = b * atoms_per_struct + a_begin + threadIdx.x / 3;
 
     float v[E], m[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-        const int e = threadIdx.x + k * T;
-        const bool ok = e < n;
-        v[k] = ok ? __ldg(x + e) : 0.f;
-        m[k] = ok ? mask_value<MASK_DTYPE>(atom_mask, m0 + a0 + k * astep) : 0.f;
+        const bool ok = static_cast<int>(threadIdx.x) + k * T < n;
+        v[k] = ok ? __ldg(x + k * T) : 0.f;
+        m[k] = ok ? mask_value<MASK_DTYPE>(atom_mask, m_first + k * astep) : 0.f;
     }
-    // pass 1: sum(nan_to_num(x * m)) on this thread's axis, sum(m) counted by the axis-0 thread of each atom
-    double s = 0.0, c = 0.0;
+    // pass 1: sum(nan_to_num(x * m)) on this thread's axis, sum(m) counted by the axis-0 thread of each atom.
+    // A thread's <= E values are added in fp32 and enter the fp64 reduction as ONE value: fp32 -> fp64 conversions
+    // run on the quarter-rate XU pipe, and one per element (as in the three-pass kernel) was what bounded both kernels.
+    float s = 0.f, c = 0.f;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
-        s += static_cast<double>(nan_to_num0(__fmul_rn(v[k], m[k])));
-        c += static_cast<double>(m[k]);
+        s += nan_to_num0(__fmul_rn(v[k], m[k]));
+        c += m[k];
     }
-    double acc[4] = {axis == 0 ? s : 0.0, axis == 1 ? s : 0.0, axis == 2 ? s : 0.0, axis == 0 ? c : 0.0};
-    block_sum4(acc, scratch);
-    if (CLUSTER) cluster_sum4(acc, exchange, 0);
-    const float count = static_cast<float>(acc[3]);
-    float mu[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) mu[k] = __fdiv_rn(static_cast<float>(acc[k]), count);
-    const float my_mu = axis == 0 ? mu[0] : (axis == 1 ? mu[1] : mu[2]);
+    double sum_axis, sum_count;
+    block_sum_by_axis(static_cast<double>(s), axis == 0 ? c : 0.f, axis, scratch, sum_axis, sum_count);
+    if (CLUSTER) {
+        // totals of the whole structure: the three axis sums and the count of every CTA of the cluster
+        double acc[4] = {scratch[kStatsMaxThreads / 32][0], scratch[kStatsMaxThreads / 32][1],
+                         scratch[kStatsMaxThreads / 32][2], scratch[kStatsMaxThreads / 32][3]};
+        cluster_sum4(acc, exchange, 0);
+        sum_axis = axis == 0 ? acc[0] : (axis == 1 ? acc[1] : acc[2]);
+        sum_count = acc[3];
+    }
+    // every thread needs the statistics of ITS axis only: one IEEE division here, one division + square root below
+    const float count = static_cast<float>(sum_count);
+    const float my_mu = __fdiv_rn(static_cast<float>(sum_axis), count);
 
     // pass 2: sum((nan_to_num(x) - mu)^2 * m)
-    double d2 = 0.0;
+    float d2 = 0.f;
 #pragma unroll
     for (int k = 0; k < E; ++k) {
         const float d = __fsub_rn(nan_to_num0(v[k]), my_mu);
-        d2 += static_cast<double>(__fmul_rn(__fmul_rn(d, d), m[k]));
+        d2 += __fmul_rn(__fmul_rn(d, d), m[k]);
     }
-    double dev[4] = {axis == 0 ? d2 : 0.0, axis == 1 ? d2 : 0.0, axis == 2 ? d2 : 0.0, 0.0};
-    block_sum4(dev, scratch);
-    if (CLUSTER) cluster_sum4(dev, exchange, 1);
-    float sd[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sd[k] = __fsqrt_rn(__fdiv_rn(static_cast<float>(dev[k]), count));
-    if (rank == 0 && threadIdx.x < 3) {
-        mu_out[b * 3 + threadIdx.x] = mu[threadIdx.x];
-        sd_out[b * 3 + threadIdx.x] = sd[threadIdx.x];
+    double dev_axis, unused;
+    block_sum_by_axis(static_cast<double>(d2), 0.f, axis, scratch, dev_axis, unused);
+    if (CLUSTER) {
+        double acc[4] = {scratch[kStatsMaxThreads / 32][0], scratch[kStatsMaxThreads / 32][1],
+                         scratch[kStatsMaxThreads / 32][2], 0.0};
+        cluster_sum4(acc, exchange, 1);
+        dev_axis = axis == 0 ? acc[0] : (axis == 1 ? acc[1] : acc[2]);
+    }
+    const float my_sd = __fsqrt_rn(__fdiv_rn(static_cast<float>(dev_axis), count));
+    if (rank == 0 && threadIdx.x < 3) {  // threads 0, 1, 2 hold axes 0, 1, 2
+        mu_out[b * 3 + threadIdx.x] = my_mu;
+        sd_out[b * 3 + threadIdx.x] = my_sd;
     }
 
     // pass 3: (x - mu) / sd on every element of the share (masked or not, NaN stays NaN), straight from registers
     if (xyz_out) {
-        const float my_sd = axis == 0 ? sd[0] : (axis == 1 ? sd[1] : sd[2]);
-        float* __restrict__ o = xyz_out + (b * atoms_per_struct + a_begin) * 3;
+        float* __restrict__ o = xyz_out + (b * atoms_per_struct + a_begin) * 3 + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < E; ++k) {
-            const int e = threadIdx.x + k * T;
-            if (e < n) o[e] = __fdiv_rn(__fsub_rn(v[k], my_mu), my_sd);
-        }
+        for (int k = 0; k < E; ++k)
+            if (static_cast<int>(threadIdx.x) + k * T < n) o[k * T] = __fdiv_rn(__fsub_rn(v[k], my_mu), my_sd);
     }
     if (CLUSTER) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
 }

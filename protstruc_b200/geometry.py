@@ -5,10 +5,8 @@ Mirrors the reference's `protstruc.geometry` surface for the hot path — `dot`,
 the type contract of its `with_tensor` adaptor (reference protstruc/decorator.py:5-53):
 numpy-only inputs give numpy outputs, any torch input gives torch outputs, numpy floats become fp32.
 
-`angle`, `dihedral` and `gram_schmidt` launch the hand-written kernels through the C-ABI
-(ps_geom_angle / ps_geom_dihedral / ps_geom_gram_schmidt).  `dot`, `norm` and `unit` are one-line
-elementwise helpers evaluated with torch on the GPU (they are not on the batched hot path; the
-kernels inline their own versions).  Nothing here computes on the CPU: inputs are moved to the
+Every function launches a hand-written kernel through the C-ABI (ps_geom_dot / ps_geom_norm / ps_geom_unit /
+ps_geom_angle / ps_geom_dihedral / ps_geom_gram_schmidt).  Nothing here computes on the CPU: inputs are moved to the
 current CUDA device, and without a GPU (or without the built library) the calls raise.
 """
 from __future__ import annotations
@@ -71,22 +69,57 @@ def _stream(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _rows(tensors):
+    """Broadcasts arrays against each other and flattens to contiguous fp32 (n, D) rows."""
+    shape = torch.broadcast_shapes(*[t.shape for t in tensors])
+    if len(shape) == 0:
+        raise ValueError("expected at least one dimension")
+    flat = [t.to(torch.float32).expand(shape).reshape(-1, shape[-1]).contiguous() for t in tensors]
+    return flat, shape
+
+
 def dot(x: ArrayLike, y: ArrayLike):
     """Inner product over the last axis, keepdim (reference geometry.py:24-26)."""
-    (x, y), saw, _ = _ingest([x, y])
-    return _egress((x * y).sum(dim=-1, keepdim=True), saw)
+    tensors, saw, dev = _ingest([x, y])
+    (fx, fy), shape = _rows(tensors)
+    out = torch.empty(fx.shape[0], dtype=torch.float32, device=dev)
+    if shape[-1] == 0:
+        out.zero_()
+    else:
+        with _cabi.on_device(dev):
+            rc = _cabi.load().ps_geom_dot(fx.data_ptr(), fy.data_ptr(), fx.shape[0], shape[-1], out.data_ptr(), _stream(dev))
+        _cabi.check(rc, "ps_geom_dot")
+    out = out.reshape(shape[:-1] + (1,))
+    kind = torch.result_type(tensors[0], tensors[1])
+    if not kind.is_floating_point:  # integer inputs give an integer product sum, like `(x * y).sum`
+        out = out.round().to(torch.int64 if kind != torch.bool else torch.int64)
+    return _egress(out, saw)
 
 
 def norm(x: ArrayLike):
     """Euclidean norm over the last axis, keepdim (reference geometry.py:29-31)."""
-    (x,), saw, _ = _ingest([x])
-    return _egress(x.norm(dim=-1, keepdim=True), saw)
+    tensors, saw, dev = _ingest([x])
+    (fx,), shape = _rows(tensors)
+    out = torch.empty(fx.shape[0], dtype=torch.float32, device=dev)
+    if shape[-1] == 0:
+        out.zero_()
+    else:
+        with _cabi.on_device(dev):
+            rc = _cabi.load().ps_geom_norm(fx.data_ptr(), fx.shape[0], shape[-1], out.data_ptr(), _stream(dev))
+        _cabi.check(rc, "ps_geom_norm")
+    return _egress(out.reshape(shape[:-1] + (1,)), saw)
 
 
 def unit(x: ArrayLike):
     """x / |x| (reference geometry.py:34-36)."""
-    (x,), saw, _ = _ingest([x])
-    return _egress(x / x.norm(dim=-1, keepdim=True), saw)
+    tensors, saw, dev = _ingest([x])
+    (fx,), shape = _rows(tensors)
+    out = torch.empty_like(fx)
+    if shape[-1] != 0:
+        with _cabi.on_device(dev):
+            rc = _cabi.load().ps_geom_unit(fx.data_ptr(), fx.shape[0], shape[-1], out.data_ptr(), _stream(dev))
+        _cabi.check(rc, "ps_geom_unit")
+    return _egress(out.reshape(shape), saw)
 
 
 def angle(a: ArrayLike, b: ArrayLike, c: ArrayLike, to_degree: bool = False):

@@ -110,15 +110,17 @@ def test_distance_kernel_variants_agree(native_lib):
 
 @pytest.mark.parametrize("B,L", [(8, 256), (6, 250), (5, 190), (3, 384)])
 def test_tile_schedules_write_the_same_bytes(native_lib, B, L):
-    """The cell schedule, the lock-step schedule (default for long structures) and its relaxed flavour only change
-    WHICH tile buffer writes a tile and when: every output byte must be identical, for the distance + mask kernel and
-    for the fused kernel, including the angle tensors."""
+    """The linear-sweep kernel (default at A = 15), and the column-strip kernel with its cell schedule, its lock-step
+    schedule and the relaxed flavour of that, only differ in WHICH tile buffer writes a tile, when, and how residue j
+    reaches the lane: every output byte must be identical, for the distance + mask kernel and for the fused kernel,
+    including the angle tensors."""
     A = 15
     xyz, mask, _ = H.synthetic_batch(600 + L, B, L, A, "bool")
     x, m = xyz.to(DEV), mask.to(DEV)
     s = torch.cuda.current_stream().cuda_stream
     outs = []
-    for variant in (0, 1 << 13, 1 << 11, 1 << 14):
+    strip = 1 << 15
+    for variant in (1 << 27, strip, strip | (1 << 13), strip | (1 << 11), strip | (1 << 14)):
         d = torch.full((B, L, L, A, A), -1.0, device=DEV)
         dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
         _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
@@ -357,6 +359,27 @@ def test_virtual_cb_option_vs_oracle(native_lib):
     H.assert_angles_close(phi, rp, angle_conditioning(x5, "phi"), "phi(virtual CB)", circular=False)
 
 
+@pytest.mark.parametrize("B,L,A,kind", [(2, 96, 15, "bool"), (3, 45, 15, "bool"), (2, 40, 15, "float"), (2, 20, 25, "bool"),
+                                        (2, 140, 5, "bool"), (1, 31, 15, "bool")])
+def test_compact_feature_planes_equal_the_strided_views(native_lib, B, L, A, kind):
+    """inter_residue_geometry_compact: the six dense (B, L, L) planes written by the fused launch (read back from the
+    finished tile) are bit-identical to the reference-style outputs — the angle tensors and the strided d_ca / d_cb /
+    d_no views of the full distance tensor — for the staged kernel, the fp32-mask path and the any-A fallback."""
+    xyz, mask, _ = H.synthetic_batch(900 + L, B, L, A, kind)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    ref = sb.inter_residue_geometry()
+    guard = torch.full((6 * B * L * L + 64,), -77.0, device=DEV)
+    buf = guard[32:32 + 6 * B * L * L].view(6, B, L, L)
+    got = sb.inter_residue_geometry_compact(out=buf)
+    assert got["compact"].data_ptr() == buf.data_ptr()
+    for name in ("omega", "theta", "phi", "d_ca", "d_cb", "d_no"):
+        assert got[name].is_contiguous() and tuple(got[name].shape) == (B, L, L)
+        assert torch.equal(torch.nan_to_num(got[name], nan=-5.0), torch.nan_to_num(ref[name], nan=-5.0)), name
+    assert torch.equal(torch.nan_to_num(got["dist"], nan=-5.0), torch.nan_to_num(ref["d_ca"]._base, nan=-5.0))
+    assert torch.equal(got["dist_mask"], ref["d_ca_mask"]._base)
+    assert bool((guard[:32] == -77.0).all()) and bool((guard[-32:] == -77.0).all())
+
+
 # ------------------------------------------------------------------------------ K3 backbone
 @pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
 def test_backbone_features_match_reference_golden(native_lib, name):
@@ -486,6 +509,37 @@ def test_standardize_statistics_vs_oracle_config4_slice(native_lib):
     assert torch.allclose(sb.get_xyz().cpu(), ref_xyz, rtol=1e-4, atol=1e-5, equal_nan=True)
     valid = sb.get_xyz()[mask.to(DEV)]
     assert not bool(torch.isnan(valid).any())  # reference tests/test_StructureBatch.py:218-226
+
+
+@pytest.mark.parametrize("B,L,A,kind", [(1024, 128, 15, "bool"), (7, 229, 15, "bool"), (3, 701, 15, "float"), (300, 33, 15, "bool"),
+                                        (2, 2101, 15, "bool"), (1, 3000, 15, "bool"), (5, 10, 7, "float"), (1, 1, 15, "bool")])
+def test_standardize_register_resident_kernel_vs_oracle_and_three_pass_kernel(native_lib, B, L, A, kind):
+    """K4: the register-resident single-read kernel (default; one CTA or a cluster of 2-8 CTAs per structure) against
+    the CPU oracle (reference protstruc.py:696-734 per structure) and against the three-pass kernel of round 1 —
+    same element arithmetic, so the statistics agree to the last bits of the fp64 partial sums."""
+    xyz, mask, _ = H.synthetic_batch(4000 + L, B, L, A, kind)
+    x = xyz.to(DEV)
+    m = mask.to(DEV).contiguous()
+    code = _cabi.PS_MASK_BOOL if kind == "bool" else _cabi.PS_MASK_F32
+    s = torch.cuda.current_stream().cuda_stream
+    res = []
+    for variant in (0, 1):
+        mu, sd = torch.full((B, 3), -1.0, device=DEV), torch.full((B, 3), -1.0, device=DEV)
+        out = torch.full_like(x, -99.0)
+        _cabi.check(native_lib.ps_masked_stats_ex(x.data_ptr(), m.data_ptr(), code, B, L, A, mu.data_ptr(), sd.data_ptr(),
+                                                  out.data_ptr(), variant, s), "ps_masked_stats_ex")
+        res.append((mu.cpu(), sd.cpu(), out.cpu()))
+    (mu0, sd0, x0), (mu1, sd1, x1) = res
+    assert torch.allclose(mu0, mu1, rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert torch.allclose(sd0, sd1, rtol=1e-6, atol=1e-7, equal_nan=True)
+    assert torch.equal(torch.isnan(x0), torch.isnan(x1))
+    assert torch.allclose(x0, x1, rtol=1e-5, atol=1e-5, equal_nan=True)
+    if B * L <= 8192:
+        rx, rmu, rsd = orc.standardize_per_structure(xyz, mask)
+        assert torch.allclose(mu0, rmu, rtol=1e-5, atol=1e-5, equal_nan=True)
+        assert torch.allclose(sd0, rsd, rtol=1e-5, atol=1e-6, equal_nan=True)
+        H.assert_same_nan(x0, rx, "standardized xyz")
+        assert torch.allclose(x0, rx, rtol=1e-4, atol=1e-5, equal_nan=True)
 
 
 @pytest.mark.parametrize("B,L,kind", [(2, 2101, "bool"), (3, 701, "float"), (1, 4097, "bool"), (5, 300, "bool")])
@@ -708,6 +762,19 @@ def test_geometry_functions_vs_oracle_random(native_lib):
     ang = ps.geometry.angle(*pts[:3])
     H.assert_angles_close(ang, orc.planar_angle(*pts[:3]), H.planar_conditioning(*[p.double() for p in pts[:3]]),
                           "geometry.angle", circular=False)
+    # dot / norm / unit are kernels too (row a9): points (D = 3) bit for bit, other widths to rounding
+    for D in (3, 7, 1):
+        u, v = 5.0 * torch.randn(4, 250, D, generator=g), 5.0 * torch.randn(4, 250, D, generator=g)
+        got_dot, got_norm, got_unit = ps.geometry.dot(u, v), ps.geometry.norm(u), ps.geometry.unit(u)
+        assert got_dot.shape == (4, 250, 1) and got_norm.shape == (4, 250, 1) and got_unit.shape == (4, 250, D)
+        if D == 3:
+            assert torch.equal(got_dot.cpu(), orc.dot(u, v)) and torch.equal(got_norm.cpu(), orc.norm(u))
+            assert torch.equal(got_unit.cpu(), u / orc.norm(u))
+        else:
+            assert torch.allclose(got_dot.cpu(), orc.dot(u, v), rtol=1e-5, atol=1e-4)
+            assert torch.allclose(got_norm.cpu(), orc.norm(u), rtol=1e-6) and torch.allclose(got_unit.cpu(), u / orc.norm(u), rtol=1e-6, atol=1e-7)
+    assert torch.isnan(ps.geometry.unit(torch.zeros(2, 3))).all()  # 0 / 0, like the reference
+    assert isinstance(ps.geometry.unit(np.ones((2, 3), dtype=np.float32)), np.ndarray)
     fr = ps.geometry.gram_schmidt(*pts[:3]).cpu()
     ref_fr = orc.frames_from_points(*pts[:3])
     sin = H.planar_conditioning(*[p.double() for p in pts[:3]])  # angle between (a-b) and (c-b)

@@ -248,6 +248,9 @@ def test_native_pdb_ingest_matches_the_python_restatement_on_the_reference_files
     files = sorted(glob.glob("/root/reference/tests/*.pdb")) + sorted(glob.glob("/root/reference/docs/tutorials/*.pdb"))
     assert len(files) >= 10
     pins = {"6dc4.pdb": 437, "1REX.pdb": 130, "4EOT.pdb": 184, "15c8_HL.pdb": 229, "1a6v_HL.pdb": 229}
+    import json
+    text_pins = json.loads((H.GOLDEN / "pdb_pins.json").read_text())
+    assert len(text_pins) == len(files)
     for f in files:
         a = pdb_ingest.read_pdb_arrays(f)
         x, m, c, ids = reader.read_structure(f)
@@ -256,6 +259,14 @@ def test_native_pdb_ingest_matches_the_python_restatement_on_the_reference_files
         name = os.path.basename(f)
         if name in pins:
             assert a["xyz"].shape[0] == pins[name], f
+        # text-level pins from a third, independent code path (tests/golden/make_pdb_pins.py): residues after gap
+        # filling, heavy atoms that survive the filters, the sum of their coordinates, chain order
+        pin = text_pins[f"{os.path.basename(os.path.dirname(f))}/{name}"]
+        assert a["xyz"].shape[0] == pin["residues_with_gap_fill"], f
+        assert int(a["atom_mask"].sum()) == pin["heavy_atoms"], f
+        assert int(a["atom_mask"].any(axis=1).sum()) == pin["residues_with_atoms"], f
+        assert abs(float(np.nansum(a["xyz"].astype(np.float64))) - pin["coordinate_sum"]) < 0.05, f
+        assert "".join(a["chain_ids"]) == pin["chains"], f
     batch = ps.StructureBatch.from_pdb(["/root/reference/tests/15c8_HL.pdb", "/root/reference/tests/1ad0_DC.pdb",
                                         "/root/reference/tests/5cjx_HL.pdb"], device="cpu")
     assert len(batch.get_xyz()) == 3  # reference tests/test_StructureBatch.py:56-65
