@@ -290,7 +290,8 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * not fit in shared memory); bits 16-23 = any-A tile kernel: pairs per tile in units of its alignment quantum
  * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA; bit 15 = A = 15: the column-strip kernel of
  * round 1 instead of the linear-sweep kernel (comparison hook; the environment variable PROTSTRUC_B200_K1 = strip | sweep
- * does the same for a whole process, bit 27 = sweep regardless of it).
+ * does the same for a whole process, bit 27 = sweep regardless of it); bits 28-30 = linear-sweep kernel: the issuing lane
+ * sleeps n x 100 ns after handing a tile to the TMA engine (pacing probe).
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,

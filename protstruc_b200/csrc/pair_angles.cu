@@ -183,16 +183,16 @@ __device__ __forceinline__ float atan2_single(float y, float x, bool in_range) {
     return copysignf(a, y);
 }
 
-// atan2 of two (y, x) pairs at once.
-__device__ __forceinline__ float2 atan2_pair(float2 y, float2 x) {
+// atan2 of two (y, x) pairs at once, WITHOUT the branch to the out-of-range path: ok0 / ok1 say whether a lane's
+// result is valid (false for zero, huge, infinite and NaN operands).  The caller patches such lanes with atan2_single
+// after all of its straight-line work, so that independent angle evaluations can be interleaved by the scheduler.
+__device__ __forceinline__ float2 atan2_pair_core(float2 y, float2 x, bool& ok0, bool& ok1) {
     const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
     const bool sw0 = ay0 > ax0, sw1 = ay1 > ax1;
     const float mx0 = max_nan(ax0, ay0), mn0 = min_nan(ax0, ay0);
     const float mx1 = max_nan(ax1, ay1), mn1 = min_nan(ax1, ay1);
-    const bool ok0 = (mx0 > 1e-30f) & (mx0 < 1e30f);  // false for zero, huge, infinite and NaN (of either operand)
-    const bool ok1 = (mx1 > 1e-30f) & (mx1 < 1e30f);
-    // a lane out of range (zeros, huge, infinite, NaN — e.g. a missing atom in one of the two pairs): each lane on its own
-    if (!(ok0 & ok1)) return make_float2(atan2_single(y.x, x.x, ok0), atan2_single(y.y, x.y, ok1));
+    ok0 = (mx0 > 1e-30f) & (mx0 < 1e30f);
+    ok1 = (mx1 > 1e-30f) & (mx1 < 1e30f);
     const float2 t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rcp_mufu(mx0), rcp_mufu(mx1)));
     const float2 s = __fmul2_rn(t, t);
     float2 p = f2(2.622234402e-03f);
@@ -250,16 +250,89 @@ __device__ __forceinline__ float2 acos_pair(float2 c) {
 // flags (1 = CA_i or CB_i missing: the whole row is NaN; 2 = N_i missing: theta of the row is NaN), padding.
 constexpr int kRowRecord = 16;
 
+// omega / theta / phi of one row record against the thread's pair of residues j (both pairs at once).
+struct JPair {
+    P3 ca, cb, b2;      // CA_j, CB_j, omega's b2 = CB_j - CA_j
+    bool nan0, nan1;    // CB_j missing (lane x / lane y)
+    int diag_k;         // row (relative to the CTA's first row) whose diagonal entry is lane x of this pair
+};
+
+template <bool ALL3>
+__device__ __forceinline__ void eval_row(const float4* __restrict__ rec4, int k, const JPair& jp, bool want_omega,
+                                         bool want_theta, bool want_phi, float2& w, float2& t, float2& f) {
+    const float4 q0 = rec4[4 * k + 0], q1 = rec4[4 * k + 1], q2 = rec4[4 * k + 2], q3 = rec4[4 * k + 3];
+    const int row_flags = __float_as_int(q3.x);
+    const float2 nan2 = f2(__int_as_float(0x7fc00000));
+    w = t = f = nan2;
+    if ((row_flags & 1) || (jp.nan0 && jp.nan1)) return;
+    const P3 b0{f2(q0.x), f2(q0.y), f2(q0.z)};
+    const P3 cbi{f2(q1.x), f2(q1.y), f2(q1.z)};
+    const P3 bc = sub_p3(jp.cb, cbi);  // CB_j - CB_i: theta's b2, phi's bc
+    // Straight-line part: the three angles are independent chains; nothing branches until all of them are done.
+    float2 yw = f2(0.f), xw = f2(0.f), yt = f2(0.f), xt = f2(0.f), c = f2(0.f);
+    bool okw0 = true, okw1 = true, okt0 = true, okt1 = true, okf0 = true, okf1 = true;
+    const bool do_theta = (ALL3 || want_theta) && !(row_flags & 2);
+    if (ALL3 || want_omega) {
+        const P3 b1 = sub_p3(jp.ca, cbi);
+        const P3 n1 = cross_p3(b0, b1);
+        const P3 n2 = cross_p3(jp.b2, b1);
+        xw = dot_p3(n1, n2);
+        const float2 sn = dot_p3(n1, jp.b2);
+        const float2 bb = dot_p3(b1, b1);
+        const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
+        yw = neg2(__fmul2_rn(sn, nb1));
+        w = atan2_pair_core(yw, xw, okw0, okw1);
+    }
+    if (do_theta) {
+        const P3 tn1{f2(q2.x), f2(q2.y), f2(q2.z)};
+        const P3 tb1{f2(-q0.x), f2(-q0.y), f2(-q0.z)};
+        const P3 n2 = cross_p3(bc, tb1);
+        xt = dot_p3(tn1, n2);
+        const float2 sn = dot_p3(tn1, bc);
+        yt = neg2(__fmul2_rn(sn, f2(q0.w)));
+        t = atan2_pair_core(yt, xt, okt0, okt1);
+    }
+    if (ALL3 || want_phi) {
+        const float2 d = dot_p3(b0, bc);
+        const float2 cc = dot_p3(bc, bc);
+        float2 r = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
+        r = __fmul2_rn(r, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), r), r, f2(1.5f)));  // Newton step
+        c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), r);
+        // (a lane whose CB_j is missing is NaN either way and must not drag its partner into the exact path)
+        okf0 = (fabsf(c.x) <= 0.999f) | jp.nan0;
+        okf1 = (fabsf(c.y) <= 0.999f) | jp.nan1;
+        f = acos_pair(c);
+    }
+    // Rare part: lanes out of range (zeros: the diagonal, zero-padded residues, coincident atoms; NaN: a missing atom in
+    // one of the two pairs; |cos| within 1e-3 of 1) are redone one by one.
+    if (!(okw0 & okw1 & okt0 & okt1 & okf0 & okf1)) {
+        if (!okw0) w.x = atan2_single(yw.x, xw.x, false);
+        if (!okw1) w.y = atan2_single(yw.y, xw.y, false);
+        if (!okt0) t.x = atan2_single(yt.x, xt.x, false);
+        if (!okt1) t.y = atan2_single(yt.y, xt.y, false);
+        const V3 ba{q0.x, q0.y, q0.z};
+        if (!okf0) f.x = trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
+        if (!okf1) f.y = trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
+    }
+    if (ALL3 || want_omega) {
+        const int dk = k - jp.diag_k;  // 0: lane x is the diagonal entry, 1: lane y
+        if (dk == 0) w.x = q2.w;
+        if (dk == 1) w.y = q2.w;
+    }
+}
+
 // Loop order: a thread OWNS pairs of residues j (one pair when L <= 2 * blockDim.x) and walks the CTA's rows with them
 // in registers, so per (row, pair of j) the only memory traffic is the broadcast read of the row record and the three
 // 64-bit stores; nothing that depends on j alone (its coordinates, its NaN flags, the position of the diagonal) is
 // redone per row.  (The first packed version walked j inside a row: with one j-pair per thread and row it re-read the
 // row record, the coordinates and the flags for every pair and spent a quarter of its issue slots on addressing.)
-template <bool VIRTUAL_CB, bool ALL3>
-__global__ void __launch_bounds__(256, 3) trrosetta_fast_kernel(const float* __restrict__ xyz, float* __restrict__ omega,
-                                                             float* __restrict__ theta, float* __restrict__ phi, int L,
-                                                             int A, int rows_per_cta, int blocks_per_structure,
-                                                             int vector_stores) {
+// ROWS rows are evaluated per iteration: a row is one long dependent chain (differences -> cross products -> dot
+// products -> MUFU -> polynomial), and with ~20 resident warps per SM the second, independent chain is what fills
+// the issue slots the first one leaves (ncu of the one-row loop: issue-active 64 %, top stall `wait`).
+template <bool VIRTUAL_CB, bool ALL3, int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 1 ? 3 : 2) trrosetta_fast_kernel(
+    const float* __restrict__ xyz, float* __restrict__ omega, float* __restrict__ theta, float* __restrict__ phi, int L,
+    int A, int rows_per_cta, int blocks_per_structure, int vector_stores) {
     extern __shared__ __align__(16) float fast_smem[];
     const int Lp = (L + 1) & ~1;  // residues j padded to whole pairs
     float* const srow = fast_smem;  // rows_per_cta records of kRowRecord floats (16-byte aligned)
@@ -326,81 +399,53 @@ __global__ void __launch_bounds__(256, 3) trrosetta_fast_kernel(const float* __r
     const float2* __restrict__ pcb_z = reinterpret_cast<const float2*>(scb_z);
     const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(srow);
     const int npairs = Lp >> 1;
-    const float2 nan2 = f2(__int_as_float(0x7fc00000));
     const long long first_out = (b * L + row0) * L;  // element (b, row0, 0) of the outputs
 
-    for (int jp = threadIdx.x; jp < npairs; jp += blockDim.x) {
-        const P3 caj{pca_x[jp], pca_y[jp], pca_z[jp]};
-        const P3 cbj{pcb_x[jp], pcb_y[jp], pcb_z[jp]};
-        const P3 b2 = sub_p3(cbj, caj);  // omega's b2 = CB_j - CA_j depends on j alone
+    auto store = [&](long long o, int j, float2 w, float2 t, float2 f) {
+        if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
+            if (want_omega) *reinterpret_cast<float2*>(omega + o) = w;
+            if (want_theta) *reinterpret_cast<float2*>(theta + o) = t;
+            if (want_phi) *reinterpret_cast<float2*>(phi + o) = f;
+        } else {
+            if (want_omega) omega[o] = w.x;
+            if (want_theta) theta[o] = t.x;
+            if (want_phi) phi[o] = f.x;
+            if (j + 1 < L) {
+                if (want_omega) omega[o + 1] = w.y;
+                if (want_theta) theta[o + 1] = t.y;
+                if (want_phi) phi[o + 1] = f.y;
+            }
+        }
+    };
+
+    for (int jpi = threadIdx.x; jpi < npairs; jpi += blockDim.x) {
+        JPair jp;
+        jp.ca = P3{pca_x[jpi], pca_y[jpi], pca_z[jpi]};
+        jp.cb = P3{pcb_x[jpi], pcb_y[jpi], pcb_z[jpi]};
+        jp.b2 = sub_p3(jp.cb, jp.ca);
         // Missing atoms are NaN coordinates (protstruc/pdb.py:133-135) and make the angle NaN whatever the other atoms
-        // are: such pairs (and rows, below) are answered without arithmetic — with half of the atoms missing that is
-        // 15 of 16 pairs — instead of dragging NaN through the IEEE fall-backs of atan2 / acos.
-        const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jp];
-        const bool nan0 = fl & 0x0001, nan1 = fl & 0x0100;
-        const bool pair_nan = nan0 && nan1;
-        const int j = 2 * jp;
-        const int diag_k = (j >> 1 << 1) - row0;  // row (relative to row0) whose diagonal lies in this pair: j or j + 1
+        // are: such pairs (and rows) are answered without arithmetic — with half of the atoms missing that is 15 of
+        // 16 pairs — instead of dragging NaN through the IEEE fall-backs of atan2 / acos.
+        const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jpi];
+        jp.nan0 = fl & 0x0001;
+        jp.nan1 = fl & 0x0100;
+        const int j = 2 * jpi;
+        jp.diag_k = j - row0;
         long long o = first_out + j;
-        for (int k = 0; k < nrows; ++k, o += L) {
-            const float4 q0 = rows4[4 * k + 0], q1 = rows4[4 * k + 1], q2 = rows4[4 * k + 2], q3 = rows4[4 * k + 3];
-            const int row_flags = __float_as_int(q3.x);
-            float2 w = nan2, t = nan2, f = nan2;
-            if (!((row_flags & 1) || pair_nan)) {
-                const P3 b0{f2(q0.x), f2(q0.y), f2(q0.z)};
-                const P3 cbi{f2(q1.x), f2(q1.y), f2(q1.z)};
-                const P3 bc = sub_p3(cbj, cbi);  // CB_j - CB_i: theta's b2, phi's bc
-                if (want_omega) {
-                    const P3 b1 = sub_p3(caj, cbi);
-                    const P3 n1 = cross_p3(b0, b1);
-                    const P3 n2 = cross_p3(b2, b1);
-                    const float2 x = dot_p3(n1, n2);
-                    const float2 sn = dot_p3(n1, b2);
-                    const float2 bb = dot_p3(b1, b1);
-                    const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
-                    w = atan2_pair(neg2(__fmul2_rn(sn, nb1)), x);
-                    const int dk = k - diag_k;  // 0: lane x is the diagonal entry, 1: lane y
-                    if (dk == 0) w.x = q2.w;
-                    if (dk == 1) w.y = q2.w;
-                }
-                if (want_theta && !(row_flags & 2)) {
-                    const P3 tn1{f2(q2.x), f2(q2.y), f2(q2.z)};
-                    const P3 tb1{f2(-q0.x), f2(-q0.y), f2(-q0.z)};
-                    const P3 n2 = cross_p3(bc, tb1);
-                    const float2 x = dot_p3(tn1, n2);
-                    const float2 sn = dot_p3(tn1, bc);
-                    t = atan2_pair(neg2(__fmul2_rn(sn, f2(q0.w))), x);
-                }
-                if (want_phi) {
-                    const float2 d = dot_p3(b0, bc);
-                    const float2 cc = dot_p3(bc, bc);
-                    float2 r = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
-                    r = __fmul2_rn(r, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), r), r, f2(1.5f)));  // Newton step
-                    const float2 c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), r);
-                    // (a lane whose CB_j is missing is NaN either way and must not drag its partner into the exact path)
-                    const bool ok0 = (fabsf(c.x) <= 0.999f) | nan0, ok1 = (fabsf(c.y) <= 0.999f) | nan1;
-                    f = acos_pair(c);
-                    if (!(ok0 & ok1)) {
-                        const V3 ba{q0.x, q0.y, q0.z};
-                        if (!ok0) f.x = trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
-                        if (!ok1) f.y = trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
-                    }
-                }
+        int k = 0;
+        if (ROWS == 2) {
+            for (; k + 1 < nrows; k += 2, o += 2ll * L) {
+                float2 w0, t0, f0, w1, t1, f1;
+                eval_row<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, w0, t0, f0);
+                eval_row<ALL3>(rows4, k + 1, jp, want_omega, want_theta, want_phi, w1, t1, f1);
+                store(o, j, w0, t0, f0);
+                store(o + L, j, w1, t1, f1);
             }
-            if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
-                if (want_omega) *reinterpret_cast<float2*>(omega + o) = w;
-                if (want_theta) *reinterpret_cast<float2*>(theta + o) = t;
-                if (want_phi) *reinterpret_cast<float2*>(phi + o) = f;
-            } else {
-                if (want_omega) omega[o] = w.x;
-                if (want_theta) theta[o] = t.x;
-                if (want_phi) phi[o] = f.x;
-                if (j + 1 < L) {
-                    if (want_omega) omega[o + 1] = w.y;
-                    if (want_theta) theta[o + 1] = t.y;
-                    if (want_phi) phi[o + 1] = f.y;
-                }
-            }
+        }
+        for (; k < nrows; ++k, o += L) {
+            float2 w, t, f;
+            eval_row<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, w, t, f);
+            store(o, j, w, t, f);
         }
     }
 }
@@ -481,7 +526,8 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
 }
 
 // variant: 0 = default (the packed kernel whenever the structure fits in shared memory), 1 = the exact-sequence
-// kernel of round 1 (tuning / comparison hook, ps_trrosetta_angles_ex).
+// kernel of round 1, 2 = the packed kernel with one row per iteration (tuning / comparison hooks,
+// ps_trrosetta_angles_ex).
 int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
                                   float* theta, float* phi, int variant, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE,
@@ -504,24 +550,30 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
                         static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
-    if (variant == 0 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
+    const int rows_mode = variant == 2 ? 1 : 2;
+    if (variant != 1 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
         int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread (several beyond 512 residues)
         if (threads > 256) threads = 256;
         auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
         const int vector_stores = (L % 2 == 0) && aligned8(omega) && aligned8(theta) && aligned8(phi);
         const bool all3 = omega && theta && phi;
-#define PS_FAST(VCB, ALL)                                                                                             \
+#define PS_FAST(VCB, ALL, ROWS)                                                                                       \
     do {                                                                                                              \
-        cudaError_t err = cudaFuncSetAttribute(trrosetta_fast_kernel<VCB, ALL>,                                       \
+        cudaError_t err = cudaFuncSetAttribute(trrosetta_fast_kernel<VCB, ALL, ROWS>,                                 \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);              \
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");                 \
-        trrosetta_fast_kernel<VCB, ALL><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                      \
+        trrosetta_fast_kernel<VCB, ALL, ROWS><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                \
             xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);                         \
     } while (0)
+        const bool two_rows = rows_mode != 1;  // default: two rows per iteration
         if (use_virtual_cb) {
-            if (all3) PS_FAST(true, true); else PS_FAST(true, false);
+            if (all3 && two_rows) PS_FAST(true, true, 2);
+            else if (all3) PS_FAST(true, true, 1);
+            else PS_FAST(true, false, 1);
         } else {
-            if (all3) PS_FAST(false, true); else PS_FAST(false, false);
+            if (all3 && two_rows) PS_FAST(false, true, 2);
+            else if (all3) PS_FAST(false, true, 1);
+            else PS_FAST(false, false, 1);
         }
 #undef PS_FAST
         return check_launch("trrosetta_fast_kernel");

@@ -558,7 +558,10 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
     const int AA = A * A;
     float* tile_f32 = reinterpret_cast<float*>(cols_smem);
     uint8_t* tile_u8 = cols_smem + (kF32 ? round_up16(P * AA * 4) : 0);
-    float4* xi = reinterpret_cast<float4*>(tile_u8 + (kU8 ? round_up16(P * AA) : 0));
+    // residue-i staging, structure of arrays: per staged row four runs of Ae floats (x, y, z, mask), Ae = A rounded up
+    // to even, so that the column loop takes TWO atoms of residue i per LDS.64 and evaluates them as one f32x2 value
+    const int Ae = (A + 1) & ~1;
+    float* xi = reinterpret_cast<float*>(tile_u8 + (kU8 ? round_up16(P * AA) : 0));
     const int tid = threadIdx.x;
     const bool few_rows = P <= L;  // a tile then touches at most two residue-i rows
     const bool any_bulk = p.bulk_f32 || p.bulk_u8;
@@ -591,17 +594,24 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
         const float* __restrict__ mbf = static_cast<const float*>(p.atom_mask) + structure_atom0;
         // the engine must have read the previous tile before anyone overwrites it
         if (any_bulk && tid == 0) bulk_wait_read_all();
-        for (int k = tid; k < nrows * A; k += blockDim.x) {
-            const int atom = i0 * A + k;  // relative to structure b0 (rows may run into structure b0 + 1)
+        for (int k = tid; k < nrows * Ae; k += blockDim.x) {
+            const int rr = k / Ae, a = k - rr * Ae;
+            const int atom = (i0 + rr) * A + a;  // relative to structure b0 (rows may run into structure b0 + 1)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kXyz) {
-                v.x = __ldg(xb + atom * 3);
-                v.y = __ldg(xb + atom * 3 + 1);
-                v.z = __ldg(xb + atom * 3 + 2);
+            if (a < A) {
+                if (kXyz) {
+                    v.x = __ldg(xb + atom * 3);
+                    v.y = __ldg(xb + atom * 3 + 1);
+                    v.z = __ldg(xb + atom * 3 + 2);
+                }
+                if (KIND == kF32MaskOnly) v.w = __ldg(mbf + atom);
+                else if (kMaskIn) v.w = __ldg(mb8 + atom) != 0 ? 1.f : 0.f;
             }
-            if (KIND == kF32MaskOnly) v.w = __ldg(mbf + atom);
-            else if (kMaskIn) v.w = __ldg(mb8 + atom) != 0 ? 1.f : 0.f;
-            xi[k] = v;
+            float* row = xi + rr * 4 * Ae + a;
+            row[0] = v.x;
+            row[Ae] = v.y;
+            row[2 * Ae] = v.z;
+            row[3 * Ae] = v.w;
         }
         __syncthreads();
 
@@ -628,21 +638,42 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
             }
             if (KIND == kF32MaskOnly) mj = __ldg(mbf + atom_j);
             else if (kMaskIn) mj = __ldg(mb8 + atom_j) != 0 ? 1.f : 0.f;
-            const float4* __restrict__ ri = xi + r * A;
+            const float2* __restrict__ rx = reinterpret_cast<const float2*>(xi + r * 4 * Ae);
+            const float2* __restrict__ ry = rx + (Ae >> 1);
+            const float2* __restrict__ rz = ry + (Ae >> 1);
+            const float2* __restrict__ rw = rz + (Ae >> 1);
             const int off = pl * AA + c;
             float* of = tile_f32 + off;
             uint8_t* ob = tile_u8 + off;
-#pragma unroll 4
-            for (int a = 0; a < A; ++a) {
-                const float4 v = ri[a];
+            const float2 xj2 = make_float2(xj, xj), yj2 = make_float2(yj, yj), zj2 = make_float2(zj, zj);
+            const float2 mj2 = make_float2(mj, mj);
+            const bool mj_set = mj != 0.f;
+            // two atoms a, a + 1 of residue i per step; the odd atom of an odd A is the padded (zero) half, not stored
+#pragma unroll 2
+            for (int h = 0; h < (Ae >> 1); ++h) {
+                const int a = 2 * h;
+                const bool second = a + 1 < A;
                 if (kXyz) {
-                    const float dx = xj - v.x;
-                    const float dy = yj - v.y;
-                    const float dz = zj - v.z;
-                    of[a * A] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                    const float2 vx = rx[h], vy = ry[h], vz = rz[h];
+                    const float2 dx = __fadd2_rn(xj2, make_float2(-vx.x, -vx.y));
+                    const float2 dy = __fadd2_rn(yj2, make_float2(-vy.x, -vy.y));
+                    const float2 dz = __fadd2_rn(zj2, make_float2(-vz.x, -vz.y));
+                    const float2 ss = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                    of[a * A] = sqrt_mode<SQRT>(ss.x);
+                    if (second) of[(a + 1) * A] = sqrt_mode<SQRT>(ss.y);
                 }
-                if (KIND == kF32MaskOnly) of[a * A] = __fmul_rn(v.w, mj);
-                if (kU8) ob[a * A] = (mj != 0.f && v.w != 0.f) ? 1 : 0;
+                if (KIND == kF32MaskOnly || kU8) {
+                    const float2 vw = rw[h];
+                    if (KIND == kF32MaskOnly) {
+                        const float2 prod = __fmul2_rn(vw, mj2);
+                        of[a * A] = prod.x;
+                        if (second) of[(a + 1) * A] = prod.y;
+                    }
+                    if (kU8) {
+                        ob[a * A] = (mj_set && vw.x != 0.f) ? 1 : 0;
+                        if (second) ob[(a + 1) * A] = (mj_set && vw.y != 0.f) ? 1 : 0;
+                    }
+                }
             }
         }
 
@@ -823,7 +854,7 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
     auto smem_for = [&](long long pairs) -> long long {
         const long long max_rows = (pairs + L - 2) / L + 2;  // residue-i rows a tile can touch
         return (f32 ? round_up16(static_cast<int>(pairs * AA * 4)) : 0) + (u8 ? round_up16(static_cast<int>(pairs * AA)) : 0) +
-               max_rows * A * static_cast<long long>(sizeof(float4));
+               max_rows * ((A + 1) & ~1) * static_cast<long long>(sizeof(float4));  // residue-i staging (x, y, z, mask runs)
     };
     if (step * bytes_per_pair > kSmemCap || smem_for(step) > kSmemCap) return PS_OK;  // row kernel
     // Candidates: multiples of `step` up to the budget, 128 or 256 threads.  Score = issue efficiency at the
@@ -1018,7 +1049,7 @@ bool pair_sweep_supported(const float* xyz, const void* atom_mask, int mask_dtyp
                           int L, int A);
 int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask, float* omega,
                     float* theta, float* phi, float* d_ca, float* d_cb, float* d_no, int B, int L, int sqrt_id,
-                    int slots_override, int stores_only, cudaStream_t stream);
+                    int slots_override, int stores_only, int pace_ns, cudaStream_t stream);
 
 // Diagnostic: plain 128-bit stores of a non-uniform pattern, linear sweep (what a copy kernel's write side
 // does).  Gives the store ceiling of the memory system for comparison with the TMA bulk-store path.
@@ -1112,7 +1143,7 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     const bool want_strip = ((variant >> 15) & 1) || (env_choice == 1 && !((variant >> 27) & 1));
     if (!force_generic && !want_strip && pair_sweep_supported(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A))
         return pair_sweep_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, d_ca, d_cb, d_no, B, L,
-                               sqrt_id, warps_override, (variant >> 10) & 1, stream);
+                               sqrt_id, warps_override, (variant >> 10) & 1, ((variant >> 28) & 7) * 100, stream);
 
     // the staged kernel needs L >= pairs per tile (a tile then touches at most two residue-i rows)
     const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14) || (A == 4);

@@ -61,6 +61,7 @@ struct SweepParams {
     long long num_pairs;
     long long num_tiles;
     int stores_only;
+    int pace_ns;  // tuning hook: the issuing lane sleeps this long after handing a tile to the engine
 };
 
 template <int KIND>
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
                 if (kBool) bulk_store_s2g(static_cast<uint8_t*>(p.mask_out) + elem0, tile_mask, G::kMaskBytes);
                 if (kF32) bulk_store_s2g(static_cast<float*>(p.mask_out) + elem0, tile_mask, G::kDistBytes);
                 bulk_commit();
+                if (p.pace_ns) __nanosleep(p.pace_ns);
             }
         } else {
             // tail tile (num_pairs % 32 != 0): byte count is not 16-B granular, copy by hand
@@ -600,8 +602,9 @@ bool pair_sweep_supported(const float* xyz, const void* atom_mask, int mask_dtyp
 
 int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask, float* omega,
                     float* theta, float* phi, float* d_ca, float* d_cb, float* d_no, int B, int L, int sqrt_id,
-                    int slots_override, int stores_only, cudaStream_t stream) {
+                    int slots_override, int stores_only, int pace_ns, cudaStream_t stream) {
     SweepParams p;
+    p.pace_ns = pace_ns;
     p.xyz = xyz;
     p.atom_mask = atom_mask;
     p.dist = dist;

@@ -84,7 +84,8 @@ def main():
         xyz, _ = inputs(B, L, A, nan_masked, ragged)
         om = torch.empty(B, L, L, device=DEV)
         th, ph = torch.empty_like(om), torch.empty_like(om)
-        for variant, label in ((0, "packed FP32 (default)"), (1, "exact sequence (round 1)")):
+        for variant, label in ((0, "packed FP32 (default)"), (2, "packed FP32, one row per iteration"),
+                               (1, "exact sequence (round 1)")):
             def run(variant=variant):
                 _cabi.check(lib.ps_trrosetta_angles_ex(xyz.data_ptr(), B, L, A, 0, om.data_ptr(), th.data_ptr(),
                                                        ph.data_ptr(), variant, s), "k2f")
@@ -98,6 +99,25 @@ def main():
             best, med = time_call(run_virtual)
             add(f"K2f omega+theta+phi {tag} [packed, virtual CB]", best, med, B * (L * L * 12 + L * 5 * 12))
         del om, th, ph
+
+    # ---- any-A tile kernel (run-time atom count): the reference's own tests use A = 25, atom37 users A = 37
+    for (B, L, A) in ((24, 256, 25), (12, 256, 37), (40, 256, 20), (16, 512, 15)):
+        xyz, mask = inputs(B, L, A)
+        dist = torch.empty(B, L, L, A, A, device=DEV)
+        dmask = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        force = (1 << 8) if A == 15 else 0
+
+        def run_cols():
+            _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(), B, L, A,
+                                                 force, s), "cols")
+        best, med = time_call(run_cols, flush=False)
+        add(f"K1 any-A tile kernel dist+boolmask B{B} L{L} A{A}", best, med, B * L * L * A * A * 5)
+
+        def run_cols_dist():
+            _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), None, 0, dist.data_ptr(), None, B, L, A, force, s), "cols d")
+        best, med = time_call(run_cols_dist, flush=False)
+        add(f"K1 any-A tile kernel dist only B{B} L{L} A{A}", best, med, B * L * L * A * A * 4)
+        del dist, dmask
 
     # ---- K4 standardize: register-resident single-read kernel vs the three-pass kernel
     for (B, L, A, tag) in ((1024, 128, 15, "config4 B1024 L128"), (256, 512, 15, "B256 L512"), (16, 512, 15, "B16 L512"),
