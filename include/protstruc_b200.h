@@ -90,7 +90,8 @@ int ps_pair_angles(const float* xyz, int B, int L, int A,
  */
 int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
                         float* omega, float* theta, float* phi, void* stream);
-/* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel), 1 = the exact-operation-sequence kernel. */
+/* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel), 1 = the exact-operation-sequence kernel,
+ * 3 = packed-FP32 kernel with two rows per loop iteration. */
 int ps_trrosetta_angles_ex(const float* xyz, int B, int L, int A, int virtual_cb,
                            float* omega, float* theta, float* phi, int variant, void* stream);
 
@@ -142,7 +143,8 @@ int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chai
  */
 int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype,
                     int B, int L, int A, float* mu, float* sd, float* xyz_out, void* stream);
-/* Comparison hook: variant 0 = default (register-resident single-read kernel), 1 = the three-pass kernel of round 1. */
+/* Comparison hook: variant 0 = default (register-resident single-read kernels), 1 = the three-pass kernel of round 1,
+ * 2 = the scalar-mapped register-resident kernel also where the quad kernel applies. */
 int ps_masked_stats_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                        int B, int L, int A, float* mu, float* sd, float* xyz_out, int variant, void* stream);
 
@@ -291,7 +293,8 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * (0 = choose); bit 24 / 25 = any-A tile kernel: 128 / 256 threads per CTA; bit 15 = A = 15: the column-strip kernel of
  * round 1 instead of the linear-sweep kernel (comparison hook; the environment variable PROTSTRUC_B200_K1 = strip | sweep
  * does the same for a whole process, bit 27 = sweep regardless of it); bits 28-30 = linear-sweep kernel: the issuing lane
- * sleeps n x 100 ns after handing a tile to the TMA engine (pacing probe).
+ * sleeps n x 100 ns after handing a tile to the TMA engine (pacing probe); bit 26 = linear-sweep kernel without its per-kind
+ * pacing defaults (non-ftz square root for distances + byte mask, 400 ns for distances + fp32 mask).
  */
 int ps_pair_dist_mask_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                          float* dist, void* dist_mask,

@@ -526,7 +526,7 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
 }
 
 // variant: 0 = default (the packed kernel whenever the structure fits in shared memory), 1 = the exact-sequence
-// kernel of round 1, 2 = the packed kernel with one row per iteration (tuning / comparison hooks,
+// kernel of round 1, 3 = the packed kernel with two rows per iteration (tuning / comparison hooks,
 // ps_trrosetta_angles_ex).
 int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
                                   float* theta, float* phi, int variant, cudaStream_t stream) {
@@ -542,15 +542,16 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
     // Packed kernel: the structure's CA / CB (6 floats per residue) plus the row records must fit in shared memory.
     const int Lp = (L + 1) & ~1;
     // rows per CTA: as many as possible (the staging of the structure is amortised over them) while the grid still
-    // holds >= 2 CTAs per SM; at least 4, at most 64
+    // holds >= 8 CTAs per SM (several waves: the CTAs of a launch differ a lot in cost when atoms are missing); at least 4,
+    // at most 64
     int rows_per_cta = 64;
-    while (rows_per_cta > 4 && rows / rows_per_cta < 2ll * sms) rows_per_cta /= 2;
+    while (rows_per_cta > 4 && rows / rows_per_cta < 8ll * sms) rows_per_cta /= 2;
     if (rows_per_cta > L) rows_per_cta = L;
     const size_t smem = (static_cast<size_t>(6) * Lp + static_cast<size_t>(rows_per_cta) * kRowRecord) * sizeof(float) +
                         static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
-    const int rows_mode = variant == 2 ? 1 : 2;
+    const int rows_mode = variant == 3 ? 2 : 1;
     if (variant != 1 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
         int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread (several beyond 512 residues)
         if (threads > 256) threads = 256;
@@ -565,7 +566,7 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
         trrosetta_fast_kernel<VCB, ALL, ROWS><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                \
             xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);                         \
     } while (0)
-        const bool two_rows = rows_mode != 1;  // default: two rows per iteration
+        const bool two_rows = rows_mode == 2;  // default: one row per iteration (24 warps / SM beat two rows at 16)
         if (use_virtual_cb) {
             if (all3 && two_rows) PS_FAST(true, true, 2);
             else if (all3) PS_FAST(true, true, 1);

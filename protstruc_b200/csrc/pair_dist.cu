@@ -648,32 +648,47 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
             const float2 xj2 = make_float2(xj, xj), yj2 = make_float2(yj, yj), zj2 = make_float2(zj, zj);
             const float2 mj2 = make_float2(mj, mj);
             const bool mj_set = mj != 0.f;
-            // two atoms a, a + 1 of residue i per step; the odd atom of an odd A is the padded (zero) half, not stored
+            // two atoms a, a + 1 of residue i per step, running output pointers (no index arithmetic in the loop); the
+            // last atom of an odd A is done on its own (its pair partner is the zero padding of the staging area)
+            const int row_step = 2 * A;
+            float* of1 = of + A;
+            uint8_t* ob1 = ob + A;
+            const int full = A >> 1;
 #pragma unroll 2
-            for (int h = 0; h < (Ae >> 1); ++h) {
-                const int a = 2 * h;
-                const bool second = a + 1 < A;
+            for (int h = 0; h < full; ++h) {
                 if (kXyz) {
                     const float2 vx = rx[h], vy = ry[h], vz = rz[h];
                     const float2 dx = __fadd2_rn(xj2, make_float2(-vx.x, -vx.y));
                     const float2 dy = __fadd2_rn(yj2, make_float2(-vy.x, -vy.y));
                     const float2 dz = __fadd2_rn(zj2, make_float2(-vz.x, -vz.y));
                     const float2 ss = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                    of[a * A] = sqrt_mode<SQRT>(ss.x);
-                    if (second) of[(a + 1) * A] = sqrt_mode<SQRT>(ss.y);
+                    *of = sqrt_mode<SQRT>(ss.x);
+                    *of1 = sqrt_mode<SQRT>(ss.y);
                 }
                 if (KIND == kF32MaskOnly || kU8) {
                     const float2 vw = rw[h];
                     if (KIND == kF32MaskOnly) {
                         const float2 prod = __fmul2_rn(vw, mj2);
-                        of[a * A] = prod.x;
-                        if (second) of[(a + 1) * A] = prod.y;
+                        *of = prod.x;
+                        *of1 = prod.y;
                     }
                     if (kU8) {
-                        ob[a * A] = (mj_set && vw.x != 0.f) ? 1 : 0;
-                        if (second) ob[(a + 1) * A] = (mj_set && vw.y != 0.f) ? 1 : 0;
+                        *ob = (mj_set && vw.x != 0.f) ? 1 : 0;
+                        *ob1 = (mj_set && vw.y != 0.f) ? 1 : 0;
                     }
                 }
+                of += row_step;
+                of1 += row_step;
+                ob += row_step;
+                ob1 += row_step;
+            }
+            if (A & 1) {
+                if (kXyz) {
+                    const float dx = xj - rx[full].x, dy = yj - ry[full].x, dz = zj - rz[full].x;
+                    *of = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                }
+                if (KIND == kF32MaskOnly) *of = __fmul_rn(rw[full].x, mj);
+                if (kU8) *ob = (mj_set && rw[full].x != 0.f) ? 1 : 0;
             }
         }
 
@@ -1142,8 +1157,22 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     }();
     const bool want_strip = ((variant >> 15) & 1) || (env_choice == 1 && !((variant >> 27) & 1));
     if (!force_generic && !want_strip && pair_sweep_supported(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A))
+    {
+        // Pacing defaults of the linear-sweep kernel (profiles/r2_pace_probe.json; the same for every length): HOW
+        // FAST a tile buffer comes back with its next tile moves the achieved HBM bandwidth by 5-10 %.  The distance +
+        // byte-mask kernel gains 5 % with the non-ftz MUFU square root (three more issue slots per element, spread
+        // over the tile: 6.46 -> 6.83 TB/s); the distance + fp32-mask kernel, whose two 28.8 KB stores per tile come
+        // back to back, gains 9 % when the issuing lane waits 400 ns after handing them to the engine (6.25 -> 6.8);
+        // distances only and the fused kernel are at their best undisturbed.  Bit 26 switches these defaults off.
+        int sweep_sqrt = sqrt_id, pace_ns = ((variant >> 28) & 7) * 100;
+        if (!((variant >> 26) & 1)) {
+            const bool angles = omega || theta || phi;
+            if (dist_mask && mask_dtype == PS_MASK_BOOL && !angles && sqrt_id == 0) sweep_sqrt = 1;
+            if (dist_mask && mask_dtype == PS_MASK_F32 && pace_ns == 0) pace_ns = 400;
+        }
         return pair_sweep_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, d_ca, d_cb, d_no, B, L,
-                               sqrt_id, warps_override, (variant >> 10) & 1, ((variant >> 28) & 7) * 100, stream);
+                               sweep_sqrt, warps_override, (variant >> 10) & 1, pace_ns, stream);
+    }
 
     // the staged kernel needs L >= pairs per tile (a tile then touches at most two residue-i rows)
     const bool staged_atom_count = (A == 15) || (A == 5) || (A == 10) || (A == 14) || (A == 4);

@@ -356,6 +356,183 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_regs_kernel(
     if (CLUSTER) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Quad variant of the register-resident kernel: the default whenever a structure holds a multiple of 4 atoms and the
+// arrays are 16-byte aligned (A = 15 with L a multiple of 4, A = 4 / 8 / 12 / 16 / 20 ... with any L).
+//
+// ncu of the scalar-mapped kernel above at BASELINE config 4: 314 thread-instructions per atom, IPC 2.1, i.e. bound by
+// the NUMBER of instructions: 32-bit loads / stores with their 64-bit addressing, one byte load + conversion per
+// element for the mask, an IEEE division (12 instructions) per element, nan_to_num twice per element.  Here a thread
+// owns Q groups of FOUR CONSECUTIVE ATOMS: 12 floats = three 128-bit loads with a fixed axis pattern
+// (x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3), the four mask bytes = one 32-bit load, results leave as three 128-bit
+// stores; finiteness is tested once per element (a finite coordinate times a 0 / 1 mask needs no nan_to_num); the
+// division by the deviation is a reciprocal + one correction step (the fast path of the IEEE division without its
+// range checks; non-finite quotients are redone with the IEEE division); mean / deviation are computed by three lanes
+// per warp and shuffled.  Arithmetic per element is otherwise unchanged (reference op order).
+__device__ __forceinline__ float quad_get(const float4 (&v)[3], int s) {
+    const float4 q = v[s >> 2];
+    return (s & 3) == 0 ? q.x : ((s & 3) == 1 ? q.y : ((s & 3) == 2 ? q.z : q.w));
+}
+__device__ __forceinline__ void quad_set(float4 (&v)[3], int s, float val) {
+    float4& q = v[s >> 2];
+    if ((s & 3) == 0) q.x = val;
+    else if ((s & 3) == 1) q.y = val;
+    else if ((s & 3) == 2) q.z = val;
+    else q.w = val;
+}
+
+// Sums three doubles and one float over the block; totals valid in every thread.  scratch: [warps + 1][4].
+__device__ __forceinline__ void block_sum3(double (&v)[3], float& c, double (*scratch)[4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();  // scratch reuse across calls
+    if (lane == 0) {
+        scratch[warp][0] = v[0];
+        scratch[warp][1] = v[1];
+        scratch[warp][2] = v[2];
+        scratch[warp][3] = static_cast<double>(c);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += scratch[w][threadIdx.x];
+        scratch[kStatsMaxThreads / 32][threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = scratch[kStatsMaxThreads / 32][k];
+    c = static_cast<float>(scratch[kStatsMaxThreads / 32][3]);
+}
+
+template <int MASK_DTYPE, int Q, bool CLUSTER>
+__global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
+    const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
+    float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
+    namespace cg = cooperative_groups;
+    __shared__ double scratch[kStatsMaxThreads / 32 + 1][4];
+    __shared__ double exchange[CLUSTER ? 2 : 1][4];
+    const int ranks = CLUSTER ? static_cast<int>(cg::this_cluster().num_blocks()) : 1;
+    const int rank = CLUSTER ? static_cast<int>(cg::this_cluster().block_rank()) : 0;
+    const long long b = blockIdx.x / ranks;
+    const int quads = atoms_per_struct >> 2;
+    const int share = (quads + ranks - 1) / ranks;  // quads per CTA
+    const int q_begin = rank * share;
+    const int nq = (q_begin + share < quads ? q_begin + share : quads) - q_begin;  // may be <= 0 for the last ranks
+    const long long first_atom = b * atoms_per_struct + 4ll * q_begin;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(xyz + first_atom * 3);
+    const int T = blockDim.x;
+
+    float4 v[Q][3];
+    float m[Q][4];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const int q = threadIdx.x + k * T;
+        const bool ok = q < nq;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[k][i] = ok ? __ldg(x4 + 3 * q + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MASK_DTYPE == PS_MASK_BOOL) {
+            const uint32_t w = ok ? __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(atom_mask) + first_atom) + q) : 0u;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[k][a] = ((w >> (8 * a)) & 0xFFu) != 0u ? 1.f : 0.f;
+        } else {
+            const float4 w = ok ? __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(atom_mask) + first_atom) + q)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            m[k][0] = w.x; m[k][1] = w.y; m[k][2] = w.z; m[k][3] = w.w;
+        }
+    }
+    constexpr float kMax = 3.4028234663852886e38f;
+    // pass 1: sum(nan_to_num(x * m)) per axis, sum(m); per-thread partials in fp32 (<= 4 Q values per axis)
+    float s[3] = {0.f, 0.f, 0.f}, c = 0.f;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            float t = __fmul_rn(quad_get(v[k], e), m[k][e / 3]);
+            if (!(fabsf(t) <= kMax)) t = nan_to_num0(t);
+            s[e % 3] += t;
+        }
+        c += (m[k][0] + m[k][1]) + (m[k][2] + m[k][3]);
+    }
+    double acc[3] = {static_cast<double>(s[0]), static_cast<double>(s[1]), static_cast<double>(s[2])};
+    block_sum3(acc, c, scratch);
+    if (CLUSTER) {
+        double a4[4] = {acc[0], acc[1], acc[2], static_cast<double>(c)};
+        cluster_sum4(a4, exchange, 0);
+        acc[0] = a4[0]; acc[1] = a4[1]; acc[2] = a4[2];
+        c = static_cast<float>(a4[3]);
+    }
+    // mean: lanes 0 .. 2 of every warp take one IEEE division each, the warp shares the results
+    const int lane = threadIdx.x & 31;
+    const float count = c;
+    const float my_num = static_cast<float>(lane % 3 == 0 ? acc[0] : (lane % 3 == 1 ? acc[1] : acc[2]));
+    const float my_mu = __fdiv_rn(my_num, count);
+    float mu[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) mu[k] = __shfl_sync(0xffffffffu, my_mu, k);
+
+    // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
+    float d2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+            float x = quad_get(v[k], e);
+            if (!(fabsf(x) <= kMax)) x = nan_to_num0(x);
+            const float d = __fsub_rn(x, mu[e % 3]);
+            d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
+        }
+    }
+    double dev[3] = {static_cast<double>(d2[0]), static_cast<double>(d2[1]), static_cast<double>(d2[2])};
+    float unused = 0.f;
+    block_sum3(dev, unused, scratch);
+    if (CLUSTER) {
+        double a4[4] = {dev[0], dev[1], dev[2], 0.0};
+        cluster_sum4(a4, exchange, 1);
+        dev[0] = a4[0]; dev[1] = a4[1]; dev[2] = a4[2];
+    }
+    const float my_dev = static_cast<float>(lane % 3 == 0 ? dev[0] : (lane % 3 == 1 ? dev[1] : dev[2]));
+    const float my_sd = __fsqrt_rn(__fdiv_rn(my_dev, count));
+    const float my_rcp = __frcp_rn(my_sd);
+    float sd[3], rcp[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        sd[k] = __shfl_sync(0xffffffffu, my_sd, k);
+        rcp[k] = __shfl_sync(0xffffffffu, my_rcp, k);
+    }
+    if (rank == 0 && threadIdx.x < 3) {
+        mu_out[b * 3 + threadIdx.x] = my_mu;
+        sd_out[b * 3 + threadIdx.x] = my_sd;
+    }
+
+    // pass 3: (x - mu) / sd on every element (masked or not, NaN stays NaN), straight from registers
+    if (xyz_out) {
+        float4* __restrict__ o4 = reinterpret_cast<float4*>(xyz_out + first_atom * 3);
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const int q = threadIdx.x + k * T;
+            if (q >= nq) continue;
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const float d = __fsub_rn(quad_get(v[k], e), mu[e % 3]);
+                // d / sd: reciprocal, one correction of the quotient (what the IEEE division does for operands in
+                // range); a non-finite outcome — sd = 0, infinite or NaN operands — is settled by the IEEE division
+                float qt = __fmul_rn(d, rcp[e % 3]);
+                qt = __fmaf_rn(__fmaf_rn(-qt, sd[e % 3], d), rcp[e % 3], qt);
+                if (!(fabsf(qt) <= kMax)) qt = __fdiv_rn(d, sd[e % 3]);
+                quad_set(v[k], e, qt);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) o4[3 * q + i] = v[k][i];
+        }
+    }
+    if (CLUSTER) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
+}
+
 // The per-structure elementwise maps run on a 2-D grid: blockIdx.y walks the structures, blockIdx.x / threadIdx.x
 // the structure's L*A*3 floats with fully coalesced scalar accesses.  The axis of an element is its 32-bit offset
 // inside the structure mod 3 (a multiply-shift); no per-element 64-bit division.
@@ -485,7 +662,8 @@ dim3 per_structure_grid(int per_b, int B) {
 
 }  // namespace
 
-// legacy != 0 forces the three-pass kernel of round 1 (comparison hook, ps_masked_stats_ex).
+// legacy: 0 = default (quad kernel where the shape allows, else the scalar-mapped register kernel), 1 = the three-pass
+// kernel of round 1, 2 = the scalar-mapped register kernel (comparison hooks, ps_masked_stats_ex).
 int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
                               float* mu, float* sd, float* xyz_out, int legacy, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "masked_stats: B=%d L=%d A=%d must be > 0",
@@ -501,6 +679,58 @@ int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_
     PS_REQUIRE(static_cast<long long>(B) * 8 < (1ll << 31), PS_ERR_BAD_SHAPE, "masked_stats: B=%d too large", B);
     const bool is_bool = mask_dtype == PS_MASK_BOOL;
 
+    // ---- quad kernel: structures of a multiple of 4 atoms, 16-byte aligned arrays (the usual case)
+    auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    if (legacy == 0 && atoms % 4 == 0 && aligned16(xyz) && aligned16(xyz_out) && aligned16(atom_mask)) {
+        constexpr int kMaxQ = 4, kMaxTq = 512;
+        const int quads = atoms / 4;
+        int ranks_q = 1;
+        while (ranks_q < 8 && quads / (ranks_q * 2) >= 32 &&
+               (static_cast<long long>(B) * ranks_q < 2ll * sms || (quads + ranks_q - 1) / ranks_q > kMaxQ * kMaxTq))
+            ranks_q *= 2;
+        const int share_q = (quads + ranks_q - 1) / ranks_q;
+        if (share_q <= kMaxQ * kMaxTq) {
+            // two quads (24 floats) per thread once a CTA's share allows >= 128 threads that way: fewer warps in the
+            // block reductions for the same data in flight
+            int q_per_thread = share_q >= 256 ? 2 : 1;
+            while ((share_q + q_per_thread - 1) / q_per_thread > kMaxTq) q_per_thread *= 2;
+            int threads = ((share_q + q_per_thread - 1) / q_per_thread + 31) / 32 * 32;
+            if (threads < 32) threads = 32;
+            cudaLaunchConfig_t config = {};
+            config.gridDim = dim3(static_cast<unsigned>(B) * ranks_q, 1, 1);
+            config.blockDim = dim3(threads, 1, 1);
+            config.dynamicSmemBytes = 0;
+            config.stream = stream;
+            cudaLaunchAttribute attribute[1];
+            attribute[0].id = cudaLaunchAttributeClusterDimension;
+            attribute[0].val.clusterDim.x = ranks_q;
+            attribute[0].val.clusterDim.y = 1;
+            attribute[0].val.clusterDim.z = 1;
+            config.attrs = attribute;
+            config.numAttrs = ranks_q > 1 ? 1 : 0;
+            cudaError_t err = cudaSuccess;
+#define PS_STATS_QUAD(Q)                                                                                              \
+    do {                                                                                                              \
+        if (ranks_q > 1)                                                                                              \
+            err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, Q, true>, xyz,        \
+                                               atom_mask, atoms, mu, sd, xyz_out)                                    \
+                          : cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_F32, Q, true>, xyz,         \
+                                               atom_mask, atoms, mu, sd, xyz_out);                                   \
+        else                                                                                                          \
+            err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, Q, false>, xyz,       \
+                                               atom_mask, atoms, mu, sd, xyz_out)                                    \
+                          : cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_F32, Q, false>, xyz,        \
+                                               atom_mask, atoms, mu, sd, xyz_out);                                   \
+    } while (0)
+            if (q_per_thread == 1) PS_STATS_QUAD(1);
+            else if (q_per_thread == 2) PS_STATS_QUAD(2);
+            else PS_STATS_QUAD(4);
+#undef PS_STATS_QUAD
+            if (err != cudaSuccess) return cuda_fail(err, "cudaLaunchKernelEx(masked_stats_quad_kernel)");
+            return check_launch("masked_stats_quad_kernel");
+        }
+    }
+
     // ---- register-resident kernel: one cluster of `ranks` CTAs per structure, each thread holds E floats.
     // ranks: split a structure over a thread-block cluster until the grid holds >= 2 CTAs per SM (few structures)
     // or a CTA's share fits in registers (large structures); a CTA keeps >= 128 atoms.
@@ -510,7 +740,7 @@ int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_
            (static_cast<long long>(B) * ranks < 2ll * sms || (atoms + ranks - 1) / ranks * 3 > kMaxE * kMaxT))
         ranks *= 2;
     const int share_floats = (atoms + ranks - 1) / ranks * 3;
-    if (share_floats <= kMaxE * kMaxT && !legacy) {
+    if (share_floats <= kMaxE * kMaxT && legacy != 1) {
         // threads: a multiple of 96 (whole warps, every thread on one axis), ~8 floats per thread for small shares
         int threads = (share_floats / 8 + 95) / 96 * 96;
         if (threads < 96) threads = 96;

@@ -512,28 +512,32 @@ def test_standardize_statistics_vs_oracle_config4_slice(native_lib):
 
 
 @pytest.mark.parametrize("B,L,A,kind", [(1024, 128, 15, "bool"), (7, 229, 15, "bool"), (3, 701, 15, "float"), (300, 33, 15, "bool"),
-                                        (2, 2101, 15, "bool"), (1, 3000, 15, "bool"), (5, 10, 7, "float"), (1, 1, 15, "bool")])
+                                        (2, 2101, 15, "bool"), (1, 3000, 15, "bool"), (5, 10, 7, "float"), (1, 1, 15, "bool"),
+                                        (16, 512, 15, "bool"), (64, 128, 16, "float"), (2, 4096, 15, "bool"), (9, 4, 15, "bool"),
+                                        (3, 8, 4, "float")])
 def test_standardize_register_resident_kernel_vs_oracle_and_three_pass_kernel(native_lib, B, L, A, kind):
-    """K4: the register-resident single-read kernel (default; one CTA or a cluster of 2-8 CTAs per structure) against
-    the CPU oracle (reference protstruc.py:696-734 per structure) and against the three-pass kernel of round 1 —
-    same element arithmetic, so the statistics agree to the last bits of the fp64 partial sums."""
+    """K4: the register-resident single-read kernels (default: the quad kernel — 128-bit loads, four atoms per group —
+    where a structure holds a multiple of 4 atoms, else the scalar-mapped one; one CTA or a cluster of 2-8 CTAs per
+    structure) against the CPU oracle (reference protstruc.py:696-734 per structure) and against the three-pass
+    kernel of round 1 — same element arithmetic, so the statistics agree to the last bits of the partial sums."""
     xyz, mask, _ = H.synthetic_batch(4000 + L, B, L, A, kind)
     x = xyz.to(DEV)
     m = mask.to(DEV).contiguous()
     code = _cabi.PS_MASK_BOOL if kind == "bool" else _cabi.PS_MASK_F32
     s = torch.cuda.current_stream().cuda_stream
     res = []
-    for variant in (0, 1):
+    for variant in (0, 2, 1):  # default, scalar-mapped register kernel, three-pass kernel
         mu, sd = torch.full((B, 3), -1.0, device=DEV), torch.full((B, 3), -1.0, device=DEV)
         out = torch.full_like(x, -99.0)
         _cabi.check(native_lib.ps_masked_stats_ex(x.data_ptr(), m.data_ptr(), code, B, L, A, mu.data_ptr(), sd.data_ptr(),
                                                   out.data_ptr(), variant, s), "ps_masked_stats_ex")
         res.append((mu.cpu(), sd.cpu(), out.cpu()))
-    (mu0, sd0, x0), (mu1, sd1, x1) = res
-    assert torch.allclose(mu0, mu1, rtol=1e-6, atol=1e-6, equal_nan=True)
-    assert torch.allclose(sd0, sd1, rtol=1e-6, atol=1e-7, equal_nan=True)
-    assert torch.equal(torch.isnan(x0), torch.isnan(x1))
-    assert torch.allclose(x0, x1, rtol=1e-5, atol=1e-5, equal_nan=True)
+    (mu0, sd0, x0), (mu2, sd2, x2), (mu1, sd1, x1) = res
+    for mu_v, sd_v, x_v in ((mu2, sd2, x2), (mu1, sd1, x1)):
+        assert torch.allclose(mu0, mu_v, rtol=1e-6, atol=1e-6, equal_nan=True)
+        assert torch.allclose(sd0, sd_v, rtol=1e-6, atol=1e-7, equal_nan=True)
+        assert torch.equal(torch.isnan(x0), torch.isnan(x_v))
+        assert torch.allclose(x0, x_v, rtol=1e-5, atol=1e-5, equal_nan=True)
     if B * L <= 8192:
         rx, rmu, rsd = orc.standardize_per_structure(xyz, mask)
         assert torch.allclose(mu0, rmu, rtol=1e-5, atol=1e-5, equal_nan=True)

@@ -84,7 +84,7 @@ def main():
         xyz, _ = inputs(B, L, A, nan_masked, ragged)
         om = torch.empty(B, L, L, device=DEV)
         th, ph = torch.empty_like(om), torch.empty_like(om)
-        for variant, label in ((0, "packed FP32 (default)"), (2, "packed FP32, one row per iteration"),
+        for variant, label in ((0, "packed FP32 (default)"), (3, "packed FP32, two rows per iteration"),
                                (1, "exact sequence (round 1)")):
             def run(variant=variant):
                 _cabi.check(lib.ps_trrosetta_angles_ex(xyz.data_ptr(), B, L, A, 0, om.data_ptr(), th.data_ptr(),
@@ -125,7 +125,8 @@ def main():
         xyz, mask = inputs(B, L, A)
         mu, sd = torch.empty(B, 3, device=DEV), torch.empty(B, 3, device=DEV)
         xo = torch.empty_like(xyz)
-        for variant, label in ((0, "register-resident (default)"), (1, "three-pass (round 1)")):
+        for variant, label in ((0, "register-resident (default)"), (2, "register-resident, scalar mapping"),
+                               (1, "three-pass (round 1)")):
             def run(variant=variant):
                 _cabi.check(lib.ps_masked_stats_ex(xyz.data_ptr(), mask.data_ptr(), 0, B, L, A, mu.data_ptr(), sd.data_ptr(),
                                                    xo.data_ptr(), variant, s), "k4")
