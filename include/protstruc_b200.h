@@ -259,6 +259,16 @@ int ps_diffuse_steps(const float* x, const float* betas, int T,
                      uint64_t seed, uint64_t step0, uint64_t elem_offset,
                      float* out, int B, int64_t per_b, void* stream);
 
+/*
+ * K5t — the same T steps with EVERY intermediate state kept: trajectory (T, B, per_b) f32, slice t = the state after
+ * step t (what the reference's tutorial loop collects, docs/tutorials/diffusing_xyz_coordinates.ipynb).  T launches of
+ * the one-step kernel issued back to back by the library (no per-step host round trip); bit-identical to T calls of
+ * ps_diffuse.
+ */
+int ps_diffuse_trajectory(const float* x, const float* betas, int T,
+                          uint64_t seed, uint64_t step0, uint64_t elem_offset,
+                          float* trajectory, int B, int64_t per_b, void* stream);
+
 /* Fills `out` with the N(0,1) stream ps_diffuse would use (for distribution tests). */
 int ps_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t step,
                      uint64_t elem_offset, void* stream);

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ps_diffuse": (c_int, [_fp, _fp, _fp, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_diffuse_steps": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64,
                                  c_void_p]),
+    "ps_diffuse_trajectory": (c_int, [_fp, _fp, c_int, c_uint64, c_uint64, c_uint64, _fp, c_int, c_int64, c_void_p]),
     "ps_philox_normal": (c_int, [_fp, c_int64, c_uint64, c_uint64, c_uint64, c_void_p]),
     "ps_geom_dot": (c_int, [_fp, _fp, c_int64, c_int, _fp, c_void_p]),
     "ps_geom_norm": (c_int, [_fp, c_int64, c_int, _fp, c_void_p]),

@@ -34,6 +34,8 @@ int translate_impl(const float*, const float*, int, int, int, int, float*, cudaS
 int center_of_mass_impl(const float*, int, int, int, int, float*, cudaStream_t);
 int diffuse_impl(const float*, const float*, int, const float*, uint64_t, uint64_t, uint64_t, float*,
                  int, long long, cudaStream_t);
+int diffuse_trajectory_impl(const float*, const float*, int, uint64_t, uint64_t, uint64_t, float*, int, long long,
+                            cudaStream_t);
 int philox_normal_impl(float*, long long, uint64_t, uint64_t, uint64_t, cudaStream_t);
 int kabsch_impl(const float*, const float*, const uint8_t*, int, int, int, float*, float*, cudaStream_t);
 int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, float*, uint8_t*,
@@ -295,6 +297,11 @@ int ps_diffuse_steps(const float* x, const float* betas, int T, uint64_t seed, u
                      uint64_t elem_offset, float* out, int B, int64_t per_b, void* stream) {
     return ps::diffuse_impl(x, betas, T, nullptr, seed, step0, elem_offset, out, B, per_b,
                             PS_STREAM(stream));
+}
+
+int ps_diffuse_trajectory(const float* x, const float* betas, int T, uint64_t seed, uint64_t step0,
+                          uint64_t elem_offset, float* trajectory, int B, int64_t per_b, void* stream) {
+    return ps::diffuse_trajectory_impl(x, betas, T, seed, step0, elem_offset, trajectory, B, per_b, PS_STREAM(stream));
 }
 
 int ps_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t step, uint64_t elem_offset,

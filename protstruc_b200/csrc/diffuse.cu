@@ -357,6 +357,32 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
     return check_launch("diffuse_philox_kernel");
 }
 
+// T steps as T back-to-back launches of the one-step kernel, each writing its result into its own slice of a
+// (T, B, per_b) trajectory buffer (what the reference's tutorial loop collects for its animation:
+// `for t in range(T): sb.diffuse_xyz(beta[t]); frames.append(sb.get_xyz())`).  The loop runs HERE, on the host side of
+// the C-ABI: ~2 us per launch instead of the ~15 us a Python-level call costs, so the 300-step schedule of BASELINE
+// config 4 is bound by the GPU time of the steps again.  Same noise stream as ps_diffuse / ps_diffuse_steps.
+int diffuse_trajectory_impl(const float* x, const float* betas, int T, uint64_t seed, uint64_t step0,
+                            uint64_t elem_offset, float* trajectory, int B, long long per_b, cudaStream_t stream) {
+    PS_REQUIRE(B > 0 && per_b > 0 && T > 0, PS_ERR_BAD_SHAPE,
+               "diffuse_trajectory: B=%d per_b=%lld T=%d must be > 0", B, per_b, T);
+    PS_REQUIRE(x && betas && trajectory, PS_ERR_NULL_POINTER, "diffuse_trajectory: NULL pointer");
+    const long long total = per_b * B;
+    const int shift = static_cast<int>(elem_offset & 3u);
+    const long long groups = (total + shift + 3) / 4;
+    PS_REQUIRE((groups + 255) / 256 < (1ll << 31), PS_ERR_BAD_SHAPE, "diffuse_trajectory: %lld elements", total);
+    const unsigned grid = static_cast<unsigned>((groups + 255) / 256);
+    const float* src = x;
+    for (int t = 0; t < T; ++t) {
+        float* dst = trajectory + static_cast<long long>(t) * total;
+        diffuse_philox_step_kernel<<<grid, 256, 0, stream>>>(src, betas + static_cast<long long>(t) * B, seed,
+                                                             step0 + static_cast<uint64_t>(t), elem_offset / 4, shift,
+                                                             per_b, total, dst);
+        src = dst;
+    }
+    return check_launch("diffuse_philox_step_kernel");
+}
+
 int philox_normal_impl(float* out, long long n, uint64_t seed, uint64_t step, uint64_t elem_offset,
                        cudaStream_t stream) {
     PS_REQUIRE(n >= 0, PS_ERR_BAD_SHAPE, "philox_normal: n=%lld", n);

@@ -781,3 +781,37 @@ class StructureBatch:
                                       self._noise_elem_offset, out.data_ptr(), B, L * A * 3, self._stream())
         _cabi.check(rc, "ps_diffuse_steps")
         self.xyz = out
+
+    def diffusion_loop(self, betas: torch.Tensor, return_trajectory: bool = False,
+                       generator: Optional[torch.Generator] = None) -> Optional[torch.Tensor]:
+        """The reference's diffusion loop — `for t in range(T): sb.diffuse_xyz(betas[t])` (README.md:131-146,
+        docs/tutorials/diffusing_xyz_coordinates.ipynb) — without a Python round trip per step (extension).
+        `betas` is (T, B) or (T,) (one schedule for all structures).  Rebinds `self.xyz` to the final state.
+
+        `return_trajectory=False`: one fused kernel, the state stays in registers for all T steps.
+        `return_trajectory=True`: returns the (T, B, L, A, 3) tensor of every intermediate state (slice t = after step
+        t, what the tutorial collects for its animation); the T one-step launches are issued back to back by the
+        native library.  Either way the result is bit-identical to the T single calls on the same noise stream."""
+        dev = self.xyz.device
+        B, L, A = self._dims()
+        betas = betas.to(device=dev, dtype=torch.float32)
+        if betas.ndim == 1:
+            betas = betas[:, None].expand(betas.shape[0], B)
+        betas = betas.contiguous()
+        if betas.ndim != 2 or betas.shape[1] != B:
+            raise ValueError(f"`betas` must have shape (T,) or (T, {B}), got {tuple(betas.shape)}")
+        T = betas.shape[0]
+        if not return_trajectory:
+            self.diffuse_xyz_steps(betas, generator=generator)
+            return None
+        trajectory = torch.empty((T, B, L, A, 3), dtype=torch.float32, device=dev)
+        if T == 0 or self._is_empty():
+            return trajectory
+        lib = self._lib()
+        seed, step0 = _philox.reserve(T, generator)
+        with _cabi.on_device(dev):
+            rc = lib.ps_diffuse_trajectory(self.xyz.data_ptr(), betas.data_ptr(), T, seed, step0, self._noise_elem_offset,
+                                           trajectory.data_ptr(), B, L * A * 3, self._stream())
+        _cabi.check(rc, "ps_diffuse_trajectory")
+        self.xyz = trajectory[T - 1]
+        return trajectory

@@ -646,6 +646,31 @@ def test_diffusion_distribution_fused_steps_and_shard_invariance(native_lib):
     assert abs(z.mean().item()) < 0.02 and abs(z.std().item() - 1.0) < 0.02
 
 
+def test_diffusion_loop_equals_the_reference_style_python_loop(native_lib):
+    """`diffusion_loop` (fused, and with the trajectory kept) against T separate `diffuse_xyz` calls on the same noise
+    stream: bit-identical states at every step (reference loop: README.md:131-146)."""
+    B, L, A, T = 4, 61, 15, 25
+    xyz, mask, _ = H.synthetic_batch(61, B, L, A, "bool", nan_masked=False, full_length=True)
+    betas = orc.cosine_variance_schedule(300)[40:40 + T]
+    ps.manual_seed(31)
+    ref = ps.StructureBatch.from_xyz(xyz, mask)
+    states = []
+    for t in range(T):
+        ref.diffuse_xyz(betas[t].repeat(B))
+        states.append(ref.get_xyz().clone())
+    ps.manual_seed(31)
+    a = ps.StructureBatch.from_xyz(xyz, mask)
+    assert a.diffusion_loop(betas) is None
+    assert torch.equal(a.get_xyz(), states[-1])
+    ps.manual_seed(31)
+    b = ps.StructureBatch.from_xyz(xyz, mask)
+    traj = b.diffusion_loop(betas[:, None].repeat(1, B), return_trajectory=True)
+    assert tuple(traj.shape) == (T, B, L, A, 3) and torch.equal(traj, torch.stack(states))
+    assert b.get_xyz().data_ptr() == traj[T - 1].data_ptr()
+    with pytest.raises(ValueError):
+        b.diffusion_loop(torch.zeros(3, B + 1))
+
+
 def test_philox_stream_is_addressed_per_element_for_any_shard_offset(native_lib):
     """north_star / SURVEY 8(e): results independent of the number of GPUs.  L = 229 (the real 1a6v_HL length) gives
     10,305 floats per structure, so shard offsets are not multiples of 4; the stream is addressed per element
