@@ -437,14 +437,27 @@ def main():
         barrier()
         gather_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
         barrier()
+        # overlapped: the gather of step k-1's planes runs on a SIDE stream (NCCL orders a collective after the stream it
+        # is called on, so calling it on the compute stream would serialise it behind step k's kernel) while step k's
+        # kernel fills the other ring slot; a slot is only rewritten after its gather has finished
+        side = torch.cuda.Stream(dev)
+        produced = [torch.cuda.Event() for _ in range(2)]
+        gathered_ev = [torch.cuda.Event() for _ in range(2)]
         e0.record(stream)
-        pending = None
-        for k in range(reps):
-            compact_launch(ring[k % 2])        # this step's kernel ...
-            if pending is not None:
-                pending.wait()                 # ... overlaps the gather of the previous step's planes
-            pending = do_gather(ring[k % 2], async_op=True)
-        pending.wait()
+        for k in range(reps + 1):
+            slot = k % 2
+            if k < reps:
+                if k >= 2:
+                    stream.wait_event(gathered_ev[slot])   # the gather that last read this slot is done
+                compact_launch(ring[slot])
+                produced[slot].record(stream)
+            if k >= 1:
+                prev = (k - 1) % 2
+                with torch.cuda.stream(side):
+                    side.wait_event(produced[prev])
+                    do_gather(ring[prev])
+                    gathered_ev[prev].record(side)
+        stream.wait_stream(side)
         e1.record(stream)
         barrier()
         overlapped_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
