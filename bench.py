@@ -245,8 +245,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="m")
     ap.add_argument("--batch", type=int, default=64, help="structures per GPU per step (workload m)")
     ap.add_argument("--c5-chunk", type=int, default=128, help="structures per launch (workload c5)")
-    ap.add_argument("--e2e-batch", type=int, default=8, help="structures per GPU per end-to-end call")
-    ap.add_argument("--e2e-structures", type=int, default=200, help="structures per GPU timed end to end (>= 1 s)")
+    ap.add_argument("--e2e-batch", type=int, default=4, help="structures per GPU per end-to-end call")
+    ap.add_argument("--e2e-structures", type=int, default=200, help="structures per GPU timed end to end (>= 1 s at N = 1)")
+    ap.add_argument("--e2e-seconds", type=float, default=2.5, help="N > 1: every rank keeps making calls at least this long")
     ap.add_argument("--cpu-sample", type=int, default=96, help="structures timed for the CPU baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-gather", action="store_true", help="also time the optional NVLink gather of compact features")
@@ -350,7 +351,6 @@ def main():
     # ---------------------------------------------------------------- end-to-end arm (`e2e`)
     # pinned host inputs -> GPU -> EVERY result byte back in pinned host memory, through the C-ABI host entry
     Be = min(args.e2e_batch, max(n_local, 1))
-    e2e_calls = max(1, (args.e2e_structures + Be - 1) // Be)
     all_cpus = os.sched_getaffinity(0)
     host_cpus = bind_host_thread_near_gpu(dev.index)  # host buffers next to this GPU's PCIe link (multi-rank runs)
     pipe = HostFeaturePipeline(chunk=2, L=L, A=N_ATOM, device=dev)
@@ -359,9 +359,18 @@ def main():
     out_h = HostFeaturePipeline.allocate_host_outputs(Be, L, N_ATOM, pinned=True)
     pipe.run(xyz_h, mask_h, out_h)  # warm-up (page-locks, first touch)
     barrier()
+    # N = 1: `--e2e-structures` structures (>= 1 s).  N > 1: every rank makes whole calls for `--e2e-seconds`:
+    # on a multi-GPU box the ranks' PCIe paths differ (this pool: 7.7 vs 18.5 GB/s per GPU when all eight stream), so a
+    # fixed, equal number of calls per rank would time the slowest link while the others idle; value = all structures
+    # of all ranks / the longest rank time, i.e. the aggregate throughput of the box.
     t0 = time.perf_counter()
-    for _ in range(e2e_calls):
+    e2e_calls = 0
+    while True:
         pipe.run(xyz_h, mask_h, out_h)
+        e2e_calls += 1
+        if (world == 1 and e2e_calls * Be >= args.e2e_structures) or \
+                (world > 1 and time.perf_counter() - t0 >= args.e2e_seconds):
+            break
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_total = sum_over_ranks(float(Be * e2e_calls))
@@ -391,6 +400,8 @@ def main():
     d2h_per_structure = pipe.d2h_bytes(1)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(Be), "d2h_bytes_per_step": pipe.d2h_bytes(Be),
            "steps": e2e_calls, "batch": Be, "seconds": e2e_s, "structures": e2e_total,
+           "mode": "rank 0 made `steps` calls of `batch` structures; N > 1: every rank makes whole calls for >= e2e-seconds, "
+                   "value = structures of all ranks / longest rank time",
            "d2h_gbs": e2e_value * d2h_per_structure / 1e9,
            "ceiling_gbs": ceiling_gbs, "frac_of_ceiling": e2e_value * d2h_per_structure / 1e9 / ceiling_gbs,
            "ceiling": "aggregate device->host rate of plain cudaMemcpyAsync into pinned memory, all ranks at once, no kernel "
@@ -461,10 +472,36 @@ def main():
         e1.record(stream)
         barrier()
         overlapped_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        # the same pipeline with SMs left free for NCCL: the fused kernel is persistent (one CTA per SM holding most of its
+        # registers and shared memory), so the collective's CTAs can only run beside it on SMs it does not occupy
+        overlapped_reserved = {}
+        for reserve in (8, 16, 32):
+            lib.ps_reserve_sms(reserve)
+            barrier()
+            e0.record(stream)
+            for k in range(reps + 1):
+                slot = k % 2
+                if k < reps:
+                    if k >= 2:
+                        stream.wait_event(gathered_ev[slot])
+                    compact_launch(ring[slot])
+                    produced[slot].record(stream)
+                if k >= 1:
+                    prev = (k - 1) % 2
+                    with torch.cuda.stream(side):
+                        side.wait_event(produced[prev])
+                        do_gather(ring[prev])
+                        gathered_ev[prev].record(side)
+            stream.wait_stream(side)
+            e1.record(stream)
+            barrier()
+            overlapped_reserved[str(reserve)] = max_over_ranks(e0.elapsed_time(e1) / reps)
+        lib.ps_reserve_sms(0)
         sent = 6 * Bg * L * L * 4
         gather = {"structures_per_rank": Bg, "bytes_sent_per_rank": sent, "bytes_received_per_rank": sent * (world - 1),
                   "fused_kernel_with_compact_planes_ms": kernel_ms, "gather_alone_ms": gather_ms,
                   "kernel_plus_gather_overlapped_ms_per_step": overlapped_ms,
+                  "overlapped_ms_per_step_by_sms_left_to_nccl": overlapped_reserved,
                   "busbw_gbs": sent * (world - 1) / (gather_ms / 1e3) / 1e9 if world > 1 else None,
                   "nvlink_peak_gbs": {"nominal_per_direction": 900.0, "measured_peer_copy": 770.0},
                   "frac_of_nominal": sent * (world - 1) / (gather_ms / 1e3) / 1e9 / 900.0 if world > 1 else None,

@@ -47,6 +47,13 @@ int ps_abi_version(void);                 /* bumps on any signature change      
 const char* ps_build_info(void);          /* "sm_100a nvcc <ver> ..."                  */
 const char* ps_last_error_string(void);   /* message of the last failing call (thread) */
 int ps_device_sm_count(int device);       /* >0, or negative ps_status                 */
+/*
+ * Leaves `n` SMs of the device to other work: every launcher sizes its grid for (SM count - n) SMs from now on
+ * (process-wide; 0 restores the default).  The fused tile kernels are persistent, one CTA per SM with most of its
+ * shared memory and registers, so a collective on another stream (the optional NCCL gather of compact features) can
+ * only run BESIDE them on SMs they leave free.  Returns the previous setting, or a negative ps_status.
+ */
+int ps_reserve_sms(int n);
 
 /*
  * K1 — all-atom pairwise distance matrix with the pair mask fused in.

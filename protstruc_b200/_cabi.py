@@ -37,6 +37,7 @@ SIGNATURES = {
     "ps_build_info": (c_char_p, []),
     "ps_last_error_string": (c_char_p, []),
     "ps_device_sm_count": (c_int, [c_int]),
+    "ps_reserve_sms": (c_int, [c_int]),
     "ps_pair_dist_mask": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_void_p]),
     "ps_pair_dist_mask_ex": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "ps_pair_angles": (c_int, [_fp, c_int, c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), c_int,

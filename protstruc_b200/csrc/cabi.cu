@@ -77,6 +77,10 @@ int check_launch(const char* kernel_name) {
     return PS_OK;
 }
 
+namespace {
+int g_reserved_sms = 0;  // ps_reserve_sms: SMs the persistent kernels leave to concurrently running work
+}
+
 int sm_count_for_current_device() {
     static thread_local int cached_dev = -1;
     static thread_local int cached_sms = 0;
@@ -90,7 +94,8 @@ int sm_count_for_current_device() {
         cached_dev = dev;
         cached_sms = sms;
     }
-    return cached_sms;
+    const int usable = cached_sms - g_reserved_sms;
+    return usable > 0 ? usable : 1;
 }
 
 }  // namespace ps
@@ -109,6 +114,16 @@ const char* ps_build_info(void) {
 }
 
 const char* ps_last_error_string(void) { return ps::g_last_error; }
+
+int ps_reserve_sms(int n) {
+    if (n < 0) {
+        ps::set_error("ps_reserve_sms: n=%d must be >= 0", n);
+        return PS_ERR_BAD_SHAPE;
+    }
+    const int before = ps::g_reserved_sms;
+    ps::g_reserved_sms = n;
+    return before;
+}
 
 int ps_device_sm_count(int device) {
     int sms = 0;
