@@ -497,11 +497,41 @@ def main():
             barrier()
             overlapped_reserved[str(reserve)] = max_over_ranks(e0.elapsed_time(e1) / reps)
         lib.ps_reserve_sms(0)
+        # the all-gather FUSED into the feature kernel: the angle warp stores the six compact values of its pair straight
+        # into every rank's gathered buffer over NVLink peer memory (multicast through the NVSwitch where available)
+        fused_push = {}
+        if world > 1:
+            import protstruc_b200 as ps_pkg
+
+            sb_local = ps_pkg.StructureBatch.from_xyz(xyz[:Bg], mask[:Bg])
+            for label, use_mc in (("multicast", True), ("unicast", False)):
+                try:
+                    fg = sharding.FusedFeatureGather(Bg, L, use_multicast=use_mc)
+                    if use_mc and fg.multicast_ptr is None:
+                        fused_push[label] = "no multicast support on this box"
+                        continue
+                    fg.run(sb_local, dist_out=dist_t[:Bg], dist_mask_out=mask_t[:Bg])
+                    barrier()
+                    e0.record(stream)
+                    for _ in range(reps):
+                        fg.run(sb_local, dist_out=dist_t[:Bg], dist_mask_out=mask_t[:Bg])
+                    e1.record(stream)
+                    barrier()
+                    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+                    do_gather(ring[0])   # reference result of the same inputs over NCCL
+                    torch.cuda.synchronize()
+                    want = gathered["compact"].view(world, 6, Bg, L, L).permute(1, 0, 2, 3, 4).contiguous()
+                    same = torch.equal(want.view(torch.int32), fg.buffer.view(torch.int32))
+                    fused_push[label] = {"ms_per_step": ms, "equals_nccl_gather": bool(same)}
+                    del fg, want
+                except Exception as exc:  # noqa: BLE001 - report what the box answered
+                    fused_push[label] = f"{type(exc).__name__}: {exc}"
         sent = 6 * Bg * L * L * 4
         gather = {"structures_per_rank": Bg, "bytes_sent_per_rank": sent, "bytes_received_per_rank": sent * (world - 1),
                   "fused_kernel_with_compact_planes_ms": kernel_ms, "gather_alone_ms": gather_ms,
                   "kernel_plus_gather_overlapped_ms_per_step": overlapped_ms,
                   "overlapped_ms_per_step_by_sms_left_to_nccl": overlapped_reserved,
+                  "fused_kernel_with_in_kernel_all_gather": fused_push,
                   "busbw_gbs": sent * (world - 1) / (gather_ms / 1e3) / 1e9 if world > 1 else None,
                   "nvlink_peak_gbs": {"nominal_per_direction": 900.0, "measured_peer_copy": 770.0},
                   "frac_of_nominal": sent * (world - 1) / (gather_ms / 1e3) / 1e9 / 900.0 if world > 1 else None,

@@ -127,6 +127,25 @@ int ps_inter_residue_geometry_compact(const float* xyz, const void* atom_mask, i
                                       int B, int L, int A, void* stream);
 
 /*
+ * The same launch FUSED WITH THE ALL-GATHER of the compact features over NVLink / NVSwitch peer memory (optional
+ * exchange step of a batch-sharded job; one process per GPU).  Every rank owns a symmetric buffer
+ * gathered (6, world, shard, L, L) f32 — feature-major: omega, theta, phi, d_ca, d_cb, d_no; then rank; then the
+ * rank's `shard` structures — and passes the addresses of ALL ranks' buffers as mapped into its own address space
+ * (peer_buffers[0 .. world), its own included; e.g. torch.distributed._symmetric_memory's buffer_ptrs), or
+ * additionally ONE NVSwitch multicast address of the buffer (multicast_buffer, may be NULL).  The angle warp of the tile
+ * kernel stores the six values of its residue pair straight into rank `rank`'s slab of every peer buffer — one
+ * multimem.st through the switch when a multicast address is given, else one store per peer — so the transfer rides
+ * on the kernel tile by tile; there is no separate collective and no staging buffer.  The caller makes the stores
+ * visible with a barrier across the ranks after the kernel (symmetric memory's barrier, or any collective).
+ * B <= shard structures of this rank; needs the linear-sweep kernel (A = 15, L >= 32, 16-byte aligned arrays),
+ * PS_ERR_BAD_SHAPE otherwise (use ps_inter_residue_geometry_compact + an NCCL all-gather there).
+ */
+int ps_inter_residue_geometry_push(const float* xyz, const void* atom_mask, int mask_dtype,
+                                   float* dist, void* dist_mask,
+                                   void* const* peer_buffers, int world, int rank, void* multicast_buffer,
+                                   int shard, int B, int L, int A, void* stream);
+
+/*
  * K3 — per-residue backbone features.
  * Replaces StructureBatch.backbone_dihedrals (protstruc/protstruc.py:486-541) with the
  * terminal masks of :435-453, and StructureBatch.backbone_orientations (:543-571) →

@@ -47,6 +47,8 @@ SIGNATURES = {
     "ps_inter_residue_geometry": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
                                           c_void_p]),
     "ps_inter_residue_geometry_compact": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, c_int, c_int, c_int, c_void_p]),
+    "ps_inter_residue_geometry_push": (c_int, [_fp, _fp, c_int, _fp, _fp, POINTER(c_void_p), c_int, c_int, c_void_p, c_int,
+                                               c_int, c_int, c_int, c_void_p]),
     "ps_inter_residue_geometry_ex": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,
                                              c_int, c_void_p]),
     "ps_backbone": (c_int, [_fp, _fp, _fp, c_int, c_int, c_int, c_int, c_int, c_int, _fp, _fp, _fp,

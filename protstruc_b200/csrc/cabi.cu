@@ -42,6 +42,9 @@ int topk_nearest_impl(const float*, const uint8_t*, const float*, int, int, int,
                       cudaStream_t);
 int debug_fill_pattern_impl(float*, long long, int, cudaStream_t);
 int pair_dist_last_plan_impl(long long*, int);
+void pair_sweep_set_push_target(void* const*, int, void*, long long, long long);
+int pair_sweep_max_peers();
+bool pair_sweep_supported(const float*, const void*, int, const float*, const void*, int, int);
 struct HostPipeline;
 int host_pipeline_create_impl(int, int, int, HostPipeline**);
 int host_pipeline_destroy_impl(HostPipeline*);
@@ -187,6 +190,37 @@ int ps_inter_residue_geometry_compact(const float* xyz, const void* atom_mask, i
     return ps::pair_dist_mask_compact_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, compact, compact + plane,
                                            compact + 2 * plane, compact + 3 * plane, compact + 4 * plane,
                                            compact + 5 * plane, B, L, A, 0, PS_STREAM(stream));
+}
+
+int ps_inter_residue_geometry_push(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
+                                   void* dist_mask, void* const* peer_buffers, int world, int rank,
+                                   void* multicast_buffer, int shard, int B, int L, int A, void* stream) {
+    if (!(dist && dist_mask && atom_mask && peer_buffers)) {
+        ps::set_error("inter_residue_geometry_push: all inputs and outputs are required");
+        return PS_ERR_NULL_POINTER;
+    }
+    if (world < 1 || world > ps::pair_sweep_max_peers() || rank < 0 || rank >= world || B < 1 || B > shard || L < 1) {
+        ps::set_error("inter_residue_geometry_push: world=%d (1..%d) rank=%d B=%d shard=%d L=%d", world,
+                      ps::pair_sweep_max_peers(), rank, B, shard, L);
+        return PS_ERR_BAD_SHAPE;
+    }
+    for (int r = 0; r < world; ++r) {
+        if (peer_buffers[r] == nullptr) {
+            ps::set_error("inter_residue_geometry_push: peer buffer %d is NULL", r);
+            return PS_ERR_NULL_POINTER;
+        }
+    }
+    if (!ps::pair_sweep_supported(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A)) {
+        ps::set_error("inter_residue_geometry_push: needs the linear-sweep kernel (A = 15, L >= 32, 16-byte aligned "
+                      "arrays); use ps_inter_residue_geometry_compact + an NCCL all-gather for other shapes");
+        return PS_ERR_BAD_SHAPE;
+    }
+    const long long slab = static_cast<long long>(shard) * L * L;
+    ps::pair_sweep_set_push_target(peer_buffers, world, multicast_buffer, slab * world, slab * rank);
+    // variant bit 27: the linear-sweep kernel regardless of the PROTSTRUC_B200_K1 environment override; bit 26: no pacing
+    // defaults (they are chosen for the UNFUSED kinds, this launch evaluates the angles)
+    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr, nullptr, B, L, A,
+                                   (1 << 27) | (1 << 26), PS_STREAM(stream));
 }
 
 int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,

@@ -44,6 +44,7 @@ constexpr int kStageMaskU8Bytes = 62 * kSweepA + 48 + 16;                // two 
 constexpr int kStageMaskF32Bytes = (38 * kSweepA * 4 + 48 + 15) / 16 * 16;
 
 enum SweepKind { kSweepDistBool = 0, kSweepDistOnly = 1, kSweepDistF32 = 2 };
+constexpr int kMaxPeers = 8;
 
 struct SweepParams {
     const float* __restrict__ xyz;
@@ -62,6 +63,15 @@ struct SweepParams {
     long long num_tiles;
     int stores_only;
     int pace_ns;  // tuning hook: the issuing lane sleeps this long after handing a tile to the engine
+    // Fused all-gather of the compact features (optional): every rank's gathered buffer (6, world, shard, L, L) as
+    // mapped into THIS GPU's address space over NVLink (peer[r], r = 0 .. n_peers-1, own buffer included), or ONE
+    // NVSwitch multicast address that reaches all of them (mc).  The angle warp stores omega / theta / phi and the
+    // three compact distance planes of its pair straight into them: the transfer rides on the kernel, tile by tile.
+    float* peer[kMaxPeers];
+    float* mc;
+    int n_peers;
+    long long peer_plane;   // floats between two feature planes of a gathered buffer: world * shard * L * L
+    long long peer_offset;  // this rank's slab inside a plane: rank * shard * L * L
 };
 
 template <int KIND>
@@ -106,6 +116,17 @@ __device__ __forceinline__ void bulk_load_g2s(void* sdst, const void* gsrc, uint
                  :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(sdst))), "l"(gsrc), "r"(bytes),
                     "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
                  : "memory");
+}
+
+// One value of one compact feature plane to every rank of the job: a multicast store through the NVSwitch when the
+// buffer has a multicast mapping (one packet leaves this GPU, the switch replicates it), else one store per peer.
+__device__ __forceinline__ void push_to_peers(const SweepParams& p, int feature, long long pair, float v) {
+    const long long at = feature * p.peer_plane + p.peer_offset + pair;
+    if (p.mc != nullptr) {
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p.mc + at), "f"(v) : "memory");
+    } else {
+        for (int r = 0; r < p.n_peers; ++r) p.peer[r][at] = v;
+    }
 }
 
 // One contiguous run of residues j of a tile and where its 16-byte aligned superset lands in the staging areas.
@@ -492,11 +513,17 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
                     const V3 ca_j{xj[0].y, yj[0].y, zj[0].y};  // atom 1 = second half of pack 0
                     const V3 cb_j{xj[2].x, yj[2].x, zj[2].x};  // atom 4 = first half of pack 2
                     float w, t, f;
-                    trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, p.omega != nullptr, p.theta != nullptr,
-                                     p.phi != nullptr, w, t, f);
+                    const bool push = p.n_peers > 0;
+                    trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, push || p.omega != nullptr,
+                                     push || p.theta != nullptr, push || p.phi != nullptr, w, t, f);
                     if (p.omega) p.omega[pair] = w;
                     if (p.theta) p.theta[pair] = t;
                     if (p.phi) p.phi[pair] = f;
+                    if (push) {
+                        push_to_peers(p, 0, pair, w);
+                        push_to_peers(p, 1, pair, t);
+                        push_to_peers(p, 2, pair, f);
+                    }
                 }
             }
         }
@@ -531,11 +558,19 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
         if constexpr (ANGLES) {
             // compact (B, L, L) copies of dist[..., CA, CA], [..., CB, CB], [..., N, O] (optional gather of compact
             // features): read back from the finished tile, which stays in shared memory until this buffer's next tile
-            if (does_angles && p.d_ca != nullptr && !p.stores_only && lane < np) {
+            if (does_angles && (p.d_ca != nullptr || p.n_peers > 0) && !p.stores_only && lane < np) {
                 const float* blk = tile_f32 + lane * G::kElemsPerPair;
-                p.d_ca[pair] = blk[1 * A + 1];
-                p.d_cb[pair] = blk[4 * A + 4];
-                p.d_no[pair] = blk[0 * A + 3];
+                const float dca = blk[1 * A + 1], dcb = blk[4 * A + 4], dno = blk[0 * A + 3];
+                if (p.d_ca != nullptr) {
+                    p.d_ca[pair] = dca;
+                    p.d_cb[pair] = dcb;
+                    p.d_no[pair] = dno;
+                }
+                if (p.n_peers > 0) {
+                    push_to_peers(p, 3, pair, dca);
+                    push_to_peers(p, 4, pair, dcb);
+                    push_to_peers(p, 5, pair, dno);
+                }
             }
         }
         __syncwarp();  // staging buffer of the upcoming tile is complete
@@ -600,11 +635,38 @@ bool pair_sweep_supported(const float* xyz, const void* atom_mask, int mask_dtyp
            aligned(dist_mask);
 }
 
+// Peer buffers of the fused all-gather for the NEXT pair_sweep_impl call of this thread (set by the push entry point).
+struct PushTarget {
+    float* peer[kMaxPeers] = {};
+    float* mc = nullptr;
+    int n_peers = 0;
+    long long plane = 0, offset = 0;
+};
+thread_local PushTarget g_push_target;
+
+void pair_sweep_set_push_target(void* const* peers, int n_peers, void* multicast, long long plane, long long offset) {
+    PushTarget t;
+    for (int r = 0; r < n_peers && r < kMaxPeers; ++r) t.peer[r] = static_cast<float*>(peers[r]);
+    t.mc = static_cast<float*>(multicast);
+    t.n_peers = n_peers;
+    t.plane = plane;
+    t.offset = offset;
+    g_push_target = t;
+}
+
+int pair_sweep_max_peers() { return kMaxPeers; }
+
 int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask, float* omega,
                     float* theta, float* phi, float* d_ca, float* d_cb, float* d_no, int B, int L, int sqrt_id,
                     int slots_override, int stores_only, int pace_ns, cudaStream_t stream) {
     SweepParams p;
     p.pace_ns = pace_ns;
+    for (int r = 0; r < kMaxPeers; ++r) p.peer[r] = g_push_target.peer[r];
+    p.mc = g_push_target.mc;
+    p.n_peers = g_push_target.n_peers;
+    p.peer_plane = g_push_target.plane;
+    p.peer_offset = g_push_target.offset;
+    g_push_target = PushTarget();  // one launch only
     p.xyz = xyz;
     p.atom_mask = atom_mask;
     p.dist = dist;
@@ -620,7 +682,7 @@ int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, flo
     p.num_pairs = p.num_rows * L;
     p.num_tiles = (p.num_pairs + kTilePairs - 1) / kTilePairs;
     p.stores_only = stores_only;
-    const bool angles = omega || theta || phi;
+    const bool angles = omega || theta || phi || p.n_peers > 0;
     if (dist_mask == nullptr)
         return angles ? launch_sweep_sqrt<kSweepDistOnly, true>(p, sqrt_id, slots_override, stream)
                       : launch_sweep_sqrt<kSweepDistOnly, false>(p, sqrt_id, slots_override, stream);

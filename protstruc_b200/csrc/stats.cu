@@ -446,17 +446,29 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
         }
     }
     constexpr float kMax = 3.4028234663852886e38f;
-    // pass 1: sum(nan_to_num(x * m)) per axis, sum(m); per-thread partials in fp32 (<= 4 Q values per axis)
+    // pass 1: sum(nan_to_num(x * m)) per axis, sum(m); per-thread partials in fp32 (<= 4 Q values per axis).
+    // Straight-line: NaN (a missing atom — half of the atoms of a real batch) becomes 0 by a select, infinities only
+    // raise a flag, and a thread that saw one redoes its sums through the full nan_to_num.  `inf_x` is reused by pass 2.
     float s[3] = {0.f, 0.f, 0.f}, c = 0.f;
+    bool inf_x = false, inf_xm = false;
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
-            float t = __fmul_rn(quad_get(v[k], e), m[k][e / 3]);
-            if (!(fabsf(t) <= kMax)) t = nan_to_num0(t);
-            s[e % 3] += t;
+            const float x = quad_get(v[k], e);
+            const float t = __fmul_rn(x, m[k][e / 3]);
+            inf_x |= fabsf(x) > kMax;
+            inf_xm |= fabsf(t) > kMax;
+            s[e % 3] += (t == t) ? t : 0.f;
         }
         c += (m[k][0] + m[k][1]) + (m[k][2] + m[k][3]);
+    }
+    if (inf_xm) {
+        s[0] = s[1] = s[2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < Q; ++k)
+#pragma unroll
+            for (int e = 0; e < 12; ++e) s[e % 3] += nan_to_num0(__fmul_rn(quad_get(v[k], e), m[k][e / 3]));
     }
     double acc[3] = {static_cast<double>(s[0]), static_cast<double>(s[1]), static_cast<double>(s[2])};
     block_sum3(acc, c, scratch);
@@ -477,14 +489,24 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
 
     // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
     float d2[3] = {0.f, 0.f, 0.f};
+    if (!inf_x) {
 #pragma unroll
-    for (int k = 0; k < Q; ++k) {
+        for (int k = 0; k < Q; ++k) {
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {
-            float x = quad_get(v[k], e);
-            if (!(fabsf(x) <= kMax)) x = nan_to_num0(x);
-            const float d = __fsub_rn(x, mu[e % 3]);
-            d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
+            for (int e = 0; e < 12; ++e) {
+                const float x = quad_get(v[k], e);
+                const float d = __fsub_rn((x == x) ? x : 0.f, mu[e % 3]);
+                d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const float d = __fsub_rn(nan_to_num0(quad_get(v[k], e)), mu[e % 3]);
+                d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
+            }
         }
     }
     double dev[3] = {static_cast<double>(d2[0]), static_cast<double>(d2[1]), static_cast<double>(d2[2])};
@@ -516,15 +538,23 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
         for (int k = 0; k < Q; ++k) {
             const int q = threadIdx.x + k * T;
             if (q >= nq) continue;
+            // d / sd: reciprocal, one correction of the quotient (what the IEEE division does for operands in range);
+            // if an outcome is not finite although its coordinate is a number — sd = 0 or NaN, infinite operands — the
+            // group is redone with the IEEE division
+            float4 keep[3] = {v[k][0], v[k][1], v[k][2]};
+            bool redo = false;
 #pragma unroll
             for (int e = 0; e < 12; ++e) {
-                const float d = __fsub_rn(quad_get(v[k], e), mu[e % 3]);
-                // d / sd: reciprocal, one correction of the quotient (what the IEEE division does for operands in
-                // range); a non-finite outcome — sd = 0, infinite or NaN operands — is settled by the IEEE division
+                const float d = __fsub_rn(quad_get(keep, e), mu[e % 3]);
                 float qt = __fmul_rn(d, rcp[e % 3]);
                 qt = __fmaf_rn(__fmaf_rn(-qt, sd[e % 3], d), rcp[e % 3], qt);
-                if (!(fabsf(qt) <= kMax)) qt = __fdiv_rn(d, sd[e % 3]);
+                redo |= (d == d) & !(fabsf(qt) <= kMax);  // a NaN coordinate stays NaN: nothing to redo
                 quad_set(v[k], e, qt);
+            }
+            if (redo) {
+#pragma unroll
+                for (int e = 0; e < 12; ++e)
+                    quad_set(v[k], e, __fdiv_rn(__fsub_rn(quad_get(keep, e), mu[e % 3]), sd[e % 3]));
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) o4[3 * q + i] = v[k][i];

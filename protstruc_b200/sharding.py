@@ -127,3 +127,66 @@ def gather_compact_features(local: Dict[str, torch.Tensor], batch_size: int, gro
 
     handle = _PendingGather(works, finish)
     return handle if async_op else handle.wait()
+
+
+COMPACT_FEATURES = ("omega", "theta", "phi", "d_ca", "d_cb", "d_no")
+
+
+class FusedFeatureGather:
+    """The optional exchange step FUSED into the feature kernel: every rank's fused `inter_residue_geometry` launch
+    stores the six compact (B, L, L) features of its shard straight into ALL ranks' gathered buffers over NVLink /
+    NVSwitch peer memory (`ps_inter_residue_geometry_push`), tile by tile while the distance tensor is being written —
+    no separate collective, no staging buffer, nothing for NCCL to wait for.
+
+    The gathered buffer is symmetric memory (`torch.distributed._symmetric_memory`): allocated once per (shard size, L),
+    every rank's copy mapped into every other rank's address space; with NVSwitch multicast support one `multimem.st`
+    per value reaches all ranks.  `run(sb)` launches the kernel on the current stream, then a symmetric-memory barrier
+    across the ranks (device-side, on the same stream), and returns the (world * shard, L, L) tensors — structures in
+    rank order; ranks whose shard is shorter than `shard` leave the tail rows of their slab untouched.
+
+    Needs the linear-sweep kernel: A = 15, L >= 32, bool or fp32 atom mask, at most 8 ranks."""
+
+    def __init__(self, shard: int, L: int, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.shard, self.L = int(shard), int(L)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buffer = symm_mem.empty((6, self.world, self.shard, self.L, self.L), dtype=torch.float32, device=dev)
+        self.handle = symm_mem.rendezvous(self.buffer, self.group)
+        self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        mc = int(self.handle.multicast_ptr) if use_multicast else 0
+        self.multicast_ptr = mc if mc != 0 else None
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        n = self.world * self.shard
+        return {name: self.buffer[k].view(n, self.L, self.L) for k, name in enumerate(COMPACT_FEATURES)}
+
+    def run(self, sb: StructureBatch, dist_out: Optional[torch.Tensor] = None,
+            dist_mask_out: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        import ctypes
+
+        from . import _cabi
+
+        B, L, A = sb._dims()
+        if L != self.L or B > self.shard:
+            raise ValueError(f"batch of {B} x {L} residues does not fit the gathered buffer ({self.shard} x {self.L})")
+        dev = sb.xyz.device
+        mask, code = sb._mask_for_kernel(sb.atom_mask)
+        if dist_out is None:
+            dist_out = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
+        if dist_mask_out is None:
+            dist_mask_out = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
+        if B > 0:
+            peers = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
+            with _cabi.on_device(dev):
+                rc = sb._lib().ps_inter_residue_geometry_push(
+                    sb.xyz.data_ptr(), mask.data_ptr(), code, dist_out.data_ptr(), dist_mask_out.data_ptr(), peers,
+                    self.world, self.rank, self.multicast_ptr, self.shard, B, L, A, sb._stream())
+            _cabi.check(rc, "ps_inter_residue_geometry_push")
+        self.handle.barrier()  # every rank's stores have landed before anybody reads
+        out = self.views()
+        out.update(dist=dist_out, dist_mask=dist_mask_out)
+        return out

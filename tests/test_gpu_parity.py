@@ -380,6 +380,47 @@ def test_compact_feature_planes_equal_the_strided_views(native_lib, B, L, A, kin
     assert bool((guard[:32] == -77.0).all()) and bool((guard[-32:] == -77.0).all())
 
 
+@pytest.mark.parametrize("B,L,kind", [(3, 64, "bool"), (2, 45, "bool"), (2, 40, "float")])
+def test_fused_gather_push_writes_every_peer_buffer(native_lib, B, L, kind):
+    """ps_inter_residue_geometry_push with the "peers" emulated by three buffers on ONE GPU (the kernel only sees
+    addresses): rank 1 of a world of 3 stores its six compact planes into slab 1 of every buffer, bit-identical to the
+    reference-style outputs, and touches nothing else; the distance tensor / mask of the launch are the usual ones.
+    (The multi-GPU path over symmetric memory is exercised by tools/multi_gpu_check.py and bench.py --with-gather.)"""
+    import ctypes
+
+    A, world, rank, shard = 15, 3, 1, B + 1
+    xyz, mask, _ = H.synthetic_batch(1200 + L, B, L, A, kind)
+    sb = ps.StructureBatch.from_xyz(xyz, mask)
+    ref = sb.inter_residue_geometry()
+    m, code = sb._mask_for_kernel(sb.atom_mask)
+    bufs = [torch.full((6, world, shard, L, L), -55.0, device=DEV) for _ in range(world)]
+    dist = torch.empty(B, L, L, A, A, device=DEV)
+    dmask = torch.empty(B, L, L, A, A, dtype=m.dtype, device=DEV)
+    peers = (ctypes.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    rc = native_lib.ps_inter_residue_geometry_push(sb.get_xyz().data_ptr(), m.data_ptr(), code, dist.data_ptr(), dmask.data_ptr(),
+                                                   peers, world, rank, None, shard, B, L, A,
+                                                   torch.cuda.current_stream().cuda_stream)
+    _cabi.check(rc, "ps_inter_residue_geometry_push")
+    torch.cuda.synchronize()
+    assert _cabi.last_pair_dist_plan()["sweep"] == 1
+    names = ("omega", "theta", "phi", "d_ca", "d_cb", "d_no")
+    for buf in bufs:
+        for k, name in enumerate(names):
+            got = buf[k, rank, :B]
+            assert torch.equal(torch.nan_to_num(got, nan=-5.0), torch.nan_to_num(ref[name], nan=-5.0)), name
+        untouched = buf.clone()
+        untouched[:, rank, :B] = -55.0
+        assert bool((untouched == -55.0).all()), "the push wrote outside its slab"
+    assert torch.equal(torch.nan_to_num(dist, nan=-5.0), torch.nan_to_num(ref["d_ca"]._base, nan=-5.0))
+    assert torch.equal(dmask, ref["d_ca_mask"]._base.to(dmask.dtype))
+    # shapes the linear-sweep kernel does not take are refused, not silently gathered wrong
+    small = ps.StructureBatch.from_xyz(xyz[:, :20], mask[:, :20])
+    rc = native_lib.ps_inter_residue_geometry_push(small.get_xyz().data_ptr(), m.data_ptr(), code, dist.data_ptr(), dmask.data_ptr(),
+                                                   peers, world, rank, None, shard, B, 20, A,
+                                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == -1 and "linear-sweep" in _cabi.last_error()
+
+
 # ------------------------------------------------------------------------------ K3 backbone
 @pytest.mark.parametrize("name", SYNTHETIC + ["real_1a6v_HL"])
 def test_backbone_features_match_reference_golden(native_lib, name):

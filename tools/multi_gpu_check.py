@@ -55,10 +55,32 @@ def main():
     gathered = sharding.gather_compact_features(local, B)
     whole = features(ps.StructureBatch.from_xyz(xyz, mask, chain_idx, ids, device="cuda"), beta)
     report = {}
+    # the all-gather fused into the feature kernel (symmetric memory over NVLink): needs A = 15, L >= 32
+    try:
+        fused = sharding.FusedFeatureGather(max(sharding.shard_sizes(B, world)), L)
+        shard2 = sharding.shard_structure_batch(xyz, mask, chain_idx, ids, device="cuda")
+        pushed = fused.run(shard2)
+        torch.cuda.synchronize()
+        rows = torch.cat([torch.arange(r * fused.shard, r * fused.shard + n) for r, n in enumerate(sharding.shard_sizes(B, world))])
+        for k in sharding.COMPACT_FEATURES:
+            got = pushed[k].index_select(0, rows.to("cuda"))
+            report["fused_push_" + k] = bool(torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(whole[k].float(), nan=-7.0)))
+        report["fused_push_multicast"] = fused.multicast_ptr is not None
+        if fused.multicast_ptr is not None:  # and once more without the NVSwitch multicast (one store per peer)
+            fused_uc = sharding.FusedFeatureGather(max(sharding.shard_sizes(B, world)), L, use_multicast=False)
+            pushed_uc = fused_uc.run(shard2)
+            torch.cuda.synchronize()
+            report["fused_push_unicast_all"] = all(
+                torch.equal(torch.nan_to_num(pushed_uc[k].index_select(0, rows.to("cuda")), nan=-7.0),
+                            torch.nan_to_num(whole[k].float(), nan=-7.0)) for k in sharding.COMPACT_FEATURES)
+    except Exception as exc:  # noqa: BLE001 - report, do not hide
+        report["fused_push_error"] = f"{type(exc).__name__}: {exc}"
+    report_ok = {k: v for k, v in report.items() if isinstance(v, bool) and k != "fused_push_multicast"}
     for k in sorted(whole):
         same = torch.equal(torch.nan_to_num(gathered[k].float(), nan=-7.0), torch.nan_to_num(whole[k].float(), nan=-7.0))
         report[k] = bool(same)
-    ok = torch.tensor([int(all(report.values()))], device="cuda")
+    report_ok.update({k: v for k, v in report.items() if isinstance(v, bool) and k != "fused_push_multicast"})
+    ok = torch.tensor([int(all(report_ok.values()) and "fused_push_error" not in report)], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world_size": world, "backend": dist.get_backend(), "batch": B, "shards": sharding.shard_sizes(B, world),
