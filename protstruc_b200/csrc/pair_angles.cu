@@ -257,68 +257,91 @@ struct JPair {
     int diag_k;         // row (relative to the CTA's first row) whose diagonal entry is lane x of this pair
 };
 
+// Everything one (row, pair of j) evaluation produces before any branch: the three angle pairs from the straight-line
+// path, what the rare per-lane patches need (sine / cosine terms, the quotient, bc, ba), and which lanes need patching.
+struct RowEval {
+    float2 w, t, f;            // omega, theta, phi (lanes x / y = residues j / j + 1)
+    float2 yw, xw, yt, xt, c;  // atan2 operands of omega and theta, phi's fast cosine
+    P3 bc;                     // CB_j - CB_i
+    float bax, bay, baz;       // CA_i - CB_i
+    float diag;                // omega on the diagonal
+    bool bad;                  // some lane is out of range of the straight-line path
+    bool okw0, okw1, okt0, okt1, okf0, okf1;
+};
+
+// Straight-line part (no branch): independent chains for omega, theta, phi — and, when two rows are evaluated per
+// iteration, for the two rows — that the scheduler interleaves.
 template <bool ALL3>
-__device__ __forceinline__ void eval_row(const float4* __restrict__ rec4, int k, const JPair& jp, bool want_omega,
-                                         bool want_theta, bool want_phi, float2& w, float2& t, float2& f) {
-    const float4 q0 = rec4[4 * k + 0], q1 = rec4[4 * k + 1], q2 = rec4[4 * k + 2], q3 = rec4[4 * k + 3];
-    const int row_flags = __float_as_int(q3.x);
+__device__ __forceinline__ void eval_row_core(const float4* __restrict__ rec4, int k, const JPair& jp, bool want_omega,
+                                              bool want_theta, bool want_phi, RowEval& r) {
+    const float4 q0 = rec4[4 * k + 0], q1 = rec4[4 * k + 1], q2 = rec4[4 * k + 2];
     const float2 nan2 = f2(__int_as_float(0x7fc00000));
-    w = t = f = nan2;
-    if ((row_flags & 1) || (jp.nan0 && jp.nan1)) return;
+    r.w = r.t = r.f = nan2;
+    r.yw = r.xw = r.yt = r.xt = r.c = f2(0.f);
+    r.okw0 = r.okw1 = r.okt0 = r.okt1 = r.okf0 = r.okf1 = true;
+    r.bax = q0.x; r.bay = q0.y; r.baz = q0.z;
+    r.diag = q2.w;
     const P3 b0{f2(q0.x), f2(q0.y), f2(q0.z)};
     const P3 cbi{f2(q1.x), f2(q1.y), f2(q1.z)};
-    const P3 bc = sub_p3(jp.cb, cbi);  // CB_j - CB_i: theta's b2, phi's bc
-    // Straight-line part: the three angles are independent chains; nothing branches until all of them are done.
-    float2 yw = f2(0.f), xw = f2(0.f), yt = f2(0.f), xt = f2(0.f), c = f2(0.f);
-    bool okw0 = true, okw1 = true, okt0 = true, okt1 = true, okf0 = true, okf1 = true;
-    const bool do_theta = (ALL3 || want_theta) && !(row_flags & 2);
+    r.bc = sub_p3(jp.cb, cbi);  // CB_j - CB_i: theta's b2, phi's bc
     if (ALL3 || want_omega) {
         const P3 b1 = sub_p3(jp.ca, cbi);
         const P3 n1 = cross_p3(b0, b1);
         const P3 n2 = cross_p3(jp.b2, b1);
-        xw = dot_p3(n1, n2);
+        r.xw = dot_p3(n1, n2);
         const float2 sn = dot_p3(n1, jp.b2);
         const float2 bb = dot_p3(b1, b1);
         const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
-        yw = neg2(__fmul2_rn(sn, nb1));
-        w = atan2_pair_core(yw, xw, okw0, okw1);
+        r.yw = neg2(__fmul2_rn(sn, nb1));
+        r.w = atan2_pair_core(r.yw, r.xw, r.okw0, r.okw1);
     }
-    if (do_theta) {
+    if (ALL3 || want_theta) {  // a missing N_i makes tn1 NaN: the lanes fail the range test and are patched to NaN
         const P3 tn1{f2(q2.x), f2(q2.y), f2(q2.z)};
         const P3 tb1{f2(-q0.x), f2(-q0.y), f2(-q0.z)};
-        const P3 n2 = cross_p3(bc, tb1);
-        xt = dot_p3(tn1, n2);
-        const float2 sn = dot_p3(tn1, bc);
-        yt = neg2(__fmul2_rn(sn, f2(q0.w)));
-        t = atan2_pair_core(yt, xt, okt0, okt1);
+        const P3 n2 = cross_p3(r.bc, tb1);
+        r.xt = dot_p3(tn1, n2);
+        const float2 sn = dot_p3(tn1, r.bc);
+        r.yt = neg2(__fmul2_rn(sn, f2(q0.w)));
+        r.t = atan2_pair_core(r.yt, r.xt, r.okt0, r.okt1);
     }
     if (ALL3 || want_phi) {
-        const float2 d = dot_p3(b0, bc);
-        const float2 cc = dot_p3(bc, bc);
-        float2 r = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
-        r = __fmul2_rn(r, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), r), r, f2(1.5f)));  // Newton step
-        c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), r);
+        const float2 d = dot_p3(b0, r.bc);
+        const float2 cc = dot_p3(r.bc, r.bc);
+        float2 rs = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
+        rs = __fmul2_rn(rs, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), rs), rs, f2(1.5f)));  // Newton step
+        r.c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), rs);
         // (a lane whose CB_j is missing is NaN either way and must not drag its partner into the exact path)
-        okf0 = (fabsf(c.x) <= 0.999f) | jp.nan0;
-        okf1 = (fabsf(c.y) <= 0.999f) | jp.nan1;
-        f = acos_pair(c);
+        r.okf0 = (fabsf(r.c.x) <= 0.999f) | jp.nan0;
+        r.okf1 = (fabsf(r.c.y) <= 0.999f) | jp.nan1;
+        r.f = acos_pair(r.c);
     }
-    // Rare part: lanes out of range (zeros: the diagonal, zero-padded residues, coincident atoms; NaN: a missing atom in
-    // one of the two pairs; |cos| within 1e-3 of 1) are redone one by one.
-    if (!(okw0 & okw1 & okt0 & okt1 & okf0 & okf1)) {
-        if (!okw0) w.x = atan2_single(yw.x, xw.x, false);
-        if (!okw1) w.y = atan2_single(yw.y, xw.y, false);
-        if (!okt0) t.x = atan2_single(yt.x, xt.x, false);
-        if (!okt1) t.y = atan2_single(yt.y, xt.y, false);
-        const V3 ba{q0.x, q0.y, q0.z};
-        if (!okf0) f.x = trrosetta_phi_exact(ba, V3{bc.x.x, bc.y.x, bc.z.x});
-        if (!okf1) f.y = trrosetta_phi_exact(ba, V3{bc.x.y, bc.y.y, bc.z.y});
-    }
+    r.bad = !(r.okw0 & r.okw1 & r.okt0 & r.okt1 & r.okf0 & r.okf1);
+}
+
+// Rare part: lanes out of range (zeros: the diagonal, zero-padded residues, coincident atoms; NaN: a missing atom in one of
+// the two pairs or in the row; |cos| within 1e-3 of 1) are redone one by one; then the diagonal of omega is set.
+__device__ __forceinline__ void eval_row_patch(RowEval& r) {
+    if (!r.okw0) r.w.x = atan2_single(r.yw.x, r.xw.x, false);
+    if (!r.okw1) r.w.y = atan2_single(r.yw.y, r.xw.y, false);
+    if (!r.okt0) r.t.x = atan2_single(r.yt.x, r.xt.x, false);
+    if (!r.okt1) r.t.y = atan2_single(r.yt.y, r.xt.y, false);
+    const V3 ba{r.bax, r.bay, r.baz};
+    if (!r.okf0) r.f.x = trrosetta_phi_exact(ba, V3{r.bc.x.x, r.bc.y.x, r.bc.z.x});
+    if (!r.okf1) r.f.y = trrosetta_phi_exact(ba, V3{r.bc.x.y, r.bc.y.y, r.bc.z.y});
+}
+
+template <bool ALL3>
+__device__ __forceinline__ void eval_row_finish(RowEval& r, int k, const JPair& jp, bool want_omega) {
     if (ALL3 || want_omega) {
         const int dk = k - jp.diag_k;  // 0: lane x is the diagonal entry, 1: lane y
-        if (dk == 0) w.x = q2.w;
-        if (dk == 1) w.y = q2.w;
+        if (dk == 0) r.w.x = r.diag;
+        if (dk == 1) r.w.y = r.diag;
     }
+}
+
+// Row flags of a record: 1 = CA_i / CB_i missing (every angle of the row is NaN), 2 = N_i missing (theta is NaN).
+__device__ __forceinline__ int row_flags_of(const float4* __restrict__ rec4, int k) {
+    return __float_as_int(rec4[4 * k + 3].x);
 }
 
 // Loop order: a thread OWNS pairs of residues j (one pair when L <= 2 * blockDim.x) and walks the CTA's rows with them
@@ -432,20 +455,41 @@ __global__ void __launch_bounds__(256, ROWS == 1 ? 3 : 2) trrosetta_fast_kernel(
         const int j = 2 * jpi;
         jp.diag_k = j - row0;
         long long o = first_out + j;
+        const bool pair_nan = jp.nan0 && jp.nan1;
+        const float2 nan2 = f2(__int_as_float(0x7fc00000));
         int k = 0;
         if (ROWS == 2) {
             for (; k + 1 < nrows; k += 2, o += 2ll * L) {
-                float2 w0, t0, f0, w1, t1, f1;
-                eval_row<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, w0, t0, f0);
-                eval_row<ALL3>(rows4, k + 1, jp, want_omega, want_theta, want_phi, w1, t1, f1);
-                store(o, j, w0, t0, f0);
-                store(o + L, j, w1, t1, f1);
+                const bool skip0 = pair_nan || (row_flags_of(rows4, k) & 1);
+                const bool skip1 = pair_nan || (row_flags_of(rows4, k + 1) & 1);
+                if (skip0 && skip1) {  // nothing to compute: missing atoms make both rows NaN for this pair
+                    store(o, j, nan2, nan2, nan2);
+                    store(o + L, j, nan2, nan2, nan2);
+                    continue;
+                }
+                RowEval r0, r1;
+                eval_row_core<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, r0);
+                eval_row_core<ALL3>(rows4, k + 1, jp, want_omega, want_theta, want_phi, r1);
+                if (r0.bad | r1.bad) {
+                    if (r0.bad) eval_row_patch(r0);
+                    if (r1.bad) eval_row_patch(r1);
+                }
+                eval_row_finish<ALL3>(r0, k, jp, want_omega);
+                eval_row_finish<ALL3>(r1, k + 1, jp, want_omega);
+                store(o, j, r0.w, r0.t, r0.f);
+                store(o + L, j, r1.w, r1.t, r1.f);
             }
         }
         for (; k < nrows; ++k, o += L) {
-            float2 w, t, f;
-            eval_row<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, w, t, f);
-            store(o, j, w, t, f);
+            if (pair_nan || (row_flags_of(rows4, k) & 1)) {
+                store(o, j, nan2, nan2, nan2);
+                continue;
+            }
+            RowEval r;
+            eval_row_core<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, r);
+            if (r.bad) eval_row_patch(r);
+            eval_row_finish<ALL3>(r, k, jp, want_omega);
+            store(o, j, r.w, r.t, r.f);
         }
     }
 }
