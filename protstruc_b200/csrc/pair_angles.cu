@@ -227,11 +227,11 @@ __device__ __forceinline__ float2 acos_pair(float2 c) {
     const float2 zb = __ffma2_rn(make_float2(a0, a1), f2(-0.5f), f2(0.5f));  // (1 - |c|) / 2; negative for |c| > 1
     const float2 zs = __fmul2_rn(c, c);
     const float2 z = make_float2(big0 ? zb.x : zs.x, big1 ? zb.y : zs.y);
-    // sqrt(z) for the upper range: z * rsqrt(z) with one Newton step; z = 0 (|c| = 1) must give 0, z < 0 gives NaN
-    const float r0 = rsqrt_mufu(zb.x), r1 = rsqrt_mufu(zb.y);
-    float2 q = __fmul2_rn(zb, make_float2(r0, r1));
-    q = __ffma2_rn(__ffma2_rn(neg2(q), q, zb), __fmul2_rn(make_float2(r0, r1), f2(0.5f)), q);
-    const float2 s = make_float2(big0 ? (zb.x == 0.f ? 0.f : q.x) : a0, big1 ? (zb.y == 0.f ? 0.f : q.y) : a1);
+    // sqrt(z) for the upper range: one MUFU.SQRT (relative error 2^-23; 0 for z = 0, i.e. |c| = 1; NaN for z < 0)
+    float q0, q1;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(zb.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(zb.y));
+    const float2 s = make_float2(big0 ? q0 : a0, big1 ? q1 : a1);
     float2 p = f2(3.53822075e-02f);
     p = __ffma2_rn(p, z, f2(1.69805195e-02f));
     p = __ffma2_rn(p, z, f2(3.07629332e-02f));
@@ -352,8 +352,12 @@ __device__ __forceinline__ int row_flags_of(const float4* __restrict__ rec4, int
 // ROWS rows are evaluated per iteration: a row is one long dependent chain (differences -> cross products -> dot
 // products -> MUFU -> polynomial), and with ~20 resident warps per SM the second, independent chain is what fills
 // the issue slots the first one leaves (ncu of the one-row loop: issue-active 64 %, top stall `wait`).
+// ROWS = 2: two rows per iteration (120 registers, 16 warps / SM); ROWS = 1: one row, 77 registers, 24 warps / SM;
+// ROWS = 0 / -1 / -2: one row with the register budget of FOUR / FIVE / SIX CTAs per SM (64 / 51 / 42 registers,
+// 32 / 40 / 48 warps per SM) — the kernel is bound by dependent-issue latency, so resident warps are what it needs.
 template <bool VIRTUAL_CB, bool ALL3, int ROWS>
-__global__ void __launch_bounds__(256, ROWS == 1 ? 3 : 2) trrosetta_fast_kernel(
+__global__ void __launch_bounds__(256, ROWS == -2 ? 6 : (ROWS == -1 ? 5 : (ROWS == 0 ? 4 : (ROWS == 1 ? 3 : 2))))
+    trrosetta_fast_kernel(
     const float* __restrict__ xyz, float* __restrict__ omega, float* __restrict__ theta, float* __restrict__ phi, int L,
     int A, int rows_per_cta, int blocks_per_structure, int vector_stores) {
     extern __shared__ __align__(16) float fast_smem[];
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(256, ROWS == 1 ? 3 : 2) trrosetta_fast_kernel(
         const bool pair_nan = jp.nan0 && jp.nan1;
         const float2 nan2 = f2(__int_as_float(0x7fc00000));
         int k = 0;
-        if (ROWS == 2) {
+        if constexpr (ROWS == 2) {
             for (; k + 1 < nrows; k += 2, o += 2ll * L) {
                 const bool skip0 = pair_nan || (row_flags_of(rows4, k) & 1);
                 const bool skip1 = pair_nan || (row_flags_of(rows4, k + 1) & 1);
@@ -570,7 +574,7 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
 }
 
 // variant: 0 = default (the packed kernel whenever the structure fits in shared memory), 1 = the exact-sequence
-// kernel of round 1, 3 = the packed kernel with two rows per iteration (tuning / comparison hooks,
+// kernel of round 1, 3 = the packed kernel with two rows per iteration, 4 = with 64 registers (tuning / comparison hooks,
 // ps_trrosetta_angles_ex).
 int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
                                   float* theta, float* phi, int variant, cudaStream_t stream) {
@@ -595,7 +599,8 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
                         static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
-    const int rows_mode = variant == 3 ? 2 : 1;
+    // variant 0 (default): 64 registers; 3: two rows; 5 / 6: 51 / 42 registers; 7: 77 registers (round-2 first default)
+    const int rows_mode = variant == 3 ? 2 : (variant == 5 ? -1 : (variant == 6 ? -2 : (variant == 7 ? 1 : 0)));
     if (variant != 1 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
         int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread (several beyond 512 residues)
         if (threads > 256) threads = 256;
@@ -610,13 +615,20 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
         trrosetta_fast_kernel<VCB, ALL, ROWS><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                \
             xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);                         \
     } while (0)
-        const bool two_rows = rows_mode == 2;  // default: one row per iteration (24 warps / SM beat two rows at 16)
+        // default: one row per iteration at 64 registers (32 warps / SM: 0.41 ms at config 3; 24 warps 0.44, two rows at
+        // 16 warps 0.53)
         if (use_virtual_cb) {
-            if (all3 && two_rows) PS_FAST(true, true, 2);
+            if (all3 && rows_mode == 2) PS_FAST(true, true, 2);
+            else if (all3 && rows_mode == 0) PS_FAST(true, true, 0);
+            else if (all3 && rows_mode == -1) PS_FAST(true, true, -1);
+            else if (all3 && rows_mode == -2) PS_FAST(true, true, -2);
             else if (all3) PS_FAST(true, true, 1);
             else PS_FAST(true, false, 1);
         } else {
-            if (all3 && two_rows) PS_FAST(false, true, 2);
+            if (all3 && rows_mode == 2) PS_FAST(false, true, 2);
+            else if (all3 && rows_mode == 0) PS_FAST(false, true, 0);
+            else if (all3 && rows_mode == -1) PS_FAST(false, true, -1);
+            else if (all3 && rows_mode == -2) PS_FAST(false, true, -2);
             else if (all3) PS_FAST(false, true, 1);
             else PS_FAST(false, false, 1);
         }
