@@ -97,9 +97,9 @@ int ps_pair_angles(const float* xyz, int B, int L, int A,
  */
 int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
                         float* omega, float* theta, float* phi, void* stream);
-/* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel, 64 registers), 1 = the exact-operation-sequence
- * kernel, 3 = packed-FP32 kernel with two rows per loop iteration, 5 / 6 / 7 = the packed kernel compiled to
- * 51 / 42 / 77 registers (5, 6 or 3 CTAs per SM). All packed variants produce the same bits. */
+/* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel compiled for 3 CTAs per SM), 1 = the
+ * exact-operation-sequence kernel, 4 / 5 / 6 = the packed kernel compiled for 4 / 5 / 6 CTAs per SM.  All packed
+ * variants produce the same bits. */
 int ps_trrosetta_angles_ex(const float* xyz, int B, int L, int A, int virtual_cb,
                            float* omega, float* theta, float* phi, int variant, void* stream);
 

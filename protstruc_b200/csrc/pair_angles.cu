@@ -107,16 +107,22 @@ __global__ void __launch_bounds__(256) trrosetta_kernel(const float* __restrict_
 //    residue with the reference's exact sequence) as structure-of-arrays in shared memory, so residue j arrives as
 //    three conflict-free LDS.64 per atom instead of six strided global loads, and everything that depends on residue i
 //    only (b0, CB_i, the normal n1 of theta, |b0|, 1/|b0|) is computed once per residue, not once per thread;
-//  * atan2 = MUFU.RCP quotient + degree-15 odd minimax polynomial evaluated as FFMA2 for the two pairs, octant
-//    fix-ups; zeros, infinities, NaN and out-of-range magnitudes fall back to atan2f.
+//  * atan2 = MUFU.RCP quotient + degree-13 odd minimax polynomial evaluated as FFMA2 for the two pairs, octant
+//    fix-ups; acos = sqrt(1 - |c|) P(|c|), one range; ONE range test per loop iteration decides whether some lane
+//    (zeros, infinities, NaN, out-of-range magnitudes, |cos| near 1) is redone by the IEEE / exact-sequence path;
+//  * what bounds the kernel is the FP32 pipe, not HBM: an FFMA2 / FMUL2 / FADD2 saves an issue slot but occupies the
+//    pipe for two cycles (ncu: sm__pipe_fma_cycles_active = 2 x sm__inst_executed_pipe_fma), so the per-pair operation
+//    count is what matters: ~66 packed instructions per two pairs after moving every product of row-only vectors
+//    into the row record (theta needs two dot products per pair, no cross product).
 //
 // What keeps the special cases exact (all covered by tests/test_gpu_parity.py):
 //  * zero-padded residues and coincident atoms: a zero operand makes every fused product exactly zero, so x = y = 0
 //    arrives at the atan2f fallback as in the reference (x is given the reference's +0 sign there: ATen's sum starts
 //    from +0); norms are formed as v.v * rsqrt(v.v), which is NaN for v = 0 exactly where the reference divides 0 / 0;
-//  * the diagonal j = i: theta (b2 = CB_i - CB_i = 0) and phi (0 * inf) come out as in the reference by themselves;
-//    omega would see b0 x b0 — exactly zero only with separately rounded products — and is overwritten with its known
-//    value: 0, or NaN if CA_i / CB_i are missing or coincide (0 * 1/|b0|);
+//  * the diagonal j = i: b1 = b0 (omega) and b2 = 0 (theta, phi) make every term zero in exact arithmetic, and the
+//    values are known per residue: omega = theta = 0 — or NaN if an atom is missing or CA_i = CB_i (0 * 1/|b0|) — and
+//    phi = NaN (0 / 0).  They are computed once per row record and written after the row loop, over whatever the
+//    straight-line path produced there;
 //  * missing atoms (NaN coordinates) propagate through every product and through the select-based min / max of the
 //    atan2 (fminf / fmaxf would drop them);
 //  * phi: within 1e-3 of |cos| = 1 — where the unclamped arccos of the reference turns a last-ulp excess into NaN —
@@ -155,61 +161,67 @@ __device__ __forceinline__ float min_nan(float a, float b) {
     return r;
 }
 
-// atan2 of one (y, x): the scalar twin of the packed evaluation below (same operations in the same order, so a pair's
-// result does not depend on which lane or lane partner evaluated it).  in_range = the caller's range test.
-__device__ __forceinline__ float atan2_single(float y, float x, bool in_range) {
-    if (!in_range) {
-        if ((x != x) | (y != y)) return __int_as_float(0x7fc00000);
-        // zeros, denormal-range and huge magnitudes, infinities: IEEE atan2f; x + 0 turns a -0 cosine term into the
-        // reference's +0 (ATen's sum starts from +0)
-        return atan2f(y, x + 0.0f);
-    }
-    const float ax = fabsf(x), ay = fabsf(y);
-    const bool sw = ay > ax;
-    const float mx = max_nan(ax, ay), mn = min_nan(ax, ay);
-    const float t = __fmul_rn(mn, rcp_mufu(mx));
-    const float s = __fmul_rn(t, t);
-    float p = 2.622234402e-03f;
-    p = __fmaf_rn(p, s, -1.513249334e-02f);
-    p = __fmaf_rn(p, s, 4.112178832e-02f);
-    p = __fmaf_rn(p, s, -7.366699725e-02f);
-    p = __fmaf_rn(p, s, 1.057392880e-01f);
-    p = __fmaf_rn(p, s, -1.418597400e-01f);
-    p = __fmaf_rn(p, s, 1.999039650e-01f);
-    p = __fmaf_rn(p, s, -3.333298564e-01f);
-    float a = __fmaf_rn(__fmul_rn(t, s), p, t);
-    if (sw) a = 1.57079637f - a;
-    if (x < 0.f) a = 3.14159274f - a;
-    return copysignf(a, y);
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {  // one FMNMX3 (sm_100+)
+    float r;
+    asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min3_nan(float a, float b, float c) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
 }
 
-// atan2 of two (y, x) pairs at once, WITHOUT the branch to the out-of-range path: ok0 / ok1 say whether a lane's
-// result is valid (false for zero, huge, infinite and NaN operands).  The caller patches such lanes with atan2_single
-// after all of its straight-line work, so that independent angle evaluations can be interleaved by the scheduler.
-__device__ __forceinline__ float2 atan2_pair_core(float2 y, float2 x, bool& ok0, bool& ok1) {
-    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
-    const bool sw0 = ay0 > ax0, sw1 = ay1 > ax1;
-    const float mx0 = max_nan(ax0, ay0), mn0 = min_nan(ax0, ay0);
-    const float mx1 = max_nan(ax1, ay1), mn1 = min_nan(ax1, ay1);
-    ok0 = (mx0 > 1e-30f) & (mx0 < 1e30f);
-    ok1 = (mx1 > 1e-30f) & (mx1 < 1e30f);
-    const float2 t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rcp_mufu(mx0), rcp_mufu(mx1)));
-    const float2 s = __fmul2_rn(t, t);
-    float2 p = f2(2.622234402e-03f);
-    p = __ffma2_rn(p, s, f2(-1.513249334e-02f));
-    p = __ffma2_rn(p, s, f2(4.112178832e-02f));
-    p = __ffma2_rn(p, s, f2(-7.366699725e-02f));
-    p = __ffma2_rn(p, s, f2(1.057392880e-01f));
-    p = __ffma2_rn(p, s, f2(-1.418597400e-01f));
-    p = __ffma2_rn(p, s, f2(1.999039650e-01f));
-    p = __ffma2_rn(p, s, f2(-3.333298564e-01f));
-    const float2 a = __ffma2_rn(__fmul2_rn(t, s), p, t);
+// The packed atan2 below is valid while the larger of |x|, |y| lies in this range (MUFU.RCP of it and the quotient are
+// then normal numbers); zero (the diagonal, zero padding, coincident atoms), huge, infinite and NaN operands are not.
+constexpr float kAtanLo = 1e-30f, kAtanHi = 1e30f;
+__device__ __forceinline__ bool atan2_in_range(float ny, float x) {
+    const float mx = max_nan(fabsf(x), fabsf(ny));
+    return (mx > kAtanLo) & (mx < kAtanHi);
+}
+
+// atan2(-ny, x) of ONE out-of-range operand pair: IEEE atan2f; x + 0 turns a -0 cosine term into the reference's +0
+// (ATen's sum starts from +0).  A NaN operand is answered at once instead of being dragged through atan2f.
+__device__ __forceinline__ float atan2_slow(float ny, float x) {
+    if ((x != x) | (ny != ny)) return __int_as_float(0x7fc00000);
+    return atan2f(-ny, x + 0.0f);
+}
+
+// atan2(-ny, x) of two operand pairs at once (the callers hold the NEGATED sine term: the sign flip is folded into the
+// final sign transfer): MUFU.RCP quotient of the smaller by the larger magnitude, the degree-13 odd minimax polynomial
+// of atan on [0, 1] (|error| 3.8e-7 rad; every FFMA2 is two cycles of the FP32 pipe that bounds this kernel, and the
+// degree-17 polynomial of the first version bought accuracy below fp32 rounding), octant fix-ups — WITHOUT any range
+// test or branch: mx0 / mx1 are max(|x|, |y|) of the lanes, from which the caller decides — once for all the atan2 of
+// a loop iteration — whether some lane has to be redone by atan2_slow.  The evaluation is split into prepare / Horner
+// / finish so that the caller can interleave the dependent chains of its independent angles statement by statement
+// (with six warps per scheduler, a serial Horner chain leaves the FP32 pipe idle between its steps).
+struct AtanPair {
+    float2 t, s, p;
+    float mx0, mx1;
+    bool sw0, sw1;
+};
+__device__ __forceinline__ void atan2_prepare(float2 ny, float2 x, AtanPair& e) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(ny.x), ax1 = fabsf(x.y), ay1 = fabsf(ny.y);
+    e.mx0 = max_nan(ax0, ay0);
+    e.mx1 = max_nan(ax1, ay1);
+    e.sw0 = ay0 > ax0;
+    e.sw1 = ay1 > ax1;
+    const float mn0 = min_nan(ax0, ay0), mn1 = min_nan(ax1, ay1);
+    e.t = __fmul2_rn(make_float2(mn0, mn1), make_float2(rcp_mufu(e.mx0), rcp_mufu(e.mx1)));
+    e.s = __fmul2_rn(e.t, e.t);
+    e.p = __ffma2_rn(f2(7.353078341e-03f), e.s, f2(-3.545713666e-02f));
+}
+__device__ __forceinline__ float2 atan2_finish(const AtanPair& e, float2 ny, float2 x) {
+    const float2 a = __ffma2_rn(__fmul2_rn(e.t, e.s), e.p, e.t);
     float a0 = a.x, a1 = a.y;
-    if (sw0) a0 = 1.57079637f - a0;
-    if (sw1) a1 = 1.57079637f - a1;
+    if (e.sw0) a0 = 1.57079637f - a0;
+    if (e.sw1) a1 = 1.57079637f - a1;
     if (x.x < 0.f) a0 = 3.14159274f - a0;
     if (x.y < 0.f) a1 = 3.14159274f - a1;
-    return make_float2(copysignf(a0, y.x), copysignf(a1, y.y));
+    // a >= +0 here (or NaN): give it the sign of y = -ny with one LOP3
+    a0 = __int_as_float(__float_as_int(a0) | (~__float_as_int(ny.x) & 0x80000000));
+    a1 = __int_as_float(__float_as_int(a1) | (~__float_as_int(ny.y) & 0x80000000));
+    return make_float2(a0, a1);
 }
 
 // phi's cosine by the reference's exact sequence (geometry.py:64-71): separately rounded dot product, ATen norms,
@@ -218,36 +230,37 @@ __device__ __forceinline__ float trrosetta_phi_exact(V3 ba, V3 bc) {
     return acosf(__fdiv_rn(dot3(ba, bc), __fmul_rn(norm3(ba), norm3(bc))));
 }
 
-// acos of two cosines at once (|c| <= 1; anything else, NaN included, gives NaN): the classic two-range evaluation —
-// acos(c) = pi/2 - asin(c) for |c| <= 0.56, 2 asin(sqrt((1 - |c|) / 2)) mirrored for c < 0 above — with the odd
-// minimax polynomial of asin on [0, 0.56] (|error| < 3e-7 rad over the whole range) evaluated as FFMA2 for both lanes.
-__device__ __forceinline__ float2 acos_pair(float2 c) {
-    const float a0 = fabsf(c.x), a1 = fabsf(c.y);
-    const bool big0 = a0 > 0.56f, big1 = a1 > 0.56f;
-    const float2 zb = __ffma2_rn(make_float2(a0, a1), f2(-0.5f), f2(0.5f));  // (1 - |c|) / 2; negative for |c| > 1
-    const float2 zs = __fmul2_rn(c, c);
-    const float2 z = make_float2(big0 ? zb.x : zs.x, big1 ? zb.y : zs.y);
-    // sqrt(z) for the upper range: one MUFU.SQRT (relative error 2^-23; 0 for z = 0, i.e. |c| = 1; NaN for z < 0)
-    float q0, q1;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(zb.x));
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(zb.y));
-    const float2 s = make_float2(big0 ? q0 : a0, big1 ? q1 : a1);
-    float2 p = f2(3.53822075e-02f);
-    p = __ffma2_rn(p, z, f2(1.69805195e-02f));
-    p = __ffma2_rn(p, z, f2(3.07629332e-02f));
-    p = __ffma2_rn(p, z, f2(4.47094180e-02f));
-    p = __ffma2_rn(p, z, f2(7.49890432e-02f));
-    p = __ffma2_rn(p, z, f2(1.66667074e-01f));
-    const float2 as = __ffma2_rn(__fmul2_rn(s, z), p, s);  // asin(s)
-    float o0, o1;
-    if (big0) o0 = c.x < 0.f ? 3.14159274f - 2.f * as.x : 2.f * as.x; else o0 = 1.57079637f - copysignf(as.x, c.x);
-    if (big1) o1 = c.y < 0.f ? 3.14159274f - 2.f * as.y : 2.f * as.y; else o1 = 1.57079637f - copysignf(as.y, c.y);
+// acos of two cosines at once (|c| <= 1; anything else, NaN included, gives NaN), one range and no select:
+// acos(|c|) = sqrt(1 - |c|) * P(|c|) with the degree-6 minimax polynomial of acos(x) / sqrt(1 - x) on [0, 1]
+// (|error| of the product 9e-8 rad; 5e-7 rad with fp32 rounding and the 1-ulp MUFU.SQRT), mirrored for c < 0.
+// Split like the atan2 above.
+struct AcosPair {
+    float2 a, q, p;
+};
+__device__ __forceinline__ void acos_prepare(float2 c, AcosPair& e) {
+    e.a = make_float2(fabsf(c.x), fabsf(c.y));
+    const float2 z = __fadd2_rn(f2(1.0f), neg2(e.a));  // negative for |c| > 1: the square root is NaN
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(e.q.x) : "f"(z.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(e.q.y) : "f"(z.y));
+    e.p = __ffma2_rn(f2(2.6117212e-03f), e.a, f2(-1.2003397e-02f));
+}
+__device__ __forceinline__ float2 acos_finish(const AcosPair& e, float2 c) {
+    const float2 r = __fmul2_rn(e.q, e.p);
+    float o0 = r.x, o1 = r.y;
+    if (c.x < 0.f) o0 = 3.14159274f - o0;
+    if (c.y < 0.f) o1 = 3.14159274f - o1;
     return make_float2(o0, o1);
 }
 
-// Row-side record of one residue i (16 floats, 64-byte aligned: four broadcast LDS.128 per row): b0 = CA - CB (3),
-// |b0| (NaN for b0 = 0), CB (3), 1 / |b0| (inf for b0 = 0), tn1 = (N - CA) x (CB - CA) (3), omega on the diagonal,
-// flags (1 = CA_i or CB_i missing: the whole row is NaN; 2 = N_i missing: theta of the row is NaN), padding.
+// Row-side record of one residue i (16 floats, 64-byte aligned: four broadcast LDS.128 per row) — everything that depends
+// on residue i alone, in the form that leaves the fewest FP32 operations per pair:
+//   q0 = b0 = CA - CB (3), 1 / |b0| (inf for b0 = 0)
+//   q1 = CB (3), flags (1 = CA_i or CB_i missing: the whole row is NaN; 2 = N_i missing: theta of the row is NaN)
+//   q2 = tm = (CB - CA) x tn1 (3) with tn1 = (N - CA) x (CB - CA): theta's cosine term is the triple product
+//        tn1 . (bc x (CB - CA)) = bc . tm — one dot product per pair instead of a cross product and a dot product;
+//        omega[i, i]
+//   q3 = ts = tn1 |b0| (3; NaN for b0 = 0, where the reference divides 0 / 0): theta's NEGATED sine term is bc . ts;
+//        theta[i, i]                                  (phi[i, i] is always NaN; the diagonal is written after the loop)
 constexpr int kRowRecord = 16;
 
 // omega / theta / phi of one row record against the thread's pair of residues j (both pairs at once).
@@ -258,32 +271,31 @@ struct JPair {
 };
 
 // Everything one (row, pair of j) evaluation produces before any branch: the three angle pairs from the straight-line
-// path, what the rare per-lane patches need (sine / cosine terms, the quotient, bc, ba), and which lanes need patching.
+// path, what the rare per-lane patches need (negated sine / cosine terms, phi's cosine, bc, ba), and ONE flag saying
+// that some lane is out of range of the straight-line path (which lanes is worked out again in the patch: keeping six
+// flags alive through the loop body cost more predicate-spill instructions than the geometry has multiplications).
 struct RowEval {
-    float2 w, t, f;            // omega, theta, phi (lanes x / y = residues j / j + 1)
-    float2 yw, xw, yt, xt, c;  // atan2 operands of omega and theta, phi's fast cosine
-    P3 bc;                     // CB_j - CB_i
-    float bax, bay, baz;       // CA_i - CB_i
-    float diag;                // omega on the diagonal
-    bool bad;                  // some lane is out of range of the straight-line path
-    bool okw0, okw1, okt0, okt1, okf0, okf1;
+    float2 w, t, f;              // omega, theta, phi (lanes x / y = residues j / j + 1)
+    float2 nyw, xw, nyt, xt, c;  // atan2 operands of omega and theta (sine terms negated), phi's fast cosine
+    P3 bc;                       // CB_j - CB_i
+    float bax, bay, baz;         // CA_i - CB_i
+    bool bad;
 };
 
-// Straight-line part (no branch): independent chains for omega, theta, phi — and, when two rows are evaluated per
-// iteration, for the two rows — that the scheduler interleaves.
+// Straight-line part (no branch): independent chains for omega, theta, phi that the scheduler interleaves.
 template <bool ALL3>
-__device__ __forceinline__ void eval_row_core(const float4* __restrict__ rec4, int k, const JPair& jp, bool want_omega,
-                                              bool want_theta, bool want_phi, RowEval& r) {
-    const float4 q0 = rec4[4 * k + 0], q1 = rec4[4 * k + 1], q2 = rec4[4 * k + 2];
+__device__ __forceinline__ void eval_row_core(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                              const JPair& jp, bool want_omega, bool want_theta, bool want_phi,
+                                              RowEval& r) {
     const float2 nan2 = f2(__int_as_float(0x7fc00000));
     r.w = r.t = r.f = nan2;
-    r.yw = r.xw = r.yt = r.xt = r.c = f2(0.f);
-    r.okw0 = r.okw1 = r.okt0 = r.okt1 = r.okf0 = r.okf1 = true;
+    r.nyw = r.xw = r.nyt = r.xt = f2(1.0f);
+    r.c = f2(0.0f);
     r.bax = q0.x; r.bay = q0.y; r.baz = q0.z;
-    r.diag = q2.w;
     const P3 b0{f2(q0.x), f2(q0.y), f2(q0.z)};
     const P3 cbi{f2(q1.x), f2(q1.y), f2(q1.z)};
     r.bc = sub_p3(jp.cb, cbi);  // CB_j - CB_i: theta's b2, phi's bc
+    // ---- geometry: the operands of the two atan2 and of the acos
     if (ALL3 || want_omega) {
         const P3 b1 = sub_p3(jp.ca, cbi);
         const P3 n1 = cross_p3(b0, b1);
@@ -292,56 +304,63 @@ __device__ __forceinline__ void eval_row_core(const float4* __restrict__ rec4, i
         const float2 sn = dot_p3(n1, jp.b2);
         const float2 bb = dot_p3(b1, b1);
         const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
-        r.yw = neg2(__fmul2_rn(sn, nb1));
-        r.w = atan2_pair_core(r.yw, r.xw, r.okw0, r.okw1);
+        r.nyw = __fmul2_rn(sn, nb1);  // y = -(n1 . b2) |b1|
     }
-    if (ALL3 || want_theta) {  // a missing N_i makes tn1 NaN: the lanes fail the range test and are patched to NaN
-        const P3 tn1{f2(q2.x), f2(q2.y), f2(q2.z)};
-        const P3 tb1{f2(-q0.x), f2(-q0.y), f2(-q0.z)};
-        const P3 n2 = cross_p3(r.bc, tb1);
-        r.xt = dot_p3(tn1, n2);
-        const float2 sn = dot_p3(tn1, r.bc);
-        r.yt = neg2(__fmul2_rn(sn, f2(q0.w)));
-        r.t = atan2_pair_core(r.yt, r.xt, r.okt0, r.okt1);
+    if (ALL3 || want_theta) {  // a missing N_i makes tm / ts NaN: the lanes fail the range test and are patched to NaN
+        r.xt = dot_p3(P3{f2(q2.x), f2(q2.y), f2(q2.z)}, r.bc);
+        r.nyt = dot_p3(P3{f2(q3.x), f2(q3.y), f2(q3.z)}, r.bc);
     }
     if (ALL3 || want_phi) {
+        // cos = (b0 . bc) / (|b0| |bc|) with the raw MUFU.RSQ of |bc|^2 (relative error 2^-22.9: 1.3e-6 rad at the
+        // sin(phi) = 0.1 edge of the stated tolerance range; a Newton step on it cost four FP32-pipe instructions)
         const float2 d = dot_p3(b0, r.bc);
         const float2 cc = dot_p3(r.bc, r.bc);
-        float2 rs = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
-        rs = __fmul2_rn(rs, __ffma2_rn(__fmul2_rn(__fmul2_rn(f2(-0.5f), cc), rs), rs, f2(1.5f)));  // Newton step
-        r.c = __fmul2_rn(__fmul2_rn(d, f2(q1.w)), rs);
-        // (a lane whose CB_j is missing is NaN either way and must not drag its partner into the exact path)
-        r.okf0 = (fabsf(r.c.x) <= 0.999f) | jp.nan0;
-        r.okf1 = (fabsf(r.c.y) <= 0.999f) | jp.nan1;
-        r.f = acos_pair(r.c);
+        const float2 rs = make_float2(rsqrt_mufu(cc.x), rsqrt_mufu(cc.y));
+        r.c = __fmul2_rn(__fmul2_rn(d, f2(q0.w)), rs);
     }
-    r.bad = !(r.okw0 & r.okw1 & r.okt0 & r.okt1 & r.okf0 & r.okf1);
+    // ---- the three function evaluations, their Horner chains interleaved step by step
+    AtanPair ew, et;
+    AcosPair ef;
+    atan2_prepare(r.nyw, r.xw, ew);
+    atan2_prepare(r.nyt, r.xt, et);
+    acos_prepare(r.c, ef);
+    ew.p = __ffma2_rn(ew.p, ew.s, f2(8.210079680e-02f));
+    et.p = __ffma2_rn(et.p, et.s, f2(8.210079680e-02f));
+    ef.p = __ffma2_rn(ef.p, ef.a, f2(2.7762914e-02f));
+    ew.p = __ffma2_rn(ew.p, ew.s, f2(-1.339595112e-01f));
+    et.p = __ffma2_rn(et.p, et.s, f2(-1.339595112e-01f));
+    ef.p = __ffma2_rn(ef.p, ef.a, f2(-4.919744e-02f));
+    ew.p = __ffma2_rn(ew.p, ew.s, f2(1.986158291e-01f));
+    et.p = __ffma2_rn(et.p, et.s, f2(1.986158291e-01f));
+    ef.p = __ffma2_rn(ef.p, ef.a, f2(8.883589e-02f));
+    ew.p = __ffma2_rn(ew.p, ew.s, f2(-3.332545806e-01f));
+    et.p = __ffma2_rn(et.p, et.s, f2(-3.332545806e-01f));
+    ef.p = __ffma2_rn(ef.p, ef.a, f2(-2.1459109e-01f));
+    ef.p = __ffma2_rn(ef.p, ef.a, f2(1.5707963f));
+    if (ALL3 || want_omega) r.w = atan2_finish(ew, r.nyw, r.xw);
+    if (ALL3 || want_theta) r.t = atan2_finish(et, r.nyt, r.xt);
+    if (ALL3 || want_phi) r.f = acos_finish(ef, r.c);
+    // one range test for the four atan2 and the two acos of the iteration (NaN fails every comparison; an angle that
+    // was not asked for was given in-range operands above)
+    const float lo = min3_nan(ew.mx0, ew.mx1, min_nan(et.mx0, et.mx1));
+    const float hi = max3_nan(ew.mx0, ew.mx1, max_nan(et.mx0, et.mx1));
+    const float cm = max_nan(fabsf(r.c.x), fabsf(r.c.y));
+    r.bad = !((lo > kAtanLo) & (hi < kAtanHi) & (cm <= 0.999f));
 }
 
 // Rare part: lanes out of range (zeros: the diagonal, zero-padded residues, coincident atoms; NaN: a missing atom in one of
-// the two pairs or in the row; |cos| within 1e-3 of 1) are redone one by one; then the diagonal of omega is set.
-__device__ __forceinline__ void eval_row_patch(RowEval& r) {
-    if (!r.okw0) r.w.x = atan2_single(r.yw.x, r.xw.x, false);
-    if (!r.okw1) r.w.y = atan2_single(r.yw.y, r.xw.y, false);
-    if (!r.okt0) r.t.x = atan2_single(r.yt.x, r.xt.x, false);
-    if (!r.okt1) r.t.y = atan2_single(r.yt.y, r.xt.y, false);
+// the two pairs or in the row; |cos| within 1e-3 of 1) are found again and redone one by one.  dk = row - jp.diag_k:
+// lane x (dk = 0) or lane y (dk = 1) is the diagonal entry, whose three values are written after the row loop.
+__device__ __forceinline__ void eval_row_patch(RowEval& r, const JPair& jp, int dk) {
+    const bool live0 = dk != 0, live1 = dk != 1;
+    if (live0 && !atan2_in_range(r.nyw.x, r.xw.x)) r.w.x = atan2_slow(r.nyw.x, r.xw.x);
+    if (live1 && !atan2_in_range(r.nyw.y, r.xw.y)) r.w.y = atan2_slow(r.nyw.y, r.xw.y);
+    if (live0 && !atan2_in_range(r.nyt.x, r.xt.x)) r.t.x = atan2_slow(r.nyt.x, r.xt.x);
+    if (live1 && !atan2_in_range(r.nyt.y, r.xt.y)) r.t.y = atan2_slow(r.nyt.y, r.xt.y);
     const V3 ba{r.bax, r.bay, r.baz};
-    if (!r.okf0) r.f.x = trrosetta_phi_exact(ba, V3{r.bc.x.x, r.bc.y.x, r.bc.z.x});
-    if (!r.okf1) r.f.y = trrosetta_phi_exact(ba, V3{r.bc.x.y, r.bc.y.y, r.bc.z.y});
-}
-
-template <bool ALL3>
-__device__ __forceinline__ void eval_row_finish(RowEval& r, int k, const JPair& jp, bool want_omega) {
-    if (ALL3 || want_omega) {
-        const int dk = k - jp.diag_k;  // 0: lane x is the diagonal entry, 1: lane y
-        if (dk == 0) r.w.x = r.diag;
-        if (dk == 1) r.w.y = r.diag;
-    }
-}
-
-// Row flags of a record: 1 = CA_i / CB_i missing (every angle of the row is NaN), 2 = N_i missing (theta is NaN).
-__device__ __forceinline__ int row_flags_of(const float4* __restrict__ rec4, int k) {
-    return __float_as_int(rec4[4 * k + 3].x);
+    // (a lane whose CB_j is missing is NaN either way and needs no exact evaluation)
+    if (live0 && !jp.nan0 && !(fabsf(r.c.x) <= 0.999f)) r.f.x = trrosetta_phi_exact(ba, V3{r.bc.x.x, r.bc.y.x, r.bc.z.x});
+    if (live1 && !jp.nan1 && !(fabsf(r.c.y) <= 0.999f)) r.f.y = trrosetta_phi_exact(ba, V3{r.bc.x.y, r.bc.y.y, r.bc.z.y});
 }
 
 // Loop order: a thread OWNS pairs of residues j (one pair when L <= 2 * blockDim.x) and walks the CTA's rows with them
@@ -349,14 +368,12 @@ __device__ __forceinline__ int row_flags_of(const float4* __restrict__ rec4, int
 // 64-bit stores; nothing that depends on j alone (its coordinates, its NaN flags, the position of the diagonal) is
 // redone per row.  (The first packed version walked j inside a row: with one j-pair per thread and row it re-read the
 // row record, the coordinates and the flags for every pair and spent a quarter of its issue slots on addressing.)
-// ROWS rows are evaluated per iteration: a row is one long dependent chain (differences -> cross products -> dot
-// products -> MUFU -> polynomial), and with ~20 resident warps per SM the second, independent chain is what fills
-// the issue slots the first one leaves (ncu of the one-row loop: issue-active 64 %, top stall `wait`).
-// ROWS = 2: two rows per iteration (120 registers, 16 warps / SM); ROWS = 1: one row, 77 registers, 24 warps / SM;
-// ROWS = 0 / -1 / -2: one row with the register budget of FOUR / FIVE / SIX CTAs per SM (64 / 51 / 42 registers,
-// 32 / 40 / 48 warps per SM) — the kernel is bound by dependent-issue latency, so resident warps are what it needs.
-template <bool VIRTUAL_CB, bool ALL3, int ROWS>
-__global__ void __launch_bounds__(256, ROWS == -2 ? 6 : (ROWS == -1 ? 5 : (ROWS == 0 ? 4 : (ROWS == 1 ? 3 : 2))))
+// MIN_CTAS = resident CTAs per SM the kernel is compiled for (its register budget): a row is one long dependent chain
+// (differences -> cross products -> dot products -> MUFU -> polynomial), so resident warps are what fills the issue
+// slots.  Measured at BASELINE config 3 with the round's first loop body: 3 CTAs (77 registers) 0.44 ms, 4 (64) 0.41,
+// 5 (51, spills) 0.44, 6 (42) 0.50; two rows per iteration at 120 registers (2 CTAs) 0.53.
+template <bool VIRTUAL_CB, bool ALL3, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
     trrosetta_fast_kernel(
     const float* __restrict__ xyz, float* __restrict__ omega, float* __restrict__ theta, float* __restrict__ phi, int L,
     int A, int rows_per_cta, int blocks_per_structure, int vector_stores) {
@@ -403,18 +420,24 @@ __global__ void __launch_bounds__(256, ROWS == -2 ? 6 : (ROWS == -1 ? 5 : (ROWS 
         tn1.x = fmaf(u.y, tb1.z, -(u.z * tb1.y));
         tn1.y = fmaf(u.z, tb1.x, -(u.x * tb1.z));
         tn1.z = fmaf(u.x, tb1.y, -(u.y * tb1.x));
+        V3 tm;                                            // (CB - CA) x tn1, fused
+        tm.x = fmaf(tb1.y, tn1.z, -(tb1.z * tn1.y));
+        tm.y = fmaf(tb1.z, tn1.x, -(tb1.x * tn1.z));
+        tm.z = fmaf(tb1.x, tn1.y, -(tb1.y * tn1.x));
         const float bb = fmaf(b0.z, b0.z, fmaf(b0.y, b0.y, b0.x * b0.x));
         const float inv = rsqrt_refined(bb);              // inf * 0 = NaN for bb = 0, NaN for missing atoms
         const float inv_or_inf = bb == 0.f ? __int_as_float(0x7f800000) : inv;
+        const float nb0 = bb * inv;                       // |b0|, NaN where the reference divides 0 / 0
+        const float omega_ii = 0.0f * inv_or_inf;         // 0, or NaN (missing / coincident CA, CB)
         float* rec = srow + k * kRowRecord;
         rec[0] = b0.x; rec[1] = b0.y; rec[2] = b0.z;
-        rec[3] = bb * inv;                                // |b0|, NaN where the reference divides 0 / 0
+        rec[3] = inv_or_inf;                              // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
         rec[4] = cb.x; rec[5] = cb.y; rec[6] = cb.z;
-        rec[7] = inv_or_inf;                              // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
-        rec[8] = tn1.x; rec[9] = tn1.y; rec[10] = tn1.z;
-        rec[11] = 0.0f * inv_or_inf;                      // omega[i, i]: 0, or NaN (missing / coincident)
-        rec[12] = __int_as_float((atom_has_nan(ca) || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(n_i) ? 2 : 0));
-        rec[13] = rec[14] = rec[15] = 0.f;
+        rec[7] = __int_as_float((atom_has_nan(ca) || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(n_i) ? 2 : 0));
+        rec[8] = tm.x; rec[9] = tm.y; rec[10] = tm.z;
+        rec[11] = omega_ii;
+        rec[12] = tn1.x * nb0; rec[13] = tn1.y * nb0; rec[14] = tn1.z * nb0;
+        rec[15] = omega_ii + 0.0f * tn1.x + 0.0f * tn1.y + 0.0f * tn1.z;  // theta[i, i]: NaN also without N_i
     }
     __syncthreads();
 
@@ -427,23 +450,7 @@ __global__ void __launch_bounds__(256, ROWS == -2 ? 6 : (ROWS == -1 ? 5 : (ROWS 
     const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(srow);
     const int npairs = Lp >> 1;
     const long long first_out = (b * L + row0) * L;  // element (b, row0, 0) of the outputs
-
-    auto store = [&](long long o, int j, float2 w, float2 t, float2 f) {
-        if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
-            if (want_omega) *reinterpret_cast<float2*>(omega + o) = w;
-            if (want_theta) *reinterpret_cast<float2*>(theta + o) = t;
-            if (want_phi) *reinterpret_cast<float2*>(phi + o) = f;
-        } else {
-            if (want_omega) omega[o] = w.x;
-            if (want_theta) theta[o] = t.x;
-            if (want_phi) phi[o] = f.x;
-            if (j + 1 < L) {
-                if (want_omega) omega[o + 1] = w.y;
-                if (want_theta) theta[o + 1] = t.y;
-                if (want_phi) phi[o + 1] = f.y;
-            }
-        }
-    };
+    const float2 nan2 = f2(__int_as_float(0x7fc00000));
 
     for (int jpi = threadIdx.x; jpi < npairs; jpi += blockDim.x) {
         JPair jp;
@@ -458,42 +465,52 @@ __global__ void __launch_bounds__(256, ROWS == -2 ? 6 : (ROWS == -1 ? 5 : (ROWS 
         jp.nan1 = fl & 0x0100;
         const int j = 2 * jpi;
         jp.diag_k = j - row0;
-        long long o = first_out + j;
         const bool pair_nan = jp.nan0 && jp.nan1;
-        const float2 nan2 = f2(__int_as_float(0x7fc00000));
-        int k = 0;
-        if constexpr (ROWS == 2) {
-            for (; k + 1 < nrows; k += 2, o += 2ll * L) {
-                const bool skip0 = pair_nan || (row_flags_of(rows4, k) & 1);
-                const bool skip1 = pair_nan || (row_flags_of(rows4, k + 1) & 1);
-                if (skip0 && skip1) {  // nothing to compute: missing atoms make both rows NaN for this pair
-                    store(o, j, nan2, nan2, nan2);
-                    store(o + L, j, nan2, nan2, nan2);
-                    continue;
+        const bool second = vector_stores || (j + 1 < L);  // lane y is a residue of the structure
+        // running output pointers of (row0 + k, j): one 64-bit add per feature and row
+        float* pw = (ALL3 || want_omega) ? omega + first_out + j : nullptr;
+        float* pt = (ALL3 || want_theta) ? theta + first_out + j : nullptr;
+        float* pf = (ALL3 || want_phi) ? phi + first_out + j : nullptr;
+        auto store = [&](float2 w, float2 t, float2 f) {
+            if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
+                if (ALL3 || want_omega) *reinterpret_cast<float2*>(pw) = w;
+                if (ALL3 || want_theta) *reinterpret_cast<float2*>(pt) = t;
+                if (ALL3 || want_phi) *reinterpret_cast<float2*>(pf) = f;
+            } else {
+                if (ALL3 || want_omega) pw[0] = w.x;
+                if (ALL3 || want_theta) pt[0] = t.x;
+                if (ALL3 || want_phi) pf[0] = f.x;
+                if (second) {
+                    if (ALL3 || want_omega) pw[1] = w.y;
+                    if (ALL3 || want_theta) pt[1] = t.y;
+                    if (ALL3 || want_phi) pf[1] = f.y;
                 }
-                RowEval r0, r1;
-                eval_row_core<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, r0);
-                eval_row_core<ALL3>(rows4, k + 1, jp, want_omega, want_theta, want_phi, r1);
-                if (r0.bad | r1.bad) {
-                    if (r0.bad) eval_row_patch(r0);
-                    if (r1.bad) eval_row_patch(r1);
-                }
-                eval_row_finish<ALL3>(r0, k, jp, want_omega);
-                eval_row_finish<ALL3>(r1, k + 1, jp, want_omega);
-                store(o, j, r0.w, r0.t, r0.f);
-                store(o + L, j, r1.w, r1.t, r1.f);
             }
-        }
-        for (; k < nrows; ++k, o += L) {
-            if (pair_nan || (row_flags_of(rows4, k) & 1)) {
-                store(o, j, nan2, nan2, nan2);
+        };
+        const float4* rec = rows4;
+        for (int k = 0; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) {
+            const float4 q1 = rec[1];
+            if (pair_nan || (__float_as_int(q1.w) & 1)) {
+                store(nan2, nan2, nan2);
                 continue;
             }
+            const float4 q0 = rec[0], q2 = rec[2], q3 = rec[3];
             RowEval r;
-            eval_row_core<ALL3>(rows4, k, jp, want_omega, want_theta, want_phi, r);
-            if (r.bad) eval_row_patch(r);
-            eval_row_finish<ALL3>(r, k, jp, want_omega);
-            store(o, j, r.w, r.t, r.f);
+            eval_row_core<ALL3>(q0, q1, q2, q3, jp, want_omega, want_theta, want_phi, r);
+            if (r.bad) eval_row_patch(r, jp, k - jp.diag_k);
+            store(r.w, r.t, r.f);
+        }
+        // the diagonal entries (row0 + dk, j) and (row0 + dk + 1, j + 1) of this pair of columns, if the CTA owns them
+        const int dk = jp.diag_k;
+#pragma unroll
+        for (int lane = 0; lane < 2; ++lane) {
+            const int k = dk + lane;
+            if (k < 0 || k >= nrows || j + lane >= L) continue;
+            const float* rec_k = srow + k * kRowRecord;
+            const long long o = first_out + static_cast<long long>(k) * L + j + lane;
+            if (ALL3 || want_omega) omega[o] = rec_k[11];
+            if (ALL3 || want_theta) theta[o] = rec_k[15];
+            if (ALL3 || want_phi) phi[o] = nan2.x;
         }
     }
 }
@@ -589,9 +606,13 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
     if (sms < 0) return sms;
     // Packed kernel: the structure's CA / CB (6 floats per residue) plus the row records must fit in shared memory.
     const int Lp = (L + 1) & ~1;
+    // one pair of residues j per thread (several beyond 512 residues)
+    int threads = ((Lp / 2) + 31) / 32 * 32;
+    if (threads > 256) threads = 256;
     // rows per CTA: as many as possible (the staging of the structure is amortised over them) while the grid still
     // holds >= 8 CTAs per SM (several waves: the CTAs of a launch differ a lot in cost when atoms are missing); at least 4,
-    // at most 64
+    // at most 64.  (A wave-quantisation model — minimise ceil(CTAs / resident slots) x (rows + staging) — was measured
+    // and lost: no gain at BASELINE config 3, and 57 -> 81 us at 64 x 384 ragged, where it picked a single wave.)
     int rows_per_cta = 64;
     while (rows_per_cta > 4 && rows / rows_per_cta < 8ll * sms) rows_per_cta /= 2;
     if (rows_per_cta > L) rows_per_cta = L;
@@ -599,38 +620,32 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
                         static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
-    // variant 0 (default): 64 registers; 3: two rows; 5 / 6: 51 / 42 registers; 7: 77 registers (round-2 first default)
-    const int rows_mode = variant == 3 ? 2 : (variant == 5 ? -1 : (variant == 6 ? -2 : (variant == 7 ? 1 : 0)));
+    // variant 0 (default): 3 CTAs / SM (80 registers, no spills); 4 / 5 / 6: compiled for 4 / 5 / 6 CTAs per SM
+    const int min_ctas = variant == 4 ? 4 : (variant == 5 ? 5 : (variant == 6 ? 6 : 3));
     if (variant != 1 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
-        int threads = ((Lp / 2) + 31) / 32 * 32;  // one pair of residues j per thread (several beyond 512 residues)
-        if (threads > 256) threads = 256;
         auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
         const int vector_stores = (L % 2 == 0) && aligned8(omega) && aligned8(theta) && aligned8(phi);
         const bool all3 = omega && theta && phi;
-#define PS_FAST(VCB, ALL, ROWS)                                                                                       \
+#define PS_FAST(VCB, ALL, MINC)                                                                                       \
     do {                                                                                                              \
-        cudaError_t err = cudaFuncSetAttribute(trrosetta_fast_kernel<VCB, ALL, ROWS>,                                 \
+        cudaError_t err = cudaFuncSetAttribute(trrosetta_fast_kernel<VCB, ALL, MINC>,                                 \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);              \
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(trrosetta_fast_kernel)");                 \
-        trrosetta_fast_kernel<VCB, ALL, ROWS><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                \
+        trrosetta_fast_kernel<VCB, ALL, MINC><<<static_cast<unsigned>(ctas), threads, smem, stream>>>(                \
             xyz, omega, theta, phi, L, A, rows_per_cta, blocks_per_structure, vector_stores);                         \
     } while (0)
-        // default: one row per iteration at 64 registers (32 warps / SM: 0.41 ms at config 3; 24 warps 0.44, two rows at
-        // 16 warps 0.53)
         if (use_virtual_cb) {
-            if (all3 && rows_mode == 2) PS_FAST(true, true, 2);
-            else if (all3 && rows_mode == 0) PS_FAST(true, true, 0);
-            else if (all3 && rows_mode == -1) PS_FAST(true, true, -1);
-            else if (all3 && rows_mode == -2) PS_FAST(true, true, -2);
-            else if (all3) PS_FAST(true, true, 1);
-            else PS_FAST(true, false, 1);
+            if (all3 && min_ctas == 4) PS_FAST(true, true, 4);
+            else if (all3 && min_ctas == 5) PS_FAST(true, true, 5);
+            else if (all3 && min_ctas == 6) PS_FAST(true, true, 6);
+            else if (all3) PS_FAST(true, true, 3);
+            else PS_FAST(true, false, 3);
         } else {
-            if (all3 && rows_mode == 2) PS_FAST(false, true, 2);
-            else if (all3 && rows_mode == 0) PS_FAST(false, true, 0);
-            else if (all3 && rows_mode == -1) PS_FAST(false, true, -1);
-            else if (all3 && rows_mode == -2) PS_FAST(false, true, -2);
-            else if (all3) PS_FAST(false, true, 1);
-            else PS_FAST(false, false, 1);
+            if (all3 && min_ctas == 4) PS_FAST(false, true, 4);
+            else if (all3 && min_ctas == 5) PS_FAST(false, true, 5);
+            else if (all3 && min_ctas == 6) PS_FAST(false, true, 6);
+            else if (all3) PS_FAST(false, true, 3);
+            else PS_FAST(false, false, 3);
         }
 #undef PS_FAST
         return check_launch("trrosetta_fast_kernel");
@@ -638,11 +653,11 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
     int grid = 0;
     int rc = grid_for_rows(rows, &grid);
     if (rc != PS_OK) return rc;
-    const int threads = threads_for_L(L);
+    const int row_threads = threads_for_L(L);
     if (use_virtual_cb)
-        trrosetta_kernel<true><<<grid, threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
+        trrosetta_kernel<true><<<grid, row_threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
     else
-        trrosetta_kernel<false><<<grid, threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
+        trrosetta_kernel<false><<<grid, row_threads, 0, stream>>>(xyz, omega, theta, phi, L, A, rows);
     return check_launch("trrosetta_kernel");
 }
 
