@@ -547,14 +547,17 @@ struct ColsParams {
 
 __host__ __device__ constexpr int round_up16(int v) { return (v + 15) & ~15; }
 
-template <int KIND, int SQRT>
-__global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
+// TA > 0: the atom count is a compile-time constant (the popular counts beyond the staged 15: 25 and atom37's 37) — the
+// column loop is fully unrolled with immediate shared-memory offsets, which removes the four running-pointer
+// increments per two elements and the loop control: about half of the instructions of a column.  TA = 0: any A.
+template <int KIND, int SQRT, int TA>
+__global__ void __launch_bounds__(384) pair_cols_kernel(const ColsParams p) {
     extern __shared__ __align__(128) unsigned char cols_smem[];
     constexpr bool kF32 = kind_has_f32<KIND>();
     constexpr bool kU8 = kind_has_u8<KIND>();
     constexpr bool kXyz = (KIND == kDistBoolMask || KIND == kDistOnly);
     constexpr bool kMaskIn = (KIND != kDistOnly);
-    const int A = p.A, L = p.L, P = p.tile_pairs;
+    const int A = TA > 0 ? TA : p.A, L = p.L, P = p.tile_pairs;
     const int AA = A * A;
     float* tile_f32 = reinterpret_cast<float*>(cols_smem);
     uint8_t* tile_u8 = cols_smem + (kF32 ? round_up16(P * AA * 4) : 0);
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
                     v.z = __ldg(xb + atom * 3 + 2);
                 }
                 if (KIND == kF32MaskOnly) v.w = __ldg(mbf + atom);
-                else if (kMaskIn) v.w = __ldg(mb8 + atom) != 0 ? 1.f : 0.f;
+                else if (kMaskIn) v.w = __int_as_float(__ldg(mb8 + atom) != 0 ? 1 : 0);  // the INTEGER 0 / 1: see below
             }
             float* row = xi + rr * 4 * Ae + a;
             row[0] = v.x;
@@ -636,8 +639,9 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
                 yj = __ldg(xb + atom_j * 3 + 1);
                 zj = __ldg(xb + atom_j * 3 + 2);
             }
+            int mjm = 0;  // byte kinds: all ones if atom c of residue j is present — a mask byte is then ONE LOP3
             if (KIND == kF32MaskOnly) mj = __ldg(mbf + atom_j);
-            else if (kMaskIn) mj = __ldg(mb8 + atom_j) != 0 ? 1.f : 0.f;
+            else if (kMaskIn) mjm = __ldg(mb8 + atom_j) != 0 ? -1 : 0;
             const float2* __restrict__ rx = reinterpret_cast<const float2*>(xi + r * 4 * Ae);
             const float2* __restrict__ ry = rx + (Ae >> 1);
             const float2* __restrict__ rz = ry + (Ae >> 1);
@@ -647,48 +651,97 @@ __global__ void __launch_bounds__(256) pair_cols_kernel(const ColsParams p) {
             uint8_t* ob = tile_u8 + off;
             const float2 xj2 = make_float2(xj, xj), yj2 = make_float2(yj, yj), zj2 = make_float2(zj, zj);
             const float2 mj2 = make_float2(mj, mj);
-            const bool mj_set = mj != 0.f;
-            // two atoms a, a + 1 of residue i per step, running output pointers (no index arithmetic in the loop); the
-            // last atom of an odd A is done on its own (its pair partner is the zero padding of the staging area)
-            const int row_step = 2 * A;
-            float* of1 = of + A;
-            uint8_t* ob1 = ob + A;
-            const int full = A >> 1;
-#pragma unroll 2
-            for (int h = 0; h < full; ++h) {
+            // Two atoms a = 2h, 2h + 1 of residue i per step, written at element offsets o0, o0 + A of the column.  The
+            // staged residue-i values and the tile live in the same shared memory, so the compiler cannot move a load
+            // above an earlier tile store by itself: the loads of step h + 2 are issued, in program order, before the
+            // stores of step h (each LDS -> FADD2 otherwise waits its full shared-memory latency).
+            struct IAtoms {
+                float2 vx, vy, vz, vw;
+            };
+            auto load_i = [&](int h) {
+                IAtoms v;
+                v.vx = v.vy = v.vz = v.vw = make_float2(0.f, 0.f);
+                if (kXyz) { v.vx = rx[h]; v.vy = ry[h]; v.vz = rz[h]; }
+                if (KIND == kF32MaskOnly || kU8) v.vw = rw[h];
+                return v;
+            };
+            auto emit = [&](const IAtoms& v, int o0) {
                 if (kXyz) {
-                    const float2 vx = rx[h], vy = ry[h], vz = rz[h];
-                    const float2 dx = __fadd2_rn(xj2, make_float2(-vx.x, -vx.y));
-                    const float2 dy = __fadd2_rn(yj2, make_float2(-vy.x, -vy.y));
-                    const float2 dz = __fadd2_rn(zj2, make_float2(-vz.x, -vz.y));
+                    const float2 dx = __fadd2_rn(xj2, make_float2(-v.vx.x, -v.vx.y));
+                    const float2 dy = __fadd2_rn(yj2, make_float2(-v.vy.x, -v.vy.y));
+                    const float2 dz = __fadd2_rn(zj2, make_float2(-v.vz.x, -v.vz.y));
                     const float2 ss = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                    *of = sqrt_mode<SQRT>(ss.x);
-                    *of1 = sqrt_mode<SQRT>(ss.y);
+                    of[o0] = sqrt_mode<SQRT>(ss.x);
+                    of[o0 + A] = sqrt_mode<SQRT>(ss.y);
                 }
-                if (KIND == kF32MaskOnly || kU8) {
-                    const float2 vw = rw[h];
-                    if (KIND == kF32MaskOnly) {
-                        const float2 prod = __fmul2_rn(vw, mj2);
-                        *of = prod.x;
-                        *of1 = prod.y;
-                    }
-                    if (kU8) {
-                        *ob = (mj_set && vw.x != 0.f) ? 1 : 0;
-                        *ob1 = (mj_set && vw.y != 0.f) ? 1 : 0;
-                    }
+                if (KIND == kF32MaskOnly) {
+                    const float2 prod = __fmul2_rn(v.vw, mj2);
+                    of[o0] = prod.x;
+                    of[o0 + A] = prod.y;
                 }
-                of += row_step;
-                of1 += row_step;
-                ob += row_step;
-                ob1 += row_step;
+                if (kU8) {
+                    ob[o0] = static_cast<uint8_t>(__float_as_int(v.vw.x) & mjm);
+                    ob[o0 + A] = static_cast<uint8_t>(__float_as_int(v.vw.y) & mjm);
+                }
+            };
+            const int full = A >> 1;
+            if constexpr (TA > 0) {
+                constexpr int H = TA / 2;
+                IAtoms cur = load_i(0), nxt = load_i(H > 1 ? 1 : 0);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    IAtoms after = nxt;
+                    if (h + 2 < H) after = load_i(h + 2);
+                    emit(cur, 2 * h * TA);  // immediate offsets
+                    cur = nxt;
+                    nxt = after;
+                }
+            } else {
+                // run-time A: running output pointers (no index arithmetic in the loop).  (Loads one step ahead, as in
+                // the unrolled loop, measured slower here: 0.83 instead of 0.93 of HBM at A = 20, distances only.)
+                const int row_step = 2 * A;
+                float* of1 = of + A;
+                uint8_t* ob1 = ob + A;
+#pragma unroll 2
+                for (int h = 0; h < full; ++h) {
+                    if (kXyz) {
+                        const float2 vx = rx[h], vy = ry[h], vz = rz[h];
+                        const float2 dx = __fadd2_rn(xj2, make_float2(-vx.x, -vx.y));
+                        const float2 dy = __fadd2_rn(yj2, make_float2(-vy.x, -vy.y));
+                        const float2 dz = __fadd2_rn(zj2, make_float2(-vz.x, -vz.y));
+                        const float2 ss = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                        *of = sqrt_mode<SQRT>(ss.x);
+                        *of1 = sqrt_mode<SQRT>(ss.y);
+                    }
+                    if (KIND == kF32MaskOnly || kU8) {
+                        const float2 vw = rw[h];
+                        if (KIND == kF32MaskOnly) {
+                            const float2 prod = __fmul2_rn(vw, mj2);
+                            *of = prod.x;
+                            *of1 = prod.y;
+                        }
+                        if (kU8) {
+                            *ob = static_cast<uint8_t>(__float_as_int(vw.x) & mjm);
+                            *ob1 = static_cast<uint8_t>(__float_as_int(vw.y) & mjm);
+                        }
+                    }
+                    of += row_step;
+                    of1 += row_step;
+                    ob += row_step;
+                    ob1 += row_step;
+                }
+                of -= full * row_step;
+                ob -= full * row_step;
             }
+            // the last atom of an odd A is done on its own (its pair partner is the zero padding of the staging area)
             if (A & 1) {
+                const int o0 = 2 * full * A;
                 if (kXyz) {
                     const float dx = xj - rx[full].x, dy = yj - ry[full].x, dz = zj - rz[full].x;
-                    *of = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                    of[o0] = sqrt_mode<SQRT>(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
                 }
-                if (KIND == kF32MaskOnly) *of = __fmul_rn(rw[full].x, mj);
-                if (kU8) *ob = (mj_set && rw[full].x != 0.f) ? 1 : 0;
+                if (KIND == kF32MaskOnly) of[o0] = __fmul_rn(rw[full].x, mj);
+                if (kU8) ob[o0] = static_cast<uint8_t>(__float_as_int(rw[full].x) & mjm);
             }
         }
 
@@ -831,11 +884,11 @@ int launch_tiles_sqrt(const PairDistParams& p, int sqrt_mode_id, int slots_overr
     }
 }
 
-template <int KIND>
-int launch_cols_kind(const ColsParams& p, int sqrt_mode_id, unsigned grid, int threads, size_t smem, cudaStream_t stream) {
+template <int KIND, int TA>
+int launch_cols_kind_ta(const ColsParams& p, int sqrt_mode_id, unsigned grid, int threads, size_t smem, cudaStream_t stream) {
 #define PS_COLS(SQRT)                                                                                              \
     do {                                                                                                           \
-        auto kernel = pair_cols_kernel<KIND, SQRT>;                                                                \
+        auto kernel = pair_cols_kernel<KIND, SQRT, TA>;                                                            \
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   \
         if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_cols_kernel)");                   \
         kernel<<<grid, threads, smem, stream>>>(p);                                                                \
@@ -851,9 +904,20 @@ int launch_cols_kind(const ColsParams& p, int sqrt_mode_id, unsigned grid, int t
     return check_launch("pair_cols_kernel");
 }
 
+// Atom counts with an unrolled instantiation (besides the staged kernels of 4 / 5 / 10 / 14 / 15 atoms): 25 (the
+// reference's test fixtures) and 37 (atom37).  `generic_a` keeps the run-time-A instantiation (comparison hook).
+template <int KIND>
+int launch_cols_kind(const ColsParams& p, int sqrt_mode_id, unsigned grid, int threads, size_t smem, bool generic_a,
+                     cudaStream_t stream) {
+    if (!generic_a && p.A == 25) return launch_cols_kind_ta<KIND, 25>(p, sqrt_mode_id, grid, threads, smem, stream);
+    if (!generic_a && p.A == 37) return launch_cols_kind_ta<KIND, 37>(p, sqrt_mode_id, grid, threads, smem, stream);
+    return launch_cols_kind_ta<KIND, 0>(p, sqrt_mode_id, grid, threads, smem, stream);
+}
+
 // Picks the tile (pairs per tile, threads per CTA) for one output kind and launches.  Returns PS_OK + launched =
 // false when no tile of this atom count fits in shared memory (the caller then uses the row kernel).
-// `tune`: bits 0-7 pairs per tile in units of the quantum (0 = choose), bit 8 = 128 threads per CTA.
+// `tune` (comparison hook): bits 0-7 pairs per tile in units of the quantum (0 = choose), bits 8-11 warps per CTA
+// (0 = choose; 13 = the run-time-A instantiation with the chosen CTA size).
 int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f32, void* out_u8, int B, int L, int A,
                 int sqrt_mode_id, int tune, bool* launched, cudaStream_t stream) {
     *launched = false;
@@ -884,7 +948,9 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
         if (pairs > step && pairs - step >= num_pairs) break;
         const long long smem = smem_for(pairs);
         if (smem > kSmemCap) break;
-        for (int threads : {256, 128}) {
+        // any whole number of warps (the columns of a tile rarely fill 256 threads) up to 12: 13 warps per CTA measured
+        // 0.58 of HBM where 7 gave 0.76 (A = 25; profiles/r2t_any_a_tile_sweep_before_unrolled.json)
+        for (int threads = 384; threads >= 64; threads -= 32) {
             const long long cols = pairs * A;
             const long long passes = (cols + threads - 1) / threads;
             long long ctas = kSmemPerSm / (smem + 1024);
@@ -905,8 +971,18 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
         }
     }
     if ((tune & 0xFF) > 0 && smem_for((tune & 0xFF) * step) <= kSmemCap) best_pairs = (tune & 0xFF) * step;
-    if (tune & 0x100) best_threads = 128;
-    if (tune & 0x200) best_threads = 256;
+    const bool generic_a = ((tune >> 8) & 15) == 13;
+    // The unrolled instantiations run ahead of the fitted model: their best tiles were measured directly
+    // (profiles/r2w_any_a_tile_sweep.json: A = 25 0.75 -> 0.87 of HBM with the mask, 0.95 -> 1.03 without).
+    if (!generic_a && (tune & 0xFF) == 0 && f32 && (A == 25 || A == 37)) {
+        const long long want_pairs = A == 25 ? (u8 ? 16 : 20) : (u8 ? 4 : 12);
+        const int want_threads = A == 25 ? (u8 ? 128 : 192) : (u8 ? 160 : 256);
+        if (want_pairs % step == 0 && want_pairs <= num_pairs && smem_for(want_pairs) <= kSmemCap) {
+            best_pairs = want_pairs;
+            best_threads = want_threads;
+        }
+    }
+    if (((tune >> 8) & 15) && !generic_a) best_threads = 32 * ((tune >> 8) & 15);
     PS_REQUIRE(best_pairs * A < (1ll << 24), PS_ERR_BAD_SHAPE, "pair_dist_mask: tile of %lld pairs x %d atoms", best_pairs, A);
     ColsParams p;
     p.xyz = xyz;
@@ -936,10 +1012,10 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
     g_last_plan.tile_pairs = best_pairs;
     ++g_last_plan.launches;
     switch (kind) {
-        case kDistBoolMask: return launch_cols_kind<kDistBoolMask>(p, sqrt_mode_id, grid, best_threads, smem, stream);
-        case kDistOnly: return launch_cols_kind<kDistOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
-        case kF32MaskOnly: return launch_cols_kind<kF32MaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
-        default: return launch_cols_kind<kBoolMaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, stream);
+        case kDistBoolMask: return launch_cols_kind<kDistBoolMask>(p, sqrt_mode_id, grid, best_threads, smem, generic_a, stream);
+        case kDistOnly: return launch_cols_kind<kDistOnly>(p, sqrt_mode_id, grid, best_threads, smem, generic_a, stream);
+        case kF32MaskOnly: return launch_cols_kind<kF32MaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, generic_a, stream);
+        default: return launch_cols_kind<kBoolMaskOnly>(p, sqrt_mode_id, grid, best_threads, smem, generic_a, stream);
     }
 }
 
@@ -1180,7 +1256,7 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     const bool fast = staged_atom_count && (L >= tile_pairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
         const bool rows_only = (variant >> 12) & 1;
-        int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0x3FF, stream);
+        int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0xFFF, stream);
         if (rc != PS_OK || !want_angles) return rc;
         ++g_last_plan.launches;
         // the exact-sequence angle kernel: the same trrosetta_triple the fused tile kernel evaluates, so

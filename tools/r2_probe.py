@@ -111,7 +111,14 @@ def main():
             _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(), B, L, A,
                                                  force, s), "cols")
         best, med = time_call(run_cols, flush=False)
-        add(f"K1 any-A tile kernel dist+boolmask B{B} L{L} A{A}", best, med, B * L * L * A * A * 5)
+        add(f"K1 any-A tile kernel dist+boolmask B{B} L{L} A{A}", best, med, B * L * L * A * A * 5,
+            plan=_cabi.last_pair_dist_plan())
+
+        def run_cols_r1():
+            _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(), dmask.data_ptr(), B, L, A,
+                                                 force | (13 << 24), s), "cols generic A")
+        best, med = time_call(run_cols_r1, flush=False)
+        add(f"K1 any-A tile kernel dist+boolmask B{B} L{L} A{A} [run-time-A instantiation]", best, med, B * L * L * A * A * 5)
 
         def run_cols_dist():
             _cabi.check(lib.ps_pair_dist_mask_ex(xyz.data_ptr(), None, 0, dist.data_ptr(), None, B, L, A, force, s), "cols d")
