@@ -46,30 +46,62 @@ __device__ __forceinline__ void block_sum(double (&v)[N], double (*scratch)[N]) 
     }
 }
 
-// Cyclic Jacobi for a symmetric 3x3 matrix; eigenvectors in the columns of V, eigenvalues in w.
+// Cyclic Jacobi for a symmetric positive semi-definite 3x3 matrix; eigenvectors in the columns of V, eigenvalues in w.
+// One thread runs this per structure, so its latency is the kernel's tail: the matrix is scaled to unit trace, and the
+// rotation ANGLE is computed in fp32 (MUFU square root and reciprocal instead of three fp64 divisions and two fp64
+// square roots per rotation — an inexact angle only slows the convergence of that one rotation from "to zero" to "by
+// 1e-7"), while the rotation itself, c = rsqrt(1 + t^2), s = t c, is applied in fp64 so that V stays orthogonal to
+// fp64 accuracy.
 __device__ void jacobi_eigen3(double (&a)[3][3], double (&V)[3][3], double (&w)[3]) {
+#pragma unroll
     for (int i = 0; i < 3; ++i)
+#pragma unroll
         for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    const double trace = a[0][0] + a[1][1] + a[2][2];
+    const bool scaled = trace > 0.0 && trace < 1e300;
+    if (scaled) {
+        const double inv = 1.0 / trace;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) a[i][j] *= inv;
+    }
     for (int sweep = 0; sweep < 32; ++sweep) {
         const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
         const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
         if (off <= 1e-32 * diag || off == 0.0) break;
+        // (every loop below is unrolled: the matrices are indexed by constants only and live in registers)
+#pragma unroll
         for (int p = 0; p < 2; ++p) {
+#pragma unroll
             for (int q = p + 1; q < 3; ++q) {
                 if (a[p][q] == 0.0) continue;
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                double t;
+                if (scaled) {
+                    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), theta = d / (2 a_pq), without dividing by a_pq
+                    const float apq2 = 2.0f * static_cast<float>(a[p][q]);
+                    const float d = static_cast<float>(a[q][q] - a[p][p]);
+                    const float den = fabsf(d) + sqrtf(fmaf(d, d, apq2 * apq2));
+                    t = den > 0.f ? static_cast<double>(__fdividef(d >= 0.f ? apq2 : -apq2, den)) : 0.0;
+                    if (t == 0.0) continue;  // a_pq below fp32 range relative to the trace: nothing left to rotate
+                } else {
+                    const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                    t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                }
+                const double c = rsqrt(t * t + 1.0), s = t * c;
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {  // A <- A J
                     const double akp = a[k][p], akq = a[k][q];
                     a[k][p] = c * akp - s * akq;
                     a[k][q] = s * akp + c * akq;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {  // A <- J^T A
                     const double apk = a[p][k], aqk = a[q][k];
                     a[p][k] = c * apk - s * aqk;
                     a[q][k] = s * apk + c * aqk;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {  // V <- V J
                     const double vkp = V[k][p], vkq = V[k][q];
                     V[k][p] = c * vkp - s * vkq;
@@ -78,56 +110,12 @@ __device__ void jacobi_eigen3(double (&a)[3][3], double (&V)[3][3], double (&w)[
             }
         }
     }
-    for (int i = 0; i < 3; ++i) w[i] = a[i][i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = a[i][i];  // (scaled by 1 / trace: only their order is used)
 }
 
-__global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
-    const float* __restrict__ src, const float* __restrict__ dst, const uint8_t* __restrict__ mask,
-    int dst_rows, int n_atoms, float* __restrict__ rot, float* __restrict__ trans) {
-    __shared__ double scratch[kKabschThreads / 32][16];
-    const long long b = blockIdx.x;
-    const float* __restrict__ a = src + b * n_atoms * 3;
-    const float* __restrict__ t = dst + (dst_rows == 1 ? 0 : b) * static_cast<long long>(n_atoms) * 3;
-    const uint8_t* __restrict__ m = mask + b * n_atoms;
-
-    // ONE pass over the selected atoms: first moments (centroids, reference: a.mean(dim=-2), b.mean(dim=-2)) and
-    // the raw second moments sum a_i b_j, all in fp64, so that the centred covariance
-    //   H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j = sum a_i b_j - n ca_i cb_j
-    // loses nothing that matters (|x| ~ 1e2, n ~ 1e4: the subtraction cancels ~4 of fp64's 16 digits).
-    // The loop is latency-bound (one CTA per structure, ~15 atoms per thread): the mask bytes and BOTH coordinate
-    // triples of kKabschUnroll atoms are requested before the first use, unconditionally (an unselected atom's
-    // coordinates are discarded by the select below, so NaN there is harmless).
-    double s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k0 = threadIdx.x; k0 < n_atoms; k0 += kKabschUnroll * blockDim.x) {
-        float pa[kKabschUnroll][3], pb[kKabschUnroll][3];
-        bool sel[kKabschUnroll];
-#pragma unroll
-        for (int u = 0; u < kKabschUnroll; ++u) {
-            const int k = k0 + u * blockDim.x;
-            const bool in = k < n_atoms;
-            const int kk = in ? k : 0;
-            sel[u] = in && __ldg(m + kk) != 0;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                pa[u][c] = __ldg(a + 3 * kk + c);
-                pb[u][c] = __ldg(t + 3 * kk + c);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kKabschUnroll; ++u) {
-            if (sel[u]) {
-                const double ax = pa[u][0], ay = pa[u][1], az = pa[u][2];
-                const double bx = pb[u][0], by = pb[u][1], bz = pb[u][2];
-                s[0] += ax; s[1] += ay; s[2] += az;
-                s[3] += bx; s[4] += by; s[5] += bz;
-                s[6] += 1.0;
-                s[7] += ax * bx; s[8] += ax * by; s[9] += ax * bz;
-                s[10] += ay * bx; s[11] += ay * by; s[12] += ay * bz;
-                s[13] += az * bx; s[14] += az * by; s[15] += az * bz;
-            }
-        }
-    }
-    block_sum<16>(s, scratch);
+// Closed 3x3 solve from the sixteen masked sums (first moments 0-5, count 6, raw second moments 7-15) by ONE thread.
+__device__ void kabsch_solve(const double (&s)[16], long long b, float* __restrict__ rot, float* __restrict__ trans) {
     const double cnt = s[6];
     const double ca[3] = {s[0] / cnt, s[1] / cnt, s[2] / cnt};
     const double cb[3] = {s[3] / cnt, s[4] / cnt, s[5] / cnt};
@@ -135,7 +123,7 @@ __global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) h[i * 3 + j] = s[7 + i * 3 + j] - cnt * ca[i] * cb[j];
 
-    if (threadIdx.x == 0) {
+    {
         double H[3][3] = {{h[0], h[1], h[2]}, {h[3], h[4], h[5]}, {h[6], h[7], h[8]}};
         double K[3][3];  // H^T H
         for (int i = 0; i < 3; ++i)
@@ -193,6 +181,112 @@ __global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
     }
 }
 
+__global__ void __launch_bounds__(kKabschThreads) kabsch_kernel(
+    const float* __restrict__ src, const float* __restrict__ dst, const uint8_t* __restrict__ mask,
+    int dst_rows, int n_atoms, float* __restrict__ rot, float* __restrict__ trans) {
+    __shared__ double scratch[kKabschThreads / 32][16];
+    const long long b = blockIdx.x;
+    const float* __restrict__ a = src + b * n_atoms * 3;
+    const float* __restrict__ t = dst + (dst_rows == 1 ? 0 : b) * static_cast<long long>(n_atoms) * 3;
+    const uint8_t* __restrict__ m = mask + b * n_atoms;
+
+    // ONE pass over the selected atoms: first moments (centroids, reference: a.mean(dim=-2), b.mean(dim=-2)) and
+    // the raw second moments sum a_i b_j, all in fp64, so that the centred covariance
+    //   H[i][j] = sum_k (a_k - ca)_i (b_k - cb)_j = sum a_i b_j - n ca_i cb_j
+    // loses nothing that matters (|x| ~ 1e2, n ~ 1e4: the subtraction cancels ~4 of fp64's 16 digits).
+    // The loop is latency-bound (one CTA per structure, ~15 atoms per thread): the mask bytes and BOTH coordinate
+    // triples of kKabschUnroll atoms are requested before the first use, unconditionally (an unselected atom's
+    // coordinates are discarded by the select below, so NaN there is harmless).
+    double s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k0 = threadIdx.x; k0 < n_atoms; k0 += kKabschUnroll * blockDim.x) {
+        float pa[kKabschUnroll][3], pb[kKabschUnroll][3];
+        bool sel[kKabschUnroll];
+#pragma unroll
+        for (int u = 0; u < kKabschUnroll; ++u) {
+            const int k = k0 + u * blockDim.x;
+            const bool in = k < n_atoms;
+            const int kk = in ? k : 0;
+            sel[u] = in && __ldg(m + kk) != 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                pa[u][c] = __ldg(a + 3 * kk + c);
+                pb[u][c] = __ldg(t + 3 * kk + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kKabschUnroll; ++u) {
+            if (sel[u]) {
+                const double ax = pa[u][0], ay = pa[u][1], az = pa[u][2];
+                const double bx = pb[u][0], by = pb[u][1], bz = pb[u][2];
+                s[0] += ax; s[1] += ay; s[2] += az;
+                s[3] += bx; s[4] += by; s[5] += bz;
+                s[6] += 1.0;
+                s[7] += ax * bx; s[8] += ax * by; s[9] += ax * bz;
+                s[10] += ay * bx; s[11] += ay * by; s[12] += ay * bz;
+                s[13] += az * bx; s[14] += az * by; s[15] += az * bz;
+            }
+        }
+    }
+    block_sum<16>(s, scratch);
+    if (threadIdx.x == 0) kabsch_solve(s, b, rot, trans);
+}
+
+// The same sums with 128-bit loads: four atoms (48 B of each coordinate set, 4 mask bytes) per thread and step as
+// 3 + 3 + 1 loads instead of 28, two steps in flight, 256 threads so that two CTAs (structures) share an SM.  Needs
+// n_atoms % 4 == 0 and 16-byte aligned coordinate sets (every structure then starts on a 16-byte boundary).
+__device__ __forceinline__ void kabsch_accumulate(double (&s)[16], bool sel, float ax, float ay, float az, float bx,
+                                                  float by, float bz) {
+    if (sel) {
+        const double dax = ax, day = ay, daz = az, dbx = bx, dby = by, dbz = bz;
+        s[0] += dax; s[1] += day; s[2] += daz;
+        s[3] += dbx; s[4] += dby; s[5] += dbz;
+        s[6] += 1.0;
+        s[7] += dax * dbx; s[8] += dax * dby; s[9] += dax * dbz;
+        s[10] += day * dbx; s[11] += day * dby; s[12] += day * dbz;
+        s[13] += daz * dbx; s[14] += daz * dby; s[15] += daz * dbz;
+    }
+}
+
+constexpr int kKabschQuadThreads = 256;
+
+__global__ void __launch_bounds__(kKabschQuadThreads, 2) kabsch_quad_kernel(
+    const float* __restrict__ src, const float* __restrict__ dst, const uint8_t* __restrict__ mask,
+    int dst_rows, int n_atoms, float* __restrict__ rot, float* __restrict__ trans) {
+    __shared__ double scratch[kKabschQuadThreads / 32][16];
+    const long long b = blockIdx.x;
+    const float4* __restrict__ a4 = reinterpret_cast<const float4*>(src + b * n_atoms * 3);
+    const float4* __restrict__ t4 =
+        reinterpret_cast<const float4*>(dst + (dst_rows == 1 ? 0 : b) * static_cast<long long>(n_atoms) * 3);
+    const uint32_t* __restrict__ m4 = reinterpret_cast<const uint32_t*>(mask + b * n_atoms);
+    const int quads = n_atoms >> 2;
+    double s[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q0 = threadIdx.x; q0 < quads; q0 += 2 * blockDim.x) {
+        uint32_t m[2];
+        float4 a[2][3], t[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {  // both steps' loads are requested before the first use
+            const int q = q0 + u * blockDim.x;
+            const bool in = q < quads;
+            const int qq = in ? q : q0;
+            m[u] = in ? __ldg(m4 + qq) : 0u;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                a[u][k] = __ldg(a4 + 3 * qq + k);
+                t[u][k] = __ldg(t4 + 3 * qq + k);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            kabsch_accumulate(s, (m[u] & 0x000000ffu) != 0, a[u][0].x, a[u][0].y, a[u][0].z, t[u][0].x, t[u][0].y, t[u][0].z);
+            kabsch_accumulate(s, (m[u] & 0x0000ff00u) != 0, a[u][0].w, a[u][1].x, a[u][1].y, t[u][0].w, t[u][1].x, t[u][1].y);
+            kabsch_accumulate(s, (m[u] & 0x00ff0000u) != 0, a[u][1].z, a[u][1].w, a[u][2].x, t[u][1].z, t[u][1].w, t[u][2].x);
+            kabsch_accumulate(s, (m[u] & 0xff000000u) != 0, a[u][2].y, a[u][2].z, a[u][2].w, t[u][2].y, t[u][2].z, t[u][2].w);
+        }
+    }
+    block_sum<16>(s, scratch);
+    if (threadIdx.x == 0) kabsch_solve(s, b, rot, trans);
+}
+
 // ---- top-k nearest residues ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) min_query_distance_kernel(const float* __restrict__ xyz,
                                                                  const uint8_t* __restrict__ valid,
@@ -243,6 +337,25 @@ int kabsch_impl(const float* src, const float* dst, const uint8_t* mask, int dst
     int threads = (n_atoms / 16 + 31) / 32 * 32;
     if (threads < 64) threads = 64;
     if (threads > kKabschThreads) threads = kKabschThreads;
+    const bool quads = (n_atoms % 4 == 0) && n_atoms >= 4 * 64 &&
+                       ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0 &&
+                       (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
+    if (quads) {
+        // CTA size: the largest of 256 / 128 / 64 threads with which all B structures are resident at once (110
+        // registers per thread), else about four 4-atom steps per thread
+        const int sms = sm_count_for_current_device();
+        if (sms < 0) return sms;
+        int quad_threads = 0;
+        for (int cand : {256, 128, 64}) {
+            if (4 * cand > n_atoms) continue;
+            int per_sm = 65536 / (110 * cand);
+            if (per_sm > 32) per_sm = 32;
+            if (static_cast<long long>(per_sm) * sms >= B) { quad_threads = cand; break; }
+        }
+        if (quad_threads == 0) quad_threads = n_atoms / 16 >= 256 ? 256 : (n_atoms / 16 >= 128 ? 128 : 64);
+        kabsch_quad_kernel<<<B, quad_threads, 0, stream>>>(src, dst, mask, dst_rows, n_atoms, rot, trans);
+        return check_launch("kabsch_quad_kernel");
+    }
     kabsch_kernel<<<B, threads, 0, stream>>>(src, dst, mask, dst_rows, n_atoms, rot, trans);
     return check_launch("kabsch_kernel");
 }

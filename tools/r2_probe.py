@@ -165,6 +165,12 @@ def main():
                                       tr.data_ptr(), s), "kabsch")
         best, med = time_call(run_kabsch)
         add(f"f2 kabsch B{B} L{L} A{A}", best, med, B * L * A * 25)
+
+        def run_kabsch_small():  # 64 atoms per structure: the launch and the serial 3x3 solve, next to no data
+            _cabi.check(lib.ps_kabsch(xyz.data_ptr(), tgt.data_ptr(), m8.data_ptr(), B, B, 64, rot.data_ptr(),
+                                      tr.data_ptr(), s), "kabsch small")
+        best, med = time_call(run_kabsch_small)
+        add(f"f2 kabsch B{B} x 64 atoms (solve only)", best, med, B * 64 * 25)
         sb = ps.StructureBatch.from_xyz(xyz, mask)
         rm = sb.residue_mask.to(torch.uint8).contiguous()
         ch = sb.chain_idx.float().contiguous()
