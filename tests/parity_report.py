@@ -70,6 +70,11 @@ def main():
             for which in ("omega", "theta", "phi"):
                 r[which] = dev_stats(out[which], H.t(g[f"ref_{which}"]), angle_conditioning(xyz, which),
                                      circular=which != "phi")
+            # the standalone packed angle kernel (K2f, `trrosetta_angles`): spends the 1e-5 rad contract
+            om, th, ph = sb.trrosetta_angles()
+            for which, got in (("omega", om), ("theta", th), ("phi", ph)):
+                r[f"{which}_packed_kernel"] = dev_stats(got, H.t(g[f"ref_{which}"]), angle_conditioning(xyz, which),
+                                                        circular=which != "phi")
         dih, dmask = sb.backbone_dihedrals()
         r["bb_dihedrals"] = dev_stats(dih, H.t(g["ref_bb_dihedrals"]))
         r["bb_dihedral_mask_bit_exact"] = bool(torch.equal(dmask.cpu(), H.t(g["ref_bb_dihedral_mask"])))
