@@ -1025,6 +1025,85 @@ def test_align_matches_reference_golden(native_lib):
         src.align(ps.StructureBatch.from_xyz(g["align_target"][:2], g["atom_mask"][:2]))
 
 
+def _kabsch_fp64(a, b, m):
+    """Reference Kabsch of geometry.py:442-480 in float64: rotation R and translation t with  b ~ a R^T + t."""
+    a, b = a[m].double(), b[m].double()
+    ca, cb = a.mean(0), b.mean(0)
+    h = (a - ca).T @ (b - cb)
+    u, _, vt = torch.linalg.svd(h)
+    d = torch.sign(torch.linalg.det(vt.T @ u.T))
+    r = vt.T @ torch.diag(torch.tensor([1.0, 1.0, float(d)], dtype=torch.float64)) @ u.T
+    return r, cb - r @ ca
+
+
+@pytest.mark.parametrize("B,n_atoms", [(5, 960), (3, 7680), (40, 256), (2, 1924)])
+def test_kabsch_vector_and_scalar_kernels_agree_with_an_fp64_svd(native_lib, B, n_atoms):
+    """Round 2: structures of a multiple of 4 atoms take `kabsch_quad_kernel` (128-bit loads, fp32 Jacobi angles); a mask
+    pointer that is not 4-byte aligned keeps the scalar kernel.  Both against a float64 SVD Kabsch, through the C-ABI."""
+    g = torch.Generator().manual_seed(11 * B + n_atoms)
+    a = 30.0 * torch.randn(B, n_atoms, 3, generator=g) + 100.0 * torch.randn(B, 1, 3, generator=g)  # far from the origin
+    q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    q = q * torch.sign(torch.linalg.det(q))[:, None, None]
+    b = a @ q.transpose(1, 2) + 50.0 * torch.randn(B, 1, 3, generator=g) + 0.05 * torch.randn(B, n_atoms, 3, generator=g)
+    m = torch.rand(B, n_atoms, generator=g) < 0.6
+    a[~m] = float("nan")  # unselected atoms may hold anything
+    ad, bd = a.to(DEV).contiguous(), b.to(DEV).contiguous()
+    mbuf = torch.zeros(B * n_atoms + 8, dtype=torch.uint8, device=DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    results = []
+    for shift in (0, 1):  # 0: 4-byte aligned mask -> vector kernel; 1: scalar kernel
+        mview = mbuf[shift:shift + B * n_atoms]
+        mview.copy_(m.reshape(-1).to(torch.uint8))
+        rot = torch.full((B, 3, 3), 7.0, device=DEV)
+        tr = torch.full((B, 3), 7.0, device=DEV)
+        _cabi.check(native_lib.ps_kabsch(ad.data_ptr(), bd.data_ptr(), mview.data_ptr(), B, B, n_atoms, rot.data_ptr(),
+                                         tr.data_ptr(), s), "ps_kabsch")
+        torch.cuda.synchronize()
+        results.append((rot.cpu().double(), tr.cpu().double()))
+    for rot, tr in results:
+        for k in range(B):
+            r_ref, t_ref = _kabsch_fp64(torch.nan_to_num(a[k]), b[k], m[k])
+            assert (rot[k] - r_ref).abs().max().item() < 2e-6, (k, (rot[k] - r_ref).abs().max().item())
+            assert (tr[k] - t_ref).abs().max().item() < 5e-4, (k, (tr[k] - t_ref).abs().max().item())
+    assert (results[0][0] - results[1][0]).abs().max().item() < 1e-6
+    assert (results[0][1] - results[1][1]).abs().max().item() < 2e-4
+
+
+def test_packed_angle_kernel_register_budgets_and_unrolled_any_a_kernels_give_the_same_bits(native_lib):
+    """include/protstruc_b200.h: every packed variant of ps_trrosetta_angles_ex (3 / 4 / 5 / 6 CTAs per SM) produces
+    the same bits; the unrolled A = 25 / 37 instantiations of the any-A tile kernel equal the run-time-A instantiation."""
+    s = torch.cuda.current_stream().cuda_stream
+    same = lambda p, q: torch.equal(p.view(torch.int32), q.view(torch.int32))  # noqa: E731
+    for (B, L, A) in ((3, 100, 5), (2, 77, 15), (1, 600, 5)):
+        xyz, _, _ = H.synthetic_batch(4200 + L, B, L, A, "bool")
+        x = xyz.to(DEV).contiguous()
+        outs = {}
+        for variant in (0, 4, 5, 6):
+            o = torch.empty(3, B, L, L, device=DEV)
+            _cabi.check(native_lib.ps_trrosetta_angles_ex(x.data_ptr(), B, L, A, 0, o[0].data_ptr(), o[1].data_ptr(),
+                                                          o[2].data_ptr(), variant, s), "ps_trrosetta_angles_ex")
+            outs[variant] = o
+        torch.cuda.synchronize()
+        for variant in (4, 5, 6):
+            assert same(outs[variant], outs[0]), (B, L, A, variant)
+    force = 1 << 8
+    for (B, L, A) in ((2, 40, 25), (2, 23, 37)):
+        xyz, mask, _ = H.synthetic_batch(4300 + A, B, L, A, "bool")
+        x, m = xyz.to(DEV).contiguous(), mask.to(DEV).contiguous()
+        outs = []
+        for variant in (force, force | (13 << 24)):
+            d = torch.empty(B, L, L, A, A, device=DEV)
+            dm = torch.empty(B, L, L, A, A, dtype=torch.bool, device=DEV)
+            _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
+                                                        variant, s), "ps_pair_dist_mask_ex")
+            outs.append((d, dm))
+        torch.cuda.synchronize()
+        assert same(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), (B, L, A)
+        rd, rm = orc.pair_distances(xyz, mask)
+        H.assert_distances_close(outs[0][0], rd)
+        assert torch.equal(outs[0][1].cpu(), rm)
+
+
 def test_topk_nearest_residue_mask_and_select_match_reference_golden(native_lib):
     g = H.load_golden("frames_align_topk")
     real = H.load_golden("real_1a6v_HL")
