@@ -171,7 +171,8 @@ int ps_backbone(const float* xyz, const uint8_t* residue_mask, const float* chai
 int ps_masked_stats(const float* xyz, const void* atom_mask, int mask_dtype,
                     int B, int L, int A, float* mu, float* sd, float* xyz_out, void* stream);
 /* Comparison hook: variant 0 = default (register-resident single-read kernels), 1 = the three-pass kernel of round 1,
- * 2 = the scalar-mapped register-resident kernel also where the quad kernel applies. */
+ * 2 = the scalar-mapped register-resident kernel also where the quad kernel applies, 3 = the quad kernel restricted to
+ * one or two 4-atom groups per thread (without the dense configuration that keeps every structure resident). */
 int ps_masked_stats_ex(const float* xyz, const void* atom_mask, int mask_dtype,
                        int B, int L, int A, float* mu, float* sd, float* xyz_out, int variant, void* stream);
 

@@ -409,8 +409,46 @@ __device__ __forceinline__ void block_sum3(double (&v)[3], float& c, double (*sc
     c = static_cast<float>(scratch[kStatsMaxThreads / 32][3]);
 }
 
-template <int MASK_DTYPE, int Q, bool CLUSTER>
-__global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
+// The same totals from fp32 per-thread partials: the five shuffle levels inside a warp stay in fp32 (a pairwise tree over
+// 32 partials of <= 16 values each; a double costs two SHFL per level), the warps' sums meet in fp64 as above.
+__device__ __forceinline__ void block_sum3f(const float (&p)[3], float c, double (*scratch)[4], double (&total)[3],
+                                            float& count) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float v0 = p[0], v1 = p[1], v2 = p[2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    __syncthreads();  // scratch reuse across calls
+    if (lane == 0) {
+        scratch[warp][0] = static_cast<double>(v0);
+        scratch[warp][1] = static_cast<double>(v1);
+        scratch[warp][2] = static_cast<double>(v2);
+        scratch[warp][3] = static_cast<double>(c);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < nwarps; ++w) t += scratch[w][threadIdx.x];
+        scratch[kStatsMaxThreads / 32][threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) total[k] = scratch[kStatsMaxThreads / 32][k];
+    count = static_cast<float>(scratch[kStatsMaxThreads / 32][3]);
+}
+
+__device__ __forceinline__ float max3_abs(float a, float b, float c) {  // max(a, |b|, |c|) ignoring NaN: one FMNMX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c)));
+    return r;
+}
+
+template <int MASK_DTYPE, int Q, bool CLUSTER, int MAXT = kStatsMaxThreads, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) masked_stats_quad_kernel(
     const float* __restrict__ xyz, const void* __restrict__ atom_mask, int atoms_per_struct,
     float* __restrict__ mu_out, float* __restrict__ sd_out, float* __restrict__ xyz_out) {
     namespace cg = cooperative_groups;
@@ -446,23 +484,39 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
         }
     }
     constexpr float kMax = 3.4028234663852886e38f;
+    constexpr bool kBoolMask = MASK_DTYPE == PS_MASK_BOOL;
     // pass 1: sum(nan_to_num(x * m)) per axis, sum(m); per-thread partials in fp32 (<= 4 Q values per axis).
     // Straight-line: NaN (a missing atom — half of the atoms of a real batch) becomes 0 by a select, infinities only
     // raise a flag, and a thread that saw one redoes its sums through the full nan_to_num.  `inf_x` is reused by pass 2.
+    // With a 0 / 1 mask the product x * m is exact, so  s + nan_to_num(x * m)  is ONE fused multiply-add of the
+    // NaN-cleaned x (same bits as the reference's multiply, nan_to_num, add), and |x * m| <= |x|: one running maximum
+    // of |x| (an FMNMX3 per two elements) replaces the two infinity tests per element.
     float s[3] = {0.f, 0.f, 0.f}, c = 0.f;
     bool inf_x = false, inf_xm = false;
+    float amax = 0.f;  // max |x| over this thread's elements, NaN ignored (bool masks)
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
+        if (kBoolMask) {
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {
-            const float x = quad_get(v[k], e);
-            const float t = __fmul_rn(x, m[k][e / 3]);
-            inf_x |= fabsf(x) > kMax;
-            inf_xm |= fabsf(t) > kMax;
-            s[e % 3] += (t == t) ? t : 0.f;
+            for (int e = 0; e < 12; e += 2) {
+                const float x0 = quad_get(v[k], e), x1 = quad_get(v[k], e + 1);
+                s[e % 3] = __fmaf_rn((x0 == x0) ? x0 : 0.f, m[k][e / 3], s[e % 3]);
+                s[(e + 1) % 3] = __fmaf_rn((x1 == x1) ? x1 : 0.f, m[k][(e + 1) / 3], s[(e + 1) % 3]);
+                amax = max3_abs(amax, x0, x1);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const float x = quad_get(v[k], e);
+                const float t = __fmul_rn(x, m[k][e / 3]);
+                inf_x |= fabsf(x) > kMax;
+                inf_xm |= fabsf(t) > kMax;
+                s[e % 3] += (t == t) ? t : 0.f;
+            }
         }
         c += (m[k][0] + m[k][1]) + (m[k][2] + m[k][3]);
     }
+    if (kBoolMask) inf_x = inf_xm = amax > kMax;
     if (inf_xm) {
         s[0] = s[1] = s[2] = 0.f;
 #pragma unroll
@@ -470,8 +524,8 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
 #pragma unroll
             for (int e = 0; e < 12; ++e) s[e % 3] += nan_to_num0(__fmul_rn(quad_get(v[k], e), m[k][e / 3]));
     }
-    double acc[3] = {static_cast<double>(s[0]), static_cast<double>(s[1]), static_cast<double>(s[2])};
-    block_sum3(acc, c, scratch);
+    double acc[3];
+    block_sum3f(s, c, scratch, acc, c);
     if (CLUSTER) {
         double a4[4] = {acc[0], acc[1], acc[2], static_cast<double>(c)};
         cluster_sum4(a4, exchange, 0);
@@ -487,7 +541,7 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
 #pragma unroll
     for (int k = 0; k < 3; ++k) mu[k] = __shfl_sync(0xffffffffu, my_mu, k);
 
-    // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis
+    // pass 2: sum((nan_to_num(x) - mu)^2 * m) per axis  (0 / 1 mask: (d * d) * m is exact -> fused into the add)
     float d2[3] = {0.f, 0.f, 0.f};
     if (!inf_x) {
 #pragma unroll
@@ -496,7 +550,8 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
             for (int e = 0; e < 12; ++e) {
                 const float x = quad_get(v[k], e);
                 const float d = __fsub_rn((x == x) ? x : 0.f, mu[e % 3]);
-                d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
+                if (kBoolMask) d2[e % 3] = __fmaf_rn(__fmul_rn(d, d), m[k][e / 3], d2[e % 3]);
+                else d2[e % 3] += __fmul_rn(__fmul_rn(d, d), m[k][e / 3]);
             }
         }
     } else {
@@ -509,9 +564,9 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
             }
         }
     }
-    double dev[3] = {static_cast<double>(d2[0]), static_cast<double>(d2[1]), static_cast<double>(d2[2])};
+    double dev[3];
     float unused = 0.f;
-    block_sum3(dev, unused, scratch);
+    block_sum3f(d2, 0.f, scratch, dev, unused);
     if (CLUSTER) {
         double a4[4] = {dev[0], dev[1], dev[2], 0.0};
         cluster_sum4(a4, exchange, 1);
@@ -534,30 +589,49 @@ __global__ void __launch_bounds__(kStatsMaxThreads) masked_stats_quad_kernel(
     // pass 3: (x - mu) / sd on every element (masked or not, NaN stays NaN), straight from registers
     if (xyz_out) {
         float4* __restrict__ o4 = reinterpret_cast<float4*>(xyz_out + first_atom * 3);
+        // d / sd as reciprocal + one correction of the quotient (what the IEEE division does for operands in range).
+        // Bool masks: whether that is safe is decided ONCE per thread — its coordinates are below 1e18 in magnitude
+        // (the running maximum of pass 1), the means too, the deviations within [1e-18, 1e18] — so that no quotient
+        // can overflow or meet a zero / infinite / NaN deviation; anything else takes the IEEE division.
+        bool fast = false;
+        if (kBoolMask) {
+            fast = amax <= 1e18f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) fast = fast && (fabsf(mu[k]) <= 1e18f) && (sd[k] >= 1e-18f) && (sd[k] <= 1e18f);
+        }
 #pragma unroll
         for (int k = 0; k < Q; ++k) {
             const int q = threadIdx.x + k * T;
             if (q >= nq) continue;
-            // d / sd: reciprocal, one correction of the quotient (what the IEEE division does for operands in range);
-            // if an outcome is not finite although its coordinate is a number — sd = 0 or NaN, infinite operands — the
-            // group is redone with the IEEE division
-            float4 keep[3] = {v[k][0], v[k][1], v[k][2]};
-            bool redo = false;
+            float4 out[3];
+            if (fast) {
 #pragma unroll
-            for (int e = 0; e < 12; ++e) {
-                const float d = __fsub_rn(quad_get(keep, e), mu[e % 3]);
-                float qt = __fmul_rn(d, rcp[e % 3]);
-                qt = __fmaf_rn(__fmaf_rn(-qt, sd[e % 3], d), rcp[e % 3], qt);
-                redo |= (d == d) & !(fabsf(qt) <= kMax);  // a NaN coordinate stays NaN: nothing to redo
-                quad_set(v[k], e, qt);
+                for (int e = 0; e < 12; ++e) {
+                    const float d = __fsub_rn(quad_get(v[k], e), mu[e % 3]);
+                    float qt = __fmul_rn(d, rcp[e % 3]);
+                    qt = __fmaf_rn(__fmaf_rn(-qt, sd[e % 3], d), rcp[e % 3], qt);
+                    quad_set(out, e, qt);
+                }
+            } else {
+                // per-element test: if an outcome is not finite although its coordinate is a number — sd = 0 or NaN,
+                // infinite operands — the group is redone with the IEEE division
+                bool redo = false;
+#pragma unroll
+                for (int e = 0; e < 12; ++e) {
+                    const float d = __fsub_rn(quad_get(v[k], e), mu[e % 3]);
+                    float qt = __fmul_rn(d, rcp[e % 3]);
+                    qt = __fmaf_rn(__fmaf_rn(-qt, sd[e % 3], d), rcp[e % 3], qt);
+                    redo |= (d == d) & !(fabsf(qt) <= kMax);  // a NaN coordinate stays NaN: nothing to redo
+                    quad_set(out, e, qt);
+                }
+                if (redo) {
+#pragma unroll
+                    for (int e = 0; e < 12; ++e)
+                        quad_set(out, e, __fdiv_rn(__fsub_rn(quad_get(v[k], e), mu[e % 3]), sd[e % 3]));
+                }
             }
-            if (redo) {
 #pragma unroll
-                for (int e = 0; e < 12; ++e)
-                    quad_set(v[k], e, __fdiv_rn(__fsub_rn(quad_get(keep, e), mu[e % 3]), sd[e % 3]));
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) o4[3 * q + i] = v[k][i];
+            for (int i = 0; i < 3; ++i) o4[3 * q + i] = out[i];
         }
     }
     if (CLUSTER) cg::this_cluster().sync();  // peers may still be reading this CTA's partial sums
@@ -693,7 +767,8 @@ dim3 per_structure_grid(int per_b, int B) {
 }  // namespace
 
 // legacy: 0 = default (quad kernel where the shape allows, else the scalar-mapped register kernel), 1 = the three-pass
-// kernel of round 1, 2 = the scalar-mapped register kernel (comparison hooks, ps_masked_stats_ex).
+// kernel of round 1, 2 = the scalar-mapped register kernel, 3 = the quad kernel without the dense 4-quads-per-thread
+// configuration (comparison hooks, ps_masked_stats_ex).
 int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_dtype, int B, int L, int A,
                               float* mu, float* sd, float* xyz_out, int legacy, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "masked_stats: B=%d L=%d A=%d must be > 0",
@@ -711,7 +786,7 @@ int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_
 
     // ---- quad kernel: structures of a multiple of 4 atoms, 16-byte aligned arrays (the usual case)
     auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-    if (legacy == 0 && atoms % 4 == 0 && aligned16(xyz) && aligned16(xyz_out) && aligned16(atom_mask)) {
+    if ((legacy == 0 || legacy == 3) && atoms % 4 == 0 && aligned16(xyz) && aligned16(xyz_out) && aligned16(atom_mask)) {
         constexpr int kMaxQ = 4, kMaxTq = 512;
         const int quads = atoms / 4;
         int ranks_q = 1;
@@ -755,7 +830,32 @@ int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_
                           : cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_F32, Q, false>, xyz,        \
                                                atom_mask, atoms, mu, sd, xyz_out);                                   \
     } while (0)
-            if (q_per_thread == 1) PS_STATS_QUAD(1);
+            // Waves: a CTA's life is a serial chain (loads -> two block reductions -> normalise -> stores), so a launch
+            // that needs a second wave of CTAs pays that chain twice (config 4: 1024 CTAs of 256 threads at 62
+            // registers = 1.73 waves of 592).  Four quads per thread at <= 128 threads compiled for 7 CTAs per SM (72
+            // registers) holds 1036 CTAs at once: taken whenever it lowers the wave count.
+            bool dense4 = false;
+            if (ranks_q == 1 && legacy != 3 && share_q > 128 && share_q <= 4 * 128) {
+                auto slots = [&](int regs, int t) {
+                    int per_sm = 65536 / (regs * t);
+                    if (per_sm > 2048 / t) per_sm = 2048 / t;
+                    if (per_sm > 32) per_sm = 32;
+                    return static_cast<long long>(per_sm) * sms;
+                };
+                const int threads4 = ((share_q + 3) / 4 + 31) / 32 * 32;
+                const long long s2 = slots(64, threads), s4 = slots(72, threads4);
+                const long long waves2 = (B + s2 - 1) / s2, waves4 = (B + s4 - 1) / s4;
+                if (waves4 < waves2) {
+                    dense4 = true;
+                    config.blockDim = dim3(threads4, 1, 1);
+                }
+            }
+            if (dense4) {
+                err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, 4, false, 128, 7>, xyz,
+                                                   atom_mask, atoms, mu, sd, xyz_out)
+                              : cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_F32, 4, false, 128, 7>, xyz,
+                                                   atom_mask, atoms, mu, sd, xyz_out);
+            } else if (q_per_thread == 1) PS_STATS_QUAD(1);
             else if (q_per_thread == 2) PS_STATS_QUAD(2);
             else PS_STATS_QUAD(4);
 #undef PS_STATS_QUAD

@@ -132,8 +132,8 @@ def main():
         xyz, mask = inputs(B, L, A)
         mu, sd = torch.empty(B, 3, device=DEV), torch.empty(B, 3, device=DEV)
         xo = torch.empty_like(xyz)
-        for variant, label in ((0, "register-resident (default)"), (2, "register-resident, scalar mapping"),
-                               (1, "three-pass (round 1)")):
+        for variant, label in ((0, "register-resident (default)"), (3, "register-resident, <= 2 quads per thread"),
+                               (2, "register-resident, scalar mapping"), (1, "three-pass (round 1)")):
             def run(variant=variant):
                 _cabi.check(lib.ps_masked_stats_ex(xyz.data_ptr(), mask.data_ptr(), 0, B, L, A, mu.data_ptr(), sd.data_ptr(),
                                                    xo.data_ptr(), variant, s), "k4")
