@@ -832,29 +832,37 @@ int masked_stats_variant_impl(const float* xyz, const void* atom_mask, int mask_
     } while (0)
             // Waves: a CTA's life is a serial chain (loads -> two block reductions -> normalise -> stores), so a launch
             // that needs a second wave of CTAs pays that chain twice (config 4: 1024 CTAs of 256 threads at 62
-            // registers = 1.73 waves of 592).  Four quads per thread at <= 128 threads compiled for 7 CTAs per SM (72
-            // registers) holds 1036 CTAs at once: taken whenever it lowers the wave count.
-            bool dense4 = false;
-            if (ranks_q == 1 && legacy != 3 && share_q > 128 && share_q <= 4 * 128) {
-                auto slots = [&](int regs, int t) {
+            // registers = 1.73 waves of 592; 256 x 7680 atoms: 480 threads at 127 registers = one CTA per SM, 1.73
+            // waves of 148).  Two more builds of the 4-quads-per-thread kernel trade registers for residency — 72
+            // registers (7 CTAs of <= 128 threads per SM) and 64 registers (2 CTAs of <= 512 threads, a few spills) —
+            // and the one with the fewest waves is taken (ties: the fewest spills).
+            int dense = 0;  // 0: the choice above, 1: 72-register build, 2: 64-register build
+            // (0 / 1 masks only: the fp32-mask path keeps four more values per group and spills at these budgets)
+            if (ranks_q == 1 && legacy != 3 && share_q > 128 && is_bool) {
+                auto waves = [&](int regs, int t) {
                     int per_sm = 65536 / (regs * t);
                     if (per_sm > 2048 / t) per_sm = 2048 / t;
                     if (per_sm > 32) per_sm = 32;
-                    return static_cast<long long>(per_sm) * sms;
+                    if (per_sm < 1) per_sm = 1;
+                    const long long slots = static_cast<long long>(per_sm) * sms;
+                    return (B + slots - 1) / slots;
                 };
                 const int threads4 = ((share_q + 3) / 4 + 31) / 32 * 32;
-                const long long s2 = slots(64, threads), s4 = slots(72, threads4);
-                const long long waves2 = (B + s2 - 1) / s2, waves4 = (B + s4 - 1) / s4;
-                if (waves4 < waves2) {
-                    dense4 = true;
-                    config.blockDim = dim3(threads4, 1, 1);
+                const int regs_now = q_per_thread == 1 ? 57 : (q_per_thread == 2 ? 64 : 127);
+                long long best = waves(regs_now, threads);
+                if (threads4 <= 128 && waves(72, threads4) < best) {
+                    best = waves(72, threads4);
+                    dense = 1;
                 }
+                if (threads4 <= 512 && waves(64, threads4) < best) dense = 2;
+                if (dense) config.blockDim = dim3(threads4, 1, 1);
             }
-            if (dense4) {
-                err = is_bool ? cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, 4, false, 128, 7>, xyz,
-                                                   atom_mask, atoms, mu, sd, xyz_out)
-                              : cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_F32, 4, false, 128, 7>, xyz,
-                                                   atom_mask, atoms, mu, sd, xyz_out);
+            if (dense == 1) {
+                err = cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, 4, false, 128, 7>, xyz, atom_mask,
+                                         atoms, mu, sd, xyz_out);
+            } else if (dense == 2) {
+                err = cudaLaunchKernelEx(&config, masked_stats_quad_kernel<PS_MASK_BOOL, 4, false, 512, 2>, xyz, atom_mask,
+                                         atoms, mu, sd, xyz_out);
             } else if (q_per_thread == 1) PS_STATS_QUAD(1);
             else if (q_per_thread == 2) PS_STATS_QUAD(2);
             else PS_STATS_QUAD(4);
