@@ -98,8 +98,8 @@ int ps_pair_angles(const float* xyz, int B, int L, int A,
 int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb,
                         float* omega, float* theta, float* phi, void* stream);
 /* Tuning / comparison hook: variant 0 = default (packed-FP32 kernel compiled for 3 CTAs per SM), 1 = the
- * exact-operation-sequence kernel, 4 / 5 / 6 = the packed kernel compiled for 4 / 5 / 6 CTAs per SM.  All packed
- * variants produce the same bits. */
+ * exact-operation-sequence kernel, 4 / 5 / 6 = the packed kernel compiled for 4 / 5 / 6 CTAs per SM, 3 = two rows
+ * per loop iteration at 2 CTAs per SM.  All packed variants produce the same bits. */
 int ps_trrosetta_angles_ex(const float* xyz, int B, int L, int A, int virtual_cb,
                            float* omega, float* theta, float* phi, int variant, void* stream);
 

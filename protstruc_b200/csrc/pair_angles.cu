@@ -471,35 +471,57 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         float* pw = (ALL3 || want_omega) ? omega + first_out + j : nullptr;
         float* pt = (ALL3 || want_theta) ? theta + first_out + j : nullptr;
         float* pf = (ALL3 || want_phi) ? phi + first_out + j : nullptr;
-        auto store = [&](float2 w, float2 t, float2 f) {
+        auto store = [&](long long at, float2 w, float2 t, float2 f) {  // at = 0 or L: the row at the pointers, or the next
             if (vector_stores) {  // L even, outputs 8-byte aligned: one 64-bit store per feature
-                if (ALL3 || want_omega) *reinterpret_cast<float2*>(pw) = w;
-                if (ALL3 || want_theta) *reinterpret_cast<float2*>(pt) = t;
-                if (ALL3 || want_phi) *reinterpret_cast<float2*>(pf) = f;
+                if (ALL3 || want_omega) *reinterpret_cast<float2*>(pw + at) = w;
+                if (ALL3 || want_theta) *reinterpret_cast<float2*>(pt + at) = t;
+                if (ALL3 || want_phi) *reinterpret_cast<float2*>(pf + at) = f;
             } else {
-                if (ALL3 || want_omega) pw[0] = w.x;
-                if (ALL3 || want_theta) pt[0] = t.x;
-                if (ALL3 || want_phi) pf[0] = f.x;
+                if (ALL3 || want_omega) pw[at] = w.x;
+                if (ALL3 || want_theta) pt[at] = t.x;
+                if (ALL3 || want_phi) pf[at] = f.x;
                 if (second) {
-                    if (ALL3 || want_omega) pw[1] = w.y;
-                    if (ALL3 || want_theta) pt[1] = t.y;
-                    if (ALL3 || want_phi) pf[1] = f.y;
+                    if (ALL3 || want_omega) pw[at + 1] = w.y;
+                    if (ALL3 || want_theta) pt[at + 1] = t.y;
+                    if (ALL3 || want_phi) pf[at + 1] = f.y;
                 }
             }
         };
-        const float4* rec = rows4;
-        for (int k = 0; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) {
+        auto one_row = [&](const float4* rec, int k, long long at) {
             const float4 q1 = rec[1];
             if (pair_nan || (__float_as_int(q1.w) & 1)) {
-                store(nan2, nan2, nan2);
-                continue;
+                store(at, nan2, nan2, nan2);
+                return;
             }
             const float4 q0 = rec[0], q2 = rec[2], q3 = rec[3];
             RowEval r;
             eval_row_core<ALL3>(q0, q1, q2, q3, jp, want_omega, want_theta, want_phi, r);
             if (r.bad) eval_row_patch(r, jp, k - jp.diag_k);
-            store(r.w, r.t, r.f);
+            store(at, r.w, r.t, r.f);
+        };
+        const float4* rec = rows4;
+        int k = 0;
+        if constexpr (MIN_CTAS == 2) {
+            // tuning variant: TWO rows per iteration — two independent dependency chains per warp at 16 warps per SM
+            for (; k + 1 < nrows; k += 2, rec += 8, pw += 2 * L, pt += 2 * L, pf += 2 * L) {
+                const float4 q1a = rec[1], q1b = rec[5];
+                if (pair_nan || ((__float_as_int(q1a.w) | __float_as_int(q1b.w)) & 1)) {
+                    one_row(rec, k, 0);
+                    one_row(rec + 4, k + 1, L);
+                    continue;
+                }
+                RowEval ra, rb;
+                eval_row_core<ALL3>(rec[0], q1a, rec[2], rec[3], jp, want_omega, want_theta, want_phi, ra);
+                eval_row_core<ALL3>(rec[4], q1b, rec[6], rec[7], jp, want_omega, want_theta, want_phi, rb);
+                if (ra.bad | rb.bad) {
+                    if (ra.bad) eval_row_patch(ra, jp, k - jp.diag_k);
+                    if (rb.bad) eval_row_patch(rb, jp, k + 1 - jp.diag_k);
+                }
+                store(0, ra.w, ra.t, ra.f);
+                store(L, rb.w, rb.t, rb.f);
+            }
         }
+        for (; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) one_row(rec, k, 0);
         // the diagonal entries (row0 + dk, j) and (row0 + dk + 1, j + 1) of this pair of columns, if the CTA owns them
         const int dk = jp.diag_k;
 #pragma unroll
@@ -620,8 +642,9 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
                         static_cast<size_t>(Lp + 16);  // + one flag byte per residue
     const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
     const long long ctas = static_cast<long long>(B) * blocks_per_structure;
-    // variant 0 (default): 3 CTAs / SM (80 registers, no spills); 4 / 5 / 6: compiled for 4 / 5 / 6 CTAs per SM
-    const int min_ctas = variant == 4 ? 4 : (variant == 5 ? 5 : (variant == 6 ? 6 : 3));
+    // variant 0 (default): 3 CTAs / SM (80 registers, no spills); 4 / 5 / 6: compiled for 4 / 5 / 6 CTAs per SM;
+    // 3: two rows per iteration at 2 CTAs / SM
+    const int min_ctas = variant == 4 ? 4 : (variant == 5 ? 5 : (variant == 6 ? 6 : (variant == 3 ? 2 : 3)));
     if (variant != 1 && smem <= 200 * 1024 && ctas < (1ll << 31)) {
         auto aligned8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
         const int vector_stores = (L % 2 == 0) && aligned8(omega) && aligned8(theta) && aligned8(phi);
@@ -636,12 +659,14 @@ int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use
     } while (0)
         if (use_virtual_cb) {
             if (all3 && min_ctas == 4) PS_FAST(true, true, 4);
+            else if (all3 && min_ctas == 2) PS_FAST(true, true, 2);
             else if (all3 && min_ctas == 5) PS_FAST(true, true, 5);
             else if (all3 && min_ctas == 6) PS_FAST(true, true, 6);
             else if (all3) PS_FAST(true, true, 3);
             else PS_FAST(true, false, 3);
         } else {
             if (all3 && min_ctas == 4) PS_FAST(false, true, 4);
+            else if (all3 && min_ctas == 2) PS_FAST(false, true, 2);
             else if (all3 && min_ctas == 5) PS_FAST(false, true, 5);
             else if (all3 && min_ctas == 6) PS_FAST(false, true, 6);
             else if (all3) PS_FAST(false, true, 3);

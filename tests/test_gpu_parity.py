@@ -1078,13 +1078,13 @@ def test_packed_angle_kernel_register_budgets_and_unrolled_any_a_kernels_give_th
         xyz, _, _ = H.synthetic_batch(4200 + L, B, L, A, "bool")
         x = xyz.to(DEV).contiguous()
         outs = {}
-        for variant in (0, 4, 5, 6):
+        for variant in (0, 3, 4, 5, 6):
             o = torch.empty(3, B, L, L, device=DEV)
             _cabi.check(native_lib.ps_trrosetta_angles_ex(x.data_ptr(), B, L, A, 0, o[0].data_ptr(), o[1].data_ptr(),
                                                           o[2].data_ptr(), variant, s), "ps_trrosetta_angles_ex")
             outs[variant] = o
         torch.cuda.synchronize()
-        for variant in (4, 5, 6):
+        for variant in (3, 4, 5, 6):
             assert same(outs[variant], outs[0]), (B, L, A, variant)
     force = 1 << 8
     for (B, L, A) in ((2, 40, 25), (2, 23, 37)):

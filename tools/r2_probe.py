@@ -84,7 +84,7 @@ def main():
         xyz, _ = inputs(B, L, A, nan_masked, ragged)
         om = torch.empty(B, L, L, device=DEV)
         th, ph = torch.empty_like(om), torch.empty_like(om)
-        for variant, label in ((0, "packed FP32, 3 CTAs / SM (default)"), (4, "packed FP32, 4 CTAs / SM"),
+        for variant, label in ((0, "packed FP32, 3 CTAs / SM (default)"), (4, "packed FP32, 4 CTAs / SM"), (3, "packed FP32, two rows per iteration, 2 CTAs / SM"),
                                (1, "exact sequence (round 1)")):
             def run(variant=variant):
                 _cabi.check(lib.ps_trrosetta_angles_ex(xyz.data_ptr(), B, L, A, 0, om.data_ptr(), th.data_ptr(),
