@@ -1093,10 +1093,8 @@ template <int A>
 int dispatch_tiles(const PairDistParams& p, int mask_dtype, void* dist_mask, bool want_angles, int sqrt_id,
                    int slots_override, int wpt, cudaStream_t stream) {
     constexpr bool kAllVariants = (A == 15);
-    if (!kAllVariants) {
-        sqrt_id = kSqrtApproxFtz;
-        wpt = kDefaultWarpsPerTile;
-    }
+    (void)sqrt_id;  // only the A = 15 instantiation reads the two tuning arguments
+    (void)wpt;
     auto dist_kind = [&](auto kind_tag, bool angles) -> int {
         constexpr int KIND = decltype(kind_tag)::value;
         if constexpr (kAllVariants) {

@@ -381,36 +381,9 @@ __device__ __forceinline__ void quad_set(float4 (&v)[3], int s, float val) {
     else q.w = val;
 }
 
-// Sums three doubles and one float over the block; totals valid in every thread.  scratch: [warps + 1][4].
-__device__ __forceinline__ void block_sum3(double (&v)[3], float& c, double (*scratch)[4]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    __syncthreads();  // scratch reuse across calls
-    if (lane == 0) {
-        scratch[warp][0] = v[0];
-        scratch[warp][1] = v[1];
-        scratch[warp][2] = v[2];
-        scratch[warp][3] = static_cast<double>(c);
-    }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        double t = 0.0;
-        for (int w = 0; w < nwarps; ++w) t += scratch[w][threadIdx.x];
-        scratch[kStatsMaxThreads / 32][threadIdx.x] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v[k] = scratch[kStatsMaxThreads / 32][k];
-    c = static_cast<float>(scratch[kStatsMaxThreads / 32][3]);
-}
-
-// The same totals from fp32 per-thread partials: the five shuffle levels inside a warp stay in fp32 (a pairwise tree over
-// 32 partials of <= 16 values each; a double costs two SHFL per level), the warps' sums meet in fp64 as above.
+// Sums three fp32 per-thread partials and a count over the block; totals valid in every thread.  scratch: [warps + 1][4].
+// The five shuffle levels inside a warp stay in fp32 (a pairwise tree over 32 partials of <= 16 values each; a double
+// costs two SHFL per level), the warps' sums meet in fp64.
 __device__ __forceinline__ void block_sum3f(const float (&p)[3], float c, double (*scratch)[4], double (&total)[3],
                                             float& count) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
