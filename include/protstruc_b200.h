@@ -83,6 +83,11 @@ int ps_pair_dist_mask(const float* xyz, const void* atom_mask, int mask_dtype,
 int ps_pair_angles(const float* xyz, int B, int L, int A,
                    const int* slots_i, int n_i, const int* slots_j, int n_j,
                    int kind, float* out, void* stream);
+/* Comparison hook: variant 0 = default (packed-FP32 kernel when the points come from both residues: NaN placement of
+ * the reference, <= 1e-5 rad where min sin(bond angle) >= 0.1), 1 = the exact-operation-sequence kernel. */
+int ps_pair_angles_ex(const float* xyz, int B, int L, int A,
+                      const int* slots_i, int n_i, const int* slots_j, int n_j,
+                      int kind, float* out, int variant, void* stream);
 
 /*
  * K2f — the trRosetta-style triple in one pass over the pairs.

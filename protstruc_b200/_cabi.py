@@ -42,6 +42,8 @@ SIGNATURES = {
     "ps_pair_dist_mask_ex": (c_int, [_fp, _fp, c_int, _fp, _fp, c_int, c_int, c_int, c_int, c_void_p]),
     "ps_pair_angles": (c_int, [_fp, c_int, c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), c_int,
                                c_int, _fp, c_void_p]),
+    "ps_pair_angles_ex": (c_int, [_fp, c_int, c_int, c_int, POINTER(c_int), c_int, POINTER(c_int), c_int,
+                                  c_int, _fp, c_int, c_void_p]),
     "ps_trrosetta_angles": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_void_p]),
     "ps_trrosetta_angles_ex": (c_int, [_fp, c_int, c_int, c_int, c_int, _fp, _fp, _fp, c_int, c_void_p]),
     "ps_inter_residue_geometry": (c_int, [_fp, _fp, c_int, _fp, _fp, _fp, _fp, _fp, c_int, c_int, c_int,

@@ -15,6 +15,8 @@ int pair_dist_mask_compact_impl(const float*, const void*, int, float*, void*, f
                                 float*, float*, int, int, int, int, cudaStream_t);
 int pair_angles_impl(const float*, int, int, int, const int*, int, const int*, int, int, float*,
                      cudaStream_t);
+int pair_angles_variant_impl(const float*, int, int, int, const int*, int, const int*, int, int, float*, int,
+                             cudaStream_t);
 int trrosetta_angles_impl(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int trrosetta_angles_variant_impl(const float*, int, int, int, int, float*, float*, float*, int, cudaStream_t);
 int backbone_impl(const float*, const uint8_t*, const float*, int, int, int, int, int, int, float*,
@@ -151,6 +153,12 @@ int ps_pair_angles(const float* xyz, int B, int L, int A, const int* slots_i, in
                    const int* slots_j, int n_j, int kind, float* out, void* stream) {
     return ps::pair_angles_impl(xyz, B, L, A, slots_i, n_i, slots_j, n_j, kind, out,
                                 PS_STREAM(stream));
+}
+
+int ps_pair_angles_ex(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
+                      const int* slots_j, int n_j, int kind, float* out, int variant, void* stream) {
+    return ps::pair_angles_variant_impl(xyz, B, L, A, slots_i, n_i, slots_j, n_j, kind, out, variant,
+                                        PS_STREAM(stream));
 }
 
 int ps_trrosetta_angles(const float* xyz, int B, int L, int A, int virtual_cb, float* omega,

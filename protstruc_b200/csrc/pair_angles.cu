@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) trrosetta_kernel(const float* __restrict_
 //    straight-line path produced there;
 //  * missing atoms (NaN coordinates) propagate through every product and through the select-based min / max of the
 //    atan2 (fminf / fmaxf would drop them);
-//  * phi: within 1e-3 of |cos| = 1 — where the unclamped arccos of the reference turns a last-ulp excess into NaN —
+//  * phi: within 1e-4 of |cos| = 1 — where the unclamped arccos of the reference turns a last-ulp excess into NaN —
 //    the reference's exact sequence is issued (trrosetta_phi_exact below), as in the fused K1.
 template <typename T>
 __device__ __forceinline__ float2 f2(T v) { return make_float2(v, v); }
@@ -175,6 +175,10 @@ __device__ __forceinline__ float min3_nan(float a, float b, float c) {
 // The packed atan2 below is valid while the larger of |x|, |y| lies in this range (MUFU.RCP of it and the quotient are
 // then normal numbers); zero (the diagonal, zero padding, coincident atoms), huge, infinite and NaN operands are not.
 constexpr float kAtanLo = 1e-30f, kAtanHi = 1e30f;
+// The packed cosine (relative error < 4e-7) decides between a value and NaN of the unclamped arccos only up to this
+// |cos|; beyond it the reference's exact sequence is issued.  (1e-3 below 1 in the first version: one pair in a thousand
+// — a patch in 6 % of the warp iterations — where one in ten thousand leaves the same 250-fold margin on the decision.)
+constexpr float kCosExact = 0.9999f;
 __device__ __forceinline__ bool atan2_in_range(float ny, float x) {
     const float mx = max_nan(fabsf(x), fabsf(ny));
     return (mx > kAtanLo) & (mx < kAtanHi);
@@ -345,11 +349,11 @@ __device__ __forceinline__ void eval_row_core(const float4 q0, const float4 q1, 
     const float lo = min3_nan(ew.mx0, ew.mx1, min_nan(et.mx0, et.mx1));
     const float hi = max3_nan(ew.mx0, ew.mx1, max_nan(et.mx0, et.mx1));
     const float cm = max_nan(fabsf(r.c.x), fabsf(r.c.y));
-    r.bad = !((lo > kAtanLo) & (hi < kAtanHi) & (cm <= 0.999f));
+    r.bad = !((lo > kAtanLo) & (hi < kAtanHi) & (cm <= kCosExact));
 }
 
 // Rare part: lanes out of range (zeros: the diagonal, zero-padded residues, coincident atoms; NaN: a missing atom in one of
-// the two pairs or in the row; |cos| within 1e-3 of 1) are found again and redone one by one.  dk = row - jp.diag_k:
+// the two pairs or in the row; |cos| within 1e-4 of 1) are found again and redone one by one.  dk = row - jp.diag_k:
 // lane x (dk = 0) or lane y (dk = 1) is the diagonal entry, whose three values are written after the row loop.
 __device__ __forceinline__ void eval_row_patch(RowEval& r, const JPair& jp, int dk) {
     const bool live0 = dk != 0, live1 = dk != 1;
@@ -359,8 +363,8 @@ __device__ __forceinline__ void eval_row_patch(RowEval& r, const JPair& jp, int 
     if (live1 && !atan2_in_range(r.nyt.y, r.xt.y)) r.t.y = atan2_slow(r.nyt.y, r.xt.y);
     const V3 ba{r.bax, r.bay, r.baz};
     // (a lane whose CB_j is missing is NaN either way and needs no exact evaluation)
-    if (live0 && !jp.nan0 && !(fabsf(r.c.x) <= 0.999f)) r.f.x = trrosetta_phi_exact(ba, V3{r.bc.x.x, r.bc.y.x, r.bc.z.x});
-    if (live1 && !jp.nan1 && !(fabsf(r.c.y) <= 0.999f)) r.f.y = trrosetta_phi_exact(ba, V3{r.bc.x.y, r.bc.y.y, r.bc.z.y});
+    if (live0 && !jp.nan0 && !(fabsf(r.c.x) <= kCosExact)) r.f.x = trrosetta_phi_exact(ba, V3{r.bc.x.x, r.bc.y.x, r.bc.z.x});
+    if (live1 && !jp.nan1 && !(fabsf(r.c.y) <= kCosExact)) r.f.y = trrosetta_phi_exact(ba, V3{r.bc.x.y, r.bc.y.y, r.bc.z.y});
 }
 
 // Loop order: a thread OWNS pairs of residues j (one pair when L <= 2 * blockDim.x) and walks the CTA's rows with them
@@ -537,6 +541,187 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K2, second generation: pairwise_dihedrals / pairwise_planar_angles for ANY atom-slot lists on the packed FP32 pipe.
+//
+// pair_angles_kernel above issues the reference's operation sequence literally and is issue-bound at ~110
+// lane-instructions per pair for ONE angle (profiles/r3i_all_kernels_ncu_table.txt: 0.14 of the HBM roof, issue-active
+// 84 %).  This kernel evaluates the same angle the way the packed trRosetta kernel does — a thread owns two consecutive
+// residues j and walks the CTA's rows; every subtraction / product is an FADD2 / FMUL2 / FFMA2 for both pairs; the sine
+// term is y = -(n1 . b2) |b1| (no third cross product); atan2 / acos are the packed polynomial evaluations with ONE
+// range test per iteration and a rare per-lane patch (atan2f on the packed operands; the reference's exact cosine
+// sequence within 1e-4 of |cos| = 1, where the unclamped arccos decides between a value and NaN) — under the same
+// contract: NaN placement of the reference, <= 1e-5 rad where min sin(bond angle) >= 0.1.
+// What keeps the special cases right:
+//  * rows / residues j with a missing (NaN) atom among the requested slots are answered NaN without arithmetic;
+//  * the diagonal j = i is where two requested points can be THE SAME ATOM (omega's CA_i, CB_i, CA_i, CB_i): exact
+//    cancellations (b0 x b0 = 0) that fused multiply-adds do not reproduce, so the diagonal entry of every row is
+//    evaluated by the exact-sequence dihedral4 / angle3 after the row loop;
+//  * zero-padded residues: a zero vector makes every fused product exactly zero as well, |b1| = b1.b1 * rsqrt(b1.b1)
+//    is NaN for b1 = 0 exactly where the reference divides 0 / 0, and x = y = 0 reaches atan2f like in the reference.
+// NI (points taken from residue i) is a template parameter: differences of two row-side points are loop invariants of
+// the j walk only in the sense of scalar work per row; differences of two column-side points are hoisted by the compiler.
+constexpr int kAngleRecord = 12;  // floats per row record: up to three points (9) + flags (bit 0: a point is NaN)
+
+template <int KIND, int NI>
+__global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
+    const float* __restrict__ xyz, float* __restrict__ out, int L, int A, SlotList sl, int rows_per_cta,
+    int blocks_per_structure, int vector_stores) {
+    constexpr int N = KIND == PS_ANGLE_DIHEDRAL ? 4 : 3;
+    constexpr int NJ = N - NI;
+    static_assert(NI >= 1 && NJ >= 1 && NI <= 3, "points must come from both residues");
+    extern __shared__ __align__(16) float fast_smem[];
+    const int Lp = (L + 1) & ~1;
+    float* const srow = fast_smem;                                   // rows_per_cta records
+    float* const sj = srow + rows_per_cta * kAngleRecord;            // [NJ][3][Lp] structure of arrays
+    unsigned char* const sflag = reinterpret_cast<unsigned char*>(sj + NJ * 3 * Lp);
+
+    const long long b = blockIdx.x / blocks_per_structure;
+    const int row0 = (blockIdx.x - static_cast<int>(b) * blocks_per_structure) * rows_per_cta;
+    const int nrows = min(rows_per_cta, L - row0);
+    const float* __restrict__ xb = xyz + b * L * A * 3;
+
+    for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            V3 a{0.f, 0.f, 0.f};
+            if (r < L) a = ld3(xb + (static_cast<long long>(r) * A + sl.s[NI + k]) * 3);
+            sj[(k * 3 + 0) * Lp + r] = a.x;
+            sj[(k * 3 + 1) * Lp + r] = a.y;
+            sj[(k * 3 + 2) * Lp + r] = a.z;
+            bad |= atom_has_nan(a);
+        }
+        sflag[r] = bad ? 1 : 0;
+    }
+    for (int k = threadIdx.x; k < nrows; k += blockDim.x) {
+        float* rec = srow + k * kAngleRecord;
+        bool bad = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            V3 v{0.f, 0.f, 0.f};
+            if (a < NI) v = ld3(xb + (static_cast<long long>(row0 + k) * A + sl.s[a]) * 3);
+            rec[3 * a + 0] = v.x; rec[3 * a + 1] = v.y; rec[3 * a + 2] = v.z;
+            bad |= atom_has_nan(v);
+        }
+        rec[9] = __int_as_float(bad ? 1 : 0);
+        rec[10] = rec[11] = 0.f;
+    }
+    __syncthreads();
+
+    const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(srow);
+    const int npairs = Lp >> 1;
+    const long long first_out = (b * L + row0) * L;
+    const float2 nan2 = f2(__int_as_float(0x7fc00000));
+
+    for (int jpi = threadIdx.x; jpi < npairs; jpi += blockDim.x) {
+        P3 pj[NJ];
+#pragma unroll
+        for (int k = 0; k < NJ; ++k) {
+            pj[k].x = reinterpret_cast<const float2*>(sj + (k * 3 + 0) * Lp)[jpi];
+            pj[k].y = reinterpret_cast<const float2*>(sj + (k * 3 + 1) * Lp)[jpi];
+            pj[k].z = reinterpret_cast<const float2*>(sj + (k * 3 + 2) * Lp)[jpi];
+        }
+        const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jpi];
+        const bool nan0 = fl & 0x0001, nan1 = fl & 0x0100;
+        const bool pair_nan = nan0 && nan1;
+        const int j = 2 * jpi;
+        const bool second = vector_stores || (j + 1 < L);
+        float* po = out + first_out + j;
+        auto store = [&](float2 v) {
+            if (vector_stores) {
+                *reinterpret_cast<float2*>(po) = v;
+            } else {
+                po[0] = v.x;
+                if (second) po[1] = v.y;
+            }
+        };
+        const int dk = j - row0;  // row (relative to the CTA's first) whose diagonal entry is lane x of this pair
+        const float4* rec = rows4;
+        for (int k = 0; k < nrows; ++k, rec += 3, po += L) {
+            const float4 q2 = rec[2];
+            if (pair_nan || (__float_as_int(q2.y) & 1)) {
+                store(nan2);
+                continue;
+            }
+            const float4 q0 = rec[0], q1 = rec[1];
+            const float ri[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+            P3 pt[N];
+#pragma unroll
+            for (int a = 0; a < N; ++a) {
+                if (a < NI) pt[a] = P3{f2(ri[3 * a]), f2(ri[3 * a + 1]), f2(ri[3 * a + 2])};
+                else pt[a] = pj[a - NI];
+            }
+            float2 res;
+            if (KIND == PS_ANGLE_DIHEDRAL) {
+                const P3 b0 = sub_p3(pt[0], pt[1]);
+                const P3 b1 = sub_p3(pt[2], pt[1]);
+                const P3 b2 = sub_p3(pt[3], pt[2]);
+                const P3 n1 = cross_p3(b0, b1);
+                const P3 n2 = cross_p3(b2, b1);
+                const float2 x = dot_p3(n1, n2);
+                const float2 sn = dot_p3(n1, b2);
+                const float2 bb = dot_p3(b1, b1);
+                const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
+                const float2 ny = __fmul2_rn(sn, nb1);  // y = -(n1 . b2) |b1|
+                AtanPair e;
+                atan2_prepare(ny, x, e);
+                e.p = __ffma2_rn(e.p, e.s, f2(8.210079680e-02f));
+                e.p = __ffma2_rn(e.p, e.s, f2(-1.339595112e-01f));
+                e.p = __ffma2_rn(e.p, e.s, f2(1.986158291e-01f));
+                e.p = __ffma2_rn(e.p, e.s, f2(-3.332545806e-01f));
+                res = atan2_finish(e, ny, x);
+                const float lo = min_nan(e.mx0, e.mx1), hi = max_nan(e.mx0, e.mx1);
+                if (!((lo > kAtanLo) & (hi < kAtanHi))) {  // rare: zeros, NaN of ONE lane, out-of-range magnitudes
+                    // (the diagonal entry — coincident points, zeros — is rewritten after the loop: not patched here)
+                    if (k != dk && !atan2_in_range(ny.x, x.x)) res.x = atan2_slow(ny.x, x.x);
+                    if (k != dk + 1 && !atan2_in_range(ny.y, x.y)) res.y = atan2_slow(ny.y, x.y);
+                }
+            } else {
+                const P3 ba = sub_p3(pt[0], pt[1]);
+                const P3 bc = sub_p3(pt[2], pt[1]);
+                const float2 d = dot_p3(ba, bc);
+                const float2 nn = __fmul2_rn(dot_p3(ba, ba), dot_p3(bc, bc));  // (|ba| |bc|)^2
+                const float2 c = __fmul2_rn(d, make_float2(rsqrt_mufu(nn.x), rsqrt_mufu(nn.y)));
+                AcosPair e;
+                acos_prepare(c, e);
+                e.p = __ffma2_rn(e.p, e.a, f2(2.7762914e-02f));
+                e.p = __ffma2_rn(e.p, e.a, f2(-4.919744e-02f));
+                e.p = __ffma2_rn(e.p, e.a, f2(8.883589e-02f));
+                e.p = __ffma2_rn(e.p, e.a, f2(-2.1459109e-01f));
+                e.p = __ffma2_rn(e.p, e.a, f2(1.5707963f));
+                res = acos_finish(e, c);
+                // safe while the squared norms' product is a normal number and |cos| stays 1e-3 away from 1
+                const float cm = max_nan(fabsf(c.x), fabsf(c.y));
+                const float nlo = min_nan(nn.x, nn.y), nhi = max_nan(nn.x, nn.y);
+                if (!((cm <= kCosExact) & (nlo > kAtanLo) & (nhi < kAtanHi))) {
+                    // (a lane whose residue j misses an atom is NaN either way and needs no exact evaluation)
+                    // nor does the diagonal entry (0 / 0 for a shared vertex), which is rewritten after the loop
+                    if (!nan0 && k != dk && !((fabsf(c.x) <= kCosExact) & (nn.x > kAtanLo) & (nn.x < kAtanHi)))
+                        res.x = angle3(V3{pt[0].x.x, pt[0].y.x, pt[0].z.x}, V3{pt[1].x.x, pt[1].y.x, pt[1].z.x},
+                                       V3{pt[2].x.x, pt[2].y.x, pt[2].z.x});
+                    if (!nan1 && k != dk + 1 && !((fabsf(c.y) <= kCosExact) & (nn.y > kAtanLo) & (nn.y < kAtanHi)))
+                        res.y = angle3(V3{pt[0].x.y, pt[0].y.y, pt[0].z.y}, V3{pt[1].x.y, pt[1].y.y, pt[1].z.y},
+                                       V3{pt[2].x.y, pt[2].y.y, pt[2].z.y});
+                }
+            }
+            store(res);
+        }
+        // the diagonal entries (row0 + dk, j) and (row0 + dk + 1, j + 1): every point from the same residue — the
+        // exact-sequence evaluation (coincident atoms cancel exactly there)
+#pragma unroll
+        for (int lane = 0; lane < 2; ++lane) {
+            const int k = dk + lane, jj = j + lane;
+            if (k < 0 || k >= nrows || jj >= L) continue;
+            V3 q[4];
+#pragma unroll
+            for (int a = 0; a < N; ++a) q[a] = ld3(xb + (static_cast<long long>(jj) * A + sl.s[a]) * 3);
+            const float v = KIND == PS_ANGLE_DIHEDRAL ? dihedral4(q[0], q[1], q[2], q[3]) : angle3(q[0], q[1], q[2]);
+            out[first_out + static_cast<long long>(k) * L + jj] = v;
+        }
+    }
+}
+
 int grid_for_rows(long long rows, int* grid) {
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
@@ -558,8 +743,10 @@ int threads_for_L(int L) {
 
 }  // namespace
 
-int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
-                     const int* slots_j, int n_j, int kind, float* out, cudaStream_t stream) {
+// variant: 0 = default (the packed kernel when the points come from both residues and the structure fits in shared
+// memory), 1 = the exact-sequence kernel (comparison hook, ps_pair_angles_ex).
+int pair_angles_variant_impl(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
+                             const int* slots_j, int n_j, int kind, float* out, int variant, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE, "pair_angles: B=%d L=%d A=%d must be > 0",
                B, L, A);
     PS_REQUIRE(xyz && out, PS_ERR_NULL_POINTER, "pair_angles: NULL pointer");
@@ -584,12 +771,48 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
         sl.from_j[k] = from_j ? 1 : 0;
     }
     const long long rows = static_cast<long long>(B) * L;
+    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
+               "pair_angles: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
+    // ---- packed kernel: points from both residues, the structure's column-side atoms fit in shared memory
+    if (variant != 1 && n_i >= 1 && n_j >= 1) {
+        const int sms = sm_count_for_current_device();
+        if (sms < 0) return sms;
+        const int Lp = (L + 1) & ~1;
+        int fthreads = ((Lp / 2) + 31) / 32 * 32;
+        if (fthreads > 256) fthreads = 256;
+        int rows_per_cta = 64;
+        while (rows_per_cta > 4 && rows / rows_per_cta < 8ll * sms) rows_per_cta /= 2;
+        if (rows_per_cta > L) rows_per_cta = L;
+        const size_t smem = (static_cast<size_t>(n_j) * 3 * Lp + static_cast<size_t>(rows_per_cta) * kAngleRecord) * sizeof(float) +
+                            static_cast<size_t>(Lp + 16);
+        const int blocks_per_structure = (L + rows_per_cta - 1) / rows_per_cta;
+        const long long ctas = static_cast<long long>(B) * blocks_per_structure;
+        if (smem <= 200 * 1024 && ctas < (1ll << 31)) {
+            const int vector_stores = (L % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
+#define PS_FAST_ANGLES(KIND, NI)                                                                                      \
+    do {                                                                                                              \
+        cudaError_t err = cudaFuncSetAttribute(pair_angles_fast_kernel<KIND, NI>,                                     \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);              \
+        if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_angles_fast_kernel)");               \
+        pair_angles_fast_kernel<KIND, NI><<<static_cast<unsigned>(ctas), fthreads, smem, stream>>>(                   \
+            xyz, out, L, A, sl, rows_per_cta, blocks_per_structure, vector_stores);                                   \
+    } while (0)
+            if (kind == PS_ANGLE_DIHEDRAL) {
+                if (n_i == 1) PS_FAST_ANGLES(PS_ANGLE_DIHEDRAL, 1);
+                else if (n_i == 2) PS_FAST_ANGLES(PS_ANGLE_DIHEDRAL, 2);
+                else PS_FAST_ANGLES(PS_ANGLE_DIHEDRAL, 3);
+            } else {
+                if (n_i == 1) PS_FAST_ANGLES(PS_ANGLE_PLANAR, 1);
+                else PS_FAST_ANGLES(PS_ANGLE_PLANAR, 2);
+            }
+#undef PS_FAST_ANGLES
+            return check_launch("pair_angles_fast_kernel");
+        }
+    }
     int grid = 0;
     int rc = grid_for_rows(rows, &grid);
     if (rc != PS_OK) return rc;
     const int threads = threads_for_L(L);
-    PS_REQUIRE(static_cast<long long>(L) * A * 3 < (1ll << 31), PS_ERR_BAD_SHAPE,
-               "pair_angles: L*A*3=%lld floats per structure exceed 2^31", static_cast<long long>(L) * A * 3);
 #define PS_PAIR_ANGLES(KIND, NI) \
     pair_angles_kernel<KIND, NI><<<grid, threads, 0, stream>>>(xyz, out, L, A, sl, rows)
     if (kind == PS_ANGLE_DIHEDRAL) {
@@ -612,9 +835,14 @@ int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, 
     return check_launch("pair_angles_kernel");
 }
 
+int pair_angles_impl(const float* xyz, int B, int L, int A, const int* slots_i, int n_i,
+                     const int* slots_j, int n_j, int kind, float* out, cudaStream_t stream) {
+    return pair_angles_variant_impl(xyz, B, L, A, slots_i, n_i, slots_j, n_j, kind, out, 0, stream);
+}
+
 // variant: 0 = default (the packed kernel whenever the structure fits in shared memory), 1 = the exact-sequence
-// kernel of round 1, 3 = the packed kernel with two rows per iteration, 4 = with 64 registers (tuning / comparison hooks,
-// ps_trrosetta_angles_ex).
+// kernel of round 1, 3 = the packed kernel with two rows per iteration, 4 / 5 / 6 = other register budgets (tuning /
+// comparison hooks, ps_trrosetta_angles_ex).
 int trrosetta_angles_variant_impl(const float* xyz, int B, int L, int A, int use_virtual_cb, float* omega,
                                   float* theta, float* phi, int variant, cudaStream_t stream) {
     PS_REQUIRE(B > 0 && L > 0 && A > 0, PS_ERR_BAD_SHAPE,

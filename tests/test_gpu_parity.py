@@ -290,15 +290,38 @@ def test_inter_residue_geometry_matches_reference_golden(native_lib, name):
         assert torch.equal(out["d_no_mask"].cpu(), ref_mask[:, :, :, 0, 3])
 
 
+def pair_angles_ex(lib, sb, slots_i, slots_j, kind, variant):
+    """ps_pair_angles_ex straight through the C-ABI (kind 0 = dihedral, 1 = planar; variant 1 = exact-sequence kernel)."""
+    x = sb.get_xyz()
+    B, L, A = x.shape[:3]
+    out = torch.empty(B, L, L, device=DEV)
+    _cabi.check(lib.ps_pair_angles_ex(x.data_ptr(), B, L, A, _cabi.int_array(slots_i), len(slots_i), _cabi.int_array(slots_j),
+                                      len(slots_j), kind, out.data_ptr(), variant, torch.cuda.current_stream().cuda_stream),
+                "ps_pair_angles_ex")
+    return out
+
+
 @pytest.mark.parametrize("name", ["synthetic_small", "synthetic_A5", "real_1a6v_HL"])
 def test_pairwise_angle_methods_match_reference_golden(native_lib, name):
     g = H.load_golden(name)
     sb = make_batch(g)
     xyz = H.t(g["xyz"])
-    omega = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
-    theta = sb.pairwise_dihedrals(["N", "CA", "CB"], ["CB"])
-    phi = sb.pairwise_planar_angles(["CA", "CB"], ["CB"])
-    assert tuple(omega.shape) == tuple(g["ref_omega"].shape) and omega.dtype == torch.float32
+    # the public methods (default: the packed generic kernel): the contract — NaN placement of the reference,
+    # <= 1e-5 rad where min sin(bond angle) >= 0.1, <= 1e-6 / sin below
+    pomega = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
+    ptheta = sb.pairwise_dihedrals(["N", "CA", "CB"], ["CB"])
+    pphi = sb.pairwise_planar_angles(["CA", "CB"], ["CB"])
+    assert tuple(pomega.shape) == tuple(g["ref_omega"].shape) and pomega.dtype == torch.float32
+    H.assert_angles_close(pomega, H.t(g["ref_omega"]), angle_conditioning(xyz, "omega"), "omega (packed generic)")
+    H.assert_angles_close(ptheta, H.t(g["ref_theta"]), angle_conditioning(xyz, "theta"), "theta (packed generic)")
+    H.assert_angles_close(pphi, H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi (packed generic)", circular=False)
+    eye_l = torch.eye(xyz.shape[1], dtype=torch.bool)
+    for got, ref in ((pomega, g["ref_omega"]), (ptheta, g["ref_theta"]), (pphi, g["ref_phi"])):  # exact on the diagonal
+        assert torch.equal(torch.nan_to_num(got.cpu()[:, eye_l], nan=-9.0).abs(), torch.nan_to_num(H.t(ref)[:, eye_l], nan=-9.0).abs())
+    # the exact-sequence generic kernel (ps_pair_angles_ex variant 1): a few ulp on EVERY finite entry
+    omega = pair_angles_ex(native_lib, sb, [1, 4], [1, 4], 0, 1)
+    theta = pair_angles_ex(native_lib, sb, [0, 1, 4], [4], 0, 1)
+    phi = pair_angles_ex(native_lib, sb, [1, 4], [4], 1, 1)
     H.assert_angles_close(omega, H.t(g["ref_omega"]), angle_conditioning(xyz, "omega"), "omega", all_finite_tol=2e-6)
     H.assert_angles_close(theta, H.t(g["ref_theta"]), angle_conditioning(xyz, "theta"), "theta", all_finite_tol=2e-6)
     H.assert_angles_close(phi, H.t(g["ref_phi"]), angle_conditioning(xyz, "phi"), "phi", circular=False)
@@ -345,6 +368,21 @@ def test_pairwise_angles_at_backbone_scale_vs_oracle(native_lib):
     H.assert_angles_close(theta, rt, angle_conditioning(xyz, "theta"), "theta")
     H.assert_angles_close(phi, rp, angle_conditioning(xyz, "phi"), "phi", circular=False)
     assert bool((omega.abs() <= math.pi + 1e-6).all()) and bool((phi[~torch.isnan(phi)] >= 0).all())
+    # the generic packed kernel (pairwise_dihedrals / pairwise_planar_angles, any slot lists) at the same size: every
+    # split of the point list between the two residues, NaN-masked and ragged inputs included
+    for nan_masked in (False, True):
+        x2, m2, _ = H.synthetic_batch(5, 2, 512, 5, "bool", nan_masked=nan_masked, full_length=not nan_masked)
+        sb2 = ps.StructureBatch.from_xyz(x2, m2)
+        for si, sj in (([1, 4], [1, 4]), ([0, 1, 4], [4]), ([2], [0, 1, 2]), ([1], [4, 0, 3])):
+            got = pair_angles_ex(native_lib, sb2, si, sj, 0, 0)
+            p = H.pair_points(x2, si, sj)
+            cond = H.dihedral_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :], p[..., 3, :])
+            H.assert_angles_close(got, orc.pair_dihedrals(x2, si, sj), cond, f"generic dihedral {si} {sj}")
+        for si, sj in (([1, 4], [4]), ([1], [1, 2])):
+            got = pair_angles_ex(native_lib, sb2, si, sj, 1, 0)
+            p = H.pair_points(x2, si, sj)
+            cond = H.planar_conditioning(p[..., 0, :], p[..., 1, :], p[..., 2, :])
+            H.assert_angles_close(got, orc.pair_planar_angles(x2, si, sj), cond, f"generic planar {si} {sj}", circular=False)
 
 
 def test_virtual_cb_option_vs_oracle(native_lib):
@@ -1490,8 +1528,11 @@ def test_exact_symmetries_at_baseline_config3_size(native_lib):
     assert torch.equal(torch.flip(fo, dims=[1, 2]), omega) and torch.equal(torch.flip(ft, dims=[1, 2]), theta)
     assert torch.equal(torch.nan_to_num(torch.flip(fp, dims=[1, 2]), nan=-1.0), torch.nan_to_num(phi, nan=-1.0))
     # the generic single-feature kernels agree with the fused one (a few ulp) at this size as well
-    go = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])
-    H.assert_angles_close(omega[:2], go[:2].cpu(), angle_conditioning(xyz[:2].cpu(), "omega"), "packed K2f vs generic kernel")
+    go = sb.pairwise_dihedrals(["CA", "CB"], ["CA", "CB"])[:2].cpu()
+    cond = angle_conditioning(xyz[:2].cpu(), "omega").reshape(go.shape)
+    assert torch.equal(torch.isnan(go), torch.isnan(omega[:2].cpu()))
+    diff = H.circular_diff(torch.nan_to_num(go), torch.nan_to_num(omega[:2].cpu()))
+    assert diff[cond >= H.SIN_GATE].max().item() <= 2e-5, "packed K2f vs packed generic kernel (each within 1e-5 of the truth)"
     del mo, mt, mp, fo, ft, fp, go
 
 

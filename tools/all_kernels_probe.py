@@ -2,7 +2,7 @@
 """Launches every kernel family once at its BASELINE.json size (target for one `ncu --set full` pass).
 
     python tools/all_kernels_probe.py            # plain run
-    ncu --set full --clock-control none -k regex:'ps::' -o gpurun_out/all_kernels python tools/all_kernels_probe.py
+    ncu --set full --clock-control none -k regex:'backbone|center_of_mass|diffuse_|kabsch|local_xyz|masked_stats|pair_|rotate_kernel|scale_shift|translate|trrosetta' -o gpurun_out/all_kernels python tools/all_kernels_probe.py
 """
 import sys
 from pathlib import Path
@@ -26,13 +26,15 @@ def batch(B, L, A, p=0.5):
 
 
 # K1 fused (bench shape, smaller batch to keep the capture short), K1 distances + mask (config 2 shape, 16 structures)
-sb = batch(4, 512, 15)
+sb = batch(16, 512, 15)
 sb.inter_residue_geometry()
 sb.pairwise_distance_matrix()
-# any-A tile kernel (A = 25, the reference tests' atom count)
-batch(8, 128, 25).pairwise_distance_matrix()
+# any-A tile kernel: A = 25 (the reference tests' atom count; unrolled instantiation), A = 37 (atom37), A = 20 (run-time A)
+batch(24, 256, 25).pairwise_distance_matrix()
+batch(12, 256, 37).pairwise_distance_matrix()
+batch(40, 256, 20).pairwise_distance_matrix()
 # K2f / K2 (config 3: backbone + CB)
-c3 = batch(64, 512, 5, p=1.1)
+c3 = batch(256, 512, 5, p=1.1)
 c3.trrosetta_angles()
 c3.pairwise_dihedrals(["N", "CA", "C"], ["N"])
 c3.pairwise_planar_angles(["CA", "CB"], ["CB"])

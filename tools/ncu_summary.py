@@ -38,8 +38,48 @@ KEYS = [
 ]
 
 
+def table(rep, peak_gbs):
+    """One line per profiled launch: the digest kept as profiles/*_all_kernels_ncu_table.txt."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+
+    def num(d, key, factor=None):
+        v = float(d[col[key]].replace(",", ""))
+        u = units[col[key]]
+        return v * (factor[u] if factor else 1.0)
+
+    print(f"# One `ncu --set full --clock-control none` capture of every kernel family at its BASELINE.json size")
+    print(f"# (tools/all_kernels_probe.py; cold caches, serialised: compare shares and byte counts, not absolute times).")
+    print(f"# GB/s = (dram read + write) / duration; frac = GB/s / {peak_gbs} (MEASURED_PEAKS.json).  Outputs of the small")
+    print(f"# kernels stay in the 126 MB L2 (wr_MB ~ 0), so their DRAM figures understate the bytes they move.")
+    print(f"{'kernel':52s} {'time_us':>8s} {'rd_MB':>9s} {'wr_MB':>9s} {'GB/s':>7s} {'frac':>6s} {'dram%':>6s} {'issue%':>6s} "
+          f"{'warps%':>6s} {'fma_pipe%':>9s} {'regs':>5s}")
+    for d in data:
+        name = d[col["Kernel Name"]]
+        name = name.replace("void ", "").replace("unnamed>::", "").replace("ps::<unnamed>::", "")
+        name = name.split("(")[0] if "<" not in name else name[:name.rfind(">") + 1].split("(const")[0]
+        t = num(d, "gpu__time_duration.sum", tscale)
+        rd = num(d, "dram__bytes_read.sum", scale) / 1e6
+        wr = num(d, "dram__bytes_write.sum", scale) / 1e6
+        gbs = (rd + wr) * 1e6 / (t * 1e-6) / 1e9
+        fma = d[col["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]] if \
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active" in col else "nan"
+        print(f"{name[:52]:52s} {t:8.1f} {rd:9.1f} {wr:9.1f} {gbs:7.0f} {gbs / peak_gbs:6.2f} "
+              f"{float(d[col['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']]):6.1f} "
+              f"{float(d[col['smsp__issue_active.avg.pct_of_peak_sustained_active']]):6.1f} "
+              f"{float(d[col['sm__warps_active.avg.pct_of_peak_sustained_active']]):6.1f} {float(fma):9.1f} "
+              f"{d[col['launch__registers_per_thread']]:>5s}")
+
+
 def main():
     rep = sys.argv[1]
+    if "--table" in sys.argv:
+        table(rep, float(sys.argv[sys.argv.index("--table") + 1]))
+        return
     structures = int(sys.argv[sys.argv.index("--structures") + 1]) if "--structures" in sys.argv else None
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))

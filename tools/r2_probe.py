@@ -92,6 +92,17 @@ def main():
             best, med = time_call(run)
             add(f"K2f omega+theta+phi {tag} [{label}]", best, med, B * (L * L * 12 + L * 5 * 12),
                 pairs_per_s=B * L * L / (best / 1e3))
+        if tag.startswith("config3 (all"):
+            one = torch.empty(B, L, L, device=DEV)
+            for (si, sj, kind, what) in (([1, 4], [1, 4], 0, "dihedral CA,CB | CA,CB"), ([0, 1, 4], [4], 0, "dihedral N,CA,CB | CB"),
+                                         ([1, 4], [4], 1, "planar CA,CB | CB")):
+                for variant, label in ((0, "packed (default)"), (1, "exact sequence (round 1)")):
+                    def run_generic(si=si, sj=sj, kind=kind, variant=variant):
+                        _cabi.check(lib.ps_pair_angles_ex(xyz.data_ptr(), B, L, A, _cabi.int_array(si), len(si), _cabi.int_array(sj),
+                                                          len(sj), kind, one.data_ptr(), variant, s), "k2 generic")
+                    best, med = time_call(run_generic)
+                    add(f"K2 generic {what} {tag} [{label}]", best, med, B * (L * L * 4 + L * 5 * 12))
+            del one
         if A >= 3:
             def run_virtual():
                 _cabi.check(lib.ps_trrosetta_angles_ex(xyz.data_ptr(), B, L, A, 1, om.data_ptr(), th.data_ptr(),
