@@ -409,7 +409,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         }
         sca_x[r] = ca.x; sca_y[r] = ca.y; sca_z[r] = ca.z;
         scb_x[r] = cb.x; scb_y[r] = cb.y; scb_z[r] = cb.z;
-        sflag[r] = atom_has_nan(cb) ? 1 : 0;
+        // bit 0: CB missing (all three angles of the pair are NaN) — also set for the padding residue of an odd L;
+        // bit 1: CA missing (omega is NaN)
+        sflag[r] = (r >= L || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(ca) ? 2 : 0);
     }
     __syncthreads();
     // ---- row-side records of this CTA's residues i
@@ -460,16 +462,35 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         JPair jp;
         jp.ca = P3{pca_x[jpi], pca_y[jpi], pca_z[jpi]};
         jp.cb = P3{pcb_x[jpi], pcb_y[jpi], pcb_z[jpi]};
-        jp.b2 = sub_p3(jp.cb, jp.ca);
         // Missing atoms are NaN coordinates (protstruc/pdb.py:133-135) and make the angle NaN whatever the other atoms
-        // are: such pairs (and rows) are answered without arithmetic — with half of the atoms missing that is 15 of
-        // 16 pairs — instead of dragging NaN through the IEEE fall-backs of atan2 / acos.
+        // are: such pairs (and rows) are answered without arithmetic instead of dragging NaN through the IEEE
+        // fall-backs of atan2 / acos.  A thread with ONE lane missing an atom (a glycine next to any other residue: on
+        // real data nearly every warp holds such a thread) evaluates that lane on stand-in coordinates — its partner's
+        // CB, a point next to CB for a missing CA — so that it never leaves the straight-line path, and overwrites the
+        // lane's results with NaN before the store (one predicated branch per row for everybody else).
         const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jpi];
-        jp.nan0 = fl & 0x0001;
-        jp.nan1 = fl & 0x0100;
+        const bool cbn0 = fl & 0x0001, cbn1 = fl & 0x0100, can0 = fl & 0x0002, can1 = fl & 0x0200;
+        const bool pair_nan = cbn0 && cbn1;
+        const bool lane_nan = fl != 0 && !pair_nan;
+        if (lane_nan) {
+            if (cbn0) { jp.cb.x.x = jp.cb.x.y; jp.cb.y.x = jp.cb.y.y; jp.cb.z.x = jp.cb.z.y; }
+            if (cbn1) { jp.cb.x.y = jp.cb.x.x; jp.cb.y.y = jp.cb.y.x; jp.cb.z.y = jp.cb.z.x; }
+            if (can0 || cbn0) { jp.ca.x.x = jp.cb.x.x + 1.0f; jp.ca.y.x = jp.cb.y.x + 0.25f; jp.ca.z.x = jp.cb.z.x + 0.5f; }
+            if (can1 || cbn1) { jp.ca.x.y = jp.cb.x.y + 1.0f; jp.ca.y.y = jp.cb.y.y + 0.25f; jp.ca.z.y = jp.cb.z.y + 0.5f; }
+        }
+        jp.b2 = sub_p3(jp.cb, jp.ca);
+        jp.nan0 = jp.nan1 = false;  // no lane carries NaN from the column side any more
         const int j = 2 * jpi;
         jp.diag_k = j - row0;
-        const bool pair_nan = jp.nan0 && jp.nan1;
+        const float qnan = __int_as_float(0x7fc00000);
+        auto mask_lanes = [&](RowEval& r) {
+            if (lane_nan) {
+                if (cbn0) r.w.x = r.t.x = r.f.x = qnan;
+                else if (can0) r.w.x = qnan;
+                if (cbn1) r.w.y = r.t.y = r.f.y = qnan;
+                else if (can1) r.w.y = qnan;
+            }
+        };
         const bool second = vector_stores || (j + 1 < L);  // lane y is a residue of the structure
         // running output pointers of (row0 + k, j): one 64-bit add per feature and row
         float* pw = (ALL3 || want_omega) ? omega + first_out + j : nullptr;
@@ -501,6 +522,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
             RowEval r;
             eval_row_core<ALL3>(q0, q1, q2, q3, jp, want_omega, want_theta, want_phi, r);
             if (r.bad) eval_row_patch(r, jp, k - jp.diag_k);
+            mask_lanes(r);
             store(at, r.w, r.t, r.f);
         };
         const float4* rec = rows4;
@@ -521,6 +543,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
                     if (ra.bad) eval_row_patch(ra, jp, k - jp.diag_k);
                     if (rb.bad) eval_row_patch(rb, jp, k + 1 - jp.diag_k);
                 }
+                mask_lanes(ra);
+                mask_lanes(rb);
                 store(0, ra.w, ra.t, ra.f);
                 store(L, rb.w, rb.t, rb.f);
             }
@@ -592,7 +616,7 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
             sj[(k * 3 + 2) * Lp + r] = a.z;
             bad |= atom_has_nan(a);
         }
-        sflag[r] = bad ? 1 : 0;
+        sflag[r] = (bad || r >= L) ? 1 : 0;  // (the padding residue of an odd L counts as missing)
     }
     for (int k = threadIdx.x; k < nrows; k += blockDim.x) {
         float* rec = srow + k * kAngleRecord;
@@ -623,12 +647,27 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
             pj[k].z = reinterpret_cast<const float2*>(sj + (k * 3 + 2) * Lp)[jpi];
         }
         const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jpi];
-        const bool nan0 = fl & 0x0001, nan1 = fl & 0x0100;
-        const bool pair_nan = nan0 && nan1;
+        const bool miss0 = fl & 0x0001, miss1 = fl & 0x0100;
+        const bool pair_nan = miss0 && miss1;
+        // ONE lane missing an atom: it is evaluated on its partner's coordinates (so that it never leaves the
+        // straight-line path) and overwritten with NaN before the store
+        const bool lane_nan = (miss0 || miss1) && !pair_nan;
+        if (lane_nan) {
+#pragma unroll
+            for (int k = 0; k < NJ; ++k) {
+                if (miss0) { pj[k].x.x = pj[k].x.y; pj[k].y.x = pj[k].y.y; pj[k].z.x = pj[k].z.y; }
+                else { pj[k].x.y = pj[k].x.x; pj[k].y.y = pj[k].y.x; pj[k].z.y = pj[k].z.x; }
+            }
+        }
+        constexpr bool nan0 = false, nan1 = false;  // no lane carries NaN from the column side any more
         const int j = 2 * jpi;
         const bool second = vector_stores || (j + 1 < L);
         float* po = out + first_out + j;
         auto store = [&](float2 v) {
+            if (lane_nan) {
+                if (miss0) v.x = __int_as_float(0x7fc00000);
+                else v.y = __int_as_float(0x7fc00000);
+            }
             if (vector_stores) {
                 *reinterpret_cast<float2*>(po) = v;
             } else {

@@ -78,10 +78,16 @@ def main():
 
     # ---- K2f: BASELINE config 3 (256 x 512 backbone), packed kernel vs the exact-sequence kernel of round 1
     for (B, L, A, nan_masked, ragged, tag) in ((256, 512, 5, False, False, "config3 (all atoms valid)"),
+                                                (256, 512, 5, "gly", False, "config3 shape, 8 % of the residues without CB (glycine)"),
                                                 (256, 512, 5, True, True, "config3 shape, NaN-masked + ragged"),
                                                 (64, 384, 15, True, True, "B64 L384 A15 NaN-masked + ragged"),
                                                 (64, 511, 15, False, False, "B64 L511 (odd) A15")):
-        xyz, _ = inputs(B, L, A, nan_masked, ragged)
+        if nan_masked == "gly":
+            xyz, _ = inputs(B, L, A, False, False)
+            gly = torch.rand(B, L, device=DEV, generator=g) < 0.08
+            xyz[:, :, 4][gly] = float("nan")
+        else:
+            xyz, _ = inputs(B, L, A, nan_masked, ragged)
         om = torch.empty(B, L, L, device=DEV)
         th, ph = torch.empty_like(om), torch.empty_like(om)
         for variant, label in ((0, "packed FP32, 3 CTAs / SM (default)"), (4, "packed FP32, 4 CTAs / SM"), (3, "packed FP32, two rows per iteration, 2 CTAs / SM"),
