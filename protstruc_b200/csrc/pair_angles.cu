@@ -14,6 +14,8 @@
 // Grid: blockIdx.x = (b*L + i) row, threads stride over j.  Rows of L floats are written fully
 // coalesced.
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ps {
@@ -400,6 +402,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
     const bool want_omega = ALL3 || omega != nullptr, want_theta = ALL3 || theta != nullptr, want_phi = ALL3 || phi != nullptr;
 
     // ---- stage residue j of the whole structure: CA and CB (real or virtual), structure of arrays
+    bool special = false;
     for (int r = threadIdx.x; r < Lp; r += blockDim.x) {
         V3 ca{0.f, 0.f, 0.f}, cb{0.f, 0.f, 0.f};
         if (r < L) {
@@ -410,10 +413,17 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         sca_x[r] = ca.x; sca_y[r] = ca.y; sca_z[r] = ca.z;
         scb_x[r] = cb.x; scb_y[r] = cb.y; scb_z[r] = cb.z;
         // bit 0: CB missing (all three angles of the pair are NaN) — also set for the padding residue of an odd L;
-        // bit 1: CA missing (omega is NaN)
-        sflag[r] = (r >= L || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(ca) ? 2 : 0);
+        // bit 1: CA missing (omega is NaN); bit 2: CA = CB = 0 exactly (a zero-padded residue of a ragged batch: b2 = 0,
+        // omega is 0 — or NaN opposite a CB at the origin — by exact cancellation); bit 3: CA = 0 exactly
+        const bool ca_zero = ca.x == 0.f && ca.y == 0.f && ca.z == 0.f, cb_zero = cb.x == 0.f && cb.y == 0.f && cb.z == 0.f;
+        sflag[r] = (r >= L || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(ca) ? 2 : 0) | (r < L && ca_zero && cb_zero ? 4 : 0) |
+                   (r < L && ca_zero ? 8 : 0);
+        special |= sflag[r] != 0;
     }
-    __syncthreads();
+    // Does the structure hold ANY residue that needs the special handling below (a missing CA / CB, a zero-padded
+    // residue, the padding lane of an odd L)?  If not — every structure of a clean, full-length batch — the CTA runs
+    // the row loop without the flag tests and the lane masks (8 % of the loop's instructions).
+    const bool cta_special = __syncthreads_or(special) != 0;
     // ---- row-side records of this CTA's residues i
     for (int k = threadIdx.x; k < nrows; k += blockDim.x) {
         const int i = row0 + k;
@@ -439,7 +449,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         rec[0] = b0.x; rec[1] = b0.y; rec[2] = b0.z;
         rec[3] = inv_or_inf;                              // 1 / |b0|: 0 * inf = NaN for phi, as 0 / 0
         rec[4] = cb.x; rec[5] = cb.y; rec[6] = cb.z;
-        rec[7] = __int_as_float((atom_has_nan(ca) || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(n_i) ? 2 : 0));
+        // flags: 1 = CA_i / CB_i missing (the row is NaN), 2 = N_i missing, 4 = CA_i = CB_i = 0 exactly (a zero-padded
+        // residue: omega is 0 — NaN opposite a CA at the origin —, theta and phi are 0 / 0 = NaN), 8 = CB_i = 0 exactly
+        const bool ca_zero = ca.x == 0.f && ca.y == 0.f && ca.z == 0.f, cb_zero = cb.x == 0.f && cb.y == 0.f && cb.z == 0.f;
+        rec[7] = __int_as_float((atom_has_nan(ca) || atom_has_nan(cb) ? 1 : 0) | (atom_has_nan(n_i) ? 2 : 0) |
+                                (ca_zero && cb_zero ? 4 : 0) | (cb_zero ? 8 : 0));
         rec[8] = tm.x; rec[9] = tm.y; rec[10] = tm.z;
         rec[11] = omega_ii;
         rec[12] = tn1.x * nb0; rec[13] = tn1.y * nb0; rec[14] = tn1.z * nb0;
@@ -470,25 +484,33 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
         // lane's results with NaN before the store (one predicated branch per row for everybody else).
         const unsigned short fl = reinterpret_cast<const unsigned short*>(sflag)[jpi];
         const bool cbn0 = fl & 0x0001, cbn1 = fl & 0x0100, can0 = fl & 0x0002, can1 = fl & 0x0200;
+        // Zero-padded residues (ragged batches: xyz = 0 beyond a structure's length) are the other everyday source of
+        // out-of-range lanes: opposite a residue with CA = CB = 0, omega's b2 vanishes and the reference gets x = y = 0
+        // -> 0 by exact cancellation (NaN if CB_i is at the origin too: |b1| = 0).  Such a lane gets a stand-in CA for
+        // the arithmetic and the known omega at the store (theta and phi are ordinary values there: CB_j = 0 is a point).
+        const bool zero0 = fl & 0x0004, zero1 = fl & 0x0400, caz0 = fl & 0x0008, caz1 = fl & 0x0800;
         const bool pair_nan = cbn0 && cbn1;
-        const bool lane_nan = fl != 0 && !pair_nan;
+        const bool lane_nan = (fl & 0x0707) != 0 && !pair_nan;
         if (lane_nan) {
             if (cbn0) { jp.cb.x.x = jp.cb.x.y; jp.cb.y.x = jp.cb.y.y; jp.cb.z.x = jp.cb.z.y; }
             if (cbn1) { jp.cb.x.y = jp.cb.x.x; jp.cb.y.y = jp.cb.y.x; jp.cb.z.y = jp.cb.z.x; }
-            if (can0 || cbn0) { jp.ca.x.x = jp.cb.x.x + 1.0f; jp.ca.y.x = jp.cb.y.x + 0.25f; jp.ca.z.x = jp.cb.z.x + 0.5f; }
-            if (can1 || cbn1) { jp.ca.x.y = jp.cb.x.y + 1.0f; jp.ca.y.y = jp.cb.y.y + 0.25f; jp.ca.z.y = jp.cb.z.y + 0.5f; }
+            if (can0 || cbn0 || zero0) { jp.ca.x.x = jp.cb.x.x + 1.0f; jp.ca.y.x = jp.cb.y.x + 0.25f; jp.ca.z.x = jp.cb.z.x + 0.5f; }
+            if (can1 || cbn1 || zero1) { jp.ca.x.y = jp.cb.x.y + 1.0f; jp.ca.y.y = jp.cb.y.y + 0.25f; jp.ca.z.y = jp.cb.z.y + 0.5f; }
         }
         jp.b2 = sub_p3(jp.cb, jp.ca);
         jp.nan0 = jp.nan1 = false;  // no lane carries NaN from the column side any more
         const int j = 2 * jpi;
         jp.diag_k = j - row0;
         const float qnan = __int_as_float(0x7fc00000);
-        auto mask_lanes = [&](RowEval& r) {
+        auto mask_lanes = [&](RowEval& r, int row_flags) {
             if (lane_nan) {
+                const float zero_omega = (row_flags & 8) ? qnan : 0.f;  // opposite a zero-padded residue
                 if (cbn0) r.w.x = r.t.x = r.f.x = qnan;
                 else if (can0) r.w.x = qnan;
+                else if (zero0) r.w.x = zero_omega;
                 if (cbn1) r.w.y = r.t.y = r.f.y = qnan;
                 else if (can1) r.w.y = qnan;
+                else if (zero1) r.w.y = zero_omega;
             }
         };
         const bool second = vector_stores || (j + 1 < L);  // lane y is a residue of the structure
@@ -512,17 +534,36 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
                 }
             }
         };
-        auto one_row = [&](const float4* rec, int k, long long at) {
+        auto one_row = [&](auto special_tag, const float4* rec, int k, long long at) {
+            constexpr bool kSpecial = decltype(special_tag)::value;
             const float4 q1 = rec[1];
-            if (pair_nan || (__float_as_int(q1.w) & 1)) {
-                store(at, nan2, nan2, nan2);
+            if constexpr (!kSpecial) {  // a structure without missing atoms / zero padding: no flag can be set
+                RowEval r;
+                eval_row_core<ALL3>(rec[0], q1, rec[2], rec[3], jp, want_omega, want_theta, want_phi, r);
+                if (r.bad) eval_row_patch(r, jp, k - jp.diag_k);
+                store(at, r.w, r.t, r.f);
+                return;
+            }
+            const int row_flags = __float_as_int(q1.w);
+            if (pair_nan || (row_flags & 5)) {  // ONE test on the straight-line path for both kinds of answered rows
+                if (pair_nan || (row_flags & 1)) {
+                    store(at, nan2, nan2, nan2);
+                    return;
+                }
+                // zero-padded residue i: b0 = 0, so omega is 0 by exact cancellation (NaN where b1 = CA_j vanishes too),
+                // theta and phi are 0 / 0; no arithmetic
+                RowEval z;
+                z.w = make_float2(caz0 ? qnan : 0.f, caz1 ? qnan : 0.f);
+                z.t = z.f = nan2;
+                mask_lanes(z, row_flags);
+                store(at, z.w, z.t, z.f);
                 return;
             }
             const float4 q0 = rec[0], q2 = rec[2], q3 = rec[3];
             RowEval r;
             eval_row_core<ALL3>(q0, q1, q2, q3, jp, want_omega, want_theta, want_phi, r);
             if (r.bad) eval_row_patch(r, jp, k - jp.diag_k);
-            mask_lanes(r);
+            mask_lanes(r, row_flags);
             store(at, r.w, r.t, r.f);
         };
         const float4* rec = rows4;
@@ -531,9 +572,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
             // tuning variant: TWO rows per iteration — two independent dependency chains per warp at 16 warps per SM
             for (; k + 1 < nrows; k += 2, rec += 8, pw += 2 * L, pt += 2 * L, pf += 2 * L) {
                 const float4 q1a = rec[1], q1b = rec[5];
-                if (pair_nan || ((__float_as_int(q1a.w) | __float_as_int(q1b.w)) & 1)) {
-                    one_row(rec, k, 0);
-                    one_row(rec + 4, k + 1, L);
+                if (pair_nan || ((__float_as_int(q1a.w) | __float_as_int(q1b.w)) & 5)) {
+                    one_row(std::true_type{}, rec, k, 0);
+                    one_row(std::true_type{}, rec + 4, k + 1, L);
                     continue;
                 }
                 RowEval ra, rb;
@@ -543,13 +584,17 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
                     if (ra.bad) eval_row_patch(ra, jp, k - jp.diag_k);
                     if (rb.bad) eval_row_patch(rb, jp, k + 1 - jp.diag_k);
                 }
-                mask_lanes(ra);
-                mask_lanes(rb);
+                mask_lanes(ra, __float_as_int(q1a.w));
+                mask_lanes(rb, __float_as_int(q1b.w));
                 store(0, ra.w, ra.t, ra.f);
                 store(L, rb.w, rb.t, rb.f);
             }
         }
-        for (; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) one_row(rec, k, 0);
+        if (cta_special) {
+            for (; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) one_row(std::true_type{}, rec, k, 0);
+        } else {
+            for (; k < nrows; ++k, rec += 4, pw += L, pt += L, pf += L) one_row(std::false_type{}, rec, k, 0);
+        }
         // the diagonal entries (row0 + dk, j) and (row0 + dk + 1, j + 1) of this pair of columns, if the CTA owns them
         const int dk = jp.diag_k;
 #pragma unroll

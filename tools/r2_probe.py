@@ -79,6 +79,7 @@ def main():
     # ---- K2f: BASELINE config 3 (256 x 512 backbone), packed kernel vs the exact-sequence kernel of round 1
     for (B, L, A, nan_masked, ragged, tag) in ((256, 512, 5, False, False, "config3 (all atoms valid)"),
                                                 (256, 512, 5, "gly", False, "config3 shape, 8 % of the residues without CB (glycine)"),
+                                                (256, 512, 5, False, True, "config3 shape, ragged (lengths U[0.75 L, L], zero padding)"),
                                                 (256, 512, 5, True, True, "config3 shape, NaN-masked + ragged"),
                                                 (64, 384, 15, True, True, "B64 L384 A15 NaN-masked + ragged"),
                                                 (64, 511, 15, False, False, "B64 L511 (odd) A15")):
