@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 // K2, second generation: pairwise_dihedrals / pairwise_planar_angles for ANY atom-slot lists on the packed FP32 pipe.
 //
 // pair_angles_kernel above issues the reference's operation sequence literally and is issue-bound at ~110
-// lane-instructions per pair for ONE angle (profiles/r3i_all_kernels_ncu_table.txt: 0.14 of the HBM roof, issue-active
+// lane-instructions per pair for ONE angle (profiles/r3i_all_kernels_ncu_table_before_packed_generic.txt: 0.14 of the HBM roof, issue-active
 // 84 %).  This kernel evaluates the same angle the way the packed trRosetta kernel does — a thread owns two consecutive
 // residues j and walks the CTA's rows; every subtraction / product is an FADD2 / FMUL2 / FFMA2 for both pairs; the sine
 // term is y = -(n1 . b2) |b1| (no third cross product); atan2 / acos are the packed polynomial evaluations with ONE
