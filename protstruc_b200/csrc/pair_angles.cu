@@ -675,8 +675,32 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
         }
         rec[9] = __int_as_float(bad ? 1 : 0);
         rec[10] = rec[11] = 0.f;
+        // Everything that depends on residue i alone is formed here, once per row, instead of once per thread and row:
+        //   dihedral with three points of residue i: p2, |b1|; b1 = p2 - p1, flags; n1 = (p0 - p1) x b1
+        //   planar angle with two points of residue i: p1, |ba|^2; ba = p0 - p1, flags
+        if (KIND == PS_ANGLE_DIHEDRAL && NI == 3) {
+            const V3 p0{rec[0], rec[1], rec[2]}, p1{rec[3], rec[4], rec[5]}, p2{rec[6], rec[7], rec[8]};
+            const V3 b0 = sub3(p0, p1), b1 = sub3(p2, p1);
+            const float bb = fmaf(b1.z, b1.z, fmaf(b1.y, b1.y, b1.x * b1.x));
+            rec[0] = p2.x; rec[1] = p2.y; rec[2] = p2.z;
+            rec[3] = bb * rsqrt_mufu(bb);  // |b1|, NaN where the reference divides 0 / 0
+            rec[4] = b1.x; rec[5] = b1.y; rec[6] = b1.z;
+            rec[7] = __int_as_float(bad ? 1 : 0);
+            rec[8] = fmaf(b0.y, b1.z, -(b0.z * b1.y));
+            rec[9] = fmaf(b0.z, b1.x, -(b0.x * b1.z));
+            rec[10] = fmaf(b0.x, b1.y, -(b0.y * b1.x));
+        } else if (KIND == PS_ANGLE_PLANAR && NI == 2) {
+            const V3 p0{rec[0], rec[1], rec[2]}, p1{rec[3], rec[4], rec[5]};
+            const V3 ba = sub3(p0, p1);
+            rec[0] = p1.x; rec[1] = p1.y; rec[2] = p1.z;
+            rec[3] = fmaf(ba.z, ba.z, fmaf(ba.y, ba.y, ba.x * ba.x));
+            rec[4] = ba.x; rec[5] = ba.y; rec[6] = ba.z;
+            rec[7] = __int_as_float(bad ? 1 : 0);
+            rec[8] = p0.x; rec[9] = p0.y; rec[10] = p0.z;  // (the exact-sequence fall-back wants the points themselves)
+        }
     }
     __syncthreads();
+    constexpr bool kRowSide = (KIND == PS_ANGLE_DIHEDRAL && NI == 3) || (KIND == PS_ANGLE_PLANAR && NI == 2);
 
     const float4* __restrict__ rows4 = reinterpret_cast<const float4*>(srow);
     const int npairs = Lp >> 1;
@@ -723,12 +747,12 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
         const int dk = j - row0;  // row (relative to the CTA's first) whose diagonal entry is lane x of this pair
         const float4* rec = rows4;
         for (int k = 0; k < nrows; ++k, rec += 3, po += L) {
-            const float4 q2 = rec[2];
-            if (pair_nan || (__float_as_int(q2.y) & 1)) {
+            const float4 q2 = rec[2], q1 = rec[1];
+            if (pair_nan || (__float_as_int(kRowSide ? q1.w : q2.y) & 1)) {
                 store(nan2);
                 continue;
             }
-            const float4 q0 = rec[0], q1 = rec[1];
+            const float4 q0 = rec[0];
             const float ri[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
             P3 pt[N];
 #pragma unroll
@@ -738,16 +762,26 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
             }
             float2 res;
             if (KIND == PS_ANGLE_DIHEDRAL) {
-                const P3 b0 = sub_p3(pt[0], pt[1]);
-                const P3 b1 = sub_p3(pt[2], pt[1]);
-                const P3 b2 = sub_p3(pt[3], pt[2]);
-                const P3 n1 = cross_p3(b0, b1);
-                const P3 n2 = cross_p3(b2, b1);
-                const float2 x = dot_p3(n1, n2);
-                const float2 sn = dot_p3(n1, b2);
-                const float2 bb = dot_p3(b1, b1);
-                const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
-                const float2 ny = __fmul2_rn(sn, nb1);  // y = -(n1 . b2) |b1|
+                float2 x, ny;
+                if constexpr (NI == 3) {  // row-side record: p2, |b1|, b1, n1
+                    const P3 b1{f2(q1.x), f2(q1.y), f2(q1.z)};
+                    const P3 n1{f2(q2.x), f2(q2.y), f2(q2.z)};
+                    const P3 b2 = sub_p3(pj[0], P3{f2(q0.x), f2(q0.y), f2(q0.z)});
+                    const P3 n2 = cross_p3(b2, b1);
+                    x = dot_p3(n1, n2);
+                    ny = __fmul2_rn(dot_p3(n1, b2), f2(q0.w));  // y = -(n1 . b2) |b1|
+                } else {
+                    const P3 b0 = sub_p3(pt[0], pt[1]);
+                    const P3 b1 = sub_p3(pt[2], pt[1]);
+                    const P3 b2 = sub_p3(pt[3], pt[2]);
+                    const P3 n1 = cross_p3(b0, b1);
+                    const P3 n2 = cross_p3(b2, b1);
+                    x = dot_p3(n1, n2);
+                    const float2 sn = dot_p3(n1, b2);
+                    const float2 bb = dot_p3(b1, b1);
+                    const float2 nb1 = __fmul2_rn(bb, make_float2(rsqrt_mufu(bb.x), rsqrt_mufu(bb.y)));  // |b1|, NaN at 0
+                    ny = __fmul2_rn(sn, nb1);  // y = -(n1 . b2) |b1|
+                }
                 AtanPair e;
                 atan2_prepare(ny, x, e);
                 e.p = __ffma2_rn(e.p, e.s, f2(8.210079680e-02f));
@@ -762,10 +796,21 @@ __global__ void __launch_bounds__(256, 3) pair_angles_fast_kernel(
                     if (k != dk + 1 && !atan2_in_range(ny.y, x.y)) res.y = atan2_slow(ny.y, x.y);
                 }
             } else {
-                const P3 ba = sub_p3(pt[0], pt[1]);
-                const P3 bc = sub_p3(pt[2], pt[1]);
+                P3 ba, bc;
+                float2 aa;
+                if constexpr (NI == 2) {  // row-side record: p1, |ba|^2, ba, p0
+                    ba = P3{f2(q1.x), f2(q1.y), f2(q1.z)};
+                    bc = sub_p3(pj[0], P3{f2(q0.x), f2(q0.y), f2(q0.z)});
+                    aa = f2(q0.w);
+                    pt[0] = P3{f2(q2.x), f2(q2.y), f2(q2.z)};
+                    pt[1] = P3{f2(q0.x), f2(q0.y), f2(q0.z)};
+                } else {
+                    ba = sub_p3(pt[0], pt[1]);
+                    bc = sub_p3(pt[2], pt[1]);
+                    aa = dot_p3(ba, ba);
+                }
                 const float2 d = dot_p3(ba, bc);
-                const float2 nn = __fmul2_rn(dot_p3(ba, ba), dot_p3(bc, bc));  // (|ba| |bc|)^2
+                const float2 nn = __fmul2_rn(aa, dot_p3(bc, bc));  // (|ba| |bc|)^2
                 const float2 c = __fmul2_rn(d, make_float2(rsqrt_mufu(nn.x), rsqrt_mufu(nn.y)));
                 AcosPair e;
                 acos_prepare(c, e);
