@@ -101,7 +101,14 @@ __device__ __forceinline__ float atan2_tuned(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float sum = ax + ay;
-    if (!((mx > 1e-30f) & (mx < 1e30f) & (sum == sum))) return atan2f(y, x);
+    if (!((mx > 1e-30f) & (mx < 1e30f) & (sum == sum))) {
+        // The two everyday special cases answered in place (bit for bit what atan2f returns, without its ~50
+        // instructions): a NaN operand, and x = y = 0 — every pair that involves a zero-padded residue of a ragged
+        // batch: atan2(+-0, +0) = +-0, atan2(+-0, -0) = +-pi.
+        if (!(sum == sum)) return __int_as_float(0x7fc00000);
+        if (mx == 0.f) return copysignf(__float_as_int(x) < 0 ? 3.14159274f : 0.f, y);
+        return atan2f(y, x);
+    }
     const float r = rcp_mufu(mx);
     float t = mn * r;
     t = fmaf(r, fmaf(-t, mx, mn), t);  // quotient refined to ~1 ulp
@@ -264,7 +271,7 @@ __device__ __forceinline__ void trrosetta_triple(const TripleRowSide& r, V3 ca_j
         const float bc2 = dot3(bc, bc);
         float cosine = __fmul_rn(__fmul_rn(d, r.inv_ba_norm), rsqrt_refined(bc2));
         if (!(fabsf(cosine) <= 0.999f)) cosine = __fdiv_rn(d, __fmul_rn(r.ba_norm, norm3(bc)));
-        phi = acosf(cosine);
+        phi = cosine == cosine ? acosf(cosine) : nan;  // (0 / 0 of a zero-padded residue: NaN without the call)
     }
 }
 
