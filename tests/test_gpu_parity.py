@@ -1142,6 +1142,46 @@ def test_packed_angle_kernel_register_budgets_and_unrolled_any_a_kernels_give_th
         assert torch.equal(outs[0][1].cpu(), rm)
 
 
+@pytest.mark.parametrize("B,L,A", [(3, 8, 15), (3, 7, 15), (2, 33, 4), (5, 128, 15), (1, 4, 1)])
+def test_elementwise_maps_vector_and_scalar_paths_are_bit_exact(native_lib, B, L, A):
+    """Round 2: scale_shift / translate / rotate take 128-bit kernels when a structure is a multiple of 4 floats (atoms)
+    on 16-byte aligned arrays and the scalar kernels otherwise (a pointer offset by one float forces them).  Both must
+    return the reference's separately rounded  x * scale + shift,  x + t  bit for bit (protstruc.py:736-744, 759-788);
+    rotate within a few ulp of R x (its dot products are not contracted)."""
+    g = torch.Generator().manual_seed(100 * B + L + A)
+    n = B * L * A * 3
+    x = 20.0 * torch.randn(B, L, A, 3, generator=g)
+    x[0, 0, 0, 1] = float("nan")
+    scale, shift = torch.rand(B, 3, generator=g) + 0.5, 10.0 * torch.randn(B, 3, generator=g)
+    q, _ = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    s = torch.cuda.current_stream().cuda_stream
+    sc_d, sh_d, rot_d = scale.to(DEV), shift.to(DEV), q.contiguous().to(DEV)
+    for offset in (0, 1):  # floats: 0 = 16-byte aligned (torch allocations are), 1 = only 4-byte aligned
+        xin = torch.zeros(n + 8, device=DEV)
+        xin[offset:offset + n] = x.reshape(-1).to(DEV)
+        out = torch.full((n + 8,), -7.0, device=DEV)
+        xp, op = xin[offset:].data_ptr(), out[offset:].data_ptr()
+        view = lambda: out[offset:offset + n].view(B, L, A, 3).cpu()  # noqa: E731
+        _cabi.check(native_lib.ps_scale_shift(xp, sc_d.data_ptr(), sh_d.data_ptr(), B, L, A, op, s), "ps_scale_shift")
+        ref = x * scale[:, None, None, :] + shift[:, None, None, :]
+        assert torch.equal(torch.nan_to_num(view(), nan=-3.0), torch.nan_to_num(ref, nan=-3.0)), ("scale_shift", offset)
+        assert bool((out[:offset] == -7.0).all()) and bool((out[offset + n:] == -7.0).all())
+        for rows in (B, 1):
+            _cabi.check(native_lib.ps_translate(xp, sh_d.data_ptr(), rows, B, L, A, op, s), "ps_translate")
+            ref = x + (shift[:, None, None, :] if rows == B else shift[:1, None, None, :])
+            assert torch.equal(torch.nan_to_num(view(), nan=-3.0), torch.nan_to_num(ref, nan=-3.0)), ("translate", offset, rows)
+        _cabi.check(native_lib.ps_translate(xp, sh_d.data_ptr(), B, B, L, A, xp, s), "ps_translate in place")
+        ref = x + shift[:, None, None, :]
+        got = xin[offset:offset + n].view(B, L, A, 3).cpu()
+        assert torch.equal(torch.nan_to_num(got, nan=-3.0), torch.nan_to_num(ref, nan=-3.0)), ("translate in place", offset)
+        xin[offset:offset + n] = x.reshape(-1).to(DEV)
+        _cabi.check(native_lib.ps_rotate(xp, rot_d.data_ptr(), B, B, L, A, op, s), "ps_rotate")
+        ref = torch.einsum("bij,blaj->blai", q.double(), torch.nan_to_num(x).double())
+        finite = ~torch.isnan(x).any(-1)
+        assert (view().double() - ref)[finite].abs().max().item() < 2e-5, ("rotate", offset)
+        assert bool(torch.isnan(view()[~finite]).any())
+
+
 def test_topk_nearest_residue_mask_and_select_match_reference_golden(native_lib):
     g = H.load_golden("frames_align_topk")
     real = H.load_golden("real_1a6v_HL")
