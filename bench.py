@@ -243,8 +243,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="m")
-    ap.add_argument("--batch", type=int, default=64, help="structures per GPU per step (workload m)")
-    ap.add_argument("--c5-chunk", type=int, default=128, help="structures per launch (workload c5)")
+    ap.add_argument("--batch", type=int, default=32,
+                    help="structures per GPU per step (workload m); 32 = 9.5 GB of output per launch: the sweep by batch\n"
+                         "(profiles/r4e_bench_by_batch.txt) peaks there — 16: 22.8 k, 32: 22.9 k, 64: 22.0-22.5 k, 96: 21.5 k")
+    ap.add_argument("--c5-chunk", type=int, default=64, help="structures per launch (workload c5; 10.7 GB of output)")
     ap.add_argument("--e2e-batch", type=int, default=4, help="structures per GPU per end-to-end call")
     ap.add_argument("--e2e-structures", type=int, default=200, help="structures per GPU timed end to end (>= 1 s at N = 1)")
     ap.add_argument("--e2e-seconds", type=float, default=2.5, help="N > 1: every rank keeps making calls at least this long")
