@@ -82,7 +82,7 @@ __device__ __forceinline__ U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
 // the quarter-rate XU pipe (MUFU, I2F) its scarcest resource, so
 //  * the uniforms are built without an int->float conversion: the top 23 bits of the word become the mantissa of
 //    a float in [1, 2); u = f - (1 - 2^-24) = (k + 1/2) * 2^-23 in (0, 1), exact in fp32 (LOP3/SHF + one FADD);
-//  * the transcendental steps are the single-MUFU intrinsics: __logf (abs error 2^-21.4 on [0.5, 2]), MUFU.SQRT,
+//  * the transcendental steps are the single-MUFU intrinsics: MUFU.LG2 (lg2.approx, abs error 2^-22 on [0.5, 2]), MUFU.SQRT,
 //    and __sincosf on the angle shifted into (-pi, pi) (abs error 2^-21.4 there); sin(t - pi) = -sin t, so the
 //    stream definition z = (r sin 2*pi*u2, r cos 2*pi*u2) is unchanged.
 // Deviation from an fp64 evaluation of the same stream is < 1e-5 for 99.9 % of the samples
@@ -94,8 +94,11 @@ __device__ __forceinline__ float unit_open(uint32_t word) {
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     const float u1 = unit_open(a);
     const float u2 = unit_open(b);
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+    // -2 ln u1 = (-2 ln 2) log2 u1: u1 >= 2^-24 is never denormal, so the raw MUFU.LG2 needs none of __logf's
+    // range fix-ups (FSETP + two predicated ops per call), and the two constants fold into one FMUL
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l * -1.38629436f));
     float s, c;
     __sincosf(fmaf(u2, 6.28318548f, -3.14159274f), &s, &c);
     return make_float2(-r * s, -r * c);
