@@ -49,8 +49,10 @@ class _PhiloxStream:
         self._sessions: Dict[int, list] = {}  # id(generator) -> [generator, fingerprint, key, step]
 
     @staticmethod
-    def _fingerprint(generator: torch.Generator) -> int:
-        return hash(generator.get_state().numpy().tobytes())
+    def _fingerprint(generator: torch.Generator) -> bytes:
+        # the state itself (5 KB for the CPU generator), compared byte for byte: hashing it would cost as much
+        # again as reading it, and this sits on the per-call path of the reference-style diffusion loop
+        return generator.get_state().numpy().tobytes()
 
     def reset(self) -> None:
         self._sessions.clear()
@@ -813,5 +815,7 @@ class StructureBatch:
             rc = lib.ps_diffuse_trajectory(self.xyz.data_ptr(), betas.data_ptr(), T, seed, step0, self._noise_elem_offset,
                                            trajectory.data_ptr(), B, L * A * 3, self._stream())
         _cabi.check(rc, "ps_diffuse_trajectory")
-        self.xyz = trajectory[T - 1]
+        # a copy, not a view: in-place mutators (translate, center_at) must not edit the returned trajectory, and
+        # dropping the trajectory must free it
+        self.xyz = trajectory[T - 1].clone()
         return trajectory

@@ -745,7 +745,10 @@ def test_diffusion_loop_equals_the_reference_style_python_loop(native_lib):
     b = ps.StructureBatch.from_xyz(xyz, mask)
     traj = b.diffusion_loop(betas[:, None].repeat(1, B), return_trajectory=True)
     assert tuple(traj.shape) == (T, B, L, A, 3) and torch.equal(traj, torch.stack(states))
-    assert b.get_xyz().data_ptr() == traj[T - 1].data_ptr()
+    # the final state is a copy: an in-place mutator must not reach into the returned trajectory
+    assert torch.equal(b.get_xyz(), traj[T - 1]) and b.get_xyz().data_ptr() != traj[T - 1].data_ptr()
+    b.translate(torch.ones(B, 1, 3, device=DEV))
+    assert torch.equal(traj[T - 1], states[-1])
     with pytest.raises(ValueError):
         b.diffusion_loop(torch.zeros(3, B + 1))
 
