@@ -95,11 +95,15 @@ class HostFeaturePipeline:
                 xyz_host.dtype != torch.float32 or mask_host.dtype != torch.bool or tuple(mask_host.shape) != (B, L, A):
             raise ValueError("host inputs must be CPU tensors of shape (B, L, A, 3) fp32 and (B, L, A) bool")
         xyz_host, mask_host = xyz_host.contiguous(), mask_host.contiguous()
-        for name, dt in (("dist", torch.float32), ("dist_mask", torch.bool), ("omega", torch.float32),
-                         ("theta", torch.float32), ("phi", torch.float32)):
+        full, plane = (L, L, A, A), (L, L)
+        for name, dt, tail in (("dist", torch.float32, full), ("dist_mask", torch.bool, full),
+                               ("omega", torch.float32, plane), ("theta", torch.float32, plane),
+                               ("phi", torch.float32, plane)):
             t = out[name]
-            if t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.shape[0] < B:
-                raise ValueError(f"out[{name!r}] must be a contiguous CPU {dt} tensor with at least {B} rows")
+            if t.is_cuda or t.dtype != dt or not t.is_contiguous() or t.ndim != 1 + len(tail) or t.shape[0] < B or \
+                    tuple(t.shape[1:]) != tail:
+                raise ValueError(f"out[{name!r}] must be a contiguous CPU {dt} tensor of shape (>= {B}, "
+                                 f"{', '.join(map(str, tail))}), got {tuple(t.shape)}")
         with _cabi.on_device(self.device):
             rc = self.lib.ps_host_inter_residue_geometry(
                 self._handle, xyz_host.data_ptr(), mask_host.data_ptr(), B, out["dist"].data_ptr(),

@@ -120,6 +120,7 @@ def gather_compact_features(local: Dict[str, torch.Tensor], batch_size: int, gro
         keep.append(t)
 
     def finish() -> Dict[str, torch.Tensor]:
+        keep.clear()  # the (padded / made-contiguous) send buffers lived until the collectives were waited for
         if even:
             return gathered
         rows = torch.cat([torch.arange(r * biggest, r * biggest + n) for r, n in enumerate(sizes)])
@@ -142,17 +143,24 @@ class FusedFeatureGather:
     every rank's copy mapped into every other rank's address space; with NVSwitch multicast support one `multimem.st`
     per value reaches all ranks.  `run(sb)` launches the kernel on the current stream, then a symmetric-memory barrier
     across the ranks (device-side, on the same stream), and returns the (world * shard, L, L) tensors — structures in
-    rank order; ranks whose shard is shorter than `shard` leave the tail rows of their slab untouched.
+    rank order; ranks whose shard is shorter than `shard` leave the tail rows of their slab untouched.  The returned
+    tensors are views of the reused buffer: they are valid until the next `run` (which, with `guard_reuse`, first waits
+    on the same stream until every rank has finished reading them).
 
     Needs the linear-sweep kernel: A = 15, L >= 32, bool or fp32 atom mask, at most 8 ranks."""
 
-    def __init__(self, shard: int, L: int, group=None, use_multicast: bool = True):
+    def __init__(self, shard: int, L: int, group=None, use_multicast: bool = True, guard_reuse: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
 
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.shard, self.L = int(shard), int(L)
+        # the gathered buffer is REUSED by every `run`: a fast rank's next launch would store into a peer's buffer while
+        # that peer still reads the previous step's result.  With `guard_reuse` every `run` after the first starts with a
+        # barrier across the ranks on the current stream (device-side, ~10 us), i.e. after each rank's own readers in
+        # stream order.  Switch it off only if the caller orders the steps itself.
+        self.guard_reuse, self._runs = bool(guard_reuse), 0
         dev = torch.device("cuda", torch.cuda.current_device())
         self.buffer = symm_mem.empty((6, self.world, self.shard, self.L, self.L), dtype=torch.float32, device=dev)
         self.handle = symm_mem.rendezvous(self.buffer, self.group)
@@ -179,6 +187,9 @@ class FusedFeatureGather:
             dist_out = torch.empty(B, L, L, A, A, dtype=torch.float32, device=dev)
         if dist_mask_out is None:
             dist_mask_out = torch.empty(B, L, L, A, A, dtype=mask.dtype, device=dev)
+        if self.guard_reuse and self._runs > 0:
+            self.handle.barrier()  # nobody still reads the buffer this launch is about to overwrite
+        self._runs += 1
         if B > 0:
             peers = (ctypes.c_void_p * self.world)(*self.peer_ptrs)
             with _cabi.on_device(dev):

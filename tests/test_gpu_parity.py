@@ -1245,6 +1245,8 @@ def test_host_buffer_pipeline_matches_the_device_api(native_lib):
     assert pipe.launches == 2 * 3  # ceil(5 / 2) chunks per run
     with pytest.raises(ValueError):
         pipe.run(xyz.cuda(), mask, out)
+    with pytest.raises(ValueError):  # right number of rows, wrong trailing shape: refused before anything is written
+        pipe.run(xyz, mask, dict(out, omega=torch.empty(B, L, L - 1)))
     pipe.close()
 
 
