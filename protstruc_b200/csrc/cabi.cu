@@ -227,8 +227,12 @@ int ps_inter_residue_geometry_push(const float* xyz, const void* atom_mask, int 
     ps::pair_sweep_set_push_target(peer_buffers, world, multicast_buffer, slab * world, slab * rank);
     // variant bit 27: the linear-sweep kernel regardless of the PROTSTRUC_B200_K1 environment override; bit 26: no pacing
     // defaults (they are chosen for the UNFUSED kinds, this launch evaluates the angles)
-    return ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr, nullptr, B, L, A,
-                                   (1 << 27) | (1 << 26), PS_STREAM(stream));
+    const int rc = ps::pair_dist_mask_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, nullptr, nullptr, nullptr, B, L,
+                                           A, (1 << 27) | (1 << 26), PS_STREAM(stream));
+    // the sweep launcher consumes the target; if the call failed before reaching it, no later launch of this thread
+    // may inherit the peer pointers
+    ps::pair_sweep_set_push_target(nullptr, 0, nullptr, 0, 0);
+    return rc;
 }
 
 int ps_inter_residue_geometry_ex(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,

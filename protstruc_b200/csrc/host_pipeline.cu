@@ -34,6 +34,9 @@ namespace {
 
 void release(HostPipeline* p) {
     if (!p) return;
+    int caller_device = 0;
+    const bool switched = cudaGetDevice(&caller_device) == cudaSuccess && caller_device != p->device &&
+                          cudaSetDevice(p->device) == cudaSuccess;
     for (int s = 0; s < HostPipeline::kSlots; ++s) {
         if (p->streams[s]) cudaStreamDestroy(p->streams[s]);
         cudaFree(p->xyz[s]);
@@ -42,6 +45,7 @@ void release(HostPipeline* p) {
         cudaFree(p->dist_mask[s]);
         cudaFree(p->angles[s]);
     }
+    if (switched) cudaSetDevice(caller_device);
     delete p;
 }
 
@@ -86,6 +90,19 @@ int host_pipeline_run_impl(HostPipeline* p, const float* xyz_host, const uint8_t
     PS_REQUIRE(B > 0, PS_ERR_BAD_SHAPE, "host_pipeline_run: B=%d", B);
     PS_REQUIRE(xyz_host && mask_host && dist_host && dist_mask_host && omega_host && theta_host && phi_host,
                PS_ERR_NULL_POINTER, "host_pipeline_run: NULL host buffer");
+    // The workspaces and streams belong to the device the pipeline was created on: run there whatever the caller's
+    // current device is, and restore it on every way out.  On an error the copies already queued still target the
+    // caller's host buffers, so both streams are drained before the error is returned.
+    int caller_device = 0;
+    cudaError_t dev_err = cudaGetDevice(&caller_device);
+    if (dev_err == cudaSuccess && caller_device != p->device) dev_err = cudaSetDevice(p->device);
+    if (dev_err != cudaSuccess) return cuda_fail(dev_err, "host_pipeline_run: select device");
+    auto leave = [&](int rc) {
+        if (rc != PS_OK)
+            for (int s = 0; s < HostPipeline::kSlots; ++s) cudaStreamSynchronize(p->streams[s]);
+        if (caller_device != p->device) cudaSetDevice(caller_device);
+        return rc;
+    };
     const int L = p->L, A = p->A;
     const size_t res_floats = static_cast<size_t>(L) * A * 3, res_mask = static_cast<size_t>(L) * A;
     const size_t pairs_per = static_cast<size_t>(L) * L, elems_per = pairs_per * A * A;
@@ -98,13 +115,13 @@ int host_pipeline_run_impl(HostPipeline* p, const float* xyz_host, const uint8_t
                                           cudaMemcpyHostToDevice, st);
         if (err == cudaSuccess)
             err = cudaMemcpyAsync(p->mask[s], mask_host + start * res_mask, n * res_mask, cudaMemcpyHostToDevice, st);
-        if (err != cudaSuccess) return cuda_fail(err, "host_pipeline_run: host->device copy");
+        if (err != cudaSuccess) return leave(cuda_fail(err, "host_pipeline_run: host->device copy"));
         float* om = p->angles[s];
         float* th = om + static_cast<size_t>(p->chunk) * pairs_per;
         float* ph = th + static_cast<size_t>(p->chunk) * pairs_per;
         const int rc = pair_dist_mask_impl(p->xyz[s], p->mask[s], PS_MASK_BOOL, p->dist[s], p->dist_mask[s], om, th,
                                            ph, n, L, A, 0, st);
-        if (rc != PS_OK) return rc;
+        if (rc != PS_OK) return leave(rc);
         ++p->launches;
         err = cudaMemcpyAsync(dist_host + start * elems_per, p->dist[s], n * elems_per * sizeof(float),
                               cudaMemcpyDeviceToHost, st);
@@ -120,13 +137,13 @@ int host_pipeline_run_impl(HostPipeline* p, const float* xyz_host, const uint8_t
         if (err == cudaSuccess)
             err = cudaMemcpyAsync(phi_host + start * pairs_per, ph, n * pairs_per * sizeof(float),
                                   cudaMemcpyDeviceToHost, st);
-        if (err != cudaSuccess) return cuda_fail(err, "host_pipeline_run: device->host copy");
+        if (err != cudaSuccess) return leave(cuda_fail(err, "host_pipeline_run: device->host copy"));
     }
     for (int s = 0; s < HostPipeline::kSlots; ++s) {
         const cudaError_t err = cudaStreamSynchronize(p->streams[s]);
-        if (err != cudaSuccess) return cuda_fail(err, "host_pipeline_run: synchronize");
+        if (err != cudaSuccess) return leave(cuda_fail(err, "host_pipeline_run: synchronize"));
     }
-    return PS_OK;
+    return leave(PS_OK);
 }
 
 long long host_pipeline_launches_impl(const HostPipeline* p) { return p ? p->launches : 0; }
