@@ -289,6 +289,20 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
 }
+// The same with an L2 eviction policy for the written lines (createpolicy.fractional.L2::evict_first / evict_last).
+__device__ __forceinline__ void bulk_store_s2g_hint(void* gdst, const void* ssrc, uint32_t bytes, uint64_t policy) {
+    const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(s), "r"(bytes), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int which) {  // 1 = evict_first, 2 = evict_last
+    uint64_t policy;
+    if (which == 2)
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    else
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
 __device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

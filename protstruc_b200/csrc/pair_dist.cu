@@ -384,8 +384,14 @@ __global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_til
             fence_proxy_async_smem();
             tile_sync<WPT>(slot);
             if (is_issuer) {
-                if (kind_has_f32<KIND>()) bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
-                if (kind_has_u8<KIND>()) bulk_store_s2g(p.mask + elem0, tile_u8, G::kMaskBytes);
+                if (p.l2_hint) {
+                    const uint64_t policy = l2_policy(p.l2_hint);
+                    if (kind_has_f32<KIND>()) bulk_store_s2g_hint(p.dist + elem0, tile_f32, G::kDistBytes, policy);
+                    if (kind_has_u8<KIND>()) bulk_store_s2g_hint(p.mask + elem0, tile_u8, G::kMaskBytes, policy);
+                } else {
+                    if (kind_has_f32<KIND>()) bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
+                    if (kind_has_u8<KIND>()) bulk_store_s2g(p.mask + elem0, tile_u8, G::kMaskBytes);
+                }
                 bulk_commit();
             }
         } else {
@@ -543,6 +549,7 @@ struct ColsParams {
     int bulk_u8;       // byte output 16-B aligned: tiles whose byte range is 16-B granular leave through the engine
     long long num_pairs;
     long long num_tiles;
+    int l2_hint;       // L2 eviction policy of the bulk tile stores: 0 none, 1 evict_first, 2 evict_last
 };
 
 __host__ __device__ constexpr int round_up16(int v) { return (v + 15) & ~15; }
@@ -762,8 +769,14 @@ __global__ void __launch_bounds__(384) pair_cols_kernel(const ColsParams p) {
         if (f32_bulk || u8_bulk) fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0 && (f32_bulk || u8_bulk)) {
-            if (f32_bulk) bulk_store_s2g(p.out_f32 + elem0, tile_f32, static_cast<uint32_t>(n) * 4u);
-            if (u8_bulk) bulk_store_s2g(p.out_u8 + elem0, tile_u8, static_cast<uint32_t>(n));
+            if (p.l2_hint) {
+                const uint64_t policy = l2_policy(p.l2_hint);
+                if (f32_bulk) bulk_store_s2g_hint(p.out_f32 + elem0, tile_f32, static_cast<uint32_t>(n) * 4u, policy);
+                if (u8_bulk) bulk_store_s2g_hint(p.out_u8 + elem0, tile_u8, static_cast<uint32_t>(n), policy);
+            } else {
+                if (f32_bulk) bulk_store_s2g(p.out_f32 + elem0, tile_f32, static_cast<uint32_t>(n) * 4u);
+                if (u8_bulk) bulk_store_s2g(p.out_u8 + elem0, tile_u8, static_cast<uint32_t>(n));
+            }
             bulk_commit();
         }
         // plain coalesced stores for whatever the engine cannot take (the barrier after the next tile's staging
@@ -916,7 +929,8 @@ int launch_cols_kind(const ColsParams& p, int sqrt_mode_id, unsigned grid, int t
 
 // Picks the tile (pairs per tile, threads per CTA) for one output kind and launches.  Returns PS_OK + launched =
 // false when no tile of this atom count fits in shared memory (the caller then uses the row kernel).
-// `tune` (comparison hook): bits 0-7 pairs per tile in units of the quantum (0 = choose), bits 8-11 warps per CTA
+// `tune` (comparison hook): bits 0-7 pairs per tile in units of the quantum (0 = choose), bits 8-11 warps per CTA,
+// bits 12-13 L2 eviction policy of the bulk tile stores
 // (0 = choose; 13 = the run-time-A instantiation with the chosen CTA size).
 int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f32, void* out_u8, int B, int L, int A,
                 int sqrt_mode_id, int tune, bool* launched, cudaStream_t stream) {
@@ -997,6 +1011,9 @@ int launch_cols(const float* xyz, const void* atom_mask, int kind, float* out_f3
     p.bulk_u8 = u8_aligned ? 1 : 0;
     p.num_pairs = num_pairs;
     p.num_tiles = (num_pairs + best_pairs - 1) / best_pairs;
+    p.l2_hint = (tune >> 12) & 3;
+    if (p.l2_hint == 0 && kind == kDistBoolMask) p.l2_hint = 1;
+    if (p.l2_hint == 3) p.l2_hint = 0;
     const size_t smem = static_cast<size_t>(smem_for(best_pairs));
     const int sms = sm_count_for_current_device();
     if (sms < 0) return sms;
@@ -1138,7 +1155,7 @@ bool pair_sweep_supported(const float* xyz, const void* atom_mask, int mask_dtyp
                           int L, int A);
 int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask, float* omega,
                     float* theta, float* phi, float* d_ca, float* d_cb, float* d_no, int B, int L, int sqrt_id,
-                    int slots_override, int stores_only, int pace_ns, cudaStream_t stream);
+                    int slots_override, int stores_only, int pace_ns, int l2_hint, cudaStream_t stream);
 
 // Diagnostic: plain 128-bit stores of a non-uniform pattern, linear sweep (what a copy kernel's write side
 // does).  Gives the store ceiling of the memory system for comparison with the TMA bulk-store path.
@@ -1230,6 +1247,11 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
         return e == nullptr ? 0 : (strcmp(e, "strip") == 0 ? 1 : (strcmp(e, "sweep") == 0 ? 2 : 0));
     }();
     const bool want_strip = ((variant >> 15) & 1) || (env_choice == 1 && !((variant >> 27) & 1));
+    // tuning hook of every tile kernel: L2 eviction policy of the bulk tile stores (0 none, 1 evict_first, 2 evict_last)
+    static const int env_l2 = [] {
+        const char* e = getenv("PROTSTRUC_B200_L2HINT");
+        return e == nullptr ? 0 : (atoi(e) & 7);
+    }();
     if (!force_generic && !want_strip && pair_sweep_supported(xyz, atom_mask, mask_dtype, dist, dist_mask, L, A))
     {
         // Pacing defaults of the linear-sweep kernel (profiles/r2_pace_probe.json; the same for every length): HOW
@@ -1244,8 +1266,16 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
             if (dist_mask && mask_dtype == PS_MASK_BOOL && !angles && sqrt_id == 0) sweep_sqrt = 1;
             if (dist_mask && mask_dtype == PS_MASK_F32 && pace_ns == 0) pace_ns = 400;
         }
+        // L2 eviction policy of the tile stores (variant bits 16-18, or PROTSTRUC_B200_L2HINT for whole processes;
+        // 7 = none).  Default: evict_first for distances + byte mask — two interleaved output streams of 28.8 KB and
+        // 7.2 KB tiles; written lines that leave L2 early reach HBM closer to the order they were written in:
+        // 5.5-6.0 -> 6.6-6.8 TB/s at L = 256 / 384 / 512, unchanged at odd L (profiles/r5c_l2_hint_probe_sweep_box1.json, r5d_*_box2.jsonl: two
+        // boxes).  The fused kernel loses 2 % with any hint and the fp32-mask kernel does not care: both stay without.
+        int l2_hint = ((variant >> 16) & 7) ? ((variant >> 16) & 7) : env_l2;
+        if (l2_hint == 0 && dist_mask && mask_dtype == PS_MASK_BOOL && !(omega || theta || phi)) l2_hint = 1;
+        if (l2_hint == 7) l2_hint = 0;
         return pair_sweep_impl(xyz, atom_mask, mask_dtype, dist, dist_mask, omega, theta, phi, d_ca, d_cb, d_no, B, L,
-                               sweep_sqrt, warps_override, (variant >> 10) & 1, pace_ns, stream);
+                               sweep_sqrt, warps_override, (variant >> 10) & 1, pace_ns, l2_hint, stream);
     }
 
     // the staged kernel needs L >= pairs per tile (a tile then touches at most two residue-i rows)
@@ -1254,7 +1284,11 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     const bool fast = staged_atom_count && (L >= tile_pairs) && !force_generic && aligned16(dist) && aligned16(dist_mask);
     if (!fast) {
         const bool rows_only = (variant >> 12) & 1;
-        int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only, (variant >> 16) & 0xFFF, stream);
+        // any-A kernel: variant bits 16-27 are its tile / CTA shape, bits 28-29 the L2 policy of its bulk stores
+        // (3 = none; 0 = the default: evict_first for distances + byte mask, +6 % at 25 atoms, +1.5 % at 37, 0 at 20)
+        const int cols_l2 = ((variant >> 28) & 3) ? ((variant >> 28) & 3) : (env_l2 == 7 ? 3 : (env_l2 & 3));
+        int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only,
+                                  ((variant >> 16) & 0xFFF) | (cols_l2 << 12), stream);
         if (rc != PS_OK || !want_angles) return rc;
         ++g_last_plan.launches;
         // the exact-sequence angle kernel: the same trrosetta_triple the fused tile kernel evaluates, so
@@ -1298,6 +1332,11 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
     p.stores_only = (variant >> 10) & 1;
+    // strip kernels: variant bits 16-17 (3 = none).  Default: evict_first for the 10- and 14-atom layouts without fused
+    // angles (+7-12 % with and without the byte mask, profiles/r5e_l2_hint_probe_others.json); 5 atoms: +2 % / -3 %, none
+    p.l2_hint = ((variant >> 16) & 3) ? ((variant >> 16) & 3) : (env_l2 == 7 ? 3 : (env_l2 & 3));
+    if (p.l2_hint == 0 && (A == 10 || A == 14) && !(omega || theta || phi)) p.l2_hint = 1;
+    if (p.l2_hint == 3) p.l2_hint = 0;
     p.lockstep = ((variant >> 14) & 1) ? 3 : ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
     p.active_workers = 0;
 

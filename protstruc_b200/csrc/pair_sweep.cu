@@ -63,6 +63,8 @@ struct SweepParams {
     long long num_tiles;
     int stores_only;
     int pace_ns;  // tuning hook: the issuing lane sleeps this long after handing a tile to the engine
+    int l2_hint;  // tuning hook: L2 eviction policy of the tile stores (0 = none, 1 = evict_first, 2 = evict_last,
+                  // 3 = evict_first for the distance tile only, 4 = for the mask tile only)
     // Fused all-gather of the compact features (optional): every rank's gathered buffer (6, world, shard, L, L) as
     // mapped into THIS GPU's address space over NVLink (peer[r], r = 0 .. n_peers-1, own buffer included), or ONE
     // NVSwitch multicast address that reaches all of them (mc).  The angle warp stores omega / theta / phi and the
@@ -536,9 +538,26 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
             fence_proxy_async_smem();
             tile_sync<WPT>(slot);
             if (is_issuer) {
-                bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
-                if (kBool) bulk_store_s2g(static_cast<uint8_t*>(p.mask_out) + elem0, tile_mask, G::kMaskBytes);
-                if (kF32) bulk_store_s2g(static_cast<float*>(p.mask_out) + elem0, tile_mask, G::kDistBytes);
+                if (p.l2_hint) {  // 1 / 2: evict_first / evict_last for both tiles; 3 / 4: evict_first for one of them
+                    const uint64_t policy = l2_policy(p.l2_hint == 2 ? 2 : 1);
+                    if (p.l2_hint != 4)
+                        bulk_store_s2g_hint(p.dist + elem0, tile_f32, G::kDistBytes, policy);
+                    else
+                        bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
+                    constexpr uint32_t kMaskTileBytes = kBool ? G::kMaskBytes : G::kDistBytes;
+                    if (kBool || kF32) {
+                        if (p.l2_hint != 3)
+                            bulk_store_s2g_hint(static_cast<uint8_t*>(p.mask_out) + elem0 * (kBool ? 1 : 4), tile_mask,
+                                                kMaskTileBytes, policy);
+                        else
+                            bulk_store_s2g(static_cast<uint8_t*>(p.mask_out) + elem0 * (kBool ? 1 : 4), tile_mask,
+                                           kMaskTileBytes);
+                    }
+                } else {
+                    bulk_store_s2g(p.dist + elem0, tile_f32, G::kDistBytes);
+                    if (kBool) bulk_store_s2g(static_cast<uint8_t*>(p.mask_out) + elem0, tile_mask, G::kMaskBytes);
+                    if (kF32) bulk_store_s2g(static_cast<float*>(p.mask_out) + elem0, tile_mask, G::kDistBytes);
+                }
                 bulk_commit();
                 if (p.pace_ns) __nanosleep(p.pace_ns);
             }
@@ -658,9 +677,10 @@ int pair_sweep_max_peers() { return kMaxPeers; }
 
 int pair_sweep_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist, void* dist_mask, float* omega,
                     float* theta, float* phi, float* d_ca, float* d_cb, float* d_no, int B, int L, int sqrt_id,
-                    int slots_override, int stores_only, int pace_ns, cudaStream_t stream) {
+                    int slots_override, int stores_only, int pace_ns, int l2_hint, cudaStream_t stream) {
     SweepParams p;
     p.pace_ns = pace_ns;
+    p.l2_hint = l2_hint;
     for (int r = 0; r < kMaxPeers; ++r) p.peer[r] = g_push_target.peer[r];
     p.mc = g_push_target.mc;
     p.n_peers = g_push_target.n_peers;

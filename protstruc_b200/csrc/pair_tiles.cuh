@@ -116,6 +116,7 @@ struct PairDistParams {
     int lockstep;             // strips mapped 1:1 to workers (linear sweep of the output): 0 auto, 1 on, 2 off
     int stores_only;          // diagnostic: skip the arithmetic, only issue the tile stores (measures the
                               // memory-system ceiling of this write pattern; output content is undefined)
+    int l2_hint;              // L2 eviction policy of the tile stores: 0 none, 1 evict_first, 2 evict_last
 };
 
 // Gather the A mask bytes of one residue into a bit field (bit a = mask[a] != 0).
