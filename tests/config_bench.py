@@ -176,7 +176,7 @@ def main():
         out["configs"]["c4"] = r
 
     if want("c5"):
-        B_total, L, A, chunk = 4096, 384, 15, 128
+        B_total, L, A, chunk = 4096, 384, 15, 64  # bench.py's default chunk (profiles/r4e_bench_by_batch.txt)
         start, stop = shard_bounds(B_total, world, rank)
         n_local = stop - start
         lib = _cabi.load()
@@ -211,7 +211,7 @@ def main():
         if rank == 0:
             out["configs"]["c5"] = {
                 "what": f"4096 x 384 x 15 full pairwise feature set, batch-sharded over {world} GPU(s), chunks of {chunk} "
-                        "structures through a reused 21.5 GB output buffer",
+                        f"structures through a reused {chunk * L * L * A * A * 5 / 1e9:.1f} GB output buffer",
                 "total_bytes": B_total * per_struct, "ms_max_over_ranks": float(ms.item()),
                 "structures_per_s": B_total / float(ms.item()) * 1e3,
                 "aggregate_GBps": B_total * per_struct / float(ms.item()) / 1e6,
