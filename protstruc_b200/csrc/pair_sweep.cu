@@ -518,9 +518,15 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
                     const bool push = p.n_peers > 0;
                     trrosetta_triple(triple_row_side(n_i, ca_i, cb_i), ca_j, cb_j, push || p.omega != nullptr,
                                      push || p.theta != nullptr, push || p.phi != nullptr, w, t, f);
-                    if (p.omega) p.omega[pair] = w;
-                    if (p.theta) p.theta[pair] = t;
-                    if (p.phi) p.phi[pair] = f;
+                    if (p.l2_hint >= 5) {  // tuning hook: streaming (evict-first) stores for the angle planes
+                        if (p.omega) __stcs(p.omega + pair, w);
+                        if (p.theta) __stcs(p.theta + pair, t);
+                        if (p.phi) __stcs(p.phi + pair, f);
+                    } else {
+                        if (p.omega) p.omega[pair] = w;
+                        if (p.theta) p.theta[pair] = t;
+                        if (p.phi) p.phi[pair] = f;
+                    }
                     if (push) {
                         push_to_peers(p, 0, pair, w);
                         push_to_peers(p, 1, pair, t);
@@ -538,7 +544,8 @@ __global__ void __launch_bounds__(256, 1) pair_sweep_kernel(const SweepParams p)
             fence_proxy_async_smem();
             tile_sync<WPT>(slot);
             if (is_issuer) {
-                if (p.l2_hint) {  // 1 / 2: evict_first / evict_last for both tiles; 3 / 4: evict_first for one of them
+                if (p.l2_hint && p.l2_hint != 5) {  // 1 / 2: evict_first / evict_last for both tiles; 3 / 4: evict_first
+                                                     // for one of them; 5: angle planes only; 6: tiles and angle planes
                     const uint64_t policy = l2_policy(p.l2_hint == 2 ? 2 : 1);
                     if (p.l2_hint != 4)
                         bulk_store_s2g_hint(p.dist + elem0, tile_f32, G::kDistBytes, policy);

@@ -24,7 +24,7 @@ A = 15
 rows = []
 NOPACE = 1 << 26
 VARIANTS = (("hint0", 7 << 16), ("hint1", 1 << 16), ("hint2", 2 << 16), ("hint3", 3 << 16), ("hint4", 4 << 16),
-            ("hint0n", (7 << 16) | NOPACE), ("hint1n", (1 << 16) | NOPACE), ("default", 0))
+            ("hint5", 5 << 16), ("hint6", 6 << 16), ("hint0n", (7 << 16) | NOPACE), ("hint1n", (1 << 16) | NOPACE), ("default", 0))
 import os  # noqa: E402
 
 SWEEP_SHAPES = () if os.environ.get("PROBE_PART") == "others" else ((32, 512), (64, 256), (28, 384), (70, 229), (16, 511))
