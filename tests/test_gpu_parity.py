@@ -108,6 +108,44 @@ def test_distance_kernel_variants_agree(native_lib):
     assert torch.equal(outs[1][0], base), "non-ftz variant differs on normal-range inputs"
 
 
+@pytest.mark.parametrize("B,L,A,shift,codes", [
+    (3, 96, 15, 16, (0, 1, 2, 3, 4, 7)),   # linear-sweep kernel: default (evict_first), explicit policies, 7 = none
+    (3, 96, 10, 16, (0, 1, 2, 3)),         # column-strip kernel of the 10-atom layout: default on, 3 = none
+    (3, 96, 5, 16, (0, 1, 2, 3)),          # 5-atom layout: default off
+    (2, 64, 25, 28, (0, 1, 2, 3)),         # any-A tile kernel (unrolled 25-atom instantiation)
+    (2, 40, 20, 28, (0, 1, 2, 3)),         # any-A tile kernel, run-time atom count
+])
+def test_l2_eviction_policy_of_the_tile_stores_never_changes_a_byte(native_lib, B, L, A, shift, codes):
+    """The L2 cache hint on the bulk tile stores (DESIGN K1s, `tools/l2_hint_probe.py`) is a performance knob only:
+    every policy — and the launcher's per-kind default — writes the same distances and masks, with and without the
+    fused angles."""
+    xyz, mask, _ = H.synthetic_batch(90 + A, B, L, A, "bool")
+    x, m = xyz.to(DEV), mask.to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    base = None
+    for code in codes:
+        d = torch.full((B, L, L, A, A), -7.0, device=DEV)
+        dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
+                                                    code << shift, s), "ps_pair_dist_mask_ex")
+        got = [d.view(torch.int32), dm]
+        if A in (15, 10, 5) and shift == 16:  # fused launch on the staged layouts
+            om, th, ph = (torch.full((B, L, L), -7.0, device=DEV) for _ in range(3))
+            d2 = torch.full((B, L, L, A, A), -7.0, device=DEV)
+            dm2 = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+            fused_code = code if A != 15 else {0: 0, 1: 1, 2: 6, 3: 5, 4: 4, 7: 7}[code]  # sweep: also the angle-plane hooks
+            _cabi.check(native_lib.ps_inter_residue_geometry_ex(x.data_ptr(), m.data_ptr(), 0, d2.data_ptr(), dm2.data_ptr(),
+                                                                om.data_ptr(), th.data_ptr(), ph.data_ptr(), B, L, A,
+                                                                fused_code << shift, s), "ps_inter_residue_geometry_ex")
+            got += [d2.view(torch.int32), dm2, om.view(torch.int32), th.view(torch.int32), ph.view(torch.int32)]
+        torch.cuda.synchronize()
+        if base is None:
+            base = got
+        else:
+            for k, (a, b) in enumerate(zip(got, base)):
+                assert torch.equal(a, b), f"policy code {code} changed output {k}"
+
+
 @pytest.mark.parametrize("B,L", [(8, 256), (6, 250), (5, 190), (3, 384)])
 def test_tile_schedules_write_the_same_bytes(native_lib, B, L):
     """The linear-sweep kernel (default at A = 15), and the column-strip kernel with its cell schedule, its lock-step
