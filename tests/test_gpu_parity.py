@@ -111,7 +111,7 @@ def test_distance_kernel_variants_agree(native_lib):
 @pytest.mark.parametrize("B,L,A,shift,codes", [
     (3, 96, 15, 16, (0, 1, 2, 3, 4, 7)),   # linear-sweep kernel: default (evict_first), explicit policies, 7 = none
     (3, 96, 10, 16, (0, 1, 2, 3)),         # column-strip kernel of the 10-atom layout: default on, 3 = none
-    (3, 96, 5, 16, (0, 1, 2, 3)),          # 5-atom layout: default off
+    (2, 128, 5, 16, (0, 1, 2, 3)),         # 5-atom layout (128 pairs per tile): default off
     (2, 64, 25, 28, (0, 1, 2, 3)),         # any-A tile kernel (unrolled 25-atom instantiation)
     (2, 40, 20, 28, (0, 1, 2, 3)),         # any-A tile kernel, run-time atom count
 ])

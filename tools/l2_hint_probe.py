@@ -74,12 +74,18 @@ for B, L, A in ((24, 256, 25), (12, 256, 37), (40, 256, 20), (256, 512, 5), (64,
     dist = torch.empty(B, L, L, A, A, device="cuda")
     dm = torch.empty(B, L, L, A, A, dtype=torch.bool, device="cuda")
     shift = 16 if A in (5, 10, 14) else 28
-    for kind in ("dist+bool", "dist"):
-        nbytes = B * L * L * A * A * (5 if kind == "dist+bool" else 4)
+    om, th, ph = (torch.empty(B, L, L, device="cuda") for _ in range(3))
+    for kind in ("dist+bool", "dist") + (("fused",) if shift == 16 else ()):
+        nbytes = B * L * L * (A * A * (4 if kind == "dist" else 5) + (12 if kind == "fused" else 0))
         rec = {"B": B, "L": L, "A": A, "kind": kind, "GB": nbytes / 1e9}
         for rep in range(2):
             for hint in (3, 1, 2, 0):  # 3 = explicitly none, 0 = the launcher's default
                 def run():
+                    if kind == "fused":
+                        _cabi.check(lib.ps_inter_residue_geometry_ex(xyz.data_ptr(), mask.data_ptr(), 0, dist.data_ptr(),
+                                                                     dm.data_ptr(), om.data_ptr(), th.data_ptr(),
+                                                                     ph.data_ptr(), B, L, A, hint << shift, s), kind)
+                        return
                     with_mask = kind == "dist+bool"
                     rc = lib.ps_pair_dist_mask_ex(xyz.data_ptr(), mask.data_ptr() if with_mask else None, 0, dist.data_ptr(),
                                                   dm.data_ptr() if with_mask else None, B, L, A, hint << shift, s)
