@@ -339,7 +339,7 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * sleeps n x 100 ns after handing a tile to the TMA engine (pacing probe); bit 26 = linear-sweep kernel without its per-kind
  * pacing defaults (non-ftz square root for distances + byte mask, 400 ns for distances + fp32 mask).
  * L2 eviction policy of the bulk tile stores (0 = the launcher's default: evict_first for distances + byte mask on the
- * linear-sweep kernel, for the 10- / 14-atom strip kernels without fused angles and for the any-A tile kernel with the
+ * linear-sweep kernel, for the 10- / 14-atom strip kernels and for the any-A tile kernel with the
  * byte mask; none elsewhere): linear-sweep kernel bits 16-18 (1 = evict_first, 2 = evict_last, 3 / 4 = evict_first for
  * the distance / the mask tile only, 5 / 6 = streaming stores for the fused angle planes without / with evict_first
  * tiles, 7 = none); strip kernels bits 16-17 (1, 2, 3 = none); any-A tile kernel bits 28-29 (1, 2, 3 = none).  The

@@ -1332,10 +1332,11 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     p.chunk_members = p.strip_members;  // refined per launch once the worker count is known
     p.num_cells = p.strip_stride;
     p.stores_only = (variant >> 10) & 1;
-    // strip kernels: variant bits 16-17 (3 = none).  Default: evict_first for the 10- and 14-atom layouts without fused
-    // angles (+7-12 % with and without the byte mask, profiles/r5e_l2_hint_probe_others.json); 5 atoms: +2 % / -3 %, none
+    // strip kernels: variant bits 16-17 (3 = none).  Default: evict_first for the 10- and 14-atom layouts (+7-12 % with
+    // and without the byte mask, fused +2 % / +9 %: profiles/r5e_l2_hint_probe_others.json, r5k_*); 5 atoms: +2 % / -3 %
+    // (fused: bound by the angle triple, 0 %), none
     p.l2_hint = ((variant >> 16) & 3) ? ((variant >> 16) & 3) : (env_l2 == 7 ? 3 : (env_l2 & 3));
-    if (p.l2_hint == 0 && (A == 10 || A == 14) && !(omega || theta || phi)) p.l2_hint = 1;
+    if (p.l2_hint == 0 && (A == 10 || A == 14)) p.l2_hint = 1;
     if (p.l2_hint == 3) p.l2_hint = 0;
     p.lockstep = ((variant >> 14) & 1) ? 3 : ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
     p.active_workers = 0;
