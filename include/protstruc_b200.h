@@ -338,6 +338,9 @@ int ps_geom_gram_schmidt(const float* a, const float* b, const float* c, int64_t
  * does the same for a whole process, bit 27 = sweep regardless of it); bits 28-30 = linear-sweep kernel: the issuing lane
  * sleeps n x 100 ns after handing a tile to the TMA engine (pacing probe); bit 26 = linear-sweep kernel without its per-kind
  * pacing defaults (non-ftz square root for distances + byte mask, 400 ns for distances + fp32 mask).
+ * bit 19 = fused call on the 5- / 10-atom layouts: keep ONE fused launch (default from 32 k pairs: distance tiles, then
+ * the exact-sequence angle kernel — the fused tile kernel is angle-bound there), bit 20 = split any staged atom count
+ * and size the same way (comparison hooks; identical bits either way).
  * L2 eviction policy of the bulk tile stores (0 = the launcher's default: evict_first for distances + byte mask on the
  * linear-sweep kernel, for the 10- / 14-atom strip kernels and for the any-A tile kernel with the
  * byte mask; none elsewhere): linear-sweep kernel bits 16-18 (1 = evict_first, 2 = evict_last, 3 / 4 = evict_first for

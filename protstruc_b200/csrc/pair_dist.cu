@@ -1212,6 +1212,18 @@ __global__ void __launch_bounds__(256) gather_plane_kernel(const float* __restri
     }
 }
 
+static int launch_gather_planes(const float* dist, long long pairs, int A, float* d_ca, float* d_cb, float* d_no,
+                                cudaStream_t stream) {
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    long long blocks = (pairs + 255) / 256;
+    if (blocks > 16ll * sms) blocks = 16ll * sms;
+    ++g_last_plan.launches;
+    gather_plane_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dist, pairs, A * A, 1 * A + 1, 4 * A + 4,
+                                                                          0 * A + 3, d_ca, d_cb, d_no);
+    return check_launch("gather_plane_kernel");
+}
+
 int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mask_dtype, float* dist,
                                 void* dist_mask, float* omega, float* theta, float* phi, float* d_ca, float* d_cb,
                                 float* d_no, int B, int L, int A, int variant, cudaStream_t stream) {
@@ -1295,15 +1307,7 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
         // inter_residue_geometry returns identical bits whichever way a shape is dispatched
         rc = trrosetta_angles_variant_impl(xyz, B, L, A, 0, omega, theta, phi, 1, stream);
         if (rc != PS_OK || !want_compact) return rc;
-        const long long pairs = static_cast<long long>(B) * L * L;
-        const int sms = sm_count_for_current_device();
-        if (sms < 0) return sms;
-        long long blocks = (pairs + 255) / 256;
-        if (blocks > 16ll * sms) blocks = 16ll * sms;
-        ++g_last_plan.launches;
-        gather_plane_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(dist, pairs, A * A, 1 * A + 1, 4 * A + 4,
-                                                                              0 * A + 3, d_ca, d_cb, d_no);
-        return check_launch("gather_plane_kernel");
+        return launch_gather_planes(dist, static_cast<long long>(B) * L * L, A, d_ca, d_cb, d_no, stream);
     }
 
     PairDistParams p;
@@ -1341,18 +1345,45 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     p.lockstep = ((variant >> 14) & 1) ? 3 : ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
     p.active_workers = 0;
 
+    // Few atoms per residue make the fused launch angle-bound: a tile of the 5-atom layout holds 128 pairs but only
+    // 3,200 distances, and the triples of a tile are evaluated by ONE of its warps — 8 warps per SM cannot hide the
+    // dependent chains of 4 triples per lane.  For 5 and 10 atoms the launcher therefore splits the call: distance tiles
+    // without the angles, then the exact-sequence angle kernel at full occupancy — the SAME trrosetta_triple, so the
+    // bits do not depend on the dispatch (as for shapes that take the any-A kernel above).  Measured
+    // (profiles/r5l_split_dispatch_probe.json): 256 x 512 x 5 4.78 -> 2.39 ms, 64 x 384 x 10 1.02 -> 0.82 ms, on every
+    // input kind; 14 atoms 0.81 -> 0.78 ms (not worth a second launch), 15 atoms take the sweep kernel.  Below 32 k
+    // pairs (one structure of 181 residues) the call is launch-bound and stays ONE launch.  Variant bit 19 keeps the
+    // fused launch, bit 20 splits any staged atom count and size (comparison hooks).
+    const bool split_angles = want_angles && !((variant >> 19) & 1) &&
+                              (((A == 5 || A == 10) && p.num_pairs >= 32768) || ((variant >> 20) & 1));
+    if (split_angles) {
+        p.omega = p.theta = p.phi = nullptr;
+        p.d_ca = p.d_cb = p.d_no = nullptr;
+    }
+    const bool tile_angles = want_angles && !split_angles;
+    int rc;
     switch (A) {
         case 4:
-            return dispatch_tiles<4>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+            rc = dispatch_tiles<4>(p, mask_dtype, dist_mask, tile_angles, sqrt_id, warps_override, wpt, stream);
+            break;
         case 5:
-            return dispatch_tiles<5>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+            rc = dispatch_tiles<5>(p, mask_dtype, dist_mask, tile_angles, sqrt_id, warps_override, wpt, stream);
+            break;
         case 10:
-            return dispatch_tiles<10>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+            rc = dispatch_tiles<10>(p, mask_dtype, dist_mask, tile_angles, sqrt_id, warps_override, wpt, stream);
+            break;
         case 14:
-            return dispatch_tiles<14>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+            rc = dispatch_tiles<14>(p, mask_dtype, dist_mask, tile_angles, sqrt_id, warps_override, wpt, stream);
+            break;
         default:
-            return dispatch_tiles<15>(p, mask_dtype, dist_mask, want_angles, sqrt_id, warps_override, wpt, stream);
+            rc = dispatch_tiles<15>(p, mask_dtype, dist_mask, tile_angles, sqrt_id, warps_override, wpt, stream);
+            break;
     }
+    if (rc != PS_OK || !split_angles) return rc;
+    ++g_last_plan.launches;
+    rc = trrosetta_angles_variant_impl(xyz, B, L, A, 0, omega, theta, phi, 1, stream);
+    if (rc != PS_OK || !want_compact) return rc;
+    return launch_gather_planes(dist, static_cast<long long>(B) * L * L, A, d_ca, d_cb, d_no, stream);
 }
 
 }  // namespace ps

@@ -393,7 +393,8 @@ class StructureBatch:
     def inter_residue_geometry(self) -> Dict[str, torch.Tensor]:
         """trRosetta-style inter-residue geometry (reference protstruc.py:790-817): d_ca, d_cb, d_no
         (strided views of the full distance tensor, with masks) and omega / theta / phi, produced by
-        ONE fused kernel launch."""
+        ONE fused kernel launch (large batches of the 5- / 10-atom layouts: distance tiles, then the exact-sequence
+        angle kernel — same bits, the fused tile kernel is angle-bound with so few atoms per residue)."""
         if self.atom_mask is None:
             raise TypeError("'NoneType' object is not subscriptable (inter_residue_geometry needs atom_mask)")
         B, L, A = self._dims()

@@ -146,6 +146,35 @@ def test_l2_eviction_policy_of_the_tile_stores_never_changes_a_byte(native_lib, 
                 assert torch.equal(a, b), f"policy code {code} changed output {k}"
 
 
+@pytest.mark.parametrize("B,L,A,nan_masked", [(2, 140, 5, False), (2, 140, 5, True), (2, 70, 10, True), (1, 192, 10, True),
+                                              (1, 37, 14, True), (2, 64, 15, True)])
+def test_fused_and_split_dispatch_of_inter_residue_geometry_give_the_same_bits(native_lib, B, L, A, nan_masked):
+    """The launcher splits the fused call into distance tiles + the exact-sequence angle kernel for the 5- and 10-atom
+    layouts from 32 k pairs (angle-bound when fused).  Fused (variant bit 19), split (bit 20) and the default write
+    identical bytes."""
+    xyz, mask, _ = H.synthetic_batch(700 + A, B, L, A, "bool", nan_masked=nan_masked)
+    x, m = xyz.to(DEV), mask.to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    outs, launches = {}, {}
+    for name, variant in (("default", 0), ("fused", 1 << 19), ("split", 1 << 20)):
+        if A == 15:
+            variant |= 1 << 15  # the column-strip kernel (the sweep kernel has its own fused path)
+        d = torch.full((B, L, L, A, A), -7.0, device=DEV)
+        dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        om, th, ph = (torch.full((B, L, L), -7.0, device=DEV) for _ in range(3))
+        _cabi.check(native_lib.ps_inter_residue_geometry_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(),
+                                                            om.data_ptr(), th.data_ptr(), ph.data_ptr(), B, L, A, variant, s),
+                    "ps_inter_residue_geometry_ex")
+        torch.cuda.synchronize()
+        launches[name] = _cabi.last_pair_dist_plan()["launches"]
+        outs[name] = [t.view(torch.int32) if t.dtype == torch.float32 else t for t in (d, dm, om, th, ph)]
+    assert launches["fused"] == 1 and launches["split"] == 2
+    assert launches["default"] == (2 if A in (5, 10) and B * L * L >= 32768 else 1)  # small calls stay one launch
+    for name in ("fused", "split"):
+        for k, (a, b) in enumerate(zip(outs[name], outs["default"])):
+            assert torch.equal(a, b), f"{name} dispatch differs from the default in output {k}"
+
+
 @pytest.mark.parametrize("B,L", [(8, 256), (6, 250), (5, 190), (3, 384)])
 def test_tile_schedules_write_the_same_bytes(native_lib, B, L):
     """The linear-sweep kernel (default at A = 15), and the column-strip kernel with its cell schedule, its lock-step
