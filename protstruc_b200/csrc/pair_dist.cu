@@ -1298,7 +1298,7 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
         const bool rows_only = (variant >> 12) & 1;
         // any-A kernel: variant bits 16-27 are its tile / CTA shape, bits 28-29 the L2 policy of its bulk stores
         // (3 = none; 0 = the default: evict_first for distances + byte mask, +6 % at 25 atoms, +1.5 % at 37, 0 at 20)
-        const int cols_l2 = ((variant >> 28) & 3) ? ((variant >> 28) & 3) : (env_l2 == 7 ? 3 : (env_l2 & 3));
+        const int cols_l2 = ((variant >> 28) & 3) ? ((variant >> 28) & 3) : (env_l2 == 7 ? 3 : (env_l2 <= 2 ? env_l2 : 0));
         int rc = launch_any_shape(xyz, atom_mask, mask_dtype, dist, dist_mask, B, L, A, sqrt_id, rows_only,
                                   ((variant >> 16) & 0xFFF) | (cols_l2 << 12), stream);
         if (rc != PS_OK || !want_angles) return rc;
@@ -1339,7 +1339,7 @@ int pair_dist_mask_compact_impl(const float* xyz, const void* atom_mask, int mas
     // strip kernels: variant bits 16-17 (3 = none).  Default: evict_first for the 10- and 14-atom layouts (+7-12 % with
     // and without the byte mask, fused +2 % / +9 %: profiles/r5e_l2_hint_probe_others.json, r5k_*); 5 atoms: +2 % / -3 %
     // (fused: bound by the angle triple, 0 %), none
-    p.l2_hint = ((variant >> 16) & 3) ? ((variant >> 16) & 3) : (env_l2 == 7 ? 3 : (env_l2 & 3));
+    p.l2_hint = ((variant >> 16) & 3) ? ((variant >> 16) & 3) : (env_l2 == 7 ? 3 : (env_l2 <= 2 ? env_l2 : 0));
     if (p.l2_hint == 0 && (A == 10 || A == 14)) p.l2_hint = 1;
     if (p.l2_hint == 3) p.l2_hint = 0;
     p.lockstep = ((variant >> 14) & 1) ? 3 : ((variant >> 11) & 1) ? 1 : (((variant >> 13) & 1) ? 2 : 0);
