@@ -61,7 +61,8 @@ namespace {
 // double-buffered per-warp staging area and the row loop reads them with broadcast LDS.  The mask bits
 // of both residues come from one byte load per lane and a ballot.
 template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
-__global__ void __launch_bounds__(WPT * 256 > 384 ? 384 : WPT * 256, 1) pair_tiles_kernel(const PairDistParams p) {
+__global__ void __launch_bounds__(WPT * 256 > 384 ? (A <= 6 ? 512 : 384) : WPT * 256, 1)
+pair_tiles_kernel(const PairDistParams p) {
     using G = TileGeom<A>;
     constexpr int Q = pairs_per_lane<A>();
     static_assert(A >= 1 && 2 * A <= 32, "the mask ballot holds two residues of at most 16 atoms");
@@ -802,25 +803,34 @@ template <int A, int KIND, int SQRT, bool ANGLES, int WPT>
 int launch_tiles_wpt(const PairDistParams& p, int slots_override, cudaStream_t stream) {
     constexpr int per_slot = warp_smem_bytes<A, KIND>() + WPT * stage_bytes_per_warp<A>();
     constexpr int kMaxSmem = 227 * 1024;
-    constexpr int kMaxWarps = (WPT == 1) ? 8 : 12;
+    constexpr int kMaxWarps = (WPT == 1) ? 8 : (A <= 6 ? 16 : 12);
     int slots = kMaxSmem / per_slot;
     if (slots * WPT > kMaxWarps) slots = kMaxWarps / WPT;
     // Measured on B200 (profiles/r1g_k1_sweep_v6_cells.json): with two warps per tile, four tile buffers
     // (8 warps, 147 KB) sustain 6.1-6.3 TB/s on the distance + mask kernels, five or six buffers 3-8 % less.
-    if (WPT == 2 && kind_has_f32<KIND>() && slots > 4) slots = 4;
+    // The small layouts (4 / 5 atoms: 10-16 KB per tile) need MORE buffers to keep enough bytes in flight per SM:
+    // four buffers 4.5 / 3.3 TB/s, six 5.7 / 4.4, eight (16 warps, 128 registers) 6.5 / 5.2 with the byte mask and
+    // 6.3 / 5.3 without (profiles/r5n_small_layout_tile_buffers.jsonl; 256 x 512, 512 x 256 and 1024 x 128 residues).
+    constexpr int kDefaultSlots = A <= 6 ? 8 : 4;
+    if (WPT == 2 && kind_has_f32<KIND>() && slots > kDefaultSlots) slots = kDefaultSlots;
     if (slots_override > 0 && slots_override <= kMaxSmem / per_slot && slots_override * WPT <= kMaxWarps)
         slots = slots_override;
     if (slots < 1) {
         set_error("pair_tiles_kernel: a tile of %d B does not fit in shared memory", per_slot);
         return PS_ERR_BAD_SHAPE;
     }
+    const int sms = sm_count_for_current_device();
+    if (sms < 0) return sms;
+    if (A <= 6 && slots_override <= 0 && slots > 4) {
+        // small calls keep the four buffers per CTA they always had, so that their tiles spread over as many SMs as before
+        const long long per_sm = (p.num_tiles + sms - 1) / sms;
+        if (per_sm < slots) slots = per_sm < 4 ? 4 : static_cast<int>(per_sm);
+    }
     const int smem = slots * per_slot;
     auto kernel = pair_tiles_kernel<A, KIND, SQRT, ANGLES, WPT>;
     cudaError_t err =
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute(pair_tiles_kernel)");
-    const int sms = sm_count_for_current_device();
-    if (sms < 0) return sms;
     long long ctas = (p.num_tiles + slots - 1) / slots;
     if (ctas > sms) ctas = sms;
     PairDistParams q = p;
