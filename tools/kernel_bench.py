@@ -103,7 +103,7 @@ def main():
         _cabi.check(lib.ps_pair_dist_mask(xyz.data_ptr(), maskf.data_ptr(), 1, dist.data_ptr(), dmaskf.data_ptr(),
                                           B, L, A, s), "k1f")
     best, med = time_call(run_f32mask)
-    out["results"].append(entry(f"K1 dist + fp32 mask (2 launches) B{B} L{L} A{A}", best, med, B * L * L * A * A * 8, peak))
+    out["results"].append(entry(f"K1 dist + fp32 mask (one launch since round 2) B{B} L{L} A{A}", best, med, B * L * L * A * A * 8, peak))
     del dmaskf, maskf
 
     def run_fused():  # noqa: E306
