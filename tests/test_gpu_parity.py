@@ -175,6 +175,53 @@ def test_fused_and_split_dispatch_of_inter_residue_geometry_give_the_same_bits(n
             assert torch.equal(a, b), f"{name} dispatch differs from the default in output {k}"
 
 
+@pytest.mark.parametrize("B,L,A", [(3, 140, 5), (2, 129, 5), (3, 128, 4), (40, 256, 5)])
+def test_small_layouts_with_eight_tile_buffers_write_the_same_bytes(native_lib, B, L, A):
+    """The 4- / 5-atom strip kernels run eight tile buffers per CTA (16 warps, 512 threads) on large calls and four on
+    small ones: forced 8, forced 4, 6, the default and the any-A kernel write identical distances and masks — also for
+    the fused launch of the 5-atom layout (variant bit 19)."""
+    xyz, mask, _ = H.synthetic_batch(800 + A + L, B, L, A, "bool")
+    x, m = xyz.to(DEV), mask.to(DEV)
+    s = torch.cuda.current_stream().cuda_stream
+    outs = {}
+    for name, variant in (("default", 0), ("s8", 8 << 4), ("s4", 4 << 4), ("s6", 6 << 4), ("anyA", 1 << 8)):
+        d = torch.full((B, L, L, A, A), -7.0, device=DEV)
+        dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+        _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(), B, L, A,
+                                                    variant, s), "ps_pair_dist_mask_ex")
+        torch.cuda.synchronize()
+        if name != "anyA":
+            plan = _cabi.last_pair_dist_plan()
+            assert plan["path"] == 0 and plan["sweep"] == 0
+            if name in ("s8", "s4", "s6"):
+                assert plan["tile_buffers"] == plan["ctas"] * int(name[1:])
+        outs[name] = (d.view(torch.int32), dm)
+    if B * L * L // 128 >= 8 * 148:  # a large call: the default IS eight buffers
+        _cabi.check(native_lib.ps_pair_dist_mask_ex(x.data_ptr(), m.data_ptr(), 0, outs["default"][0].view(torch.float32).data_ptr(),
+                                                    outs["default"][1].data_ptr(), B, L, A, 0, s), "ps_pair_dist_mask_ex")
+        assert _cabi.last_pair_dist_plan()["tile_buffers"] == 8 * _cabi.last_pair_dist_plan()["ctas"]
+    for name in ("s8", "s4", "s6", "anyA"):
+        assert torch.equal(outs[name][0], outs["default"][0]), f"{name}: distances differ"
+        assert torch.equal(outs[name][1], outs["default"][1]), f"{name}: mask differs"
+    rd, rm = orc.pair_distances(xyz[:2], mask[:2])
+    H.assert_distances_close(outs["s8"][0].view(torch.float32)[:2], rd)
+    assert torch.equal(outs["s8"][1][:2].cpu(), rm)
+    if A == 5:
+        fused = {}
+        for name, variant in (("s4", (1 << 19) | (4 << 4)), ("s8", (1 << 19) | (8 << 4))):
+            d = torch.full((B, L, L, A, A), -7.0, device=DEV)
+            dm = torch.zeros(B, L, L, A, A, dtype=torch.bool, device=DEV)
+            om, th, ph = (torch.full((B, L, L), -7.0, device=DEV) for _ in range(3))
+            _cabi.check(native_lib.ps_inter_residue_geometry_ex(x.data_ptr(), m.data_ptr(), 0, d.data_ptr(), dm.data_ptr(),
+                                                                om.data_ptr(), th.data_ptr(), ph.data_ptr(), B, L, A,
+                                                                variant, s), "ps_inter_residue_geometry_ex")
+            torch.cuda.synchronize()
+            fused[name] = [t.view(torch.int32) for t in (d, om, th, ph)] + [dm]
+        for k, (a, b) in enumerate(zip(fused["s8"], fused["s4"])):
+            assert torch.equal(a, b), f"fused launch with eight buffers differs in output {k}"
+        assert torch.equal(fused["s8"][0], outs["default"][0])
+
+
 @pytest.mark.parametrize("B,L", [(8, 256), (6, 250), (5, 190), (3, 384)])
 def test_tile_schedules_write_the_same_bytes(native_lib, B, L):
     """The linear-sweep kernel (default at A = 15), and the column-strip kernel with its cell schedule, its lock-step
