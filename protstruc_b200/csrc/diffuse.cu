@@ -295,6 +295,57 @@ __global__ void __launch_bounds__(256) diffuse_philox_step_kernel(const float* _
     }
 }
 
+// The same step for structures of a multiple of four floats on 16-byte aligned arrays whose shard starts on a group
+// boundary (the usual case: config 4 has 5,760 floats per structure).  2-D grid — y walks the structures, x the
+// structure's groups of four — so a thread takes beta and its two IEEE square roots ONCE per structure instead of
+// once per group, needs no division to find its structure, and moves its groups with 128-bit loads / stores.  Same
+// counters, same Box-Muller, same rounding: bit-identical to the kernel above (ncu: ~280 instructions per group there,
+// of which the generator and the update are ~95).
+__global__ void __launch_bounds__(256) diffuse_philox_step_vec_kernel(const float4* __restrict__ x,
+                                                                      const float* __restrict__ beta, uint64_t seed,
+                                                                      uint64_t step, uint64_t group_offset,
+                                                                      unsigned groups_per_b, int B,
+                                                                      float4* __restrict__ out) {
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) {
+        const float bt = __ldg(beta + b);
+        const float sa = __fsqrt_rn(__fsub_rn(1.0f, bt));
+        const float sb = __fsqrt_rn(bt);
+        const unsigned long long base = static_cast<unsigned long long>(b) * groups_per_b;
+        for (unsigned gl = blockIdx.x * blockDim.x + threadIdx.x; gl < groups_per_b; gl += stride) {
+            const float4 v = x[base + gl];
+            float z[4];
+            normal4(base + gl + group_offset, step, seed, z);
+            out[base + gl] = make_float4(diffuse_one(v.x, z[0], sa, sb), diffuse_one(v.y, z[1], sa, sb),
+                                         diffuse_one(v.z, z[2], sa, sb), diffuse_one(v.w, z[3], sa, sb));
+        }
+    }
+}
+
+// One diffusion step on the Philox stream: picks the vector kernel when the layout allows it.
+int launch_philox_step(const float* x, const float* beta, uint64_t seed, uint64_t step, uint64_t elem_offset, int B,
+                       long long per_b, float* out, cudaStream_t stream) {
+    const int shift = static_cast<int>(elem_offset & 3u);
+    const long long total = per_b * B;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (shift == 0 && (per_b & 3) == 0 && aligned && per_b / 4 < (1ll << 31)) {
+        const unsigned groups_per_b = static_cast<unsigned>(per_b / 4);
+        // ~2 groups per thread along x keeps the generator busy while the 128-bit loads are in flight
+        unsigned gx = (groups_per_b + 511) / 512;
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        const dim3 grid(gx, static_cast<unsigned>(B < 65535 ? B : 65535), 1);
+        diffuse_philox_step_vec_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), beta, seed, step,
+                                                                 elem_offset / 4, groups_per_b, B,
+                                                                 reinterpret_cast<float4*>(out));
+        return PS_OK;
+    }
+    const long long groups = (total + shift + 3) / 4;
+    diffuse_philox_step_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(
+        x, beta, seed, step, elem_offset / 4, shift, per_b, total, out);
+    return PS_OK;
+}
+
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, long long n,
                                                             uint64_t seed, uint64_t step,
                                                             uint64_t group_offset, int shift) {
@@ -346,8 +397,7 @@ int diffuse_impl(const float* x, const float* betas, int T, const float* noise, 
     if (T == 1) {
         const long long groups = (total + shift + 3) / 4;
         PS_REQUIRE((groups + 255) / 256 < (1ll << 31), PS_ERR_BAD_SHAPE, "diffuse: %lld elements", total);
-        diffuse_philox_step_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(
-            x, betas, seed, step0, elem_offset / 4, shift, per_b, total, out);
+        launch_philox_step(x, betas, seed, step0, elem_offset, B, per_b, out, stream);
         return check_launch("diffuse_philox_step_kernel");
     }
     int rc = grid_for((total + shift + 3) / 4, &grid);
@@ -374,13 +424,11 @@ int diffuse_trajectory_impl(const float* x, const float* betas, int T, uint64_t 
     const int shift = static_cast<int>(elem_offset & 3u);
     const long long groups = (total + shift + 3) / 4;
     PS_REQUIRE((groups + 255) / 256 < (1ll << 31), PS_ERR_BAD_SHAPE, "diffuse_trajectory: %lld elements", total);
-    const unsigned grid = static_cast<unsigned>((groups + 255) / 256);
     const float* src = x;
     for (int t = 0; t < T; ++t) {
         float* dst = trajectory + static_cast<long long>(t) * total;
-        diffuse_philox_step_kernel<<<grid, 256, 0, stream>>>(src, betas + static_cast<long long>(t) * B, seed,
-                                                             step0 + static_cast<uint64_t>(t), elem_offset / 4, shift,
-                                                             per_b, total, dst);
+        launch_philox_step(src, betas + static_cast<long long>(t) * B, seed, step0 + static_cast<uint64_t>(t), elem_offset,
+                           B, per_b, dst, stream);
         src = dst;
     }
     return check_launch("diffuse_philox_step_kernel");
