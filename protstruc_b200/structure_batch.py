@@ -84,6 +84,14 @@ def _always_tensor(x):
     return torch.from_numpy(x) if isinstance(x, np.ndarray) else x
 
 
+def _as_bytes(mask: torch.Tensor) -> torch.Tensor:
+    """0 / 1 bytes of a mask for the kernels that read `const uint8_t*`: a bool tensor is reinterpreted in place (no
+    conversion kernel: these calls are latency-critical for single small structures), anything else is converted."""
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
 def _target_device(xyz: torch.Tensor, device) -> torch.device:
     if device is not None:
         return torch.device(device)
@@ -479,7 +487,7 @@ class StructureBatch:
         if want_dihedrals:
             if A < 3:
                 raise IndexError(f"index 2 is out of bounds for dimension 2 with size {A}")
-            rm = self.residue_mask.to(torch.uint8).contiguous()
+            rm = _as_bytes(self.residue_mask)
             ch = self.chain_idx.to(torch.float32).contiguous()
             keep += [rm, ch]
             dihedrals = torch.empty(B, L, 3, dtype=torch.float32, device=dev)
@@ -704,7 +712,7 @@ class StructureBatch:
             valid = valid & mask.to(dev)
         k_eff = min(int(k), int(valid.sum().item()))
         query = query_xyz.to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
-        valid_u8 = valid.to(torch.uint8).contiguous()
+        valid_u8 = _as_bytes(valid)
         scratch = torch.empty(L, dtype=torch.float32, device=dev)
         out = torch.empty(L, dtype=torch.bool, device=dev)
         with _cabi.on_device(dev):
