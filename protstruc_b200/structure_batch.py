@@ -683,7 +683,7 @@ class StructureBatch:
                 raise TypeError("align needs atom masks (or an explicit `atom_mask`)")
             atom_mask = self.atom_mask * target.get_atom_mask().to(dev)
         B, L, A = self._dims()
-        mask = atom_mask.to(dev).bool().expand(B, L, A).reshape(B, L * A).to(torch.uint8).contiguous()
+        mask = _as_bytes(atom_mask.to(dev).bool().expand(B, L, A).reshape(B, L * A))
         tgt = target.get_xyz().to(device=dev, dtype=torch.float32).contiguous()
         rot = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
         tr = torch.empty(B, 3, dtype=torch.float32, device=dev)
