@@ -63,7 +63,6 @@ for B, L in SWEEP_SHAPES:
         print(json.dumps(rec), file=sys.stderr, flush=True)
         del dmf
     del dist, dm, om, th, ph
-print(json.dumps(rows, indent=1))
 
 # ---- the other tile kernels: any-A (`pair_cols_kernel`, hint in variant bits 28-29) and the column-strip kernel of the
 # staged atom counts 5 / 10 / 14 (`pair_tiles_kernel`, bits 16-17), distances + byte mask and distances only
@@ -96,4 +95,4 @@ for B, L, A in ((24, 256, 25), (12, 256, 37), (40, 256, 20), (256, 512, 5), (64,
         others.append(rec)
         print(json.dumps(rec), file=sys.stderr, flush=True)
     del dist, dm
-print(json.dumps(others, indent=1))
+print(json.dumps({"sweep_kernel": rows, "other_tile_kernels": others}, indent=1))
